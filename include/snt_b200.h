@@ -1,0 +1,149 @@
+/* snt_b200.h — C ABI of the B200-native Show-and-Tell caption-decoder hot path.
+ *
+ * The reference (incredible-vision/show-and-tell) has no FFI of its own: its hot path is the Python
+ * nn.Module pair in models.py calling into PyTorch.  Each entry point below replaces the PyTorch call
+ * (or fused group of calls) cited next to it; `show-and-tell_b200/models.py` binds them with ctypes
+ * behind the reference's EncoderCNN / DecoderRNN module API (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *  - All tensor pointers are DEVICE pointers unless marked [host].  The caller owns every buffer,
+ *    including workspaces and tensors saved for backward; the library keeps no tensor memory.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it, there are
+ *    no hidden synchronisations.  Functions are re-entrant; one process drives one GPU.
+ *  - Return value: 0 = ok, <0 = error (SNT_E*).  `snt_last_error()` returns a thread-local message.
+ *  - Packed (time-major) layout, as torch.nn.utils.rnn.pack_padded_sequence produces it
+ *    (models.py:51): `batch_sizes[t]` = #sequences longer than t (non-increasing, host int32[T]),
+ *    off[t] = sum_{t'<t} batch_sizes[t'], packed row of (t, b) = off[t] + b, N = off[T].
+ *  - `prec`: SNT_PREC_FP32 = fp32 operands and fp32 FFMA accumulation (the "fp32-accumulate" faithful
+ *    mode); SNT_PREC_BF16 = bf16 operands on tcgen05 tensor cores with fp32 accumulation in TMEM.
+ *    Tensors marked (act) are fp32 in FP32 mode and bf16 in BF16 mode.
+ *  - There is no CPU fallback anywhere: without a CUDA device every compute entry point fails.
+ */
+#ifndef SNT_B200_H
+#define SNT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNT_ABI_VERSION 1
+#define SNT_MAX_T 128 /* longest packed sequence (timesteps) accepted */
+#define SNT_MAX_LAYERS 8
+
+enum { SNT_OK = 0, SNT_EINVAL = -1, SNT_EUNSUPPORTED = -2, SNT_ECUDA = -3, SNT_EWORKSPACE = -4 };
+enum { SNT_PREC_FP32 = 0, SNT_PREC_BF16 = 1 };
+
+int snt_abi_version(void);
+const char* snt_last_error(void);
+/* sm_count, compute capability (major*10+minor), opt-in shared memory per block of `device`. */
+int snt_device_query(int device, int* sm_count, int* cc, int64_t* smem_optin);
+/* Sticky device-side flags (bit0: token id out of range in a gather).  Synchronises `stream`. */
+int snt_read_flags(int* flags_out, int reset, void* stream);
+/* Number of CUDA kernels this library has launched in this process (optionally resetting the counter). */
+int64_t snt_launch_count(int reset);
+
+/* ---- generic dense contractions (exported for the head, the drop-in Linear and unit tests) --------
+ * C[M,N] = alpha * opA(A) . opB(B) + beta * C + bias[N]   (bias may be NULL), row-major C with ldc.
+ * transA = 0: A is [M,K] row-major (lda);  1: A is [K,M] row-major.
+ * transB = 0: B is [K,N] row-major (ldb);  1: B is [N,K] row-major  (the x.W^T case of nn.Linear). */
+int snt_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha,
+                 const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
+                 float* C, int64_t ldc, const float* bias, void* stream);
+/* Same contraction with bf16 operands (uint16 storage) on tcgen05/TMEM via TMA; C is fp32 or bf16
+ * (c_is_bf16).  Leading dimensions must be multiples of 8 elements and bases 16-byte aligned. */
+int snt_gemm_bf16(int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha,
+                  const void* A, int64_t lda, const void* B, int64_t ldb, float beta,
+                  void* C, int64_t ldc, int c_is_bf16, const float* bias, void* stream);
+/* fp32 -> bf16 (round to nearest even), n elements. */
+int snt_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ---- a1/a2  EncoderCNN head: resnet.fc Linear(2048->E) + BatchNorm1d(E, momentum=0.01) ---------------
+ * replaces models.py:27-28 applied to the pooled 2048-d features.  training!=0: batch statistics and
+ * running-stat update (unbiased variance into running_var); else running stats.
+ * saves yhat[B,E] and rstd[E] for backward.  workspace: snt_head_workspace_bytes. */
+int64_t snt_head_workspace_bytes(int prec, int64_t B, int64_t K, int64_t E);
+int snt_head_fwd(int prec, const float* pooled, const float* w_fc, const float* b_fc,
+                 const float* gamma, const float* beta, float* running_mean, float* running_var,
+                 int training, float momentum, float eps, int64_t B, int64_t K, int64_t E,
+                 float* features, float* yhat, float* rstd, void* ws, int64_t ws_bytes, void* stream);
+/* autograd of the above w.r.t. the trainable head parameters (the backbone is frozen, models.py:14-15) */
+int snt_head_bwd(int prec, const float* dfeatures, const float* pooled, const float* yhat,
+                 const float* rstd, const float* gamma, int training, int64_t B, int64_t K, int64_t E,
+                 float* d_w_fc, float* d_b_fc, float* d_gamma, float* d_beta,
+                 void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- a4-a6  embedding gather + image-feature concat + pack  (models.py:49-51) ------------------------
+ * x[off[t]+b,:] = features[b,:] (t==0) | w_emb[captions[b,t-1],:] (t>=1), for b < batch_sizes[t].
+ * Writes x_f32 and/or x_bf16 (either may be NULL). */
+int snt_embed_pack_fwd(const float* features, const float* w_emb, const int64_t* captions,
+                       int64_t cap_stride, const int32_t* batch_sizes /*[host] T*/, int T,
+                       int64_t E, int64_t V, float* x_f32, void* x_bf16, void* stream);
+/* backward: dx[N,E] -> dfeatures[B,E] (rows >= batch_sizes[0] zero) and the dense embedding gradient
+ * d_w_emb[V,E] (deterministic: rows are summed in packed-row order).  ws: snt_embed_bwd_workspace_bytes */
+int64_t snt_embed_bwd_workspace_bytes(int64_t N, int64_t V);
+int snt_embed_pack_bwd(const float* dx, const int64_t* captions, int64_t cap_stride,
+                       const int32_t* batch_sizes /*[host] T*/, int T, int64_t B, int64_t E, int64_t V,
+                       float* dfeatures, float* d_w_emb, void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- a7  one LSTM layer over the packed sequence  (models.py:52, nn.LSTM, gate rows i|f|g|o) ---------
+ * h0 = c0 = 0.  x (act) [N,In].  Saves for backward: gates[N,4H] fp32 (post-activation i,f,g,o),
+ * cs[N,H] fp32 (c_t), hs (act) [N,H] (h_t = the layer output), hprev (act) [N,H] (h_{t-1} per row). */
+int64_t snt_lstm_workspace_bytes(int prec, int64_t N, int64_t B, int64_t In, int64_t H);
+int snt_lstm_fwd(int prec, const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh,
+                 const float* b_ih, const float* b_hh, const int32_t* batch_sizes /*[host] T*/, int T,
+                 float* gates, float* cs, void* hs, void* hprev, void* ws, int64_t ws_bytes, void* stream);
+/* BPTT for that layer.  d_hs[N,H] fp32 = gradient w.r.t. the layer output (read only).  `gates` is
+ * overwritten with the pre-activation gradient dG[N,4H].  Outputs d_w_ih[4H,In], d_w_hh[4H,H],
+ * d_bias[4H] (the same vector is the gradient of both b_ih and b_hh) and dx[N,In] fp32 (may be NULL). */
+int snt_lstm_bwd(int prec, const float* d_hs, float* gates, const float* cs, const void* hprev,
+                 const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh,
+                 const int32_t* batch_sizes /*[host] T*/, int T,
+                 float* d_w_ih, float* d_w_hh, float* d_bias, float* dx,
+                 void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- a8  vocab Linear, materialising  (models.py:53) and its autograd ---------------------------------*/
+int64_t snt_linear_workspace_bytes(int prec, int64_t N, int64_t H, int64_t V);
+int snt_linear_fwd(int prec, const void* hs, const float* w_out, const float* b_out,
+                   int64_t N, int64_t H, int64_t V, float* logits, void* ws, int64_t ws_bytes, void* stream);
+int snt_linear_bwd(int prec, const float* dlogits, const void* hs, const float* w_out,
+                   int64_t N, int64_t H, int64_t V, float* d_hs, float* d_w_out, float* d_b_out,
+                   void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- a8+a9  vocab Linear fused with log-softmax + cross-entropy  (models.py:53 + train.py:53,143) -----
+ * loss = (1/N) sum_n (logsumexp_v logits[n,v] - logits[n,targets[n]]); logits[N,V] never reach HBM as
+ * a whole.  Saves lse[N].  loss is a device scalar. */
+int64_t snt_vocab_ce_workspace_bytes(int prec, int64_t N, int64_t H, int64_t V);
+int snt_vocab_ce_fwd(int prec, const void* hs, const float* w_out, const float* b_out,
+                     const int64_t* targets, int64_t N, int64_t H, int64_t V,
+                     float* lse, float* loss, void* ws, int64_t ws_bytes, void* stream);
+/* backward of the fused loss: dlogits = (softmax - onehot) * grad_scale / N formed tile-wise.
+ * `dloss` (device scalar, may be NULL = 1) multiplies grad_scale.  Outputs d_hs[N,H] fp32,
+ * d_w_out[V,H], d_b_out[V]. */
+int snt_vocab_ce_bwd(int prec, const void* hs, const float* w_out, const float* b_out,
+                     const int64_t* targets, const float* lse, const float* dloss, float grad_scale,
+                     int64_t N, int64_t H, int64_t V, float* d_hs, float* d_w_out, float* d_b_out,
+                     void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- a12  greedy decode  (models.py:56-67: fixed `steps` iterations, first-index argmax) ---------------
+ * Per-layer weight pointer arrays are [host] arrays of device pointers.  h0/c0 [L,B,H] may be NULL
+ * (zeros).  ids[B,steps] int64. */
+int64_t snt_greedy_workspace_bytes(int prec, int64_t B, int64_t E, int64_t H, int64_t V, int L);
+int snt_greedy_decode(int prec, const float* features, const float* w_emb, int L,
+                      const float* const* w_ih, const float* const* w_hh,
+                      const float* const* b_ih, const float* const* b_hh,
+                      const float* w_out, const float* b_out, const float* h0, const float* c0,
+                      int64_t B, int64_t E, int64_t H, int64_t V, int steps, int64_t* ids,
+                      void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- a11  clip_gradient (clamp to +-grad_clip) + Adam  (train.py:88-91,145-146) -------------------------
+ * In-place on p, m, v; g is read only.  `step` is the 1-based count after this update.
+ * grad_clip <= 0 disables the clamp.  grad_scale multiplies g first (1/world for averaged DP grads). */
+int snt_clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float grad_clip, float grad_scale, int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNT_B200_H */

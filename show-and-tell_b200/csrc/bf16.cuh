@@ -1,0 +1,45 @@
+// SNT_PREC_BF16 pipelines: bf16 operands on tcgen05 tensor cores (fp32 accumulation in TMEM), TMA-fed.
+// Declared here, implemented in bf16_path.cu on top of the GEMM core in gemm_tc.cu.
+#pragma once
+#include "common.cuh"
+
+namespace snt {
+namespace bf16 {
+
+// y[M,N] = a[M,K] . w[N,K]^T + bias   (fp32 in / fp32 out; operands rounded to bf16 in the workspace)
+int64_t head_extra_ws_bytes(int64_t B, int64_t K, int64_t E);
+int linear_nt(const float* a, const float* w, const float* bias, int64_t M, int64_t N, int64_t K, float* y,
+              void* ws, int64_t ws_bytes, cudaStream_t st);
+// dw[N,K] = dy[M,N]^T . a[M,K]
+int wgrad_tn(const float* dy, const float* a, int64_t M, int64_t N, int64_t K, float* dw, void* ws,
+             int64_t ws_bytes, cudaStream_t st);
+
+int64_t lstm_ws_bytes(int64_t N, int64_t B, int64_t In, int64_t H);
+int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh,
+             const float* b_ih, const float* b_hh, float* gates, float* cs, void* hs, void* hprev, void* ws,
+             int64_t ws_bytes, cudaStream_t st);
+int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* cs, const void* hprev,
+             const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh, float* d_w_ih,
+             float* d_w_hh, float* d_bias, float* dx, void* ws, int64_t ws_bytes, cudaStream_t st);
+
+int64_t linear_ws_bytes(int64_t N, int64_t H, int64_t V);
+int linear_fwd(const void* hs, const float* w_out, const float* b_out, int64_t N, int64_t H, int64_t V,
+               float* logits, void* ws, int64_t ws_bytes, cudaStream_t st);
+int linear_bwd(const float* dlogits, const void* hs, const float* w_out, int64_t N, int64_t H, int64_t V,
+               float* d_hs, float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st);
+
+int64_t vocab_ce_ws_bytes(int64_t N, int64_t H, int64_t V);
+int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, int64_t N,
+                 int64_t H, int64_t V, float* lse, float* loss, void* ws, int64_t ws_bytes, cudaStream_t st);
+int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, const float* lse,
+                 const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
+                 float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st);
+
+int64_t greedy_ws_bytes(int64_t B, int64_t E, int64_t H, int64_t V, int L);
+int greedy_decode(const float* features, const float* w_emb, int L, const float* const* w_ih,
+                  const float* const* w_hh, const float* const* b_ih, const float* const* b_hh,
+                  const float* w_out, const float* b_out, const float* h0, const float* c0, int64_t B, int64_t E,
+                  int64_t H, int64_t V, int steps, int64_t* ids, void* ws, int64_t ws_bytes, cudaStream_t st);
+
+}  // namespace bf16
+}  // namespace snt

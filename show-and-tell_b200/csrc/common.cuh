@@ -1,0 +1,85 @@
+// Shared helpers for the snt_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/snt_b200.h"
+
+namespace snt {
+
+// Packed-sequence geometry, passed to kernels BY VALUE (no H2D copy, no sync): T <= SNT_MAX_T.
+struct PackInfo {
+  int T;
+  int off[SNT_MAX_T + 1];  // off[t] = first packed row of timestep t; off[T] = N
+};
+
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+// Validates batch_sizes (positive, non-increasing, T in range) and fills PackInfo.
+int make_pack(const int32_t* batch_sizes, int T, PackInfo* out);
+int* device_flags();  // sticky device-side flag word
+void count_launch();   // bumps the process-wide kernel-launch counter (snt_launch_count)
+
+#define SNT_CHECK(expr)                                  \
+  do {                                                   \
+    int _e = (expr);                                     \
+    if (_e != SNT_OK) return _e;                         \
+  } while (0)
+#define SNT_CUDA(expr) SNT_CHECK(::snt::check_cuda((expr), #expr))
+#define SNT_LAUNCH_CHECK(name)                                   \
+  do {                                                           \
+    ::snt::count_launch();                                       \
+    SNT_CHECK(::snt::check_cuda(cudaGetLastError(), name));      \
+  } while (0)
+#define SNT_REQUIRE(cond, ...)                           \
+  do {                                                   \
+    if (!(cond)) {                                       \
+      ::snt::set_error(__VA_ARGS__);                     \
+      return SNT_EINVAL;                                 \
+    }                                                    \
+  } while (0)
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided workspace.
+struct Workspace {
+  char* base;
+  int64_t size, used;
+  Workspace(void* p, int64_t n) : base((char*)p), size(n), used(0) {}
+  template <typename T>
+  T* take(int64_t count) {
+    int64_t bytes = align_up(count * (int64_t)sizeof(T), 256);
+    if (base == nullptr || used + bytes > size) {
+      used = size + 1;
+      return nullptr;
+    }
+    T* r = (T*)(base + used);
+    used += bytes;
+    return r;
+  }
+  bool ok() const { return used <= size; }
+};
+static inline int64_t ws_bytes_for(int64_t count, int64_t elem) { return align_up(count * elem, 256); }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- internal launchers shared across translation units -------------------------------------------------
+int gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
+             int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc,
+             const float* bias, cudaStream_t st);
+
+}  // namespace snt

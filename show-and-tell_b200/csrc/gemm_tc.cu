@@ -1,0 +1,186 @@
+// Host side of the tcgen05 contraction core: tensor-map encoding (driver entry point resolved at run time, so
+// the library has no link-time dependency on libcuda and still loads on a machine without a GPU), tile-shape
+// and split-K selection, the deterministic split-K reduction and the exported snt_gemm_bf16.
+#include "gemm_tc.cuh"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace snt {
+namespace tc {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 1;
+  }
+  return n;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                   int box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return SNT_ECUDA; }
+  SNT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base %p not 16-byte aligned", base);
+  SNT_REQUIRE(ld % 8 == 0, "tensor map: leading dimension %lld not a multiple of 8 bf16", (long long)ld);
+  SNT_REQUIRE(inner >= 1 && outer >= 1 && ld >= inner, "tensor map: bad extents");
+  SNT_REQUIRE(box_inner * 2 <= 128 && box_outer <= 256, "tensor map: bad box");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: %d (inner %lld outer %lld ld %lld box %dx%d)", (int)r,
+              (long long)inner, (long long)outer, (long long)ld, box_inner, box_outer);
+    return SNT_ECUDA;
+  }
+  return SNT_OK;
+}
+
+int make_operand_tmap(CUtensorMap* out, const void* base, bool mn_major, int64_t rows, int64_t K, int64_t ld,
+                      int box_rows) {
+  if (!mn_major) return make_tmap_bf16(out, base, K, rows, ld, BK, box_rows);
+  return make_tmap_bf16(out, base, rows, K, ld, 64, BK);
+}
+
+// ---- split-K reduction: C = beta*C + bias + sum_s ws[s] -----------------------------------------------------------
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t M, int64_t N, int64_t ldc,
+                     int64_t split_stride, float beta, const float* __restrict__ bias, float* __restrict__ C,
+                     __nv_bfloat16* __restrict__ Cb) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= M * N) return;
+  const int64_t m = i / N, n = i % N;
+  const int64_t o = m * ldc + n;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += ws[(int64_t)k * split_stride + o];
+  if (bias) s += bias[n];
+  if (C) {
+    if (beta != 0.f) s += beta * C[o];
+    C[o] = s;
+  }
+  if (Cb) Cb[o] = __float2bfloat16_rn(s);
+}
+
+int64_t gemm_tc_split_ws_elems(int64_t M, int64_t ldc, int splits) { return splits > 1 ? splits * M * ldc : 0; }
+
+static int pick_bn(int64_t M, int64_t N) {
+  const int64_t num_m = (M + BM - 1) / BM;
+  const int sms = sm_count();
+  if (N >= 256 && num_m * ((N + 255) / 256) >= sms) return 256;
+  if (N >= 128 && num_m * ((N + 127) / 128) >= sms / 2) return 128;
+  return N > 64 ? 128 : 64;
+}
+
+int choose_splits(int64_t M, int64_t N, int64_t K, int bn) {
+  if (bn <= 0) bn = pick_bn(M, N);
+  const int64_t tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+  const int64_t kblocks = (K + BK - 1) / BK;
+  const int sms = sm_count();
+  if (tiles >= sms / 2 || kblocks < 8) return 1;
+  int64_t s = sms / tiles;
+  if (s > kblocks / 4) s = kblocks / 4;
+  if (s > 16) s = 16;
+  return s < 1 ? 1 : (int)s;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int run_plain(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, int64_t M, int64_t N,
+                     float alpha, float beta, float* C, __nv_bfloat16* Cb, int64_t ldc, const float* bias,
+                     int64_t split_stride, cudaStream_t st) {
+  PlainEpi<BN> e;
+  e.M = (int)M; e.N = (int)N; e.alpha = alpha; e.beta = beta; e.C = C; e.Cb = Cb; e.ldc = ldc; e.bias = bias;
+  e.split_stride = split_stride;
+  return launch_gemm_tc<BN, A_MN, B_MN, PlainEpi<BN>>(ta, tb, ts, e, st);
+}
+
+template <int BN>
+static int run_plain_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts,
+                           int64_t M, int64_t N, float alpha, float beta, float* C, __nv_bfloat16* Cb, int64_t ldc,
+                           const float* bias, int64_t split_stride, cudaStream_t st) {
+  if (!a_mn && !b_mn) return run_plain<BN, false, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st);
+  if (!a_mn && b_mn) return run_plain<BN, false, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st);
+  if (a_mn && !b_mn) return run_plain<BN, true, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st);
+  return run_plain<BN, true, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st);
+}
+
+int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A,
+            int64_t lda, const __nv_bfloat16* B, int64_t ldb, float beta, float* C, __nv_bfloat16* Cb,
+            int64_t ldc, const float* bias, int splits, float* split_ws, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return SNT_OK;
+  SNT_REQUIRE(K >= 1 && A && B && (C || Cb), "gemm_tc: bad arguments");
+  SNT_REQUIRE(M < (1 << 30) && N < (1 << 30) && K < (1 << 30), "gemm_tc: extent too large");
+  const int bn = pick_bn(M, N);
+  TileSched ts;
+  ts.num_m = (int)((M + BM - 1) / BM);
+  ts.num_n = (int)((N + bn - 1) / bn);
+  ts.kblocks = (int)((K + BK - 1) / BK);
+  if (splits < 1) splits = 1;
+  if (splits > ts.kblocks) splits = ts.kblocks;
+  ts.kblocks_per_split = (ts.kblocks + splits - 1) / splits;
+  splits = (ts.kblocks + ts.kblocks_per_split - 1) / ts.kblocks_per_split;  // no empty split
+  ts.splits = splits;
+  ts.a_row0 = 0;
+  ts.b_row0 = 0;
+  CUtensorMap ta, tb;
+  SNT_CHECK(make_operand_tmap(&ta, A, a_mn, M, K, lda, BM));
+  SNT_CHECK(make_operand_tmap(&tb, B, b_mn, N, K, ldb, bn));
+
+  float* out = C;
+  __nv_bfloat16* outb = Cb;
+  float e_alpha = alpha, e_beta = beta;
+  const float* e_bias = bias;
+  int64_t split_stride = 0;
+  if (splits > 1) {
+    SNT_REQUIRE(split_ws != nullptr, "gemm_tc: split-K needs a workspace");
+    out = split_ws; outb = nullptr; e_beta = 0.f; e_bias = nullptr;
+    split_stride = M * ldc;
+  }
+  int rc;
+  if (bn == 256) rc = run_plain_major<256>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st);
+  else if (bn == 128) rc = run_plain_major<128>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st);
+  else rc = run_plain_major<64>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st);
+  SNT_CHECK(rc);
+  if (splits > 1) {
+    const int64_t total = M * N;
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(split_ws, splits, M, N, ldc, split_stride,
+                                                                           beta, bias, C, Cb);
+    SNT_LAUNCH_CHECK("splitk_reduce_kernel");
+  }
+  return SNT_OK;
+}
+
+}  // namespace tc
+}  // namespace snt
+
+// C[M,N] = alpha*op(A).op(B) + beta*C + bias.  transA=0: A [M,K]; 1: A [K,M].  transB=0: B [K,N]; 1: B [N,K].
+extern "C" int snt_gemm_bf16(int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,
+                             int64_t lda, const void* B, int64_t ldb, float beta, void* C, int64_t ldc,
+                             int c_is_bf16, const float* bias, void* stream) {
+  using namespace snt;
+  return tc::gemm_tc(transA != 0, transB == 0, M, N, K, alpha, (const __nv_bfloat16*)A, lda,
+                     (const __nv_bfloat16*)B, ldb, c_is_bf16 ? 0.f : beta, c_is_bf16 ? nullptr : (float*)C,
+                     c_is_bf16 ? (__nv_bfloat16*)C : nullptr, ldc, bias, 1, nullptr, (cudaStream_t)stream);
+}

@@ -1,0 +1,316 @@
+// tcgen05 / TMEM / TMA contraction core for sm_100a.
+//
+//   D[M,N] (fp32, TMEM) = A . B,  bf16 operands, 128 x BN x 64 tiles, persistent CTAs, warp-specialised:
+//     warp 0  : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled shared memory, mbarrier complete_tx)
+//     warp 1  : MMA issuer     (one elected thread issues tcgen05.mma, tcgen05.commit frees the stage)
+//     warp 2  : TMEM allocator
+//     warps 4+: epilogue       (tcgen05.ld -> registers -> functor), double-buffered accumulator so the
+//                               epilogue of tile i overlaps the MMAs of tile i+1
+//   Operand layouts: "K-major" (the contraction index is contiguous in global memory) or "MN-major" (the M or N
+//   index is contiguous); both are fetched with 128B-swizzle TMA boxes and described to the tensor core with
+//   the matching shared-memory descriptors, so x.W^T, dY.W and dY^T.X all run without a transpose pass.
+//   The epilogue is a functor (plain store, LSTM gates, cross-entropy statistics, ...) given the TMEM address
+//   of its warp's 32 accumulator rows.
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace snt {
+namespace tc {
+
+constexpr int BM = 128;  // tile rows = TMEM lanes
+constexpr int BK = 64;   // 64 bf16 = 128 B = one swizzle row
+
+struct TileSched {
+  int num_m, num_n, splits;  // tile grid; tile id = (split * num_n + n) * num_m + m
+  int kblocks;               // total K blocks of BK
+  int kblocks_per_split;
+  int a_row0, b_row0;        // coordinate offsets into the M / N extents of the tensor maps
+};
+
+template <int BN>
+struct Cfg {
+  static_assert(BN == 64 || BN == 128 || BN == 256, "BN must be 64, 128 or 256");
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (128, 256 or 512 columns)
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+};
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Epi must provide:
+//   static constexpr int kWarps            (4 or 8 epilogue warps)
+//   __device__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int epi_warp, int lane) const
+// where tmem_rows addresses lane 32*(epi_warp%4), first column of this tile's accumulator.
+template <int BN, bool A_MN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(128 + 32 * Epi::kWarps, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TileSched ts, const Epi epi) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], Epi::kWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // the next kernel may begin its own prologue; its griddepcontrol.wait still
+                            // blocks until this grid has completed and flushed
+
+  const int total_tiles = ts.num_m * ts.num_n * ts.splits;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ================= TMA producer =================
+      pdl_wait();  // operands may be produced by the preceding kernel in the stream
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile % ts.num_m;
+        const int rest = tile / ts.num_m;
+        const int n_blk = rest % ts.num_n;
+        const int split = rest / ts.num_n;
+        const int kb0 = split * ts.kblocks_per_split;
+        const int kb1 = min(kb0 + ts.kblocks_per_split, ts.kblocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * C::STAGE_BYTES;
+          uint8_t* sB = sA + C::A_BYTES;
+          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sA, &tmA, &full[stage], kb * BK, ts.a_row0 + m_blk * BM);
+          } else {
+#pragma unroll
+            for (int h = 0; h < BM / 64; ++h)
+              tma_load_2d(sA + h * (BK * 128), &tmA, &full[stage], ts.a_row0 + m_blk * BM + h * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sB, &tmB, &full[stage], kb * BK, ts.b_row0 + n_blk * BN);
+          } else {
+#pragma unroll
+            for (int h = 0; h < BN / 64; ++h)
+              tma_load_2d(sB + h * (BK * 128), &tmB, &full[stage], ts.b_row0 + n_blk * BN + h * 64, kb * BK);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ================= MMA issuer =================
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = (tile / ts.num_m) / ts.num_n;
+        const int kb0 = split * ts.kblocks_per_split;
+        const int kb1 = min(kb0 + ts.kblocks_per_split, ts.kblocks);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 bf16 = 32 B along the swizzled row.  MN-major: 16 k-rows of 128 B = 2048 B.
+            const uint64_t da = A_MN ? make_smem_desc(a_addr + k * 2048, BK * 128, 1024)
+                                     : make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(b_addr + k * 2048, BK * 128, 1024)
+                                     : make_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int ew = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    pdl_wait();  // the epilogue may read tensors written by the preceding kernel (C for beta, Gx, lse, ...)
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile % ts.num_m;
+      const int rest = tile / ts.num_m;
+      const int n_blk = rest % ts.num_n;
+      const int split = rest / ts.num_n;
+      mbar_wait(&tfull[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t tmem_rows = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)((ew & 3) * 32) << 16);
+      epi.tile(tmem_rows, m_blk, n_blk, split, ew, lane);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+// 2-D bf16 tensor map with 128B swizzle: `inner` contiguous elements per row, `outer` rows, row pitch ld elements.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                   int box_outer);
+// operand map for the kernel above: mn_major=false -> [rows, K] K contiguous, box {BK, box_rows};
+// mn_major=true -> [K, rows] rows contiguous, box {64, BK}.
+int make_operand_tmap(CUtensorMap* out, const void* base, bool mn_major, int64_t rows, int64_t K, int64_t ld,
+                      int box_rows);
+int sm_count();
+
+template <int BN, bool A_MN, bool B_MN, class Epi>
+int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TileSched& ts, const Epi& epi,
+                   cudaStream_t st, bool pdl = false) {
+  using C = Cfg<BN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    SNT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int total = ts.num_m * ts.num_n * ts.splits;
+  if (total <= 0) return SNT_OK;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)min(total, sm_count()));
+  cfg.blockDim = dim3(128 + 32 * Epi::kWarps);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  count_launch();
+  SNT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, ts, epi));
+  return SNT_OK;
+}
+
+// ---- the plain epilogue: C = alpha*acc + bias[col] + beta*C, fp32 and/or bf16 out, optional split-K slices ----
+template <int BN>
+struct PlainEpi {
+  static constexpr int kWarps = 4;
+  int M, N;                // valid extent
+  float alpha, beta;
+  float* C;                // may be NULL
+  __nv_bfloat16* Cb;       // may be NULL
+  int64_t ldc;
+  const float* bias;       // may be NULL, length N
+  int64_t split_stride;    // elements between split-K partial slices of C
+
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane) const {
+    const int row = m_blk * BM + (ew & 3) * 32 + lane;
+    const bool row_ok = row < M;
+    float* crow = C ? C + (int64_t)split * split_stride + (int64_t)row * ldc : nullptr;
+    __nv_bfloat16* brow = Cb ? Cb + (int64_t)row * ldc : nullptr;
+    const bool vec_ok = crow && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+                        (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int col0 = n_blk * BN + c * 32;
+      if (col0 >= N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(tmem_rows + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v;
+          v.x = alpha * __uint_as_float(r[j]);
+          v.y = alpha * __uint_as_float(r[j + 1]);
+          v.z = alpha * __uint_as_float(r[j + 2]);
+          v.w = alpha * __uint_as_float(r[j + 3]);
+          if (bias) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          }
+          float4* dst = reinterpret_cast<float4*>(crow + col0 + j);
+          if (beta != 0.f) {
+            const float4 o = *dst;
+            v.x += beta * o.x; v.y += beta * o.y; v.z += beta * o.z; v.w += beta * o.w;
+          }
+          *dst = v;
+          if (brow) {
+            brow[col0 + j] = __float2bfloat16_rn(v.x);
+            brow[col0 + j + 1] = __float2bfloat16_rn(v.y);
+            brow[col0 + j + 2] = __float2bfloat16_rn(v.z);
+            brow[col0 + j + 3] = __float2bfloat16_rn(v.w);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col < N) {
+            float v = alpha * __uint_as_float(r[j]);
+            if (bias) v += bias[col];
+            if (crow) {
+              if (beta != 0.f) v += beta * crow[col];
+              crow[col] = v;
+            }
+            if (brow) brow[col] = __float2bfloat16_rn(v);
+          }
+        }
+      }
+    }
+  }
+};
+
+// Generic bf16 contraction, C[M,N] = alpha * op(A).op(B) + bias + beta*C.
+//   a_mn = false: A is [M,K] row-major (lda);  true: A is [K,M] row-major.
+//   b_mn = false: B is [N,K] row-major (ldb);  true: B is [K,N] row-major.
+//   C fp32 and/or Cb bf16 (same ldc).  splits > 1: partial sums go to split_ws[splits][M][ldc] and are reduced
+//   (deterministically) into C by a second kernel; bias/beta are applied there.
+int64_t gemm_tc_split_ws_elems(int64_t M, int64_t ldc, int splits);
+int choose_splits(int64_t M, int64_t N, int64_t K, int bn);
+int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A,
+            int64_t lda, const __nv_bfloat16* B, int64_t ldb, float beta, float* C, __nv_bfloat16* Cb,
+            int64_t ldc, const float* bias, int splits, float* split_ws, cudaStream_t st);
+
+}  // namespace tc
+}  // namespace snt

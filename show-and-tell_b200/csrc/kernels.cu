@@ -1,0 +1,649 @@
+// HBM-bound and pointwise kernels of the caption-decoder path: gather/concat/pack, LSTM gate math,
+// cross-entropy rows, argmax, BatchNorm, embedding-gradient scatter, clamp+Adam.  sm_100a.
+#include "kernels.cuh"
+
+namespace snt {
+
+static inline unsigned nblocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+__device__ __forceinline__ int find_step(const PackInfo& p, int row) {
+  int lo = 0, hi = p.T;  // invariant: off[lo] <= row < off[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (p.off[mid] <= row) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// a4-a6: x[off[t]+b] = features[b] (t==0) | w_emb[captions[b,t-1]]   (models.py:49-51).  One warp per row.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_pack_fwd_kernel(const __grid_constant__ PackInfo pk, const float* __restrict__ features,
+                      const float* __restrict__ w_emb, const int64_t* __restrict__ captions,
+                      int64_t cap_stride, int E, int64_t V, float* __restrict__ x_f32,
+                      __nv_bfloat16* __restrict__ x_bf16, int* flags) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  const int N = pk.off[pk.T];
+  if (row >= N) return;
+  const int t = find_step(pk, row);
+  const int b = row - pk.off[t];
+  const float* src;
+  if (t == 0) {
+    src = features + (int64_t)b * E;
+  } else {
+    int64_t tok = captions[(int64_t)b * cap_stride + (t - 1)];
+    if (tok < 0 || tok >= V) {
+      if (lane == 0) atomicOr(flags, 1);
+      src = nullptr;
+    } else {
+      src = w_emb + tok * E;
+    }
+  }
+  const int64_t o = (int64_t)row * E;
+  if ((E & 3) == 0) {
+    for (int e = lane * 4; e < E; e += 128) {
+      float4 v = src ? *reinterpret_cast<const float4*>(src + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (x_f32) *reinterpret_cast<float4*>(x_f32 + o + e) = v;
+      if (x_bf16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk2;
+        pk2.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk2.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(x_bf16 + o + e) = pk2;
+      }
+    }
+  } else {
+    for (int e = lane; e < E; e += 32) {
+      float v = src ? src[e] : 0.f;
+      if (x_f32) x_f32[o + e] = v;
+      if (x_bf16) x_bf16[o + e] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+int embed_pack_fwd(const PackInfo& pk, const float* features, const float* w_emb, const int64_t* captions,
+                   int64_t cap_stride, int64_t E, int64_t V, float* x_f32, __nv_bfloat16* x_bf16,
+                   cudaStream_t st) {
+  const int N = pk.off[pk.T];
+  embed_pack_fwd_kernel<<<nblocks(N, 8), 256, 0, st>>>(pk, features, w_emb, captions, cap_stride, (int)E, V,
+                                                      x_f32, x_bf16, device_flags());
+  SNT_LAUNCH_CHECK("embed_pack_fwd_kernel");
+  return SNT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// column sums, deterministic two pass: partial[chunk][c] then fixed-order sum over chunks
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CS_ROWS_PER_CHUNK = 256;
+int64_t colsum_partial_count(int64_t R, int64_t C) { return ((R + CS_ROWS_PER_CHUNK - 1) / CS_ROWS_PER_CHUNK) * C; }
+
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ in, int64_t R, int64_t C, int64_t ld, float* __restrict__ partial) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS_PER_CHUNK;
+  const int64_t r1 = min(R, r0 + CS_ROWS_PER_CHUNK);
+  float s = 0.f;
+  if (c < C)
+    for (int64_t r = r0 + ty; r < r1; r += 8) s += in[r * ld + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    partial[(int64_t)blockIdx.y * C + c] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int64_t chunks, int64_t C, float beta,
+                                    float* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int64_t k = 0; k < chunks; ++k) s += partial[k * C + c];
+  out[c] = (beta != 0.f ? beta * out[c] : 0.f) + s;
+}
+int colsum(const float* in, int64_t R, int64_t C, int64_t ld, float beta, float* out, float* partial,
+           cudaStream_t st) {
+  if (C <= 0) return SNT_OK;
+  const int64_t chunks = (R + CS_ROWS_PER_CHUNK - 1) / CS_ROWS_PER_CHUNK;
+  if (chunks > 0) {
+    SNT_REQUIRE(partial != nullptr, "colsum: no workspace");
+    dim3 grid(nblocks(C, 32), (unsigned)chunks);
+    colsum_partial_kernel<<<grid, 256, 0, st>>>(in, R, C, ld, partial);
+    SNT_LAUNCH_CHECK("colsum_partial_kernel");
+  }
+  colsum_final_kernel<<<nblocks(C, 256), 256, 0, st>>>(partial, chunks, C, beta, out);
+  SNT_LAUNCH_CHECK("colsum_final_kernel");
+  return SNT_OK;
+}
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+int add_vec(const float* a, const float* b, float* out, int64_t n, cudaStream_t st) {
+  if (n <= 0) return SNT_OK;
+  add_vec_kernel<<<nblocks(n, 256), 256, 0, st>>>(a, b, out, n);
+  SNT_LAUNCH_CHECK("add_vec_kernel");
+  return SNT_OK;
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n && ((reinterpret_cast<uintptr_t>(src + i) & 15) == 0) &&
+      ((reinterpret_cast<uintptr_t>(dst + i) & 7) == 0)) {
+    float4 v = *reinterpret_cast<const float4*>(src + i);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 p;
+    p.x = *reinterpret_cast<uint32_t*>(&lo);
+    p.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dst + i) = p;
+  } else {
+    for (int k = 0; k < 4 && i + k < n; ++k) dst[i + k] = __float2bfloat16_rn(src[i + k]);
+  }
+}
+int cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t st) {
+  if (n <= 0) return SNT_OK;
+  cast_bf16_kernel<<<nblocks((n + 3) / 4, 256), 256, 0, st>>>(src, dst, n);
+  SNT_LAUNCH_CHECK("cast_bf16_kernel");
+  return SNT_OK;
+}
+__global__ void cast_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+int cast_f32(const __nv_bfloat16* src, float* dst, int64_t n, cudaStream_t st) {
+  if (n <= 0) return SNT_OK;
+  cast_f32_kernel<<<nblocks(n, 256), 256, 0, st>>>(src, dst, n);
+  SNT_LAUNCH_CHECK("cast_f32_kernel");
+  return SNT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// a7 pointwise: gate rows i|f|g|o (torch/nn/modules/rnn.py), c = f*c' + i*g, h = o*tanh(c)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_act(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_act(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename ActT>
+__global__ void __launch_bounds__(256)
+lstm_point_fwd_kernel(float* __restrict__ gates_t, const float* c_prev /* may alias cs_t */, float* cs_t,
+                      ActT* __restrict__ hs_t, ActT* __restrict__ hprev_next, int bs, int bs_next, int H) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)bs * H) return;
+  const int b = (int)(idx / H), j = (int)(idx % H);
+  float* g = gates_t + (int64_t)b * 4 * H;
+  const float i_ = sigmoidf_(g[j]);
+  const float f_ = sigmoidf_(g[H + j]);
+  const float g_ = tanhf(g[2 * H + j]);
+  const float o_ = sigmoidf_(g[3 * H + j]);
+  const float cp = c_prev ? c_prev[idx] : 0.f;
+  const float c = f_ * cp + i_ * g_;
+  const float h = o_ * tanhf(c);
+  g[j] = i_; g[H + j] = f_; g[2 * H + j] = g_; g[3 * H + j] = o_;
+  cs_t[idx] = c;
+  store_act(hs_t + idx, h);
+  if (hprev_next != nullptr && b < bs_next) store_act(hprev_next + idx, h);
+}
+template <typename ActT>
+int lstm_point_fwd(float* gates_t, const float* c_prev, float* cs_t, ActT* hs_t, ActT* hprev_next, int bs,
+                   int bs_next, int64_t H, cudaStream_t st) {
+  if (bs <= 0) return SNT_OK;
+  lstm_point_fwd_kernel<ActT><<<nblocks((int64_t)bs * H, 256), 256, 0, st>>>(gates_t, c_prev, cs_t, hs_t,
+                                                                            hprev_next, bs, bs_next, (int)H);
+  SNT_LAUNCH_CHECK("lstm_point_fwd_kernel");
+  return SNT_OK;
+}
+template int lstm_point_fwd<float>(float*, const float*, float*, float*, float*, int, int, int64_t, cudaStream_t);
+template int lstm_point_fwd<__nv_bfloat16>(float*, const float*, float*, __nv_bfloat16*, __nv_bfloat16*, int,
+                                           int, int64_t, cudaStream_t);
+
+__global__ void __launch_bounds__(256)
+lstm_point_bwd_kernel(float* __restrict__ gates_t, const float* __restrict__ cs_t,
+                      const float* __restrict__ c_prev, const float* __restrict__ d_hs_t,
+                      const float* __restrict__ dh_rec, float* __restrict__ dc_state, int bs, int bs_next, int H) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)bs * H) return;
+  const int b = (int)(idx / H), j = (int)(idx % H);
+  float* g = gates_t + (int64_t)b * 4 * H;
+  const float i_ = g[j], f_ = g[H + j], g_ = g[2 * H + j], o_ = g[3 * H + j];
+  const float tc = tanhf(cs_t[idx]);
+  const float cp = c_prev ? c_prev[idx] : 0.f;
+  const bool has_next = b < bs_next;
+  const float dh = d_hs_t[idx] + (has_next ? dh_rec[idx] : 0.f);
+  const float dc = (has_next ? dc_state[idx] : 0.f) + dh * o_ * (1.f - tc * tc);
+  g[j] = dc * g_ * i_ * (1.f - i_);
+  g[H + j] = dc * cp * f_ * (1.f - f_);
+  g[2 * H + j] = dc * i_ * (1.f - g_ * g_);
+  g[3 * H + j] = dh * tc * o_ * (1.f - o_);
+  dc_state[idx] = dc * f_;
+}
+int lstm_point_bwd(float* gates_t, const float* cs_t, const float* c_prev, const float* d_hs_t,
+                   const float* dh_rec, float* dc_state, int bs, int bs_next, int64_t H, cudaStream_t st) {
+  if (bs <= 0) return SNT_OK;
+  lstm_point_bwd_kernel<<<nblocks((int64_t)bs * H, 256), 256, 0, st>>>(gates_t, cs_t, c_prev, d_hs_t, dh_rec,
+                                                                      dc_state, bs, bs_next, (int)H);
+  SNT_LAUNCH_CHECK("lstm_point_bwd_kernel");
+  return SNT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// a9: cross-entropy over rows of a logits chunk (train.py:53,143).  One block per row.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce_max(float v, float* sh) {
+  v = warp_max(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int i = 1; i < nw; ++i) r = fmaxf(r, sh[i]);
+  return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < nw; ++i) r += sh[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+ce_rows_fwd_kernel(const float* __restrict__ logits, int64_t V, int64_t ld, const int64_t* __restrict__ targets,
+                   float* __restrict__ lse, float* __restrict__ nll, int* flags) {
+  __shared__ float sh[8];
+  const int64_t r = blockIdx.x;
+  const float* row = logits + r * ld;
+  float m = -INFINITY;
+  for (int64_t v = threadIdx.x; v < V; v += 256) m = fmaxf(m, row[v]);
+  m = block_reduce_max(m, sh);
+  float s = 0.f;
+  for (int64_t v = threadIdx.x; v < V; v += 256) s += expf(row[v] - m);
+  s = block_reduce_sum(s, sh);
+  if (threadIdx.x == 0) {
+    const float l = m + logf(s);
+    lse[r] = l;
+    int64_t t = targets[r];
+    if (t < 0 || t >= V) { atomicOr(flags, 2); nll[r] = 0.f; }
+    else nll[r] = l - row[t];
+  }
+}
+int ce_rows_fwd(const float* logits, int64_t R, int64_t V, int64_t ld, const int64_t* targets, float* lse,
+                float* nll, cudaStream_t st) {
+  if (R <= 0) return SNT_OK;
+  ce_rows_fwd_kernel<<<(unsigned)R, 256, 0, st>>>(logits, V, ld, targets, lse, nll, device_flags());
+  SNT_LAUNCH_CHECK("ce_rows_fwd_kernel");
+  return SNT_OK;
+}
+
+__global__ void __launch_bounds__(256)
+ce_rows_bwd_kernel(float* __restrict__ logits, int64_t V, int64_t ld, const int64_t* __restrict__ targets,
+                   const float* __restrict__ lse, const float* __restrict__ dloss, float scale) {
+  const int64_t r = blockIdx.y;
+  const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (v >= V) return;
+  const float sc = scale * (dloss ? dloss[0] : 1.f);
+  float* p = logits + r * ld + v;
+  float d = expf(*p - lse[r]);
+  if (v == targets[r]) d -= 1.f;
+  *p = d * sc;
+}
+int ce_rows_bwd(float* logits, int64_t R, int64_t V, int64_t ld, const int64_t* targets, const float* lse,
+                const float* dloss, float scale, cudaStream_t st) {
+  if (R <= 0) return SNT_OK;
+  SNT_REQUIRE(R <= 65535, "ce_rows_bwd: chunk too tall");
+  dim3 grid(nblocks(V, 256), (unsigned)R);
+  ce_rows_bwd_kernel<<<grid, 256, 0, st>>>(logits, V, ld, targets, lse, dloss, scale);
+  SNT_LAUNCH_CHECK("ce_rows_bwd_kernel");
+  return SNT_OK;
+}
+
+__global__ void __launch_bounds__(1024)
+reduce_sum_kernel(const float* __restrict__ v, int64_t n, float scale, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) s += v[i];
+  s = block_reduce_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+int reduce_sum(const float* v, int64_t n, float scale, float* out, cudaStream_t st) {
+  reduce_sum_kernel<<<1, 1024, 0, st>>>(v, n, scale, out);
+  SNT_LAUNCH_CHECK("reduce_sum_kernel");
+  return SNT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// a12 tail: first-index argmax over the vocab row + gather of the next input (models.py:63-65)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+argmax_gather_kernel(const float* __restrict__ logits, int64_t V, int64_t ld, const float* __restrict__ w_emb,
+                     int E, int64_t* __restrict__ ids, int64_t ids_stride, float* __restrict__ x_next) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  __shared__ int best;
+  const int64_t b = blockIdx.x;
+  const float* row = logits + b * ld;
+  float m = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int64_t v = threadIdx.x; v < V; v += 256) {
+    float x = row[v];
+    if (x > m || mi == 0x7fffffff) { m = x; mi = (int)v; }  // strictly greater keeps the first index
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float om = __shfl_xor_sync(0xffffffffu, m, o);
+    int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sv[w] = m; si[w] = mi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bm = sv[0];
+    int bi = si[0];
+    for (int i = 1; i < 8; ++i)
+      if (sv[i] > bm || (sv[i] == bm && si[i] < bi)) { bm = sv[i]; bi = si[i]; }
+    best = bi;
+    ids[b * ids_stride] = bi;
+  }
+  __syncthreads();
+  if (x_next != nullptr) {
+    const float* src = w_emb + (int64_t)best * E;
+    for (int e = threadIdx.x; e < E; e += 256) x_next[b * E + e] = src[e];
+  }
+}
+int argmax_gather(const float* logits, int64_t B, int64_t V, int64_t ld, const float* w_emb, int64_t E,
+                  int64_t* ids, int64_t ids_stride, float* x_next, cudaStream_t st) {
+  if (B <= 0) return SNT_OK;
+  argmax_gather_kernel<<<(unsigned)B, 256, 0, st>>>(logits, V, ld, w_emb, (int)E, ids, ids_stride, x_next);
+  SNT_LAUNCH_CHECK("argmax_gather_kernel");
+  return SNT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// a2: BatchNorm1d over the batch (models.py:17,28; momentum 0.01).  Block = 32 features x 32 row-lanes.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+bn_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+              float* __restrict__ running_mean, float* __restrict__ running_var, int training, float momentum,
+              float eps, int B, int E, float* __restrict__ out, float* __restrict__ yhat,
+              float* __restrict__ rstd_out) {
+  __shared__ float red[32][33];
+  __shared__ float s_mean[32], s_rstd[32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + tx;
+  const bool ok = e < E;
+  if (training) {
+    float s = 0.f;
+    if (ok) for (int r = ty; r < B; r += 32) s += y[(int64_t)r * E + e];
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 32; ++i) t += red[i][tx];
+      s_mean[tx] = t / (float)B;
+    }
+    __syncthreads();
+    const float mu = s_mean[tx];
+    float q = 0.f;
+    if (ok) for (int r = ty; r < B; r += 32) { float d = y[(int64_t)r * E + e] - mu; q += d * d; }
+    __syncthreads();
+    red[ty][tx] = q;
+    __syncthreads();
+    if (ty == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 32; ++i) t += red[i][tx];
+      const float var = t / (float)B;
+      s_rstd[tx] = rsqrtf(var + eps);
+      if (ok) {
+        const float unbiased = B > 1 ? t / (float)(B - 1) : var;
+        running_mean[e] = (1.f - momentum) * running_mean[e] + momentum * mu;
+        running_var[e] = (1.f - momentum) * running_var[e] + momentum * unbiased;
+      }
+    }
+    __syncthreads();
+  } else {
+    if (ty == 0 && ok) {
+      s_mean[tx] = running_mean[e];
+      s_rstd[tx] = rsqrtf(running_var[e] + eps);
+    }
+    __syncthreads();
+  }
+  if (!ok) return;
+  const float mu = s_mean[tx], rs = s_rstd[tx], ga = gamma[e], be = beta[e];
+  if (ty == 0) rstd_out[e] = rs;
+  for (int r = ty; r < B; r += 32) {
+    const float yh = (y[(int64_t)r * E + e] - mu) * rs;
+    yhat[(int64_t)r * E + e] = yh;
+    out[(int64_t)r * E + e] = yh * ga + be;
+  }
+}
+int bn_fwd(const float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
+           int training, float momentum, float eps, int64_t B, int64_t E, float* out, float* yhat,
+           float* rstd, cudaStream_t st) {
+  bn_fwd_kernel<<<nblocks(E, 32), 1024, 0, st>>>(y, gamma, beta, running_mean, running_var, training, momentum,
+                                                 eps, (int)B, (int)E, out, yhat, rstd);
+  SNT_LAUNCH_CHECK("bn_fwd_kernel");
+  return SNT_OK;
+}
+
+__global__ void __launch_bounds__(1024)
+bn_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ yhat, const float* __restrict__ rstd,
+              const float* __restrict__ gamma, int training, int B, int E, float* __restrict__ dy,
+              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red1[32][33], red2[32][33];
+  __shared__ float s_sum[32], s_dot[32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + tx;
+  const bool ok = e < E;
+  float s = 0.f, d = 0.f;
+  if (ok)
+    for (int r = ty; r < B; r += 32) {
+      const float g = dout[(int64_t)r * E + e];
+      s += g;
+      d += g * yhat[(int64_t)r * E + e];
+    }
+  red1[ty][tx] = s;
+  red2[ty][tx] = d;
+  __syncthreads();
+  if (ty == 0) {
+    float a = 0.f, c = 0.f;
+    for (int i = 0; i < 32; ++i) { a += red1[i][tx]; c += red2[i][tx]; }
+    s_sum[tx] = a;
+    s_dot[tx] = c;
+    if (ok) { dbeta[e] = a; dgamma[e] = c; }
+  }
+  __syncthreads();
+  if (!ok) return;
+  const float ga = gamma[e], rs = rstd[e];
+  const float ms = s_sum[tx] / (float)B, md = s_dot[tx] / (float)B;
+  for (int r = ty; r < B; r += 32) {
+    const int64_t i = (int64_t)r * E + e;
+    const float g = dout[i];
+    dy[i] = training ? ga * rs * (g - ms - yhat[i] * md) : ga * rs * g;
+  }
+}
+int bn_bwd(const float* dout, const float* yhat, const float* rstd, const float* gamma, int training,
+           int64_t B, int64_t E, float* dy, float* dgamma, float* dbeta, cudaStream_t st) {
+  bn_bwd_kernel<<<nblocks(E, 32), 1024, 0, st>>>(dout, yhat, rstd, gamma, training, (int)B, (int)E, dy, dgamma,
+                                                 dbeta);
+  SNT_LAUNCH_CHECK("bn_bwd_kernel");
+  return SNT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// a10 (embedding part): dx rows t>=1 scatter-add into d_w_emb[V,E], deterministically.
+// counting sort by token (stable rank = number of earlier packed rows with the same token), then one block
+// per vocab row sums its rows in packed-row order.  Rows t==0 go to dfeatures.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+emb_tokens_kernel(const __grid_constant__ PackInfo pk, const int64_t* __restrict__ captions, int64_t cap_stride,
+                  int64_t V, int* __restrict__ tok, int* __restrict__ count, int* flags) {
+  const int n1 = pk.off[pk.T] - pk.off[1];  // rows with t >= 1
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n1) return;
+  const int row = pk.off[1] + i;
+  const int t = find_step(pk, row);
+  const int b = row - pk.off[t];
+  int64_t tk = captions[(int64_t)b * cap_stride + (t - 1)];
+  if (tk < 0 || tk >= V) { atomicOr(flags, 1); tok[i] = -1; return; }
+  tok[i] = (int)tk;
+  atomicAdd(&count[tk], 1);
+}
+// exclusive scan of count[0..V) into start[0..V], single block of 1024 threads
+__global__ void __launch_bounds__(1024)
+emb_scan_kernel(const int* __restrict__ count, int64_t V, int* __restrict__ start) {
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < V; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const int c = i < V ? count[i] : 0;
+    sh[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += v;
+      __syncthreads();
+    }
+    if (i < V) start[i] = carry + sh[threadIdx.x] - c;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) start[V] = carry;
+}
+// perm[start[tok[i]] + #{i' < i : tok[i'] == tok[i]}] = i   (stable => deterministic summation order)
+__global__ void __launch_bounds__(256)
+emb_rank_kernel(const int* __restrict__ tok, int n1, const int* __restrict__ start, int* __restrict__ perm) {
+  __shared__ int tile[1024];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int my = i < n1 ? tok[i] : -2;
+  int rank = 0;
+  const int lim = min(n1, (int)(blockIdx.x + 1) * 256);  // only rows before the end of this block matter
+  for (int base = 0; base < lim; base += 1024) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < 1024; k += 256) tile[k] = (base + k < n1) ? tok[base + k] : -3;
+    __syncthreads();
+    const int hi = min(1024, i - base);  // strictly earlier rows only
+    for (int k = 0; k < hi; ++k) rank += (tile[k] == my);
+  }
+  if (i < n1 && my >= 0) perm[start[my] + rank] = i;
+}
+__global__ void __launch_bounds__(128)
+emb_reduce_kernel(const float* __restrict__ dx1 /* dx + off[1]*E */, const int* __restrict__ start,
+                  const int* __restrict__ perm, int E, float* __restrict__ d_w_emb) {
+  extern __shared__ float part[];  // [4][E]
+  const int v = blockIdx.x;
+  const int s0 = start[v], s1 = start[v + 1];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* out = d_w_emb + (int64_t)v * E;
+  if (s1 == s0) {
+    for (int e = threadIdx.x; e < E; e += 128) out[e] = 0.f;
+    return;
+  }
+  for (int e0 = 0; e0 < E; e0 += 32 * 8) {
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int i = s0 + w; i < s1; i += 4) {
+      const float* src = dx1 + (int64_t)perm[i] * E;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = e0 + k * 32 + lane;
+        if (e < E) acc[k] += src[e];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = e0 + k * 32 + lane;
+      if (e < E) part[w * E + e] = acc[k];
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += 128) out[e] = (part[e] + part[E + e]) + (part[2 * E + e] + part[3 * E + e]);
+}
+__global__ void __launch_bounds__(256)
+dfeatures_kernel(const float* __restrict__ dx, int bs0, int64_t B, int64_t E, float* __restrict__ dfeat) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= B * E) return;
+  dfeat[i] = (i / E) < bs0 ? dx[i] : 0.f;
+}
+
+int64_t embed_bwd_ws_bytes(int64_t N, int64_t V) {
+  return ws_bytes_for(N, 4) * 2 + ws_bytes_for(V + 1, 4) * 2;
+}
+int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions, int64_t cap_stride,
+                   int64_t B, int64_t E, int64_t V, float* dfeatures, float* d_w_emb, void* ws,
+                   int64_t ws_bytes, cudaStream_t st) {
+  const int N = pk.off[pk.T];
+  const int n1 = N - pk.off[1];
+  if (dfeatures) {
+    dfeatures_kernel<<<nblocks(B * E, 256), 256, 0, st>>>(dx, pk.off[1], B, E, dfeatures);
+    SNT_LAUNCH_CHECK("dfeatures_kernel");
+  }
+  if (!d_w_emb) return SNT_OK;
+  Workspace w(ws, ws_bytes);
+  int* tok = w.take<int>(N);
+  int* perm = w.take<int>(N);
+  int* count = w.take<int>(V + 1);
+  int* start = w.take<int>(V + 1);
+  if (!w.ok()) { set_error("embed_pack_bwd: workspace too small"); return SNT_EWORKSPACE; }
+  SNT_REQUIRE(E * 4 * 4 <= 48 * 1024, "embed_pack_bwd: E too large");
+  SNT_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (V + 1), st));
+  if (n1 > 0) {
+    emb_tokens_kernel<<<nblocks(n1, 256), 256, 0, st>>>(pk, captions, cap_stride, V, tok, count, device_flags());
+    SNT_LAUNCH_CHECK("emb_tokens_kernel");
+  }
+  emb_scan_kernel<<<1, 1024, 0, st>>>(count, V, start);
+  SNT_LAUNCH_CHECK("emb_scan_kernel");
+  if (n1 > 0) {
+    emb_rank_kernel<<<nblocks(n1, 256), 256, 0, st>>>(tok, n1, start, perm);
+    SNT_LAUNCH_CHECK("emb_rank_kernel");
+  }
+  emb_reduce_kernel<<<(unsigned)V, 128, (size_t)(4 * E * sizeof(float)), st>>>(dx + (int64_t)pk.off[1] * E, start,
+                                                                              perm, (int)E, d_w_emb);
+  SNT_LAUNCH_CHECK("emb_reduce_kernel");
+  return SNT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// a11: clip_gradient (clamp) + Adam (train.py:88-91,145-146; torch.optim.Adam defaults)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+clamp_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                  float* __restrict__ v, int64_t n, float lr_over_bc1, float beta1, float beta2, float eps,
+                  float rsqrt_bc2, float grad_clip, float grad_scale) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i] * grad_scale;
+  if (grad_clip > 0.f) gi = fminf(fmaxf(gi, -grad_clip), grad_clip);
+  const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+  const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) * rsqrt_bc2 + eps;
+  p[i] = p[i] - lr_over_bc1 * (mi / denom);
+}
+int clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+               float eps, float grad_clip, float grad_scale, int64_t step, cudaStream_t st) {
+  if (n <= 0) return SNT_OK;
+  SNT_REQUIRE(step >= 1, "clamp_adam: step must be >= 1");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  clamp_adam_kernel<<<nblocks(n, 256), 256, 0, st>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps,
+                                                    (float)(1.0 / sqrt(bc2)), grad_clip, grad_scale);
+  SNT_LAUNCH_CHECK("clamp_adam_kernel");
+  return SNT_OK;
+}
+
+}  // namespace snt

@@ -27,3 +27,21 @@ def golden_params(g):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def decoder_from_params(params, prec, device="cuda"):
+    """A show_and_tell_b200.DecoderRNN carrying the given state_dict-keyed numpy weights."""
+    import torch
+    import show_and_tell_b200 as snt
+    V, E = params["embed.weight"].shape
+    H = params["lstm.weight_hh_l0"].shape[1]
+    L = sum(1 for k in params if k.startswith("lstm.weight_ih_l"))
+    dec = snt.DecoderRNN(E, H, V, L, precision=prec)
+    dec.load_state_dict({k: torch.from_numpy(np.asarray(v, np.float32)) for k, v in params.items()})
+    return dec.to(device)

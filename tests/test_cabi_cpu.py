@@ -1,0 +1,110 @@
+"""CPU-side checks (no GPU): the C-ABI library builds/loads and exports exactly what include/snt_b200.h
+declares; host-side logic of the boundary; and that the product path refuses to run without CUDA
+(there is no CPU fallback to fall into)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def snt():
+    import __graft_entry__ as ge
+    ge.build()
+    import show_and_tell_b200 as snt
+    return snt
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "snt_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(snt_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(snt):
+    lib = ctypes.CDLL(snt._lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/snt_b200.h but not exported"
+    assert sorted(snt._lib.SIGNATURES) == names       # the ctypes table binds every declared entry point
+    out = subprocess.run(["nm", "-D", "--defined-only", snt._lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T snt_" in l)
+    assert exported == names
+
+
+def test_abi_version_and_error_string(snt):
+    l = snt._lib.lib()
+    assert l.snt_abi_version() == 1
+    # argument validation happens before any CUDA call: bad precision -> SNT_EINVAL with a message
+    rc = l.snt_lstm_fwd(7, None, 8, 8, None, None, None, None, None, 1, None, None, None, None, None, 0, None)
+    assert rc == -1 and b"prec" in l.snt_last_error()
+    assert l.snt_lstm_workspace_bytes(0, 100, 10, 8, 16) > 0
+    assert l.snt_lstm_workspace_bytes(5, 100, 10, 8, 16) == -1
+    bs = (ctypes.c_int32 * 3)(2, 3, 1)   # not non-increasing
+    rc = l.snt_embed_pack_fwd(None, None, None, 4, ctypes.cast(bs, ctypes.c_void_p), 3, 8, 10, None, None, None)
+    assert rc == -1 and b"non-increasing" in l.snt_last_error()
+
+
+def test_batch_sizes_from_lengths(snt):
+    f = snt.ops.batch_sizes_from_lengths
+    assert f([3, 3, 1]).tolist() == [3, 2, 2]
+    assert f([1]).tolist() == [1]
+    assert f([20, 1]).tolist() == [2] + [1] * 19
+    for bad in ([2, 3], [2, 0], []):
+        with pytest.raises(RuntimeError):
+            f(bad)
+    with pytest.raises(RuntimeError):
+        f([5, 2], max_steps=4)
+    from oracle import snt_oracle as O
+    rng = np.random.default_rng(0)
+    l = snt.synthetic.make_lengths(257, rng)
+    T, bs, off = O.pack_info(l)
+    assert f(l).tolist() == bs.tolist()
+
+
+def test_no_cpu_fallback(snt):
+    dec = snt.DecoderRNN(8, 16, 23, 1)
+    feats, caps = torch.randn(2, 8), torch.ones(2, 3, dtype=torch.int64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dec(feats, caps, [3, 2])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dec.sample(feats)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        snt.EncoderCNN(8, backbone=False).forward_pooled(torch.randn(4, 2048))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "show-and-tell_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "snt_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, fn
+
+
+def test_state_dict_matches_reference_layout(snt):
+    dec = snt.DecoderRNN(8, 16, 23, 2)
+    sd = dec.state_dict()
+    assert sd["embed.weight"].shape == (23, 8)
+    assert sd["lstm.weight_ih_l0"].shape == (64, 8) and sd["lstm.weight_ih_l1"].shape == (64, 16)
+    assert sd["lstm.weight_hh_l1"].shape == (64, 16) and sd["lstm.bias_hh_l0"].shape == (64,)
+    assert sd["linear.weight"].shape == (23, 16) and sd["linear.bias"].shape == (23,)
+    assert float(sd["linear.bias"].abs().max()) == 0.0 and float(sd["embed.weight"].abs().max()) <= 0.1
+    enc = snt.EncoderCNN(8, backbone=False)
+    keys = set(enc.state_dict())
+    assert {"resnet.fc.weight", "resnet.fc.bias", "bn.weight", "bn.bias", "bn.running_mean", "bn.running_var",
+            "bn.num_batches_tracked"} <= keys
+    assert enc.bn.momentum == 0.01
+    g = np.load(os.path.join(ROOT, "tests", "golden", "dec_l2_b.npz"))
+    ref_keys = sorted(k[len("param."):] for k in g.files if k.startswith("param."))
+    dec2 = snt.DecoderRNN(int(g["E"]), int(g["H"]), int(g["V"]), int(g["L"]))
+    assert sorted(dec2.state_dict()) == ref_keys      # the reference module's own state_dict keys
+    for k in ref_keys:
+        assert tuple(dec2.state_dict()[k].shape) == g["param." + k].shape
