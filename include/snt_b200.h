@@ -139,9 +139,10 @@ int snt_greedy_decode(int prec, const float* features, const float* w_emb, int L
 
 /* ---- a11  clip_gradient (clamp to +-grad_clip) + Adam  (train.py:88-91,145-146) -------------------------
  * In-place on p, m, v; g is read only.  `step` is the 1-based count after this update.
- * grad_clip <= 0 disables the clamp.  grad_scale multiplies g first (1/world for averaged DP grads). */
-int snt_clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
-                   float beta2, float eps, float grad_clip, float grad_scale, int64_t step, void* stream);
+ * grad_clip <= 0 disables the clamp.  grad_scale multiplies g first (1/world for averaged DP grads).
+ * Hyper-parameters are doubles: torch.optim.Adam forms 1-beta and the bias corrections in double. */
+int snt_clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
+                   double beta2, double eps, float grad_clip, float grad_scale, int64_t step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(HERE, "libsnt_b200.so")
 PREC_FP32, PREC_BF16 = 0, 1
 PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 
-_vp, _i64, _i32, _f32, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int
+_vp, _i64, _i32, _f32, _f64, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_double, C.c_int
 _pp = C.POINTER(C.c_void_p)
 
 # name -> (restype, argtypes); mirrors include/snt_b200.h one to one
@@ -54,7 +54,7 @@ SIGNATURES = {
     "snt_greedy_workspace_bytes": (_i64, [_int, _i64, _i64, _i64, _i64, _int]),
     "snt_greedy_decode": (_int, [_int, _vp, _vp, _int, _pp, _pp, _pp, _pp, _vp, _vp, _vp, _vp,
                                  _i64, _i64, _i64, _i64, _int, _vp, _vp, _i64, _vp]),
-    "snt_clamp_adam": (_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _i64, _vp]),
+    "snt_clamp_adam": (_int, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f32, _f32, _i64, _vp]),
 }
 
 _lib = None

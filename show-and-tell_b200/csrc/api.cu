@@ -22,8 +22,8 @@ extern "C" int snt_cast_bf16(const float* src, void* dst, int64_t n, void* strea
   return cast_bf16(src, (__nv_bfloat16*)dst, n, (cudaStream_t)stream);
 }
 
-extern "C" int snt_clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
-                              float beta2, float eps, float grad_clip, float grad_scale, int64_t step,
+extern "C" int snt_clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
+                              double beta2, double eps, float grad_clip, float grad_scale, int64_t step,
                               void* stream) {
   SNT_REQUIRE(n >= 0 && (n == 0 || (p && g && m && v)), "snt_clamp_adam: bad arguments");
   return clamp_adam(p, g, m, v, n, lr, beta1, beta2, eps, grad_clip, grad_scale, step, (cudaStream_t)stream);

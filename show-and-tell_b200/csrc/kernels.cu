@@ -621,26 +621,27 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 clamp_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                  float* __restrict__ v, int64_t n, float lr_over_bc1, float beta1, float beta2, float eps,
-                  float rsqrt_bc2, float grad_clip, float grad_scale) {
+                  float* __restrict__ v, int64_t n, float step_size, float beta1, float beta2, float omb1,
+                  float omb2, float eps, float rsqrt_bc2, float grad_clip, float grad_scale) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   float gi = g[i] * grad_scale;
   if (grad_clip > 0.f) gi = fminf(fmaxf(gi, -grad_clip), grad_clip);
-  const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-  const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  const float mi = beta1 * m[i] + omb1 * gi;          // exp_avg.lerp_(grad, 1 - beta1)
+  const float vi = beta2 * v[i] + omb2 * gi * gi;     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
   m[i] = mi;
   v[i] = vi;
-  const float denom = sqrtf(vi) * rsqrt_bc2 + eps;
-  p[i] = p[i] - lr_over_bc1 * (mi / denom);
+  const float denom = sqrtf(vi) * rsqrt_bc2 + eps;    // sqrt(v) / sqrt(bias_correction2) + eps
+  p[i] = p[i] - step_size * (mi / denom);             // step_size = lr / bias_correction1
 }
-int clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-               float eps, float grad_clip, float grad_scale, int64_t step, cudaStream_t st) {
+int clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+               double eps, float grad_clip, float grad_scale, int64_t step, cudaStream_t st) {
   if (n <= 0) return SNT_OK;
   SNT_REQUIRE(step >= 1, "clamp_adam: step must be >= 1");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  clamp_adam_kernel<<<nblocks(n, 256), 256, 0, st>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps,
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  clamp_adam_kernel<<<nblocks(n, 256), 256, 0, st>>>(p, g, m, v, n, (float)(lr / bc1), (float)beta1, (float)beta2,
+                                                    (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps,
                                                     (float)(1.0 / sqrt(bc2)), grad_clip, grad_scale);
   SNT_LAUNCH_CHECK("clamp_adam_kernel");
   return SNT_OK;

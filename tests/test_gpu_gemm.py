@@ -86,7 +86,7 @@ def _bf16_case(M, N, K, tA, tB, c_bf16, seed):
 @pytest.mark.parametrize("tB", [0, 1])
 def test_gemm_bf16_tcgen05(M, N, K, tA, tB):
     err = _bf16_case(M, N, K, tA, tB, False, M + N + K + tA * 2 + tB)
-    assert err < 1e-5, f"tcgen05 GEMM tA={tA} tB={tB} {M}x{N}x{K}: rel err {err}"
+    assert err < 5e-5, f"tcgen05 GEMM tA={tA} tB={tB} {M}x{N}x{K}: rel err {err}"
 
 
 @pytest.mark.parametrize("M,N,K", [(129, 257, 72), (1024, 2048, 512)])

@@ -88,3 +88,20 @@ def test_pack_info_edges():
         O.pack_info([2, 0])
     with pytest.raises(ValueError):
         O.pack_info([])
+
+
+@pytest.mark.parametrize("name", DEC_CASES)
+def test_torch_port_matches_reference(name):
+    """The torch CPU baseline bench.py times (oracle/torch_port.py) against the reference's own outputs."""
+    import torch
+    from oracle import torch_port as TP
+    g = load_golden(name)
+    dec = TP.CaptionDecoderCPU(int(g["E"]), int(g["H"]), int(g["V"]), int(g["L"]))
+    dec.load_state_dict({k: torch.from_numpy(v) for k, v in golden_params(g).items()})
+    f, c, t = torch.from_numpy(g["features"]), torch.from_numpy(g["captions"]), torch.from_numpy(g["targets"])
+    loss = TP.train_step(dec, f, c, g["lengths"].tolist(), t)
+    assert abs(float(loss) - g["f32.loss"]) / g["f32.loss"] < 1e-6
+    for k, p in dec.named_parameters():
+        assert rel(p.grad.numpy(), g[f"f32.grad.{k}"]) < 1e-5, k
+    ids = dec.eval().sample(f).numpy()
+    np.testing.assert_array_equal(ids, g["f32.greedy_ids"])
