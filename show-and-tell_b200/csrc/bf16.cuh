@@ -35,6 +35,10 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
                  const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
                  float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st);
 
+// out[c] = beta*out[c] + sum_r in[r*ld + c] for a bf16 matrix; partial needs ((R+255)/256)*C floats
+int colsum_bf16(const __nv_bfloat16* in, int64_t R, int64_t C, int64_t ld, float beta, float* out, float* partial,
+                cudaStream_t st);
+
 int64_t greedy_ws_bytes(int64_t B, int64_t E, int64_t H, int64_t V, int L);
 int greedy_decode(const float* features, const float* w_emb, int L, const float* const* w_ih,
                   const float* const* w_hh, const float* const* b_ih, const float* const* b_hh,

@@ -11,7 +11,6 @@ namespace bf16 {
 typedef __nv_bfloat16 bf;
 
 static inline int64_t pad8(int64_t x) { return (x + 7) / 8 * 8; }
-constexpr int64_t CE_CHUNK_ROWS = 1024;
 constexpr int MAX_SPLITS = 16;
 
 #define SNT_REQUIRE_ALIGNED8(v, what)                                                                  \
@@ -80,103 +79,6 @@ int wgrad_tn(const float* dy, const float* a, int64_t M, int64_t N, int64_t K, f
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// LSTM layer
-// ---------------------------------------------------------------------------------------------------------
-struct LstmWs {
-  float* bsum; bf* w_ih; bf* w_hh; float* dh_rec; float* dc_state; float* part; bf* dg; float* sws;
-  bool ok;
-};
-static LstmWs carve_lstm(void* ws, int64_t ws_bytes, int64_t N, int64_t B, int64_t In, int64_t H) {
-  Workspace w(ws, ws_bytes);
-  LstmWs r;
-  r.bsum = w.take<float>(4 * H);
-  r.w_ih = w.take<bf>(4 * H * In);
-  r.w_hh = w.take<bf>(4 * H * H);
-  r.dh_rec = w.take<float>(B * H);
-  r.dc_state = w.take<float>(B * H);
-  r.part = w.take<float>(colsum_partial_count(N, 4 * H));
-  r.dg = w.take<bf>(N * 4 * H);
-  r.sws = w.take<float>(MAX_SPLITS * 4 * H * (In > H ? In : H));
-  r.ok = w.ok();
-  return r;
-}
-int64_t lstm_ws_bytes(int64_t N, int64_t B, int64_t In, int64_t H) {
-  return ws_bytes_for(4 * H, 4) + ws_bytes_for(4 * H * In, 2) + ws_bytes_for(4 * H * H, 2) +
-         2 * ws_bytes_for(B * H, 4) + ws_bytes_for(colsum_partial_count(N, 4 * H), 4) +
-         ws_bytes_for(N * 4 * H, 2) + ws_bytes_for(MAX_SPLITS * 4 * H * (In > H ? In : H), 4);
-}
-
-int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh,
-             const float* b_ih, const float* b_hh, float* gates, float* cs, void* hs, void* hprev, void* ws,
-             int64_t ws_bytes, cudaStream_t st) {
-  SNT_REQUIRE_ALIGNED8(In, "In");
-  SNT_REQUIRE_ALIGNED8(H, "H");
-  const int T = pk.T;
-  const int64_t N = pk.off[T], B = pk.off[1];
-  LstmWs w = carve_lstm(ws, ws_bytes, N, B, In, H);
-  if (!w.ok) { set_error("bf16 lstm_fwd: workspace too small"); return SNT_EWORKSPACE; }
-  bf* hs_b = (bf*)hs;
-  bf* hp_b = (bf*)hprev;
-  SNT_CHECK(add_vec(b_ih, b_hh, w.bsum, 4 * H, st));
-  SNT_CHECK(cast_bf16(w_ih, w.w_ih, 4 * H * In, st));
-  SNT_CHECK(cast_bf16(w_hh, w.w_hh, 4 * H * H, st));
-  // input projection of all timesteps as one tensor-core contraction: gates = x . W_ih^T + (b_ih + b_hh)
-  SNT_CHECK(tc::gemm_tc(false, false, N, 4 * H, In, 1.f, (const bf*)x, In, w.w_ih, In, 0.f, gates, nullptr, 4 * H,
-                        w.bsum, 1, nullptr, st));
-  SNT_CUDA(cudaMemsetAsync(hp_b, 0, sizeof(bf) * (size_t)B * H, st));
-  for (int t = 0; t < T; ++t) {
-    const int bs = pk.off[t + 1] - pk.off[t];
-    const int bs_next = t + 1 < T ? pk.off[t + 2] - pk.off[t + 1] : 0;
-    float* g_t = gates + (int64_t)pk.off[t] * 4 * H;
-    if (t > 0)
-      SNT_CHECK(tc::gemm_tc(false, false, bs, 4 * H, H, 1.f, hp_b + (int64_t)pk.off[t] * H, H, w.w_hh, H, 1.f, g_t,
-                            nullptr, 4 * H, nullptr, 1, nullptr, st));
-    const float* c_prev = t > 0 ? cs + (int64_t)pk.off[t - 1] * H : nullptr;
-    SNT_CHECK(lstm_point_fwd<bf>(g_t, c_prev, cs + (int64_t)pk.off[t] * H, hs_b + (int64_t)pk.off[t] * H,
-                                 bs_next > 0 ? hp_b + (int64_t)pk.off[t + 1] * H : nullptr, bs, bs_next, H, st));
-  }
-  return SNT_OK;
-}
-
-int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* cs, const void* hprev,
-             const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh, float* d_w_ih,
-             float* d_w_hh, float* d_bias, float* dx, void* ws, int64_t ws_bytes, cudaStream_t st) {
-  SNT_REQUIRE_ALIGNED8(In, "In");
-  SNT_REQUIRE_ALIGNED8(H, "H");
-  const int T = pk.T;
-  const int64_t N = pk.off[T], B = pk.off[1];
-  LstmWs w = carve_lstm(ws, ws_bytes, N, B, In, H);
-  if (!w.ok) { set_error("bf16 lstm_bwd: workspace too small"); return SNT_EWORKSPACE; }
-  SNT_CHECK(cast_bf16(w_ih, w.w_ih, 4 * H * In, st));
-  SNT_CHECK(cast_bf16(w_hh, w.w_hh, 4 * H * H, st));
-  for (int t = T - 1; t >= 0; --t) {
-    const int bs = pk.off[t + 1] - pk.off[t];
-    const int bs_next = t + 1 < T ? pk.off[t + 2] - pk.off[t + 1] : 0;
-    float* g_t = gates + (int64_t)pk.off[t] * 4 * H;
-    bf* dg_t = w.dg + (int64_t)pk.off[t] * 4 * H;
-    const float* c_prev = t > 0 ? cs + (int64_t)pk.off[t - 1] * H : nullptr;
-    SNT_CHECK(lstm_point_bwd(g_t, cs + (int64_t)pk.off[t] * H, c_prev, d_hs + (int64_t)pk.off[t] * H, w.dh_rec,
-                             w.dc_state, bs, bs_next, H, st));
-    SNT_CHECK(cast_bf16(g_t, dg_t, (int64_t)bs * 4 * H, st));
-    if (t > 0)  // dh_{t-1} = dG_t . W_hh : B operand is W_hh as [K=4H, N=H] (MN-major)
-      SNT_CHECK(tc::gemm_tc(false, true, bs, H, 4 * H, 1.f, dg_t, 4 * H, w.w_hh, H, 0.f, w.dh_rec, nullptr, H,
-                            nullptr, 1, nullptr, st));
-  }
-  int s1 = tc::choose_splits(4 * H, In, N, 0), s2 = tc::choose_splits(4 * H, H, N, 0);
-  if (s1 > MAX_SPLITS) s1 = MAX_SPLITS;
-  if (s2 > MAX_SPLITS) s2 = MAX_SPLITS;
-  SNT_CHECK(tc::gemm_tc(true, true, 4 * H, In, N, 1.f, w.dg, 4 * H, (const bf*)x, In, 0.f, d_w_ih, nullptr, In,
-                        nullptr, s1, w.sws, st));
-  SNT_CHECK(tc::gemm_tc(true, true, 4 * H, H, N, 1.f, w.dg, 4 * H, (const bf*)hprev, H, 0.f, d_w_hh, nullptr, H,
-                        nullptr, s2, w.sws, st));
-  SNT_CHECK(colsum(gates, N, 4 * H, 4 * H, 0.f, d_bias, w.part, st));
-  if (dx)
-    SNT_CHECK(tc::gemm_tc(false, true, N, In, 4 * H, 1.f, w.dg, 4 * H, w.w_ih, In, 0.f, dx, nullptr, In, nullptr, 1,
-                          nullptr, st));
-  return SNT_OK;
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // materialising vocab Linear
 // ---------------------------------------------------------------------------------------------------------
 int64_t linear_ws_bytes(int64_t N, int64_t H, int64_t V) {
@@ -207,68 +109,6 @@ int linear_bwd(const float* dlogits, const void* hs, const float* w_out, int64_t
   SNT_CHECK(tc::gemm_tc(true, true, V, H, N, 1.f, dlb, Vp, (const bf*)hs, H, 0.f, d_w_out, nullptr, H, nullptr, 1,
                         nullptr, st));
   return colsum(dlogits, N, V, V, 0.f, d_b_out, part, st);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// vocab Linear + log-softmax + CE: chunks of CE_CHUNK_ROWS rows of logits live in the workspace (L2-sized)
-// ---------------------------------------------------------------------------------------------------------
-struct CeWs { bf* wb; float* chunk; bf* chunk_b; float* nll; float* part; bool ok; int64_t R, Vp; };
-static CeWs carve_ce(void* ws, int64_t ws_bytes, int64_t N, int64_t H, int64_t V) {
-  Workspace w(ws, ws_bytes);
-  CeWs r;
-  r.R = N < CE_CHUNK_ROWS ? N : CE_CHUNK_ROWS;
-  r.Vp = pad8(V);
-  r.wb = w.take<bf>(V * H);
-  r.chunk = w.take<float>(r.R * V);
-  r.chunk_b = w.take<bf>(r.R * r.Vp);
-  r.nll = w.take<float>(N);
-  r.part = w.take<float>(colsum_partial_count(r.R, V));
-  r.ok = w.ok();
-  return r;
-}
-int64_t vocab_ce_ws_bytes(int64_t N, int64_t H, int64_t V) {
-  const int64_t R = N < CE_CHUNK_ROWS ? N : CE_CHUNK_ROWS;
-  return ws_bytes_for(V * H, 2) + ws_bytes_for(R * V, 4) + ws_bytes_for(R * pad8(V), 2) + ws_bytes_for(N, 4) +
-         ws_bytes_for(colsum_partial_count(R, V), 4);
-}
-int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, int64_t N,
-                 int64_t H, int64_t V, float* lse, float* loss, void* ws, int64_t ws_bytes, cudaStream_t st) {
-  SNT_REQUIRE_ALIGNED8(H, "H");
-  CeWs w = carve_ce(ws, ws_bytes, N, H, V);
-  if (!w.ok) { set_error("bf16 vocab_ce_fwd: workspace too small"); return SNT_EWORKSPACE; }
-  const bf* hs_b = (const bf*)hs;
-  SNT_CHECK(cast_bf16(w_out, w.wb, V * H, st));
-  for (int64_t r0 = 0; r0 < N; r0 += w.R) {
-    const int64_t r = N - r0 < w.R ? N - r0 : w.R;
-    SNT_CHECK(tc::gemm_tc(false, false, r, V, H, 1.f, hs_b + r0 * H, H, w.wb, H, 0.f, w.chunk, nullptr, V, b_out, 1,
-                          nullptr, st));
-    SNT_CHECK(ce_rows_fwd(w.chunk, r, V, V, targets + r0, lse + r0, w.nll + r0, st));
-  }
-  return reduce_sum(w.nll, N, 1.0f / (float)N, loss, st);
-}
-int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, const float* lse,
-                 const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
-                 float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
-  SNT_REQUIRE_ALIGNED8(H, "H");
-  CeWs w = carve_ce(ws, ws_bytes, N, H, V);
-  if (!w.ok) { set_error("bf16 vocab_ce_bwd: workspace too small"); return SNT_EWORKSPACE; }
-  const bf* hs_b = (const bf*)hs;
-  const float scale = grad_scale / (float)N;
-  SNT_CHECK(cast_bf16(w_out, w.wb, V * H, st));
-  for (int64_t r0 = 0; r0 < N; r0 += w.R) {
-    const int64_t r = N - r0 < w.R ? N - r0 : w.R;
-    const float acc = r0 > 0 ? 1.f : 0.f;
-    SNT_CHECK(tc::gemm_tc(false, false, r, V, H, 1.f, hs_b + r0 * H, H, w.wb, H, 0.f, w.chunk, nullptr, V, b_out, 1,
-                          nullptr, st));
-    SNT_CHECK(ce_rows_bwd(w.chunk, r, V, V, targets + r0, lse + r0, dloss, scale, st));
-    SNT_CHECK(cast2d(w.chunk, r, V, V, w.chunk_b, w.Vp, st));
-    SNT_CHECK(tc::gemm_tc(false, true, r, H, V, 1.f, w.chunk_b, w.Vp, w.wb, H, 0.f, d_hs + r0 * H, nullptr, H, nullptr,
-                          1, nullptr, st));
-    SNT_CHECK(tc::gemm_tc(true, true, V, H, r, 1.f, w.chunk_b, w.Vp, hs_b + r0 * H, H, acc, d_w_out, nullptr, H,
-                          nullptr, 1, nullptr, st));
-    SNT_CHECK(colsum(w.chunk, r, V, V, acc, d_b_out, w.part, st));
-  }
-  return SNT_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -109,27 +109,29 @@ int choose_splits(int64_t M, int64_t N, int64_t K, int bn) {
 template <int BN, bool A_MN, bool B_MN>
 static int run_plain(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, int64_t M, int64_t N,
                      float alpha, float beta, float* C, __nv_bfloat16* Cb, int64_t ldc, const float* bias,
-                     int64_t split_stride, cudaStream_t st) {
+                     int64_t split_stride, cudaStream_t st, int perm, const float* adev) {
   PlainEpi<BN> e;
   e.M = (int)M; e.N = (int)N; e.alpha = alpha; e.beta = beta; e.C = C; e.Cb = Cb; e.ldc = ldc; e.bias = bias;
-  e.split_stride = split_stride;
+  e.split_stride = split_stride; e.row_perm_h = perm; e.alpha_dev = adev;
   return launch_gemm_tc<BN, A_MN, B_MN, PlainEpi<BN>>(ta, tb, ts, e, st);
 }
 
 template <int BN>
 static int run_plain_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts,
                            int64_t M, int64_t N, float alpha, float beta, float* C, __nv_bfloat16* Cb, int64_t ldc,
-                           const float* bias, int64_t split_stride, cudaStream_t st) {
-  if (!a_mn && !b_mn) return run_plain<BN, false, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st);
-  if (!a_mn && b_mn) return run_plain<BN, false, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st);
-  if (a_mn && !b_mn) return run_plain<BN, true, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st);
-  return run_plain<BN, true, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st);
+                           const float* bias, int64_t split_stride, cudaStream_t st, int perm, const float* adev) {
+  if (!a_mn && !b_mn) return run_plain<BN, false, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev);
+  if (!a_mn && b_mn) return run_plain<BN, false, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev);
+  if (a_mn && !b_mn) return run_plain<BN, true, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev);
+  return run_plain<BN, true, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev);
 }
 
 int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A,
             int64_t lda, const __nv_bfloat16* B, int64_t ldb, float beta, float* C, __nv_bfloat16* Cb,
-            int64_t ldc, const float* bias, int splits, float* split_ws, cudaStream_t st) {
+            int64_t ldc, const float* bias, int splits, float* split_ws, cudaStream_t st, int row_perm_h,
+            const float* alpha_dev) {
   if (M <= 0 || N <= 0) return SNT_OK;
+  SNT_REQUIRE(row_perm_h == 0 || M == 4 * (int64_t)row_perm_h, "gemm_tc: row permutation needs M == 4H");
   SNT_REQUIRE(K >= 1 && A && B && (C || Cb), "gemm_tc: bad arguments");
   SNT_REQUIRE(M < (1 << 30) && N < (1 << 30) && K < (1 << 30), "gemm_tc: extent too large");
   const int bn = pick_bn(M, N);
@@ -159,9 +161,9 @@ int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, 
     split_stride = M * ldc;
   }
   int rc;
-  if (bn == 256) rc = run_plain_major<256>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st);
-  else if (bn == 128) rc = run_plain_major<128>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st);
-  else rc = run_plain_major<64>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st);
+  if (bn == 256) rc = run_plain_major<256>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev);
+  else if (bn == 128) rc = run_plain_major<128>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev);
+  else rc = run_plain_major<64>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev);
   SNT_CHECK(rc);
   if (splits > 1) {
     const int64_t total = M * N;

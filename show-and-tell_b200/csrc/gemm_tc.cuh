@@ -236,19 +236,24 @@ struct PlainEpi {
   static constexpr int kWarps = 4;
   int M, N;                // valid extent
   float alpha, beta;
+  const float* alpha_dev;  // optional device scalar multiplied into alpha (e.g. the incoming dloss)
   float* C;                // may be NULL
   __nv_bfloat16* Cb;       // may be NULL
   int64_t ldc;
   const float* bias;       // may be NULL, length N
   int64_t split_stride;    // elements between split-K partial slices of C
+  int row_perm_h;          // != 0: accumulator row 4*j+g is stored to row g*row_perm_h + j (LSTM gate un-interleave)
 
   __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane) const {
     const int row = m_blk * BM + (ew & 3) * 32 + lane;
     const bool row_ok = row < M;
-    float* crow = C ? C + (int64_t)split * split_stride + (int64_t)row * ldc : nullptr;
-    __nv_bfloat16* brow = Cb ? Cb + (int64_t)row * ldc : nullptr;
-    const bool vec_ok = crow && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
-                        (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+    const int drow = row_perm_h ? (row & 3) * row_perm_h + (row >> 2) : row;
+    const float a = alpha_dev ? alpha * alpha_dev[0] : alpha;
+    float* crow = C ? C + (int64_t)split * split_stride + (int64_t)drow * ldc : nullptr;
+    __nv_bfloat16* brow = Cb ? Cb + (int64_t)drow * ldc : nullptr;
+    const bool bias_al = !bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
+    const bool vec_ok = crow && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && bias_al;
+    const bool bvec_ok = !crow && brow && ((ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0) && bias_al;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int col0 = n_blk * BN + c * 32;
@@ -258,23 +263,28 @@ struct PlainEpi {
       tmem_ld_wait();
       if (!row_ok) continue;
       if (vec_ok && col0 + 32 <= N) {
+        float4* dst = reinterpret_cast<float4*>(crow + col0);
+        float4 o[8];
+        if (beta != 0.f) {  // all loads first: a load placed after a (possibly aliasing) store cannot be hoisted
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+          for (int q = 0; q < 8; ++q) o[q] = __ldcg(dst + q);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int j = q * 4;
           float4 v;
-          v.x = alpha * __uint_as_float(r[j]);
-          v.y = alpha * __uint_as_float(r[j + 1]);
-          v.z = alpha * __uint_as_float(r[j + 2]);
-          v.w = alpha * __uint_as_float(r[j + 3]);
+          v.x = a * __uint_as_float(r[j]);
+          v.y = a * __uint_as_float(r[j + 1]);
+          v.z = a * __uint_as_float(r[j + 2]);
+          v.w = a * __uint_as_float(r[j + 3]);
           if (bias) {
             const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
           }
-          float4* dst = reinterpret_cast<float4*>(crow + col0 + j);
           if (beta != 0.f) {
-            const float4 o = *dst;
-            v.x += beta * o.x; v.y += beta * o.y; v.z += beta * o.z; v.w += beta * o.w;
+            v.x += beta * o[q].x; v.y += beta * o[q].y; v.z += beta * o[q].z; v.w += beta * o[q].w;
           }
-          *dst = v;
+          dst[q] = v;
           if (brow) {
             brow[col0 + j] = __float2bfloat16_rn(v.x);
             brow[col0 + j + 1] = __float2bfloat16_rn(v.y);
@@ -282,12 +292,27 @@ struct PlainEpi {
             brow[col0 + j + 3] = __float2bfloat16_rn(v.w);
           }
         }
+      } else if (bvec_ok && col0 + 32 <= N) {  // bf16-only output: 4 x 16-byte stores per 32 columns
+        uint4* dst = reinterpret_cast<uint4*>(brow + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int j = q * 8 + h * 2;
+            float v0 = a * __uint_as_float(r[j]), v1 = a * __uint_as_float(r[j + 1]);
+            if (bias) { v0 += bias[col0 + j]; v1 += bias[col0 + j + 1]; }
+            __nv_bfloat162 t = __floats2bfloat162_rn(v0, v1);
+            pk[h] = *reinterpret_cast<uint32_t*>(&t);
+          }
+          dst[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = col0 + j;
           if (col < N) {
-            float v = alpha * __uint_as_float(r[j]);
+            float v = a * __uint_as_float(r[j]);
             if (bias) v += bias[col];
             if (crow) {
               if (beta != 0.f) v += beta * crow[col];
@@ -310,7 +335,8 @@ int64_t gemm_tc_split_ws_elems(int64_t M, int64_t ldc, int splits);
 int choose_splits(int64_t M, int64_t N, int64_t K, int bn);
 int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A,
             int64_t lda, const __nv_bfloat16* B, int64_t ldb, float beta, float* C, __nv_bfloat16* Cb,
-            int64_t ldc, const float* bias, int splits, float* split_ws, cudaStream_t st);
+            int64_t ldc, const float* bias, int splits, float* split_ws, cudaStream_t st, int row_perm_h = 0,
+            const float* alpha_dev = nullptr);
 
 }  // namespace tc
 }  // namespace snt

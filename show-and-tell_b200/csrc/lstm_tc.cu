@@ -1,0 +1,340 @@
+// a7 / a10 on tensor cores: the LSTM recurrence with the gate math fused into the contraction's epilogue.
+//
+// Layout trick: gate rows of W_ih / W_hh / bias are interleaved per hidden unit, r' = 4*j + g (g = i,f,g,o), so any
+// accumulator tile holds all four gates of its hidden units and one epilogue thread (= one batch row) can finish
+// c_t and h_t straight out of TMEM.  Pre-activations never reach HBM:
+//   forward step t : TMEM = h_{t-1}[bs_t,H] . W_hh'^T ; epilogue adds the batched input projection Gx'[t]
+//                    (one tcgen05 GEMM over all timesteps), applies sigma/tanh, writes c_t, h_t (bf16, also as next
+//                    step's A operand) and the bf16 activations kept for BPTT.
+//   backward step t: TMEM = dG'_{t+1}[bs_{t+1},4H] . W_hh' ; epilogue adds dL/dh_t, runs the cell backward and
+//                    writes dG'_t as bf16 — the A operand of step t-1 and of the weight-gradient GEMMs.
+// Steps are chained with programmatic dependent launch, so each step's prologue overlaps its predecessor's tail.
+#include "bf16.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace snt {
+namespace bf16 {
+
+typedef __nv_bfloat16 bf;
+constexpr int MAX_SPLITS = 16;
+constexpr float LOG2E_F = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2f_(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.f, 1.f + ex2f_(-x * LOG2E_F)); }
+__device__ __forceinline__ float tanh_(float x) {
+  const float e = ex2f_(-2.f * LOG2E_F * fabsf(x));  // in (0,1]: no overflow
+  const float t = __fdividef(1.f - e, 1.f + e);
+  return copysignf(t, x);
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf2(uint32_t u) {
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+
+// ---- weight preparation: fp32 gate-major rows -> bf16 unit-interleaved rows ------------------------------------------
+__global__ void __launch_bounds__(128)
+perm_rows_bf16_kernel(const float* __restrict__ w, int H, int cols, bf* __restrict__ out) {
+  const int rp = blockIdx.x;  // 4*j + g
+  const int src = (rp & 3) * H + (rp >> 2);
+  for (int c = threadIdx.x; c < cols; c += 128) out[(int64_t)rp * cols + c] = __float2bfloat16_rn(w[(int64_t)src * cols + c]);
+}
+__global__ void perm_bias_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh, int H,
+                                 float* __restrict__ out) {
+  const int rp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rp >= 4 * H) return;
+  const int src = (rp & 3) * H + (rp >> 2);
+  out[rp] = b_ih[src] + b_hh[src];
+}
+__global__ void unperm_vec_kernel(const float* __restrict__ in, int H, float* __restrict__ out) {
+  const int rp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rp >= 4 * H) return;
+  out[(rp & 3) * H + (rp >> 2)] = in[rp];
+}
+
+// ---- forward step epilogue ---------------------------------------------------------------------------------------------
+struct LstmFwdEpi {
+  static constexpr int kWarps = 4;
+  int bs, bs_next, H;
+  const float* gx;      // [bs, 4H]   input projection + biases of this step's rows, interleaved columns
+  const float* c_prev;  // [>=bs, H]  c_{t-1} (NULL at t = 0)
+  float* cs;            // [bs, H]    c_t
+  bf* hs;               // [bs, H]    h_t (layer output rows of this step)
+  bf* hprev_next;       // [bs_next, H] h_t again, at the packed rows of step t+1 (NULL at the last step)
+  bf* act;              // [bs, 4H]   sigma(i), sigma(f), tanh(g), sigma(o), interleaved, kept for BPTT
+
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane) const {
+    const int row = m_blk * tc::BM + ew * 32 + lane;
+    const bool ok = row < bs;
+    const int H4 = 4 * H;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int col0 = n_blk * 128 + c * 32;
+      if (col0 >= H4) break;  // warp-uniform
+      uint32_t r[32];
+      tc::tmem_ld32(tmem_rows + (uint32_t)(c * 32), r);
+      tc::tmem_ld_wait();
+      if (!ok) continue;
+      const int j0 = col0 >> 2;
+      const float4* g4 = reinterpret_cast<const float4*>(gx + (int64_t)row * H4 + col0);
+      float4 g[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) g[u] = __ldg(g4 + u);
+      float cp[8];
+      if (c_prev) {
+        const float4 a = *reinterpret_cast<const float4*>(c_prev + (int64_t)row * H + j0);
+        const float4 b = *reinterpret_cast<const float4*>(c_prev + (int64_t)row * H + j0 + 4);
+        cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w; cp[4] = b.x; cp[5] = b.y; cp[6] = b.z; cp[7] = b.w;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cp[u] = 0.f;
+      }
+      float cn[8], hn[8];
+      uint32_t ap[16];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float i_ = sigm(__uint_as_float(r[4 * u]) + g[u].x);
+        const float f_ = sigm(__uint_as_float(r[4 * u + 1]) + g[u].y);
+        const float g_ = tanh_(__uint_as_float(r[4 * u + 2]) + g[u].z);
+        const float o_ = sigm(__uint_as_float(r[4 * u + 3]) + g[u].w);
+        cn[u] = f_ * cp[u] + i_ * g_;
+        hn[u] = o_ * tanh_(cn[u]);
+        ap[2 * u] = pack_bf2(i_, f_);
+        ap[2 * u + 1] = pack_bf2(g_, o_);
+      }
+      float4* cd = reinterpret_cast<float4*>(cs + (int64_t)row * H + j0);
+      cd[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+      cd[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+      const uint4 hv = make_uint4(pack_bf2(hn[0], hn[1]), pack_bf2(hn[2], hn[3]), pack_bf2(hn[4], hn[5]),
+                                  pack_bf2(hn[6], hn[7]));
+      *reinterpret_cast<uint4*>(hs + (int64_t)row * H + j0) = hv;
+      if (row < bs_next) *reinterpret_cast<uint4*>(hprev_next + (int64_t)row * H + j0) = hv;
+      uint4* ad = reinterpret_cast<uint4*>(act + (int64_t)row * H4 + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ad[q] = make_uint4(ap[4 * q], ap[4 * q + 1], ap[4 * q + 2], ap[4 * q + 3]);
+    }
+  }
+};
+
+// ---- backward step epilogue ------------------------------------------------------------------------------------------
+struct LstmBwdEpi {
+  static constexpr int kWarps = 4;
+  int bs, bs_next, H;
+  const float* d_hs;    // [bs, H]   dL/dh_t from the layer above / the vocab projection
+  const bf* act;        // [bs, 4H]  saved activations of step t
+  const float* cs;      // [bs, H]   c_t
+  const float* c_prev;  // [>=bs, H] c_{t-1} (NULL at t = 0)
+  float* dc_state;      // [B, H]    in: dL/dc_t carried from step t+1 (rows < bs_next); out: dL/dc_{t-1}
+  bf* dg;               // [bs, 4H]  out: gradient w.r.t. the pre-activations, interleaved columns
+
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane) const {
+    const int row = m_blk * tc::BM + ew * 32 + lane;
+    const bool ok = row < bs;
+    const bool has_next = row < bs_next;  // rows that were still alive at step t+1 carry recurrent gradient
+    const int H4 = 4 * H;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int j0 = n_blk * 64 + c * 32;
+      if (j0 >= H) break;  // warp-uniform
+      uint32_t r[32];
+      tc::tmem_ld32(tmem_rows + (uint32_t)(c * 32), r);
+      tc::tmem_ld_wait();
+      if (!ok) continue;
+#pragma unroll
+      for (int sub = 0; sub < 4; ++sub) {
+        const int ju = j0 + sub * 8;
+        if (ju < H) {
+          const int64_t o1 = (int64_t)row * H + ju;
+          const float4 dh0 = *reinterpret_cast<const float4*>(d_hs + o1), dh1 = *reinterpret_cast<const float4*>(d_hs + o1 + 4);
+          const float4 c0 = *reinterpret_cast<const float4*>(cs + o1), c1 = *reinterpret_cast<const float4*>(cs + o1 + 4);
+          float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, s0 = p0, s1 = p0;
+          if (c_prev) { p0 = *reinterpret_cast<const float4*>(c_prev + o1); p1 = *reinterpret_cast<const float4*>(c_prev + o1 + 4); }
+          if (has_next) { s0 = *reinterpret_cast<const float4*>(dc_state + o1); s1 = *reinterpret_cast<const float4*>(dc_state + o1 + 4); }
+          const uint4* a4 = reinterpret_cast<const uint4*>(act + (int64_t)row * H4 + 4 * ju);
+          uint32_t a[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { const uint4 v = a4[q]; a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w; }
+          const float dhv[8] = {dh0.x, dh0.y, dh0.z, dh0.w, dh1.x, dh1.y, dh1.z, dh1.w};
+          const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+          const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          float dcn[8];
+          uint32_t go[16];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float2 if_ = unpack_bf2(a[2 * u]), go_ = unpack_bf2(a[2 * u + 1]);
+            const float i_ = if_.x, f_ = if_.y, g_ = go_.x, o_ = go_.y;
+            const float tc_ = tanh_(cv[u]);
+            const float dh = dhv[u] + (has_next ? __uint_as_float(r[sub * 8 + u]) : 0.f);
+            const float dc = sv[u] + dh * o_ * (1.f - tc_ * tc_);
+            go[2 * u] = pack_bf2(dc * g_ * i_ * (1.f - i_), dc * pv[u] * f_ * (1.f - f_));
+            go[2 * u + 1] = pack_bf2(dc * i_ * (1.f - g_ * g_), dh * tc_ * o_ * (1.f - o_));
+            dcn[u] = dc * f_;
+          }
+          float4* sd = reinterpret_cast<float4*>(dc_state + o1);
+          sd[0] = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+          sd[1] = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
+          uint4* gd = reinterpret_cast<uint4*>(dg + (int64_t)row * H4 + 4 * ju);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gd[q] = make_uint4(go[4 * q], go[4 * q + 1], go[4 * q + 2], go[4 * q + 3]);
+        }
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct LstmWs {
+  float* bsum; bf* w_ih; bf* w_hh; float* gx; float* dc_state; float* cpart; float* tmp; float* sws; bool ok;
+};
+static int64_t csb_partials(int64_t R, int64_t C) { return ((R + 255) / 256) * C; }
+static LstmWs carve(void* ws, int64_t ws_bytes, int64_t N, int64_t B, int64_t In, int64_t H) {
+  Workspace w(ws, ws_bytes);
+  LstmWs r;
+  r.bsum = w.take<float>(4 * H);
+  r.w_ih = w.take<bf>(4 * H * In);
+  r.w_hh = w.take<bf>(4 * H * H);
+  r.gx = w.take<float>(N * 4 * H);
+  r.dc_state = w.take<float>(B * H);
+  r.cpart = w.take<float>(csb_partials(N, 4 * H));
+  r.tmp = w.take<float>(4 * H);
+  r.sws = w.take<float>(MAX_SPLITS * 4 * H * (In > H ? In : H));
+  r.ok = w.ok();
+  return r;
+}
+int64_t lstm_ws_bytes(int64_t N, int64_t B, int64_t In, int64_t H) {
+  return 2 * ws_bytes_for(4 * H, 4) + ws_bytes_for(4 * H * In, 2) + ws_bytes_for(4 * H * H, 2) +
+         ws_bytes_for(N * 4 * H, 4) + ws_bytes_for(B * H, 4) + ws_bytes_for(csb_partials(N, 4 * H), 4) +
+         ws_bytes_for(MAX_SPLITS * 4 * H * (In > H ? In : H), 4);
+}
+
+static int prep_weights(const LstmWs& w, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                        int64_t In, int64_t H, cudaStream_t st) {
+  perm_rows_bf16_kernel<<<(unsigned)(4 * H), 128, 0, st>>>(w_ih, (int)H, (int)In, w.w_ih);
+  SNT_LAUNCH_CHECK("perm_rows_bf16_kernel");
+  perm_rows_bf16_kernel<<<(unsigned)(4 * H), 128, 0, st>>>(w_hh, (int)H, (int)H, w.w_hh);
+  SNT_LAUNCH_CHECK("perm_rows_bf16_kernel");
+  if (b_ih) {
+    perm_bias_kernel<<<(unsigned)((4 * H + 255) / 256), 256, 0, st>>>(b_ih, b_hh, (int)H, w.bsum);
+    SNT_LAUNCH_CHECK("perm_bias_kernel");
+  }
+  return SNT_OK;
+}
+
+#define SNT_REQ8(v, what)                                                                               \
+  do {                                                                                                  \
+    if ((v) % 8 != 0) {                                                                                 \
+      set_error("bf16 mode: %s=%lld must be a multiple of 8 (TMA row pitch is 16 bytes)", what,         \
+                (long long)(v));                                                                        \
+      return SNT_EUNSUPPORTED;                                                                          \
+    }                                                                                                   \
+  } while (0)
+
+// `gates` (caller-owned, N*4H*4 bytes) holds, in bf16 mode: [0, N*4H) bf16 saved activations (interleaved columns),
+// [N*4H, 2*N*4H) bf16 pre-activation gradients written by lstm_bwd.
+int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh,
+             const float* b_ih, const float* b_hh, float* gates, float* cs, void* hs, void* hprev, void* ws,
+             int64_t ws_bytes, cudaStream_t st) {
+  SNT_REQ8(In, "In");
+  SNT_REQ8(H, "H");
+  const int T = pk.T;
+  const int64_t N = pk.off[T], B = pk.off[1];
+  LstmWs w = carve(ws, ws_bytes, N, B, In, H);
+  if (!w.ok) { set_error("bf16 lstm_fwd: workspace too small"); return SNT_EWORKSPACE; }
+  bf* hs_b = (bf*)hs;
+  bf* hp_b = (bf*)hprev;
+  bf* act = (bf*)gates;
+  SNT_CHECK(prep_weights(w, w_ih, w_hh, b_ih, b_hh, In, H, st));
+  // the input projection of every timestep as ONE tensor-core contraction: Gx' = x . W_ih'^T + (b_ih + b_hh)'
+  SNT_CHECK(tc::gemm_tc(false, false, N, 4 * H, In, 1.f, (const bf*)x, In, w.w_ih, In, 0.f, w.gx, nullptr, 4 * H,
+                        w.bsum, 1, nullptr, st));
+  SNT_CUDA(cudaMemsetAsync(hp_b, 0, sizeof(bf) * (size_t)B * H, st));  // h_{-1} = 0
+  CUtensorMap ta, tb;
+  SNT_CHECK(tc::make_operand_tmap(&ta, hp_b, false, N, H, H, tc::BM));
+  SNT_CHECK(tc::make_operand_tmap(&tb, w.w_hh, false, 4 * H, H, H, 128));
+  for (int t = 0; t < T; ++t) {
+    const int bs = pk.off[t + 1] - pk.off[t];
+    const int bs_next = t + 1 < T ? pk.off[t + 2] - pk.off[t + 1] : 0;
+    tc::TileSched ts;
+    ts.num_m = (bs + tc::BM - 1) / tc::BM;
+    ts.num_n = (int)((4 * H + 127) / 128);
+    ts.splits = 1;
+    ts.kblocks = (int)((H + tc::BK - 1) / tc::BK);
+    ts.kblocks_per_split = ts.kblocks;
+    ts.a_row0 = pk.off[t];
+    ts.b_row0 = 0;
+    LstmFwdEpi e;
+    e.bs = bs; e.bs_next = bs_next; e.H = (int)H;
+    e.gx = w.gx + (int64_t)pk.off[t] * 4 * H;
+    e.c_prev = t > 0 ? cs + (int64_t)pk.off[t - 1] * H : nullptr;
+    e.cs = cs + (int64_t)pk.off[t] * H;
+    e.hs = hs_b + (int64_t)pk.off[t] * H;
+    e.hprev_next = bs_next > 0 ? hp_b + (int64_t)pk.off[t + 1] * H : nullptr;
+    e.act = act + (int64_t)pk.off[t] * 4 * H;
+    SNT_CHECK((tc::launch_gemm_tc<128, false, false, LstmFwdEpi>(ta, tb, ts, e, st, /*pdl=*/t > 0)));
+  }
+  return SNT_OK;
+}
+
+int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* cs, const void* hprev,
+             const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh, float* d_w_ih,
+             float* d_w_hh, float* d_bias, float* dx, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  SNT_REQ8(In, "In");
+  SNT_REQ8(H, "H");
+  const int T = pk.T;
+  const int64_t N = pk.off[T], B = pk.off[1];
+  LstmWs w = carve(ws, ws_bytes, N, B, In, H);
+  if (!w.ok) { set_error("bf16 lstm_bwd: workspace too small"); return SNT_EWORKSPACE; }
+  const bf* act = (const bf*)gates;
+  bf* dg = (bf*)gates + N * 4 * H;
+  SNT_CHECK(prep_weights(w, w_ih, w_hh, nullptr, nullptr, In, H, st));
+  CUtensorMap ta, tb;
+  SNT_CHECK(tc::make_operand_tmap(&ta, dg, false, N, 4 * H, 4 * H, tc::BM));
+  SNT_CHECK(tc::make_operand_tmap(&tb, w.w_hh, true, H, 4 * H, H, 64));
+  for (int t = T - 1; t >= 0; --t) {
+    const int bs = pk.off[t + 1] - pk.off[t];
+    const int bs_next = t + 1 < T ? pk.off[t + 2] - pk.off[t + 1] : 0;
+    tc::TileSched ts;
+    ts.num_m = (bs + tc::BM - 1) / tc::BM;
+    ts.num_n = (int)((H + 63) / 64);
+    ts.splits = 1;
+    ts.kblocks = (int)((4 * H + tc::BK - 1) / tc::BK);
+    ts.kblocks_per_split = ts.kblocks;
+    ts.a_row0 = pk.off[t + 1];  // dG'_{t+1}; for t = T-1 this is past the tensor (zero fill) and unused
+    ts.b_row0 = 0;
+    LstmBwdEpi e;
+    e.bs = bs; e.bs_next = bs_next; e.H = (int)H;
+    e.d_hs = d_hs + (int64_t)pk.off[t] * H;
+    e.act = act + (int64_t)pk.off[t] * 4 * H;
+    e.cs = cs + (int64_t)pk.off[t] * H;
+    e.c_prev = t > 0 ? cs + (int64_t)pk.off[t - 1] * H : nullptr;
+    e.dc_state = w.dc_state;
+    e.dg = dg + (int64_t)pk.off[t] * 4 * H;
+    SNT_CHECK((tc::launch_gemm_tc<64, false, true, LstmBwdEpi>(ta, tb, ts, e, st, /*pdl=*/t < T - 1)));
+  }
+  // weight gradients over the whole packed sequence (rows come out interleaved: un-permute on store)
+  int s1 = tc::choose_splits(4 * H, In, N, 0), s2 = tc::choose_splits(4 * H, H, N, 0);
+  if (s1 > MAX_SPLITS) s1 = MAX_SPLITS;
+  if (s2 > MAX_SPLITS) s2 = MAX_SPLITS;
+  SNT_CHECK(tc::gemm_tc(true, true, 4 * H, In, N, 1.f, dg, 4 * H, (const bf*)x, In, 0.f, d_w_ih, nullptr, In,
+                        nullptr, s1, w.sws, st, (int)H));
+  SNT_CHECK(tc::gemm_tc(true, true, 4 * H, H, N, 1.f, dg, 4 * H, (const bf*)hprev, H, 0.f, d_w_hh, nullptr, H,
+                        nullptr, s2, w.sws, st, (int)H));
+  SNT_CHECK(colsum_bf16(dg, N, 4 * H, 4 * H, 0.f, w.tmp, w.cpart, st));
+  unperm_vec_kernel<<<(unsigned)((4 * H + 255) / 256), 256, 0, st>>>(w.tmp, (int)H, d_bias);
+  SNT_LAUNCH_CHECK("unperm_vec_kernel");
+  if (dx)
+    SNT_CHECK(tc::gemm_tc(false, true, N, In, 4 * H, 1.f, dg, 4 * H, w.w_ih, In, 0.f, dx, nullptr, In, nullptr, 1,
+                          nullptr, st));
+  return SNT_OK;
+}
+
+}  // namespace bf16
+}  // namespace snt

@@ -1,0 +1,350 @@
+// a8+a9 on tensor cores: vocab Linear fused with log-softmax + cross-entropy (models.py:53 + train.py:53,143).
+//
+// forward : one tcgen05 pass logits = Hs . W_out^T whose epilogue reduces each 128-column slab of a row to an
+//           online-softmax partial (max, sum-exp) straight out of TMEM — logits are never written anywhere.
+//           A finishing kernel merges the partials into lse[n] and the mean NLL.
+// backward: the same contraction is recomputed per chunk of rows; its epilogue forms
+//           dlogits = (softmax - onehot) * scale in registers and stores it as bf16 into an L2-resident chunk
+//           buffer, which two more tcgen05 contractions consume (dHs = dlogits.W_out, dW_out += dlogits^T.Hs).
+#include "bf16.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace snt {
+namespace bf16 {
+
+typedef __nv_bfloat16 bf;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr int CE_BN = 256;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---- target logit: tl[n] = Hs[n,:] . W[target[n],:] + b[target[n]]  (one warp per row) ---------------------------
+__global__ void __launch_bounds__(256)
+ce_target_logit_kernel(const bf* __restrict__ hs, const bf* __restrict__ w, const float* __restrict__ bias,
+                       const int64_t* __restrict__ targets, int64_t N, int H, int64_t V, float* __restrict__ tl,
+                       int* flags) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const int64_t t = targets[row];
+  if (t < 0 || t >= V) {
+    if (lane == 0) { atomicOr(flags, 2); tl[row] = 0.f; }
+    return;
+  }
+  const bf* a = hs + row * H;
+  const bf* b = w + t * H;
+  float acc = 0.f;
+  for (int k = lane * 8; k < H; k += 256) {  // H % 8 == 0
+    const uint4 va = *reinterpret_cast<const uint4*>(a + k);
+    const uint4 vb = *reinterpret_cast<const uint4*>(b + k);
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&va);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&vb);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 fa = __bfloat1622float2(pa[i]), fb = __bfloat1622float2(pb[i]);
+      acc = fmaf(fa.x, fb.x, acc);
+      acc = fmaf(fa.y, fb.y, acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) tl[row] = acc + bias[t];
+}
+
+// ---- forward epilogue: per (row, 128-column slab) online-softmax partial in the log2 domain ------------------------
+struct CeFwdEpi {
+  static constexpr int kWarps = 8;
+  int M;                 // rows
+  int V;                 // valid columns
+  const float* bias;     // [V]
+  float2* part;          // [num_slabs][M] (max2, sum2): sum_j 2^(y_j - max2), y = logit * log2(e)
+
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane) const {
+    const int half = ew >> 2;
+    const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
+    float m = -INFINITY, s = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < CE_BN / 64; ++c) {
+      const int cofs = half * (CE_BN / 2) + c * 32;
+      const int col0 = n_blk * CE_BN + cofs;
+      if (col0 >= V) break;  // warp-uniform
+      uint32_t r[32];
+      tc::tmem_ld32(tmem_rows + (uint32_t)cofs, r);
+      tc::tmem_ld_wait();
+      float y[32];
+      if (col0 + 32 <= V) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
+          y[j] = (__uint_as_float(r[j]) + b.x) * LOG2E;
+          y[j + 1] = (__uint_as_float(r[j + 1]) + b.y) * LOG2E;
+          y[j + 2] = (__uint_as_float(r[j + 2]) + b.z) * LOG2E;
+          y[j + 3] = (__uint_as_float(r[j + 3]) + b.w) * LOG2E;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          y[j] = (col0 + j < V) ? (__uint_as_float(r[j]) + bias[col0 + j]) * LOG2E : -INFINITY;
+      }
+      float cm = y[0];
+#pragma unroll
+      for (int j = 1; j < 32; ++j) cm = fmaxf(cm, y[j]);
+      const float mn = fmaxf(m, cm);
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc += ex2(y[j] - mn);
+      s = s * ex2(m - mn) + acc;  // m = -inf on the first chunk: ex2(-inf) = 0
+      m = mn;
+    }
+    if (row < M) part[(int64_t)(n_blk * 2 + half) * M + row] = make_float2(m, s);
+  }
+};
+
+// lse[n] = ln2 * (M + log2 sum_k s_k 2^(m_k - M)); nll[n] = lse - tl
+__global__ void __launch_bounds__(256)
+ce_finish_kernel(const float2* __restrict__ part, int slabs, int64_t N, const float* __restrict__ tl,
+                 float* __restrict__ lse, float* __restrict__ nll) {
+  const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (row >= N) return;
+  float M = -INFINITY;
+  for (int k = 0; k < slabs; ++k) M = fmaxf(M, part[(int64_t)k * N + row].x);
+  float S = 0.f;
+  for (int k = 0; k < slabs; ++k) {
+    const float2 p = part[(int64_t)k * N + row];
+    if (p.y > 0.f) S += p.y * exp2f(p.x - M);
+  }
+  const float l = (M + log2f(S)) * LN2;
+  lse[row] = l;
+  nll[row] = l - tl[row];
+}
+
+// ---- backward epilogue: dlogits = (2^(y - lse2) - onehot) * scale -> bf16 chunk ------------------------------------
+struct CeBwdEpi {
+  static constexpr int kWarps = 8;
+  int M;                    // rows in this chunk
+  int V;
+  const float* bias;        // [V]
+  const float* lse;         // [M] (chunk-local pointer)
+  const int64_t* targets;   // [M]
+  bf* out;                  // [M, ldo] bf16: softmax - onehot, UNSCALED (the 1/N and dloss factors are folded
+                            // into the consumers' alpha: scaling first would round every target entry the same way)
+  int64_t ldo;
+
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane) const {
+    const int half = ew >> 2;
+    const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
+    const bool row_ok = row < M;
+    const float l2 = row_ok ? lse[row] * LOG2E : 0.f;
+    const int tgt = row_ok ? (int)targets[row] : -1;
+    bf* orow = out + (int64_t)row * ldo;
+#pragma unroll 1
+    for (int c = 0; c < CE_BN / 64; ++c) {
+      const int cofs = half * (CE_BN / 2) + c * 32;
+      const int col0 = n_blk * CE_BN + cofs;
+      if (col0 >= V) break;  // warp-uniform
+      uint32_t r[32];
+      tc::tmem_ld32(tmem_rows + (uint32_t)cofs, r);
+      tc::tmem_ld_wait();
+      if (!row_ok) continue;
+      const int trel = tgt - col0;
+      if (col0 + 32 <= V) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
+          float p0 = ex2((__uint_as_float(r[j]) + b.x) * LOG2E - l2);
+          float p1 = ex2((__uint_as_float(r[j + 1]) + b.y) * LOG2E - l2);
+          float p2 = ex2((__uint_as_float(r[j + 2]) + b.z) * LOG2E - l2);
+          float p3 = ex2((__uint_as_float(r[j + 3]) + b.w) * LOG2E - l2);
+          if (trel == j) p0 -= 1.f;
+          if (trel == j + 1) p1 -= 1.f;
+          if (trel == j + 2) p2 -= 1.f;
+          if (trel == j + 3) p3 -= 1.f;
+          __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
+          pk[j / 2] = *reinterpret_cast<uint32_t*>(&lo);
+          pk[j / 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(orow + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col < V) {
+            float p = ex2((__uint_as_float(r[j]) + bias[col]) * LOG2E - l2);
+            if (trel == j) p -= 1.f;
+            orow[col] = __float2bfloat16_rn(p);
+          }
+        }
+      }
+    }
+  }
+};
+
+// ---- column sums of a bf16 matrix (for d_b_out), deterministic two pass -----------------------------------------------
+constexpr int CSB_ROWS = 256;
+__global__ void __launch_bounds__(256)
+colsum_bf16_partial_kernel(const bf* __restrict__ in, int64_t R, int64_t C, int64_t ld, float* __restrict__ partial) {
+  // block: 64 column-pairs x 4 row lanes; each thread sums a bf16x2 column pair
+  __shared__ float2 red[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int64_t c = ((int64_t)blockIdx.x * 64 + tx) * 2;
+  const int64_t r0 = (int64_t)blockIdx.y * CSB_ROWS, r1 = min(R, r0 + CSB_ROWS);
+  float2 s = make_float2(0.f, 0.f);
+  if (c + 1 < C) {
+    for (int64_t r = r0 + ty; r < r1; r += 4) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(in + r * ld + c));
+      s.x += v.x; s.y += v.y;
+    }
+  } else if (c < C) {
+    for (int64_t r = r0 + ty; r < r1; r += 4) s.x += __bfloat162float(in[r * ld + c]);
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float2 t = red[0][tx];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) { t.x += red[i][tx].x; t.y += red[i][tx].y; }
+    partial[(int64_t)blockIdx.y * C + c] = t.x;
+    if (c + 1 < C) partial[(int64_t)blockIdx.y * C + c + 1] = t.y;
+  }
+}
+__global__ void colsum_bf16_final_kernel(const float* __restrict__ partial, int64_t chunks, int64_t C, float beta,
+                                         float* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int64_t k = 0; k < chunks; ++k) s += partial[k * C + c];
+  out[c] = (beta != 0.f ? beta * out[c] : 0.f) + s;
+}
+static int64_t colsum_bf16_partials(int64_t R, int64_t C) { return ((R + CSB_ROWS - 1) / CSB_ROWS) * C; }
+int colsum_bf16(const bf* in, int64_t R, int64_t C, int64_t ld, float beta, float* out, float* partial,
+                       cudaStream_t st) {
+  const int64_t chunks = (R + CSB_ROWS - 1) / CSB_ROWS;
+  dim3 grid((unsigned)((C + 127) / 128), (unsigned)chunks);
+  colsum_bf16_partial_kernel<<<grid, 256, 0, st>>>(in, R, C, ld, partial);
+  SNT_LAUNCH_CHECK("colsum_bf16_partial_kernel");
+  colsum_bf16_final_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(partial, chunks, C, beta, out);
+  SNT_LAUNCH_CHECK("colsum_bf16_final_kernel");
+  return SNT_OK;
+}
+
+__global__ void scale_vec_kernel(const float* __restrict__ in, int64_t n, float scale, const float* __restrict__ dloss,
+                                 float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * scale * (dloss ? dloss[0] : 1.f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+static inline int64_t pad8(int64_t x) { return (x + 7) / 8 * 8; }
+constexpr int64_t BWD_CHUNK_ROWS = 2048;  // 2048 x 10000 bf16 = 41 MB of dlogits: stays in the 126 MB L2
+constexpr int MAX_SPLITS = 16;
+
+struct CeWs {
+  bf* wb; float2* part; float* tl; float* nll; bf* dl; float* cpart; float* sws; float* db;
+  int slabs; int64_t R, Vp; bool ok;
+};
+static CeWs carve(void* ws, int64_t ws_bytes, int64_t N, int64_t H, int64_t V) {
+  Workspace w(ws, ws_bytes);
+  CeWs r;
+  r.slabs = (int)((V + CE_BN - 1) / CE_BN) * 2;
+  r.R = N < BWD_CHUNK_ROWS ? N : BWD_CHUNK_ROWS;
+  r.Vp = pad8(V);
+  r.wb = w.take<bf>(V * H);
+  r.part = w.take<float2>((int64_t)r.slabs * N);
+  r.tl = w.take<float>(N);
+  r.nll = w.take<float>(N);
+  r.dl = w.take<bf>(r.R * r.Vp);
+  r.cpart = w.take<float>(colsum_bf16_partials(r.R, V));
+  r.sws = w.take<float>(MAX_SPLITS * r.R * H);
+  r.db = w.take<float>(V);
+  r.ok = w.ok();
+  return r;
+}
+int64_t vocab_ce_ws_bytes(int64_t N, int64_t H, int64_t V) {
+  const int64_t slabs = ((V + CE_BN - 1) / CE_BN) * 2;
+  const int64_t R = N < BWD_CHUNK_ROWS ? N : BWD_CHUNK_ROWS;
+  return ws_bytes_for(V * H, 2) + ws_bytes_for(slabs * N, 8) + 2 * ws_bytes_for(N, 4) + ws_bytes_for(R * pad8(V), 2) +
+         ws_bytes_for(colsum_bf16_partials(R, V), 4) + ws_bytes_for(MAX_SPLITS * R * H, 4) + ws_bytes_for(V, 4);
+}
+
+static int make_sched(int64_t M, int64_t Ncols, int64_t K, tc::TileSched* ts) {
+  ts->num_m = (int)((M + tc::BM - 1) / tc::BM);
+  ts->num_n = (int)((Ncols + CE_BN - 1) / CE_BN);
+  ts->splits = 1;
+  ts->kblocks = (int)((K + tc::BK - 1) / tc::BK);
+  ts->kblocks_per_split = ts->kblocks;
+  ts->a_row0 = 0;
+  ts->b_row0 = 0;
+  return SNT_OK;
+}
+
+int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, int64_t N,
+                 int64_t H, int64_t V, float* lse, float* loss, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  if (H % 8 != 0) { set_error("bf16 mode: H=%lld must be a multiple of 8", (long long)H); return SNT_EUNSUPPORTED; }
+  SNT_REQUIRE(V < (1LL << 31) && N < (1LL << 31), "vocab_ce_fwd: extent too large");
+  CeWs w = carve(ws, ws_bytes, N, H, V);
+  if (!w.ok) { set_error("bf16 vocab_ce_fwd: workspace too small"); return SNT_EWORKSPACE; }
+  const bf* hs_b = (const bf*)hs;
+  SNT_CHECK(cast_bf16(w_out, w.wb, V * H, st));
+  ce_target_logit_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(hs_b, w.wb, b_out, targets, N, (int)H, V, w.tl,
+                                                                 device_flags());
+  SNT_LAUNCH_CHECK("ce_target_logit_kernel");
+  CUtensorMap ta, tb;
+  SNT_CHECK(tc::make_operand_tmap(&ta, hs_b, false, N, H, H, tc::BM));
+  SNT_CHECK(tc::make_operand_tmap(&tb, w.wb, false, V, H, H, CE_BN));
+  tc::TileSched ts;
+  make_sched(N, V, H, &ts);
+  CeFwdEpi e;
+  e.M = (int)N; e.V = (int)V; e.bias = b_out; e.part = w.part;
+  SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeFwdEpi>(ta, tb, ts, e, st)));
+  ce_finish_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w.part, w.slabs, N, w.tl, lse, w.nll);
+  SNT_LAUNCH_CHECK("ce_finish_kernel");
+  return reduce_sum(w.nll, N, 1.0f / (float)N, loss, st);
+}
+
+int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, const float* lse,
+                 const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
+                 float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  if (H % 8 != 0) { set_error("bf16 mode: H=%lld must be a multiple of 8", (long long)H); return SNT_EUNSUPPORTED; }
+  CeWs w = carve(ws, ws_bytes, N, H, V);
+  if (!w.ok) { set_error("bf16 vocab_ce_bwd: workspace too small"); return SNT_EWORKSPACE; }
+  const bf* hs_b = (const bf*)hs;
+  const float scale = grad_scale / (float)N;
+  SNT_CHECK(cast_bf16(w_out, w.wb, V * H, st));
+  CUtensorMap tb;
+  SNT_CHECK(tc::make_operand_tmap(&tb, w.wb, false, V, H, H, CE_BN));
+  for (int64_t r0 = 0; r0 < N; r0 += w.R) {
+    const int64_t r = N - r0 < w.R ? N - r0 : w.R;
+    const float acc = r0 > 0 ? 1.f : 0.f;
+    CUtensorMap ta;
+    SNT_CHECK(tc::make_operand_tmap(&ta, hs_b + r0 * H, false, r, H, H, tc::BM));
+    tc::TileSched ts;
+    make_sched(r, V, H, &ts);
+    CeBwdEpi e;
+    e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;
+    e.out = w.dl; e.ldo = w.Vp;
+    SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeBwdEpi>(ta, tb, ts, e, st)));
+    // dHs[r,H] = dlogits[r,V] . W_out[V,H]      (B operand MN-major)
+    int sp = tc::choose_splits(r, H, V, 0);
+    if (sp > MAX_SPLITS) sp = MAX_SPLITS;
+    SNT_CHECK(tc::gemm_tc(false, true, r, H, V, scale, w.dl, w.Vp, w.wb, H, 0.f, d_hs + r0 * H, nullptr, H, nullptr, sp,
+                          w.sws, st, 0, dloss));
+    // dW_out[V,H] += dlogits^T[V,r] . Hs[r,H]   (both operands MN-major)
+    SNT_CHECK(tc::gemm_tc(true, true, V, H, r, scale, w.dl, w.Vp, hs_b + r0 * H, H, acc, d_w_out, nullptr, H, nullptr, 1,
+                          nullptr, st, 0, dloss));
+    SNT_CHECK(colsum_bf16(w.dl, r, V, w.Vp, acc, w.db, w.cpart, st));
+  }
+  scale_vec_kernel<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(w.db, V, scale, dloss, d_b_out);
+  SNT_LAUNCH_CHECK("scale_vec_kernel");
+  return SNT_OK;
+}
+
+}  // namespace bf16
+}  // namespace snt
