@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--prec", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-greedy", action="store_true")
+    ap.add_argument("--stages", action="store_true", help="also print per-entry-point GPU time (CUDA events) to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -250,6 +251,17 @@ def main():
     torch.cuda.synchronize()
     clocks = sampler.stop()
     clocks["sampled_over"] = "timed region + continuation of the same step to >= 1.5 s"
+
+    if args.stages and rank == 0:
+        snt._lib.profile_begin()
+        for _ in range(5):
+            step_resident()
+        prof = snt._lib.profile_end()
+        tot = sum(t for _, t in prof.values())
+        for name, (n, t) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+            print(f"[stages] {name:24s} calls/step {n / 5:5.1f}  {t / 5 * 1e3:9.1f} us/step  {100 * t / tot:5.1f}%",
+                  file=sys.stderr)
+        print(f"[stages] sum {tot / 5 * 1e3:.1f} us/step", file=sys.stderr)
 
     for _ in range(2):
         step_e2e()

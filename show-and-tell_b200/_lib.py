@@ -88,10 +88,38 @@ def check(rc, what=""):
         raise SntError(f"{what} failed ({rc}): {msg}")
 
 
+_profile = None  # when a list: (name, start_event, end_event) per C-ABI call, see profile_begin/profile_end
+
+
 def call(name, *args):
     global LAUNCHES
     LAUNCHES += 1
+    if _profile is None:
+        check(getattr(lib(), name)(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(lib(), name)(*args), name)
+    e1.record()
+    _profile.append((name, e0, e1))
+
+
+def profile_begin():
+    """Start recording a CUDA-event pair around every C-ABI call (diagnostics; adds event overhead)."""
+    global _profile
+    _profile = []
+
+
+def profile_end():
+    """-> {entry point: (calls, total GPU milliseconds)} since profile_begin()."""
+    global _profile
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in _profile or []:
+        n, t = out.get(name, (0, 0.0))
+        out[name] = (n + 1, t + e0.elapsed_time(e1))
+    _profile = None
+    return out
 
 
 def ptr(t):

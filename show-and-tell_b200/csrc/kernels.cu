@@ -483,94 +483,119 @@ int bn_bwd(const float* dout, const float* yhat, const float* rstd, const float*
 // counting sort by token (stable rank = number of earlier packed rows with the same token), then one block
 // per vocab row sums its rows in packed-row order.  Rows t==0 go to dfeatures.
 // ---------------------------------------------------------------------------------------------------------
+// Stable counting sort of the token rows in ONE single-block kernel (deterministic summation order):
+//   1. count[] zeroed (shared memory when V fits, else the global scratch),
+//   2. warp 0 walks the rows in packed order, 32 at a time: rank[i] = count[tok] + #earlier lanes with the same
+//      token (match_any), then bumps count[tok] by the group size,
+//   3. block-wide exclusive scan of count -> start[0..V],
+//   4. perm[start[tok[i]] + rank[i]] = i.
+__global__ void __launch_bounds__(1024)
+emb_sort_kernel(const int* __restrict__ tok, int n1, int V, int* __restrict__ gcount, int* __restrict__ rank,
+                int* __restrict__ start, int* __restrict__ perm, int use_smem) {
+  extern __shared__ int s_count[];
+  __shared__ int s_scan[1024];
+  __shared__ int s_carry;
+  int* count = use_smem ? s_count : gcount;
+  for (int i = threadIdx.x; i < V; i += 1024) count[i] = 0;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    for (int base = 0; base < n1; base += 32) {
+      const int i = base + lane;
+      const int t = i < n1 ? tok[i] : -1 - lane;  // distinct negatives never match
+      const unsigned peers = __match_any_sync(0xffffffffu, t);
+      const int before = __popc(peers & ((1u << lane) - 1u));
+      const int c0 = t >= 0 ? count[t] : 0;
+      if (t >= 0) rank[i] = c0 + before;
+      __syncwarp();  // every lane of a token group has read count[t] before its leader bumps it
+      if (t >= 0 && before == 0) count[t] = c0 + __popc(peers);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < V; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int c = i < V ? count[i] : 0;
+    s_scan[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_scan[threadIdx.x] += v;
+      __syncthreads();
+    }
+    if (i < V) start[i] = s_carry + s_scan[threadIdx.x] - c;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry += s_scan[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) start[V] = s_carry;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n1; i += 1024) {
+    const int t = tok[i];
+    if (t >= 0) perm[start[t] + rank[i]] = i;
+  }
+}
 __global__ void __launch_bounds__(256)
-emb_tokens_kernel(const __grid_constant__ PackInfo pk, const int64_t* __restrict__ captions, int64_t cap_stride,
-                  int64_t V, int* __restrict__ tok, int* __restrict__ count, int* flags) {
+emb_tok_kernel(const __grid_constant__ PackInfo pk, const int64_t* __restrict__ captions, int64_t cap_stride,
+               int64_t V, int* __restrict__ tok, int* flags) {
   const int n1 = pk.off[pk.T] - pk.off[1];  // rows with t >= 1
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n1) return;
   const int row = pk.off[1] + i;
   const int t = find_step(pk, row);
   const int b = row - pk.off[t];
-  int64_t tk = captions[(int64_t)b * cap_stride + (t - 1)];
+  const int64_t tk = captions[(int64_t)b * cap_stride + (t - 1)];
   if (tk < 0 || tk >= V) { atomicOr(flags, 1); tok[i] = -1; return; }
   tok[i] = (int)tk;
-  atomicAdd(&count[tk], 1);
 }
-// exclusive scan of count[0..V) into start[0..V], single block of 1024 threads
-__global__ void __launch_bounds__(1024)
-emb_scan_kernel(const int* __restrict__ count, int64_t V, int* __restrict__ start) {
-  __shared__ int sh[1024];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int64_t base = 0; base < V; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    const int c = i < V ? count[i] : 0;
-    sh[threadIdx.x] = c;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      int v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += v;
-      __syncthreads();
-    }
-    if (i < V) start[i] = carry + sh[threadIdx.x] - c;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += sh[1023];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) start[V] = carry;
-}
-// perm[start[tok[i]] + #{i' < i : tok[i'] == tok[i]}] = i   (stable => deterministic summation order)
+// One block (8 warps) per vocabulary row that occurs; d_w_emb is pre-zeroed.  Warp w sums rows w, w+8, ... of the
+// token's segment (4 rows in flight), then the 8 partials are combined in a fixed order.
 __global__ void __launch_bounds__(256)
-emb_rank_kernel(const int* __restrict__ tok, int n1, const int* __restrict__ start, int* __restrict__ perm) {
-  __shared__ int tile[1024];
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  const int my = i < n1 ? tok[i] : -2;
-  int rank = 0;
-  const int lim = min(n1, (int)(blockIdx.x + 1) * 256);  // only rows before the end of this block matter
-  for (int base = 0; base < lim; base += 1024) {
-    __syncthreads();
-    for (int k = threadIdx.x; k < 1024; k += 256) tile[k] = (base + k < n1) ? tok[base + k] : -3;
-    __syncthreads();
-    const int hi = min(1024, i - base);  // strictly earlier rows only
-    for (int k = 0; k < hi; ++k) rank += (tile[k] == my);
-  }
-  if (i < n1 && my >= 0) perm[start[my] + rank] = i;
-}
-__global__ void __launch_bounds__(128)
-emb_reduce_kernel(const float* __restrict__ dx1 /* dx + off[1]*E */, const int* __restrict__ start,
-                  const int* __restrict__ perm, int E, float* __restrict__ d_w_emb) {
-  extern __shared__ float part[];  // [4][E]
+emb_reduce8_kernel(const float* __restrict__ dx1 /* dx + off[1]*E */, const int* __restrict__ start,
+                   const int* __restrict__ perm, int E, float* __restrict__ d_w_emb) {
+  extern __shared__ float part[];  // [8][E]
   const int v = blockIdx.x;
   const int s0 = start[v], s1 = start[v + 1];
+  if (s1 == s0) return;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* out = d_w_emb + (int64_t)v * E;
-  if (s1 == s0) {
-    for (int e = threadIdx.x; e < E; e += 128) out[e] = 0.f;
+  if (s1 - s0 == 1) {  // the common case: a plain row copy
+    const float* src = dx1 + (int64_t)perm[s0] * E;
+    for (int e = threadIdx.x; e < E; e += 256) out[e] = src[e];
     return;
   }
-  for (int e0 = 0; e0 < E; e0 += 32 * 8) {
-    float acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    for (int i = s0 + w; i < s1; i += 4) {
-      const float* src = dx1 + (int64_t)perm[i] * E;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int e = e0 + k * 32 + lane;
-        if (e < E) acc[k] += src[e];
+  for (int e0 = 0; e0 < E; e0 += 128) {  // each lane owns 4 consecutive floats of a 128-wide slab
+    const int e = e0 + lane * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e < E) {
+      int i = s0 + w;
+      for (; i + 24 < s1; i += 32) {
+        const float4 a = *reinterpret_cast<const float4*>(dx1 + (int64_t)perm[i] * E + e);
+        const float4 b = *reinterpret_cast<const float4*>(dx1 + (int64_t)perm[i + 8] * E + e);
+        const float4 c = *reinterpret_cast<const float4*>(dx1 + (int64_t)perm[i + 16] * E + e);
+        const float4 d = *reinterpret_cast<const float4*>(dx1 + (int64_t)perm[i + 24] * E + e);
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+        acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+        acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
       }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int e = e0 + k * 32 + lane;
-      if (e < E) part[w * E + e] = acc[k];
+      for (; i < s1; i += 8) {
+        const float4 a = *reinterpret_cast<const float4*>(dx1 + (int64_t)perm[i] * E + e);
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+      }
+      *reinterpret_cast<float4*>(part + w * E + e) = acc;
     }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < E; e += 128) out[e] = (part[e] + part[E + e]) + (part[2 * E + e] + part[3 * E + e]);
+  for (int e = threadIdx.x; e < E; e += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k * E + e];
+    out[e] = t;
+  }
 }
 __global__ void __launch_bounds__(256)
 dfeatures_kernel(const float* __restrict__ dx, int bs0, int64_t B, int64_t E, float* __restrict__ dfeat) {
@@ -580,7 +605,7 @@ dfeatures_kernel(const float* __restrict__ dx, int bs0, int64_t B, int64_t E, fl
 }
 
 int64_t embed_bwd_ws_bytes(int64_t N, int64_t V) {
-  return ws_bytes_for(N, 4) * 2 + ws_bytes_for(V + 1, 4) * 2;
+  return ws_bytes_for(N, 4) * 3 + ws_bytes_for(V + 1, 4) * 2;
 }
 int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions, int64_t cap_stride,
                    int64_t B, int64_t E, int64_t V, float* dfeatures, float* d_w_emb, void* ws,
@@ -595,24 +620,29 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
   Workspace w(ws, ws_bytes);
   int* tok = w.take<int>(N);
   int* perm = w.take<int>(N);
+  int* rank = w.take<int>(N);
   int* count = w.take<int>(V + 1);
   int* start = w.take<int>(V + 1);
   if (!w.ok()) { set_error("embed_pack_bwd: workspace too small"); return SNT_EWORKSPACE; }
-  SNT_REQUIRE(E * 4 * 4 <= 48 * 1024, "embed_pack_bwd: E too large");
-  SNT_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (V + 1), st));
-  if (n1 > 0) {
-    emb_tokens_kernel<<<nblocks(n1, 256), 256, 0, st>>>(pk, captions, cap_stride, V, tok, count, device_flags());
-    SNT_LAUNCH_CHECK("emb_tokens_kernel");
+  SNT_REQUIRE(E % 4 == 0 && E * 8 * 4 <= 96 * 1024, "embed_pack_bwd: E must be a multiple of 4 and <= 3072");
+  SNT_REQUIRE(V < (1LL << 31), "embed_pack_bwd: V too large");
+  SNT_CUDA(cudaMemsetAsync(d_w_emb, 0, sizeof(float) * (size_t)V * E, st));
+  if (n1 <= 0) return SNT_OK;
+  emb_tok_kernel<<<nblocks(n1, 256), 256, 0, st>>>(pk, captions, cap_stride, V, tok, device_flags());
+  SNT_LAUNCH_CHECK("emb_tok_kernel");
+  const size_t table = sizeof(int) * (size_t)V;
+  const int use_smem = table <= 160 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SNT_CUDA(cudaFuncSetAttribute(emb_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SNT_CUDA(cudaFuncSetAttribute(emb_reduce8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
   }
-  emb_scan_kernel<<<1, 1024, 0, st>>>(count, V, start);
-  SNT_LAUNCH_CHECK("emb_scan_kernel");
-  if (n1 > 0) {
-    emb_rank_kernel<<<nblocks(n1, 256), 256, 0, st>>>(tok, n1, start, perm);
-    SNT_LAUNCH_CHECK("emb_rank_kernel");
-  }
-  emb_reduce_kernel<<<(unsigned)V, 128, (size_t)(4 * E * sizeof(float)), st>>>(dx + (int64_t)pk.off[1] * E, start,
-                                                                              perm, (int)E, d_w_emb);
-  SNT_LAUNCH_CHECK("emb_reduce_kernel");
+  emb_sort_kernel<<<1, 1024, use_smem ? table : 0, st>>>(tok, n1, (int)V, count, rank, start, perm, use_smem);
+  SNT_LAUNCH_CHECK("emb_sort_kernel");
+  emb_reduce8_kernel<<<(unsigned)V, 256, (size_t)(8 * E * sizeof(float)), st>>>(dx + (int64_t)pk.off[1] * E, start,
+                                                                               perm, (int)E, d_w_emb);
+  SNT_LAUNCH_CHECK("emb_reduce8_kernel");
   return SNT_OK;
 }
 

@@ -189,30 +189,48 @@ struct CeBwdEpi {
 
 // ---- column sums of a bf16 matrix (for d_b_out), deterministic two pass -----------------------------------------------
 constexpr int CSB_ROWS = 256;
+// block = 32 column groups (8 bf16 = one 16-byte load each -> 256 columns) x 8 row lanes; 4 rows in flight per thread
 __global__ void __launch_bounds__(256)
 colsum_bf16_partial_kernel(const bf* __restrict__ in, int64_t R, int64_t C, int64_t ld, float* __restrict__ partial) {
-  // block: 64 column-pairs x 4 row lanes; each thread sums a bf16x2 column pair
-  __shared__ float2 red[4][64];
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  const int64_t c = ((int64_t)blockIdx.x * 64 + tx) * 2;
+  __shared__ float red[8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = ((int64_t)blockIdx.x * 32 + tx) * 8;
   const int64_t r0 = (int64_t)blockIdx.y * CSB_ROWS, r1 = min(R, r0 + CSB_ROWS);
-  float2 s = make_float2(0.f, 0.f);
-  if (c + 1 < C) {
-    for (int64_t r = r0 + ty; r < r1; r += 4) {
-      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(in + r * ld + c));
-      s.x += v.x; s.y += v.y;
-    }
-  } else if (c < C) {
-    for (int64_t r = r0 + ty; r < r1; r += 4) s.x += __bfloat162float(in[r * ld + c]);
-  }
-  red[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && c < C) {
-    float2 t = red[0][tx];
+  float s[8];
 #pragma unroll
-    for (int i = 1; i < 4; ++i) { t.x += red[i][tx].x; t.y += red[i][tx].y; }
-    partial[(int64_t)blockIdx.y * C + c] = t.x;
-    if (c + 1 < C) partial[(int64_t)blockIdx.y * C + c + 1] = t.y;
+  for (int k = 0; k < 8; ++k) s[k] = 0.f;
+  auto add8 = [&](const uint4& v) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(p[k]);
+      s[2 * k] += f.x;
+      s[2 * k + 1] += f.y;
+    }
+  };
+  if (c + 8 <= C) {  // ld % 8 == 0 and c % 8 == 0: aligned 16-byte loads
+    int64_t r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      const uint4 a = __ldcg(reinterpret_cast<const uint4*>(in + r * ld + c));
+      const uint4 b = __ldcg(reinterpret_cast<const uint4*>(in + (r + 8) * ld + c));
+      const uint4 d = __ldcg(reinterpret_cast<const uint4*>(in + (r + 16) * ld + c));
+      const uint4 e = __ldcg(reinterpret_cast<const uint4*>(in + (r + 24) * ld + c));
+      add8(a); add8(b); add8(d); add8(e);
+    }
+    for (; r < r1; r += 8) add8(__ldcg(reinterpret_cast<const uint4*>(in + r * ld + c)));
+  } else if (c < C) {
+    for (int64_t r = r0 + ty; r < r1; r += 8)
+      for (int k = 0; k < 8 && c + k < C; ++k) s[k] += __bfloat162float(in[r * ld + c + k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[ty][tx * 8 + k] = s[k];
+  __syncthreads();
+  const int64_t cc = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (cc < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    partial[(int64_t)blockIdx.y * C + cc] = t;
   }
 }
 __global__ void colsum_bf16_final_kernel(const float* __restrict__ partial, int64_t chunks, int64_t C, float beta,
@@ -227,7 +245,7 @@ static int64_t colsum_bf16_partials(int64_t R, int64_t C) { return ((R + CSB_ROW
 int colsum_bf16(const bf* in, int64_t R, int64_t C, int64_t ld, float beta, float* out, float* partial,
                        cudaStream_t st) {
   const int64_t chunks = (R + CSB_ROWS - 1) / CSB_ROWS;
-  dim3 grid((unsigned)((C + 127) / 128), (unsigned)chunks);
+  dim3 grid((unsigned)((C + 255) / 256), (unsigned)chunks);
   colsum_bf16_partial_kernel<<<grid, 256, 0, st>>>(in, R, C, ld, partial);
   SNT_LAUNCH_CHECK("colsum_bf16_partial_kernel");
   colsum_bf16_final_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(partial, chunks, C, beta, out);
