@@ -498,19 +498,30 @@ emb_sort_kernel(const int* __restrict__ tok, int n1, int V, int* __restrict__ gc
   int* count = use_smem ? s_count : gcount;
   for (int i = threadIdx.x; i < V; i += 1024) count[i] = 0;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    for (int base = 0; base < n1; base += 32) {
-      const int i = base + lane;
-      const int t = i < n1 ? tok[i] : -1 - lane;  // distinct negatives never match
-      const unsigned peers = __match_any_sync(0xffffffffu, t);
-      const int before = __popc(peers & ((1u << lane) - 1u));
-      const int c0 = t >= 0 ? count[t] : 0;
-      if (t >= 0) rank[i] = c0 + before;
-      __syncwarp();  // every lane of a token group has read count[t] before its leader bumps it
-      if (t >= 0 && before == 0) count[t] = c0 + __popc(peers);
-      __syncwarp();
+  // rows are staged through shared memory 1024 at a time so the ordered pass of warp 0 never waits on HBM
+  for (int sbase = 0; sbase < n1; sbase += 1024) {
+    const int gi = sbase + threadIdx.x;
+    s_scan[threadIdx.x] = gi < n1 ? tok[gi] : -1;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      const int lim = min(1024, n1 - sbase);
+      for (int base = 0; base < lim; base += 32) {
+        const int i = base + lane;
+        const int t0 = s_scan[i];
+        const int t = t0 >= 0 ? t0 : -1 - lane;  // distinct negatives never match
+        const unsigned peers = __match_any_sync(0xffffffffu, t);
+        const int before = __popc(peers & ((1u << lane) - 1u));
+        const int c0 = t >= 0 ? count[t] : 0;
+        __syncwarp();  // every lane of a token group has read count[t] before its leader bumps it
+        if (t >= 0 && before == 0) count[t] = c0 + __popc(peers);
+        s_scan[i] = c0 + before;  // this row's rank within its token (slot reused)
+        __syncwarp();
+      }
     }
+    __syncthreads();
+    if (gi < n1) rank[gi] = s_scan[threadIdx.x];
+    __syncthreads();
   }
   __syncthreads();
   if (threadIdx.x == 0) s_carry = 0;
@@ -649,20 +660,38 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
 // ---------------------------------------------------------------------------------------------------------
 // a11: clip_gradient (clamp) + Adam (train.py:88-91,145-146; torch.optim.Adam defaults)
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, float step_size, float beta1,
+                                      float beta2, float omb1, float omb2, float eps, float rsqrt_bc2, float grad_clip,
+                                      float grad_scale) {
+  float gi = g * grad_scale;
+  if (grad_clip > 0.f) gi = fminf(fmaxf(gi, -grad_clip), grad_clip);
+  m = beta1 * m + omb1 * gi;          // exp_avg.lerp_(grad, 1 - beta1)
+  v = beta2 * v + omb2 * gi * gi;     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float denom = sqrtf(v) * rsqrt_bc2 + eps;    // sqrt(v) / sqrt(bias_correction2) + eps
+  p = p - step_size * (m / denom);                   // step_size = lr / bias_correction1
+}
 __global__ void __launch_bounds__(256)
 clamp_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                   float* __restrict__ v, int64_t n, float step_size, float beta1, float beta2, float omb1,
-                  float omb2, float eps, float rsqrt_bc2, float grad_clip, float grad_scale) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+                  float omb2, float eps, float rsqrt_bc2, float grad_clip, float grad_scale, int vec) {
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
   if (i >= n) return;
-  float gi = g[i] * grad_scale;
-  if (grad_clip > 0.f) gi = fminf(fmaxf(gi, -grad_clip), grad_clip);
-  const float mi = beta1 * m[i] + omb1 * gi;          // exp_avg.lerp_(grad, 1 - beta1)
-  const float vi = beta2 * v[i] + omb2 * gi * gi;     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-  m[i] = mi;
-  v[i] = vi;
-  const float denom = sqrtf(vi) * rsqrt_bc2 + eps;    // sqrt(v) / sqrt(bias_correction2) + eps
-  p[i] = p[i] - step_size * (mi / denom);             // step_size = lr / bias_correction1
+  if (vec && i + 3 < n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i), mm = *reinterpret_cast<float4*>(m + i),
+           vv = *reinterpret_cast<float4*>(v + i);
+    const float4 gg = *reinterpret_cast<const float4*>(g + i);
+    adam1(pp.x, gg.x, mm.x, vv.x, step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip, grad_scale);
+    adam1(pp.y, gg.y, mm.y, vv.y, step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip, grad_scale);
+    adam1(pp.z, gg.z, mm.z, vv.z, step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip, grad_scale);
+    adam1(pp.w, gg.w, mm.w, vv.w, step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip, grad_scale);
+    *reinterpret_cast<float4*>(p + i) = pp;
+    *reinterpret_cast<float4*>(m + i) = mm;
+    *reinterpret_cast<float4*>(v + i) = vv;
+  } else {
+    for (int k = 0; k < 4 && i + k < n; ++k)
+      adam1(p[i + k], g[i + k], m[i + k], v[i + k], step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip,
+            grad_scale);
+  }
 }
 int clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                double eps, float grad_clip, float grad_scale, int64_t step, cudaStream_t st) {
@@ -670,9 +699,12 @@ int clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, double l
   SNT_REQUIRE(step >= 1, "clamp_adam: step must be >= 1");
   const double bc1 = 1.0 - pow(beta1, (double)step);
   const double bc2 = 1.0 - pow(beta2, (double)step);
-  clamp_adam_kernel<<<nblocks(n, 256), 256, 0, st>>>(p, g, m, v, n, (float)(lr / bc1), (float)beta1, (float)beta2,
-                                                    (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps,
-                                                    (float)(1.0 / sqrt(bc2)), grad_clip, grad_scale);
+  const int vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                    reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  clamp_adam_kernel<<<nblocks((n + 3) / 4, 256), 256, 0, st>>>(p, g, m, v, n, (float)(lr / bc1), (float)beta1,
+                                                              (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
+                                                              (float)eps, (float)(1.0 / sqrt(bc2)), grad_clip,
+                                                              grad_scale, vec);
   SNT_LAUNCH_CHECK("clamp_adam_kernel");
   return SNT_OK;
 }

@@ -261,7 +261,15 @@ __global__ void scale_vec_kernel(const float* __restrict__ in, int64_t n, float 
 
 // ---------------------------------------------------------------------------------------------------------------------
 static inline int64_t pad8(int64_t x) { return (x + 7) / 8 * 8; }
-constexpr int64_t BWD_CHUNK_ROWS = 2048;  // 2048 x 10000 bf16 = 41 MB of dlogits: stays in the 126 MB L2
+// rows of dlogits alive at once: (SMs/4) row tiles make dHs (BN=128) exactly one wave and the softmax-grad pass a whole
+// number of waves; capped so the bf16 chunk stays around 3/4 of the 126 MB L2 (37*128 x 10000 x 2 B = 95 MB)
+static int64_t bwd_chunk_rows(int64_t N, int64_t V) {
+  int64_t tiles = tc::sm_count() / 4;
+  if (tiles < 1) tiles = 1;
+  while (tiles > 1 && tiles * 128 * ((V + 7) / 8 * 8) * 2 > (int64_t)96 << 20) --tiles;
+  const int64_t r = tiles * 128;
+  return N < r ? N : r;
+}
 constexpr int MAX_SPLITS = 16;
 
 struct CeWs {
@@ -272,7 +280,7 @@ static CeWs carve(void* ws, int64_t ws_bytes, int64_t N, int64_t H, int64_t V) {
   Workspace w(ws, ws_bytes);
   CeWs r;
   r.slabs = (int)((V + CE_BN - 1) / CE_BN) * 2;
-  r.R = N < BWD_CHUNK_ROWS ? N : BWD_CHUNK_ROWS;
+  r.R = bwd_chunk_rows(N, V);
   r.Vp = pad8(V);
   r.wb = w.take<bf>(V * H);
   r.part = w.take<float2>((int64_t)r.slabs * N);
@@ -280,16 +288,16 @@ static CeWs carve(void* ws, int64_t ws_bytes, int64_t N, int64_t H, int64_t V) {
   r.nll = w.take<float>(N);
   r.dl = w.take<bf>(r.R * r.Vp);
   r.cpart = w.take<float>(colsum_bf16_partials(r.R, V));
-  r.sws = w.take<float>(MAX_SPLITS * r.R * H);
+  r.sws = w.take<float>(MAX_SPLITS * 1024 * H);
   r.db = w.take<float>(V);
   r.ok = w.ok();
   return r;
 }
 int64_t vocab_ce_ws_bytes(int64_t N, int64_t H, int64_t V) {
   const int64_t slabs = ((V + CE_BN - 1) / CE_BN) * 2;
-  const int64_t R = N < BWD_CHUNK_ROWS ? N : BWD_CHUNK_ROWS;
+  const int64_t R = bwd_chunk_rows(N, V);
   return ws_bytes_for(V * H, 2) + ws_bytes_for(slabs * N, 8) + 2 * ws_bytes_for(N, 4) + ws_bytes_for(R * pad8(V), 2) +
-         ws_bytes_for(colsum_bf16_partials(R, V), 4) + ws_bytes_for(MAX_SPLITS * R * H, 4) + ws_bytes_for(V, 4);
+         ws_bytes_for(colsum_bf16_partials(R, V), 4) + ws_bytes_for(MAX_SPLITS * 1024 * H, 4) + ws_bytes_for(V, 4);
 }
 
 static int make_sched(int64_t M, int64_t Ncols, int64_t K, tc::TileSched* ts) {
@@ -352,11 +360,31 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
     // dHs[r,H] = dlogits[r,V] . W_out[V,H]      (B operand MN-major)
     int sp = tc::choose_splits(r, H, V, 0);
     if (sp > MAX_SPLITS) sp = MAX_SPLITS;
+    if ((int64_t)sp * r > MAX_SPLITS * 1024) sp = (int)(MAX_SPLITS * 1024 / r);  // partials must fit the scratch
+    if (sp < 1) sp = 1;
     SNT_CHECK(tc::gemm_tc(false, true, r, H, V, scale, w.dl, w.Vp, w.wb, H, 0.f, d_hs + r0 * H, nullptr, H, nullptr, sp,
                           w.sws, st, 0, dloss));
-    // dW_out[V,H] += dlogits^T[V,r] . Hs[r,H]   (both operands MN-major)
-    SNT_CHECK(tc::gemm_tc(true, true, V, H, r, scale, w.dl, w.Vp, hs_b + r0 * H, H, acc, d_w_out, nullptr, H, nullptr, 1,
-                          nullptr, st, 0, dloss));
+    // dW_out[V,H] += dlogits^T[V,r] . Hs[r,H]   (both operands MN-major).  ceil(V/128) x (H/256) tiles rarely fill
+    // whole waves: the row tiles that fill complete waves run unsplit, the few left over are split along K so they
+    // occupy all SMs instead of a nearly empty last wave.
+    {
+      const int64_t n_tiles = (H + 255) / 256, m_tiles = (V + 127) / 128;
+      const int64_t sms = tc::sm_count();
+      int64_t m_main = m_tiles;
+      if (H >= 256 && m_tiles * n_tiles > sms && (m_tiles * n_tiles) % sms != 0 && (m_tiles * n_tiles) % sms < sms / 2)
+        m_main = (m_tiles * n_tiles / sms) * sms / n_tiles;
+      const int64_t v_main = m_main < m_tiles ? m_main * 128 : V;
+      SNT_CHECK(tc::gemm_tc(true, true, v_main, H, r, scale, w.dl, w.Vp, hs_b + r0 * H, H, acc, d_w_out, nullptr, H,
+                            nullptr, 1, nullptr, st, 0, dloss));
+      if (v_main < V) {
+        const int64_t v_tail = V - v_main;  // <= 1024 rows by construction when sms <= 296
+        int sp = (int)(sms / (((v_tail + 127) / 128) * n_tiles));
+        if (sp > MAX_SPLITS) sp = MAX_SPLITS;
+        if (v_tail > 1024) sp = 1;
+        SNT_CHECK(tc::gemm_tc(true, true, v_tail, H, r, scale, w.dl + v_main, w.Vp, hs_b + r0 * H, H, acc,
+                              d_w_out + v_main * H, nullptr, H, nullptr, sp, w.sws, st, 0, dloss));
+      }
+    }
     SNT_CHECK(colsum_bf16(w.dl, r, V, w.Vp, acc, w.db, w.cpart, st));
   }
   scale_vec_kernel<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(w.db, V, scale, dloss, d_b_out);
