@@ -144,6 +144,11 @@ int snt_greedy_decode(int prec, const float* features, const float* w_emb, int L
 int snt_clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
                    double beta2, double eps, float grad_clip, float grad_scale, int64_t step, void* stream);
 
+/* The same update for `count` parameter tensors in one launch: [host] arrays of device pointers and sizes. */
+int snt_clamp_adam_multi(int count, float* const* p, const float* const* g, float* const* m, float* const* v,
+                         const int64_t* n, double lr, double beta1, double beta2, double eps, float grad_clip,
+                         float grad_scale, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,14 @@ extern "C" int snt_clamp_adam(float* p, const float* g, float* m, float* v, int6
   return clamp_adam(p, g, m, v, n, lr, beta1, beta2, eps, grad_clip, grad_scale, step, (cudaStream_t)stream);
 }
 
+extern "C" int snt_clamp_adam_multi(int count, float* const* p, const float* const* g, float* const* m,
+                                    float* const* v, const int64_t* n, double lr, double beta1, double beta2,
+                                    double eps, float grad_clip, float grad_scale, int64_t step, void* stream) {
+  SNT_REQUIRE(count >= 0 && (count == 0 || (p && g && m && v && n)), "snt_clamp_adam_multi: bad arguments");
+  return clamp_adam_multi(count, p, g, m, v, n, lr, beta1, beta2, eps, grad_clip, grad_scale, step,
+                          (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // a1/a2: encoder head
 // ------------------------------------------------------------------------------------------------------------

@@ -483,75 +483,15 @@ int bn_bwd(const float* dout, const float* yhat, const float* rstd, const float*
 // counting sort by token (stable rank = number of earlier packed rows with the same token), then one block
 // per vocab row sums its rows in packed-row order.  Rows t==0 go to dfeatures.
 // ---------------------------------------------------------------------------------------------------------
-// Stable counting sort of the token rows in ONE single-block kernel (deterministic summation order):
-//   1. count[] zeroed (shared memory when V fits, else the global scratch),
-//   2. warp 0 walks the rows in packed order, 32 at a time: rank[i] = count[tok] + #earlier lanes with the same
-//      token (match_any), then bumps count[tok] by the group size,
-//   3. block-wide exclusive scan of count -> start[0..V],
-//   4. perm[start[tok[i]] + rank[i]] = i.
-__global__ void __launch_bounds__(1024)
-emb_sort_kernel(const int* __restrict__ tok, int n1, int V, int* __restrict__ gcount, int* __restrict__ rank,
-                int* __restrict__ start, int* __restrict__ perm, int use_smem) {
-  extern __shared__ int s_count[];
-  __shared__ int s_scan[1024];
-  __shared__ int s_carry;
-  int* count = use_smem ? s_count : gcount;
-  for (int i = threadIdx.x; i < V; i += 1024) count[i] = 0;
-  __syncthreads();
-  // rows are staged through shared memory 1024 at a time so the ordered pass of warp 0 never waits on HBM
-  for (int sbase = 0; sbase < n1; sbase += 1024) {
-    const int gi = sbase + threadIdx.x;
-    s_scan[threadIdx.x] = gi < n1 ? tok[gi] : -1;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      const int lim = min(1024, n1 - sbase);
-      for (int base = 0; base < lim; base += 32) {
-        const int i = base + lane;
-        const int t0 = s_scan[i];
-        const int t = t0 >= 0 ? t0 : -1 - lane;  // distinct negatives never match
-        const unsigned peers = __match_any_sync(0xffffffffu, t);
-        const int before = __popc(peers & ((1u << lane) - 1u));
-        const int c0 = t >= 0 ? count[t] : 0;
-        __syncwarp();  // every lane of a token group has read count[t] before its leader bumps it
-        if (t >= 0 && before == 0) count[t] = c0 + __popc(peers);
-        s_scan[i] = c0 + before;  // this row's rank within its token (slot reused)
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    if (gi < n1) rank[gi] = s_scan[threadIdx.x];
-    __syncthreads();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  for (int base = 0; base < V; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int c = i < V ? count[i] : 0;
-    s_scan[threadIdx.x] = c;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      const int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
-      __syncthreads();
-      s_scan[threadIdx.x] += v;
-      __syncthreads();
-    }
-    if (i < V) start[i] = s_carry + s_scan[threadIdx.x] - c;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry += s_scan[1023];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) start[V] = s_carry;
-  __syncthreads();
-  for (int i = threadIdx.x; i < n1; i += 1024) {
-    const int t = tok[i];
-    if (t >= 0) perm[start[t] + rank[i]] = i;
-  }
-}
+// Deterministic scatter-add of the token rows into d_w_emb[V,E] in five small, fully parallel kernels:
+//   emb_tok_kernel     token of every packed row t >= 1 and a histogram (integer atomics: order-independent)
+//   emb_scan_kernel    exclusive scan of the histogram -> start[0..V]
+//   emb_place_kernel   each row claims a slot of its token's segment (arbitrary order)
+//   emb_segsort_kernel every segment with > 1 member is put into ascending row order (rank by counting)
+//   emb_reduce8_kernel one block per occurring token sums its rows in that fixed order
 __global__ void __launch_bounds__(256)
 emb_tok_kernel(const __grid_constant__ PackInfo pk, const int64_t* __restrict__ captions, int64_t cap_stride,
-               int64_t V, int* __restrict__ tok, int* flags) {
+               int64_t V, int* __restrict__ tok, int* __restrict__ count, int* flags) {
   const int n1 = pk.off[pk.T] - pk.off[1];  // rows with t >= 1
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n1) return;
@@ -561,9 +501,68 @@ emb_tok_kernel(const __grid_constant__ PackInfo pk, const int64_t* __restrict__ 
   const int64_t tk = captions[(int64_t)b * cap_stride + (t - 1)];
   if (tk < 0 || tk >= V) { atomicOr(flags, 1); tok[i] = -1; return; }
   tok[i] = (int)tk;
+  atomicAdd(&count[tk], 1);
+}
+// exclusive scan of count[0..V) into start[0..V] (and cursor := start), single block: warp-shuffle scan of 1024-wide slabs
+__global__ void __launch_bounds__(1024)
+emb_scan_kernel(const int* __restrict__ count, int V, int* __restrict__ start, int* __restrict__ cursor) {
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < V; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int c = i < V ? count[i] : 0;
+    int x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int s = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += y;
+      }
+      wsum[lane] = s;  // inclusive scan of the warp totals
+    }
+    __syncthreads();
+    const int excl = carry_s + (w > 0 ? wsum[w - 1] : 0) + x - c;
+    if (i < V) { start[i] = excl; cursor[i] = excl; }
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s += wsum[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) start[V] = carry_s;
+}
+__global__ void __launch_bounds__(256)
+emb_place_kernel(const int* __restrict__ tok, int n1, int* __restrict__ cursor, int* __restrict__ perm0) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n1) return;
+  const int t = tok[i];
+  if (t >= 0) perm0[atomicAdd(&cursor[t], 1)] = i;
+}
+__global__ void __launch_bounds__(256)
+emb_segsort_kernel(const int* __restrict__ start, const int* __restrict__ perm0, int* __restrict__ perm) {
+  const int v = blockIdx.x;
+  const int s0 = start[v], n = start[v + 1] - s0;
+  if (n <= 0) return;
+  if (n == 1) { if (threadIdx.x == 0) perm[s0] = perm0[s0]; return; }
+  for (int a = threadIdx.x; a < n; a += 256) {
+    const int mine = perm0[s0 + a];
+    int rank = 0;
+    for (int b = 0; b < n; ++b) rank += (perm0[s0 + b] < mine);  // row indices are distinct
+    perm[s0 + rank] = mine;
+  }
 }
 // One block (8 warps) per vocabulary row that occurs; d_w_emb is pre-zeroed.  Warp w sums rows w, w+8, ... of the
-// token's segment (4 rows in flight), then the 8 partials are combined in a fixed order.
+// token's (sorted) segment with 4 rows x E/128 slabs in flight, then the 8 partials are combined in a fixed order.
+template <int SLABS>
 __global__ void __launch_bounds__(256)
 emb_reduce8_kernel(const float* __restrict__ dx1 /* dx + off[1]*E */, const int* __restrict__ start,
                    const int* __restrict__ perm, int E, float* __restrict__ d_w_emb) {
@@ -575,31 +574,50 @@ emb_reduce8_kernel(const float* __restrict__ dx1 /* dx + off[1]*E */, const int*
   float* out = d_w_emb + (int64_t)v * E;
   if (s1 - s0 == 1) {  // the common case: a plain row copy
     const float* src = dx1 + (int64_t)perm[s0] * E;
-    for (int e = threadIdx.x; e < E; e += 256) out[e] = src[e];
+    for (int e = threadIdx.x * 4; e < E; e += 1024) *reinterpret_cast<float4*>(out + e) = *reinterpret_cast<const float4*>(src + e);
     return;
   }
-  for (int e0 = 0; e0 < E; e0 += 128) {  // each lane owns 4 consecutive floats of a 128-wide slab
-    const int e = e0 + lane * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (e < E) {
-      int i = s0 + w;
-      for (; i + 24 < s1; i += 32) {
-        const float4 a = *reinterpret_cast<const float4*>(dx1 + (int64_t)perm[i] * E + e);
-        const float4 b = *reinterpret_cast<const float4*>(dx1 + (int64_t)perm[i + 8] * E + e);
-        const float4 c = *reinterpret_cast<const float4*>(dx1 + (int64_t)perm[i + 16] * E + e);
-        const float4 d = *reinterpret_cast<const float4*>(dx1 + (int64_t)perm[i + 24] * E + e);
-        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-        acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
-        acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
-        acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+  float4 acc[SLABS];
+#pragma unroll
+  for (int k = 0; k < SLABS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int i = s0 + w;
+  for (; i + 24 < s1; i += 32) {
+    const float* r0 = dx1 + (int64_t)perm[i] * E + lane * 4;
+    const float* r1 = dx1 + (int64_t)perm[i + 8] * E + lane * 4;
+    const float* r2 = dx1 + (int64_t)perm[i + 16] * E + lane * 4;
+    const float* r3 = dx1 + (int64_t)perm[i + 24] * E + lane * 4;
+    float4 a[SLABS], b[SLABS], c[SLABS], d[SLABS];
+#pragma unroll
+    for (int k = 0; k < SLABS; ++k) {
+      if (k * 128 + lane * 4 < E) {
+        a[k] = *reinterpret_cast<const float4*>(r0 + k * 128);
+        b[k] = *reinterpret_cast<const float4*>(r1 + k * 128);
+        c[k] = *reinterpret_cast<const float4*>(r2 + k * 128);
+        d[k] = *reinterpret_cast<const float4*>(r3 + k * 128);
+      } else {
+        a[k] = b[k] = c[k] = d[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      for (; i < s1; i += 8) {
-        const float4 a = *reinterpret_cast<const float4*>(dx1 + (int64_t)perm[i] * E + e);
-        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-      }
-      *reinterpret_cast<float4*>(part + w * E + e) = acc;
+    }
+#pragma unroll
+    for (int k = 0; k < SLABS; ++k) {
+      acc[k].x += a[k].x; acc[k].y += a[k].y; acc[k].z += a[k].z; acc[k].w += a[k].w;
+      acc[k].x += b[k].x; acc[k].y += b[k].y; acc[k].z += b[k].z; acc[k].w += b[k].w;
+      acc[k].x += c[k].x; acc[k].y += c[k].y; acc[k].z += c[k].z; acc[k].w += c[k].w;
+      acc[k].x += d[k].x; acc[k].y += d[k].y; acc[k].z += d[k].z; acc[k].w += d[k].w;
     }
   }
+  for (; i < s1; i += 8) {
+    const float* r0 = dx1 + (int64_t)perm[i] * E + lane * 4;
+#pragma unroll
+    for (int k = 0; k < SLABS; ++k)
+      if (k * 128 + lane * 4 < E) {
+        const float4 a = *reinterpret_cast<const float4*>(r0 + k * 128);
+        acc[k].x += a.x; acc[k].y += a.y; acc[k].z += a.z; acc[k].w += a.w;
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < SLABS; ++k)
+    if (k * 128 + lane * 4 < E) *reinterpret_cast<float4*>(part + w * E + k * 128 + lane * 4) = acc[k];
   __syncthreads();
   for (int e = threadIdx.x; e < E; e += 256) {
     float t = 0.f;
@@ -616,7 +634,7 @@ dfeatures_kernel(const float* __restrict__ dx, int bs0, int64_t B, int64_t E, fl
 }
 
 int64_t embed_bwd_ws_bytes(int64_t N, int64_t V) {
-  return ws_bytes_for(N, 4) * 3 + ws_bytes_for(V + 1, 4) * 2;
+  return ws_bytes_for(N, 4) * 3 + ws_bytes_for(V + 1, 4) * 3;
 }
 int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions, int64_t cap_stride,
                    int64_t B, int64_t E, int64_t V, float* dfeatures, float* d_w_emb, void* ws,
@@ -630,29 +648,31 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
   if (!d_w_emb) return SNT_OK;
   Workspace w(ws, ws_bytes);
   int* tok = w.take<int>(N);
+  int* perm0 = w.take<int>(N);
   int* perm = w.take<int>(N);
-  int* rank = w.take<int>(N);
   int* count = w.take<int>(V + 1);
   int* start = w.take<int>(V + 1);
+  int* cursor = w.take<int>(V + 1);
   if (!w.ok()) { set_error("embed_pack_bwd: workspace too small"); return SNT_EWORKSPACE; }
-  SNT_REQUIRE(E % 4 == 0 && E * 8 * 4 <= 96 * 1024, "embed_pack_bwd: E must be a multiple of 4 and <= 3072");
+  SNT_REQUIRE(E % 4 == 0 && E <= 1024, "embed_pack_bwd: E must be a multiple of 4 and <= 1024");
   SNT_REQUIRE(V < (1LL << 31), "embed_pack_bwd: V too large");
   SNT_CUDA(cudaMemsetAsync(d_w_emb, 0, sizeof(float) * (size_t)V * E, st));
   if (n1 <= 0) return SNT_OK;
-  emb_tok_kernel<<<nblocks(n1, 256), 256, 0, st>>>(pk, captions, cap_stride, V, tok, device_flags());
+  SNT_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(V + 1), st));
+  emb_tok_kernel<<<nblocks(n1, 256), 256, 0, st>>>(pk, captions, cap_stride, V, tok, count, device_flags());
   SNT_LAUNCH_CHECK("emb_tok_kernel");
-  const size_t table = sizeof(int) * (size_t)V;
-  const int use_smem = table <= 160 * 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SNT_CUDA(cudaFuncSetAttribute(emb_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    SNT_CUDA(cudaFuncSetAttribute(emb_reduce8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
-  emb_sort_kernel<<<1, 1024, use_smem ? table : 0, st>>>(tok, n1, (int)V, count, rank, start, perm, use_smem);
-  SNT_LAUNCH_CHECK("emb_sort_kernel");
-  emb_reduce8_kernel<<<(unsigned)V, 256, (size_t)(8 * E * sizeof(float)), st>>>(dx + (int64_t)pk.off[1] * E, start,
-                                                                               perm, (int)E, d_w_emb);
+  emb_scan_kernel<<<1, 1024, 0, st>>>(count, (int)V, start, cursor);
+  SNT_LAUNCH_CHECK("emb_scan_kernel");
+  emb_place_kernel<<<nblocks(n1, 256), 256, 0, st>>>(tok, n1, cursor, perm0);
+  SNT_LAUNCH_CHECK("emb_place_kernel");
+  emb_segsort_kernel<<<(unsigned)V, 256, 0, st>>>(start, perm0, perm);
+  SNT_LAUNCH_CHECK("emb_segsort_kernel");
+  const float* dx1 = dx + (int64_t)pk.off[1] * E;
+  const size_t sm = (size_t)(8 * E * sizeof(float));
+  const int slabs = (int)((E + 127) / 128);
+  if (slabs <= 2) emb_reduce8_kernel<2><<<(unsigned)V, 256, sm, st>>>(dx1, start, perm, (int)E, d_w_emb);
+  else if (slabs <= 4) emb_reduce8_kernel<4><<<(unsigned)V, 256, sm, st>>>(dx1, start, perm, (int)E, d_w_emb);
+  else emb_reduce8_kernel<8><<<(unsigned)V, 256, sm, st>>>(dx1, start, perm, (int)E, d_w_emb);
   SNT_LAUNCH_CHECK("emb_reduce8_kernel");
   return SNT_OK;
 }
@@ -693,6 +713,76 @@ clamp_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
             grad_scale);
   }
 }
+// multi-tensor variant: one launch updates up to ADAM_MAX_TENSORS parameter tensors (pointer table by value)
+constexpr int ADAM_MAX_TENSORS = 24;
+struct AdamTable {
+  float* p[ADAM_MAX_TENSORS];
+  const float* g[ADAM_MAX_TENSORS];
+  float* m[ADAM_MAX_TENSORS];
+  float* v[ADAM_MAX_TENSORS];
+  long long n[ADAM_MAX_TENSORS];
+  int block0[ADAM_MAX_TENSORS + 1];  // first block of each tensor (1024 elements per block)
+  int count;
+};
+__global__ void __launch_bounds__(256)
+clamp_adam_multi_kernel(const __grid_constant__ AdamTable tb, float step_size, float beta1, float beta2, float omb1,
+                        float omb2, float eps, float rsqrt_bc2, float grad_clip, float grad_scale) {
+  int k = 0;
+  while (k + 1 < tb.count && (int)blockIdx.x >= tb.block0[k + 1]) ++k;
+  const long long n = tb.n[k];
+  const long long i = ((long long)(blockIdx.x - tb.block0[k]) * 256 + threadIdx.x) * 4;
+  if (i >= n) return;
+  float* p = tb.p[k];
+  const float* g = tb.g[k];
+  float* m = tb.m[k];
+  float* v = tb.v[k];
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  if (vec && i + 3 < n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i), mm = *reinterpret_cast<float4*>(m + i),
+           vv = *reinterpret_cast<float4*>(v + i);
+    const float4 gg = *reinterpret_cast<const float4*>(g + i);
+    adam1(pp.x, gg.x, mm.x, vv.x, step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip, grad_scale);
+    adam1(pp.y, gg.y, mm.y, vv.y, step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip, grad_scale);
+    adam1(pp.z, gg.z, mm.z, vv.z, step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip, grad_scale);
+    adam1(pp.w, gg.w, mm.w, vv.w, step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip, grad_scale);
+    *reinterpret_cast<float4*>(p + i) = pp;
+    *reinterpret_cast<float4*>(m + i) = mm;
+    *reinterpret_cast<float4*>(v + i) = vv;
+  } else {
+    for (int q = 0; q < 4 && i + q < n; ++q)
+      adam1(p[i + q], g[i + q], m[i + q], v[i + q], step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip,
+            grad_scale);
+  }
+}
+int clamp_adam_multi(int count, float* const* p, const float* const* g, float* const* m, float* const* v,
+                     const int64_t* n, double lr, double beta1, double beta2, double eps, float grad_clip,
+                     float grad_scale, int64_t step, cudaStream_t st) {
+  SNT_REQUIRE(step >= 1, "clamp_adam_multi: step must be >= 1");
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  for (int base = 0; base < count; base += ADAM_MAX_TENSORS) {
+    AdamTable tb;
+    tb.count = 0;
+    int blocks = 0;
+    for (int k = base; k < count && tb.count < ADAM_MAX_TENSORS; ++k) {
+      if (n[k] <= 0) continue;
+      SNT_REQUIRE(p[k] && g[k] && m[k] && v[k], "clamp_adam_multi: NULL tensor %d", k);
+      const int c = tb.count++;
+      tb.p[c] = p[k]; tb.g[c] = g[k]; tb.m[c] = m[k]; tb.v[c] = v[k]; tb.n[c] = n[k];
+      tb.block0[c] = blocks;
+      blocks += (int)((n[k] + 1023) / 1024);
+    }
+    if (tb.count == 0) continue;
+    tb.block0[tb.count] = blocks;
+    clamp_adam_multi_kernel<<<blocks, 256, 0, st>>>(tb, (float)(lr / bc1), (float)beta1, (float)beta2,
+                                                   (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps,
+                                                   (float)(1.0 / sqrt(bc2)), grad_clip, grad_scale);
+    SNT_LAUNCH_CHECK("clamp_adam_multi_kernel");
+  }
+  return SNT_OK;
+}
+
 int clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                double eps, float grad_clip, float grad_scale, int64_t step, cudaStream_t st) {
   if (n <= 0) return SNT_OK;

@@ -51,4 +51,8 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
 int clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                double eps, float grad_clip, float grad_scale, int64_t step, cudaStream_t st);
 
+int clamp_adam_multi(int count, float* const* p, const float* const* g, float* const* m, float* const* v,
+                     const int64_t* n, double lr, double beta1, double beta2, double eps, float grad_clip,
+                     float grad_scale, int64_t step, cudaStream_t st);
+
 }  // namespace snt

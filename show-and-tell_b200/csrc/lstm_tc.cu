@@ -63,7 +63,7 @@ __global__ void unperm_vec_kernel(const float* __restrict__ in, int H, float* __
 struct LstmFwdEpi {
   static constexpr int kWarps = 4;
   int bs, bs_next, H;
-  const float* gx;      // [bs, 4H]   input projection + biases of this step's rows, interleaved columns
+  const bf* gx;         // [bs, 4H]   input projection + biases of this step's rows (bf16), interleaved columns
   const float* c_prev;  // [>=bs, H]  c_{t-1} (NULL at t = 0)
   float* cs;            // [bs, H]    c_t
   bf* hs;               // [bs, H]    h_t (layer output rows of this step)
@@ -83,10 +83,15 @@ struct LstmFwdEpi {
       tc::tmem_ld_wait();
       if (!ok) continue;
       const int j0 = col0 >> 2;
-      const float4* g4 = reinterpret_cast<const float4*>(gx + (int64_t)row * H4 + col0);
+      const uint4* g4 = reinterpret_cast<const uint4*>(gx + (int64_t)row * H4 + col0);
       float4 g[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) g[u] = __ldg(g4 + u);
+      for (int q = 0; q < 4; ++q) {  // 8 bf16 = 2 hidden units per 16-byte load
+        const uint4 v = __ldg(g4 + q);
+        const float2 a = unpack_bf2(v.x), b = unpack_bf2(v.y), c2 = unpack_bf2(v.z), d = unpack_bf2(v.w);
+        g[2 * q] = make_float4(a.x, a.y, b.x, b.y);
+        g[2 * q + 1] = make_float4(c2.x, c2.y, d.x, d.y);
+      }
       float cp[8];
       if (c_prev) {
         const float4 a = *reinterpret_cast<const float4*>(c_prev + (int64_t)row * H + j0);
@@ -192,7 +197,7 @@ struct LstmBwdEpi {
 
 // ---------------------------------------------------------------------------------------------------------------------
 struct LstmWs {
-  float* bsum; bf* w_ih; bf* w_hh; float* gx; float* dc_state; float* cpart; float* tmp; float* sws; bool ok;
+  float* bsum; bf* w_ih; bf* w_hh; bf* gx; float* dc_state; float* cpart; float* tmp; float* sws; bool ok;
 };
 static int64_t csb_partials(int64_t R, int64_t C) { return ((R + 255) / 256) * C; }
 static LstmWs carve(void* ws, int64_t ws_bytes, int64_t N, int64_t B, int64_t In, int64_t H) {
@@ -201,7 +206,7 @@ static LstmWs carve(void* ws, int64_t ws_bytes, int64_t N, int64_t B, int64_t In
   r.bsum = w.take<float>(4 * H);
   r.w_ih = w.take<bf>(4 * H * In);
   r.w_hh = w.take<bf>(4 * H * H);
-  r.gx = w.take<float>(N * 4 * H);
+  r.gx = w.take<bf>(N * 4 * H);
   r.dc_state = w.take<float>(B * H);
   r.cpart = w.take<float>(csb_partials(N, 4 * H));
   r.tmp = w.take<float>(4 * H);
@@ -211,7 +216,7 @@ static LstmWs carve(void* ws, int64_t ws_bytes, int64_t N, int64_t B, int64_t In
 }
 int64_t lstm_ws_bytes(int64_t N, int64_t B, int64_t In, int64_t H) {
   return 2 * ws_bytes_for(4 * H, 4) + ws_bytes_for(4 * H * In, 2) + ws_bytes_for(4 * H * H, 2) +
-         ws_bytes_for(N * 4 * H, 4) + ws_bytes_for(B * H, 4) + ws_bytes_for(csb_partials(N, 4 * H), 4) +
+         ws_bytes_for(N * 4 * H, 2) + ws_bytes_for(B * H, 4) + ws_bytes_for(csb_partials(N, 4 * H), 4) +
          ws_bytes_for(MAX_SPLITS * 4 * H * (In > H ? In : H), 4);
 }
 
@@ -253,7 +258,7 @@ int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const flo
   bf* act = (bf*)gates;
   SNT_CHECK(prep_weights(w, w_ih, w_hh, b_ih, b_hh, In, H, st));
   // the input projection of every timestep as ONE tensor-core contraction: Gx' = x . W_ih'^T + (b_ih + b_hh)'
-  SNT_CHECK(tc::gemm_tc(false, false, N, 4 * H, In, 1.f, (const bf*)x, In, w.w_ih, In, 0.f, w.gx, nullptr, 4 * H,
+  SNT_CHECK(tc::gemm_tc(false, false, N, 4 * H, In, 1.f, (const bf*)x, In, w.w_ih, In, 0.f, nullptr, w.gx, 4 * H,
                         w.bsum, 1, nullptr, st));
   SNT_CUDA(cudaMemsetAsync(hp_b, 0, sizeof(bf) * (size_t)B * H, st));  // h_{-1} = 0
   CUtensorMap ta, tb;

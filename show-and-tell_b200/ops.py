@@ -354,3 +354,21 @@ def clamp_adam_(p, g, m, v, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_cl
             raise RuntimeError("clamp_adam_ needs contiguous fp32 tensors")
     call("snt_clamp_adam", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(betas[0]), float(betas[1]),
          float(eps), float(grad_clip if grad_clip is not None else 0.0), float(grad_scale), int(step), stream_ptr())
+
+
+@torch.no_grad()
+def clamp_adam_multi_(params, grads, ms, vs, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_clip=0.1,
+                      grad_scale=1.0):
+    """clamp_adam_ for a list of tensors in ONE kernel launch (train.py:88-91,145-146 over all param groups)."""
+    k = len(params)
+    if k == 0:
+        return
+    for t in (*params, *grads, *ms, *vs):
+        require_cuda(t)
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("clamp_adam_multi_ needs contiguous fp32 tensors")
+    arr = lambda ts: (C.c_void_p * k)(*[t.data_ptr() for t in ts])
+    sizes = (C.c_int64 * k)(*[p.numel() for p in params])
+    call("snt_clamp_adam_multi", k, arr(params), arr(grads), arr(ms), arr(vs), sizes, float(lr), float(betas[0]),
+         float(betas[1]), float(eps), float(grad_clip if grad_clip is not None else 0.0), float(grad_scale), int(step),
+         stream_ptr())

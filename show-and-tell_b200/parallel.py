@@ -96,8 +96,8 @@ class DataParallelStep:
                     dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group)
         if self.optimizer:
             self.t += 1
-            for p, m, v in zip(self.params, self.m, self.v):
-                if p.grad is not None:
-                    ops.clamp_adam_(p.data, p.grad.contiguous(), m, v, self.t, self.lr, self.betas, self.eps,
-                                    self.grad_clip)
+            live = [(p.data, p.grad.contiguous(), m, v) for p, m, v in zip(self.params, self.m, self.v)
+                    if p.grad is not None]
+            ops.clamp_adam_multi_([x[0] for x in live], [x[1] for x in live], [x[2] for x in live],
+                                  [x[3] for x in live], self.t, self.lr, self.betas, self.eps, self.grad_clip)
         return loss.detach()

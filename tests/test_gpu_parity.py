@@ -166,6 +166,22 @@ def test_clamp_adam_vs_reference_golden():
     np.testing.assert_allclose(v.cpu().numpy(), g["exp_avg_sq"], rtol=1e-5, atol=1e-10)
 
 
+def test_clamp_adam_multi_matches_single():
+    import show_and_tell_b200 as snt
+    g = torch.Generator(device="cuda").manual_seed(0)
+    shapes = [(7,), (1000, 33), (5, 5), (4096,), (3,)] * 6          # 30 tensors: more than one table
+    ps = [torch.randn(s, device="cuda", generator=g) for s in shapes]
+    gs = [torch.randn(s, device="cuda", generator=g) * 0.3 for s in shapes]
+    ref = [(p.clone(), torch.zeros_like(p), torch.zeros_like(p)) for p in ps]
+    ms, vs = [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps]
+    for step in (1, 2, 3):
+        snt.ops.clamp_adam_multi_(ps, gs, ms, vs, step)
+        for (rp, rm, rv), gg in zip(ref, gs):
+            snt.ops.clamp_adam_(rp, gg, rm, rv, step)
+    for p, m, v, (rp, rm, rv) in zip(ps, ms, vs, ref):
+        assert torch.equal(p, rp) and torch.equal(m, rm) and torch.equal(v, rv)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # seeded mid-size cases against the CPU oracle (fp64)
 # ---------------------------------------------------------------------------------------------------------
