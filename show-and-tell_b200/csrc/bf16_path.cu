@@ -111,76 +111,5 @@ int linear_bwd(const float* dlogits, const void* hs, const float* w_out, int64_t
   return colsum(dlogits, N, V, V, 0.f, d_b_out, part, st);
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// greedy decode
-// ---------------------------------------------------------------------------------------------------------
-int64_t greedy_ws_bytes(int64_t B, int64_t E, int64_t H, int64_t V, int L) {
-  int64_t b = ws_bytes_for(B * E, 4) + ws_bytes_for(B * E, 2) + ws_bytes_for(V * H, 2) +
-              ws_bytes_for(B * 4 * H, 4) + ws_bytes_for(B * V, 4);
-  for (int k = 0; k < L; ++k) {
-    const int64_t in = k == 0 ? E : H;
-    b += ws_bytes_for(B * H, 2) + ws_bytes_for(B * H, 4) + ws_bytes_for(4 * H, 4) + ws_bytes_for(4 * H * in, 2) +
-         ws_bytes_for(4 * H * H, 2);
-  }
-  return b;
-}
-int greedy_decode(const float* features, const float* w_emb, int L, const float* const* w_ih,
-                  const float* const* w_hh, const float* const* b_ih, const float* const* b_hh,
-                  const float* w_out, const float* b_out, const float* h0, const float* c0, int64_t B, int64_t E,
-                  int64_t H, int64_t V, int steps, int64_t* ids, void* ws, int64_t ws_bytes, cudaStream_t st) {
-  SNT_REQUIRE_ALIGNED8(E, "E");
-  SNT_REQUIRE_ALIGNED8(H, "H");
-  Workspace w(ws, ws_bytes);
-  float* x_f = w.take<float>(B * E);
-  bf* x_b = w.take<bf>(B * E);
-  bf* wout_b = w.take<bf>(V * H);
-  float* gates = w.take<float>(B * 4 * H);
-  float* logits = w.take<float>(B * V);
-  bf *h[SNT_MAX_LAYERS], *wih[SNT_MAX_LAYERS], *whh[SNT_MAX_LAYERS];
-  float *c[SNT_MAX_LAYERS], *bsum[SNT_MAX_LAYERS];
-  for (int k = 0; k < L; ++k) {
-    const int64_t in = k == 0 ? E : H;
-    h[k] = w.take<bf>(B * H);
-    c[k] = w.take<float>(B * H);
-    bsum[k] = w.take<float>(4 * H);
-    wih[k] = w.take<bf>(4 * H * in);
-    whh[k] = w.take<bf>(4 * H * H);
-  }
-  if (!w.ok()) { set_error("bf16 greedy_decode: workspace too small"); return SNT_EWORKSPACE; }
-  SNT_CHECK(cast_bf16(w_out, wout_b, V * H, st));
-  SNT_CHECK(cast_bf16(features, x_b, B * E, st));
-  for (int k = 0; k < L; ++k) {
-    const int64_t in = k == 0 ? E : H;
-    SNT_CHECK(add_vec(b_ih[k], b_hh[k], bsum[k], 4 * H, st));
-    SNT_CHECK(cast_bf16(w_ih[k], wih[k], 4 * H * in, st));
-    SNT_CHECK(cast_bf16(w_hh[k], whh[k], 4 * H * H, st));
-    if (h0) {
-      SNT_CHECK(cast_bf16(h0 + (int64_t)k * B * H, h[k], B * H, st));
-      SNT_CUDA(cudaMemcpyAsync(c[k], c0 + (int64_t)k * B * H, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, st));
-    } else {
-      SNT_CUDA(cudaMemsetAsync(h[k], 0, sizeof(bf) * B * H, st));
-      SNT_CUDA(cudaMemsetAsync(c[k], 0, sizeof(float) * B * H, st));
-    }
-  }
-  for (int s = 0; s < steps; ++s) {
-    const bf* inp = x_b;
-    int64_t in = E;
-    for (int k = 0; k < L; ++k) {
-      SNT_CHECK(tc::gemm_tc(false, false, B, 4 * H, in, 1.f, inp, in, wih[k], in, 0.f, gates, nullptr, 4 * H, bsum[k],
-                            1, nullptr, st));
-      SNT_CHECK(tc::gemm_tc(false, false, B, 4 * H, H, 1.f, h[k], H, whh[k], H, 1.f, gates, nullptr, 4 * H, nullptr,
-                            1, nullptr, st));
-      SNT_CHECK(lstm_point_fwd<bf>(gates, c[k], c[k], h[k], nullptr, (int)B, 0, H, st));
-      inp = h[k];
-      in = H;
-    }
-    SNT_CHECK(tc::gemm_tc(false, false, B, V, H, 1.f, inp, H, wout_b, H, 0.f, logits, nullptr, V, b_out, 1, nullptr,
-                          st));
-    SNT_CHECK(argmax_gather(logits, B, V, V, w_emb, E, ids + s, steps, x_f, st));
-    SNT_CHECK(cast_bf16(x_f, x_b, B * E, st));
-  }
-  return SNT_OK;
-}
-
 }  // namespace bf16
 }  // namespace snt

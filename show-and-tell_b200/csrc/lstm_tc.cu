@@ -68,7 +68,7 @@ struct LstmFwdEpi {
   float* cs;            // [bs, H]    c_t
   bf* hs;               // [bs, H]    h_t (layer output rows of this step)
   bf* hprev_next;       // [bs_next, H] h_t again, at the packed rows of step t+1 (NULL at the last step)
-  bf* act;              // [bs, 4H]   sigma(i), sigma(f), tanh(g), sigma(o), interleaved, kept for BPTT
+  bf* act;              // [bs, 4H]   sigma(i), sigma(f), tanh(g), sigma(o), interleaved, kept for BPTT (NULL: skip)
 
   __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane) const {
     const int row = m_blk * tc::BM + ew * 32 + lane;
@@ -121,9 +121,11 @@ struct LstmFwdEpi {
                                   pack_bf2(hn[6], hn[7]));
       *reinterpret_cast<uint4*>(hs + (int64_t)row * H + j0) = hv;
       if (row < bs_next) *reinterpret_cast<uint4*>(hprev_next + (int64_t)row * H + j0) = hv;
-      uint4* ad = reinterpret_cast<uint4*>(act + (int64_t)row * H4 + col0);
+      if (act) {  // training only
+        uint4* ad = reinterpret_cast<uint4*>(act + (int64_t)row * H4 + col0);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) ad[q] = make_uint4(ap[4 * q], ap[4 * q + 1], ap[4 * q + 2], ap[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) ad[q] = make_uint4(ap[4 * q], ap[4 * q + 1], ap[4 * q + 2], ap[4 * q + 3]);
+      }
     }
   }
 };
@@ -338,6 +340,170 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
   if (dx)
     SNT_CHECK(tc::gemm_tc(false, true, N, In, 4 * H, 1.f, dg, 4 * H, w.w_ih, In, 0.f, dx, nullptr, In, nullptr, 1,
                           nullptr, st));
+  return SNT_OK;
+}
+
+// =====================================================================================================================
+// a12: greedy decode (models.py:56-67) on the same fused kernels.  Per step and layer: one tcgen05 GEMM for the input
+// projection (bf16 out), one for the recurrence with the gate epilogue; then the vocab projection whose epilogue
+// reduces every 128-column slab of a row to (max, first index) — logits never leave TMEM — and a finishing kernel
+// that picks the first global maximum, writes the token id and gathers the next input embedding.
+// =====================================================================================================================
+struct ArgmaxEpi {
+  static constexpr int kWarps = 8;
+  int M, V;
+  const float* bias;
+  float2* part;  // [slabs][M]: (max logit, index as int bits)
+
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane) const {
+    const int half = ew >> 2;
+    const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int cofs = half * 128 + c * 32;
+      const int col0 = n_blk * 256 + cofs;
+      if (col0 >= V) break;  // warp-uniform
+      uint32_t r[32];
+      tc::tmem_ld32(tmem_rows + (uint32_t)cofs, r);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = col0 + j;
+        if (col < V) {
+          const float x = __uint_as_float(r[j]) + __ldg(bias + col);
+          if (x > best || bi == 0x7fffffff) { best = x; bi = col; }  // strict '>' keeps the first maximum
+        }
+      }
+    }
+    if (row < M) part[(int64_t)(n_blk * 2 + half) * M + row] = make_float2(best, __int_as_float(bi));
+  }
+};
+
+// one warp per row: first global maximum over the slab partials, id out, next input = bf16(W_emb[id])
+__global__ void __launch_bounds__(256)
+argmax_finish_kernel(const float2* __restrict__ part, int slabs, int64_t B, const float* __restrict__ w_emb, int E,
+                     int64_t* __restrict__ ids, int64_t ids_stride, bf* __restrict__ x_next) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int k = lane; k < slabs; k += 32) {
+    const float2 p = part[(int64_t)k * B + row];
+    const int idx = __float_as_int(p.y);
+    if (idx != 0x7fffffff && (p.x > best || (p.x == best && idx < bi) || bi == 0x7fffffff)) { best = p.x; bi = idx; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi != 0x7fffffff && (ob > best || (ob == best && oi < bi) || bi == 0x7fffffff)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) ids[row * ids_stride] = bi;
+  const float* src = w_emb + (int64_t)bi * E;
+  for (int e = lane * 4; e < E; e += 128) {  // E % 8 == 0
+    const float4 v = *reinterpret_cast<const float4*>(src + e);
+    uint2 o;
+    o.x = pack_bf2(v.x, v.y);
+    o.y = pack_bf2(v.z, v.w);
+    *reinterpret_cast<uint2*>(x_next + row * E + e) = o;
+  }
+}
+
+int64_t greedy_ws_bytes(int64_t B, int64_t E, int64_t H, int64_t V, int L) {
+  const int64_t slabs = ((V + 255) / 256) * 2;
+  int64_t b = ws_bytes_for(B * E, 2) + ws_bytes_for(V * H, 2) + ws_bytes_for(B * 4 * H, 2) + ws_bytes_for(slabs * B, 8);
+  for (int k = 0; k < L; ++k) {
+    const int64_t in = k == 0 ? E : H;
+    b += 2 * ws_bytes_for(B * H, 2) + ws_bytes_for(B * H, 4) + ws_bytes_for(4 * H, 4) + ws_bytes_for(4 * H * in, 2) +
+         ws_bytes_for(4 * H * H, 2);
+  }
+  return b;
+}
+
+int greedy_decode(const float* features, const float* w_emb, int L, const float* const* w_ih,
+                  const float* const* w_hh, const float* const* b_ih, const float* const* b_hh,
+                  const float* w_out, const float* b_out, const float* h0, const float* c0, int64_t B, int64_t E,
+                  int64_t H, int64_t V, int steps, int64_t* ids, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  SNT_REQ8(E, "E");
+  SNT_REQ8(H, "H");
+  SNT_REQUIRE(B < (1LL << 31) && V < (1LL << 31), "greedy_decode: extent too large");
+  const int slabs = (int)((V + 255) / 256) * 2;
+  Workspace w(ws, ws_bytes);
+  bf* x = w.take<bf>(B * E);
+  bf* wout = w.take<bf>(V * H);
+  bf* gx = w.take<bf>(B * 4 * H);
+  float2* part = w.take<float2>((int64_t)slabs * B);
+  bf *h[SNT_MAX_LAYERS][2], *wih[SNT_MAX_LAYERS], *whh[SNT_MAX_LAYERS];
+  float *c[SNT_MAX_LAYERS], *bsum[SNT_MAX_LAYERS];
+  for (int k = 0; k < L; ++k) {
+    const int64_t in = k == 0 ? E : H;
+    h[k][0] = w.take<bf>(B * H);
+    h[k][1] = w.take<bf>(B * H);
+    c[k] = w.take<float>(B * H);
+    bsum[k] = w.take<float>(4 * H);
+    wih[k] = w.take<bf>(4 * H * in);
+    whh[k] = w.take<bf>(4 * H * H);
+  }
+  if (!w.ok()) { set_error("bf16 greedy_decode: workspace too small"); return SNT_EWORKSPACE; }
+  SNT_CHECK(cast_bf16(w_out, wout, V * H, st));
+  SNT_CHECK(cast_bf16(features, x, B * E, st));
+  CUtensorMap th[SNT_MAX_LAYERS][2], tw[SNT_MAX_LAYERS], tout_a[2], tout_b;
+  for (int k = 0; k < L; ++k) {
+    const int64_t in = k == 0 ? E : H;
+    LstmWs lw;
+    lw.w_ih = wih[k]; lw.w_hh = whh[k]; lw.bsum = bsum[k];
+    SNT_CHECK(prep_weights(lw, w_ih[k], w_hh[k], b_ih[k], b_hh[k], in, H, st));
+    if (h0) {
+      SNT_CHECK(cast_bf16(h0 + (int64_t)k * B * H, h[k][0], B * H, st));
+      SNT_CUDA(cudaMemcpyAsync(c[k], c0 + (int64_t)k * B * H, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, st));
+    } else {
+      SNT_CUDA(cudaMemsetAsync(h[k][0], 0, sizeof(bf) * B * H, st));
+      SNT_CUDA(cudaMemsetAsync(c[k], 0, sizeof(float) * B * H, st));
+    }
+    for (int q = 0; q < 2; ++q) SNT_CHECK(tc::make_operand_tmap(&th[k][q], h[k][q], false, B, H, H, tc::BM));
+    SNT_CHECK(tc::make_operand_tmap(&tw[k], whh[k], false, 4 * H, H, H, 128));
+  }
+  for (int q = 0; q < 2; ++q) SNT_CHECK(tc::make_operand_tmap(&tout_a[q], h[L - 1][q], false, B, H, H, tc::BM));
+  SNT_CHECK(tc::make_operand_tmap(&tout_b, wout, false, V, H, H, 256));
+  for (int s = 0; s < steps; ++s) {
+    const int cur = s & 1, nxt = cur ^ 1;  // h[k][cur] = h_{s-1}, h[k][nxt] = h_s
+    const bf* inp = x;
+    int64_t in = E;
+    for (int k = 0; k < L; ++k) {
+      SNT_CHECK(tc::gemm_tc(false, false, B, 4 * H, in, 1.f, inp, in, wih[k], in, 0.f, nullptr, gx, 4 * H, bsum[k], 1,
+                            nullptr, st));
+      tc::TileSched ts;
+      ts.num_m = (int)((B + tc::BM - 1) / tc::BM);
+      ts.num_n = (int)((4 * H + 127) / 128);
+      ts.splits = 1;
+      ts.kblocks = (int)((H + tc::BK - 1) / tc::BK);
+      ts.kblocks_per_split = ts.kblocks;
+      ts.a_row0 = 0;
+      ts.b_row0 = 0;
+      LstmFwdEpi e;
+      e.bs = (int)B; e.bs_next = 0; e.H = (int)H; e.gx = gx; e.c_prev = c[k]; e.cs = c[k];
+      e.hs = h[k][nxt]; e.hprev_next = nullptr; e.act = nullptr;
+      SNT_CHECK((tc::launch_gemm_tc<128, false, false, LstmFwdEpi>(th[k][cur], tw[k], ts, e, st, true)));
+      inp = h[k][nxt];
+      in = H;
+    }
+    tc::TileSched ts;
+    ts.num_m = (int)((B + tc::BM - 1) / tc::BM);
+    ts.num_n = (int)((V + 255) / 256);
+    ts.splits = 1;
+    ts.kblocks = (int)((H + tc::BK - 1) / tc::BK);
+    ts.kblocks_per_split = ts.kblocks;
+    ts.a_row0 = 0;
+    ts.b_row0 = 0;
+    ArgmaxEpi e;
+    e.M = (int)B; e.V = (int)V; e.bias = b_out; e.part = part;
+    SNT_CHECK((tc::launch_gemm_tc<256, false, false, ArgmaxEpi>(tout_a[nxt], tout_b, ts, e, st, true)));
+    argmax_finish_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(part, slabs, B, w_emb, (int)E, ids + s, steps, x);
+    SNT_LAUNCH_CHECK("argmax_finish_kernel");
+  }
   return SNT_OK;
 }
 

@@ -313,6 +313,27 @@ def test_full_size_bf16_matches_fp32_mode():
     assert rel_err(d16, d32) < 1e-2
 
 
+def test_scaled_config_bf16_matches_fp32_mode():
+    """BASELINE.json configs[3]: embed 512, hidden 1024, 2-layer LSTM, 32k vocab, batch 2048 (fused vocab CE)."""
+    import show_and_tell_b200 as snt
+    B, E, H, V, L = 2048, 512, 1024, 32000, 2
+    torch.manual_seed(0)
+    dec = snt.DecoderRNN(E, H, V, L, precision="fp32").cuda()
+    b = snt.synthetic.make_batch(B, V, embed=E, seed=1)
+    targets = _t(snt.synthetic.pack_host(b["captions"], b["lengths"]))
+    feats, caps = _t(b["features"]), _t(b["captions"])
+    l32, g32, d32 = _run_loss(dec, feats, caps, b["lengths"], targets)
+    assert abs(l32 - np.log(V)) < 0.05
+    dec.precision = "bf16"
+    l16, g16, d16 = _run_loss(dec, feats, caps, b["lengths"], targets)
+    l16b, g16b, _ = _run_loss(dec, feats, caps, b["lengths"], targets)
+    assert l16 == l16b and all(np.array_equal(g16[k], g16b[k]) for k in g16)      # deterministic
+    assert abs(l16 - l32) / l32 < 1e-3
+    for k in g32:
+        assert rel_err(g16[k], g32[k]) < 1e-2, (k, rel_err(g16[k], g32[k]))
+    assert rel_err(d16, d32) < 1e-2
+
+
 def test_full_size_greedy_fp32_vs_bf16_first_token():
     import show_and_tell_b200 as snt
     B, E, H, V = 4096, 256, 512, 10000
