@@ -129,7 +129,7 @@ static int run_plain_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CU
 int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A,
             int64_t lda, const __nv_bfloat16* B, int64_t ldb, float beta, float* C, __nv_bfloat16* Cb,
             int64_t ldc, const float* bias, int splits, float* split_ws, cudaStream_t st, int row_perm_h,
-            const float* alpha_dev) {
+            const float* alpha_dev, bool keep_partials, int* splits_used) {
   if (M <= 0 || N <= 0) return SNT_OK;
   SNT_REQUIRE(row_perm_h == 0 || M == 4 * (int64_t)row_perm_h, "gemm_tc: row permutation needs M == 4H");
   SNT_REQUIRE(K >= 1 && A && B && (C || Cb), "gemm_tc: bad arguments");
@@ -155,7 +155,8 @@ int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, 
   float e_alpha = alpha, e_beta = beta;
   const float* e_bias = bias;
   int64_t split_stride = 0;
-  if (splits > 1) {
+  if (splits_used) *splits_used = splits;
+  if (splits > 1 || keep_partials) {
     SNT_REQUIRE(split_ws != nullptr, "gemm_tc: split-K needs a workspace");
     out = split_ws; outb = nullptr; e_beta = 0.f; e_bias = nullptr;
     split_stride = M * ldc;
@@ -165,7 +166,7 @@ int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, 
   else if (bn == 128) rc = run_plain_major<128>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev);
   else rc = run_plain_major<64>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev);
   SNT_CHECK(rc);
-  if (splits > 1) {
+  if (splits > 1 && !keep_partials) {
     const int64_t total = M * N;
     splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(split_ws, splits, M, N, ldc, split_stride,
                                                                            beta, bias, C, Cb);

@@ -483,12 +483,15 @@ int bn_bwd(const float* dout, const float* yhat, const float* rstd, const float*
 // counting sort by token (stable rank = number of earlier packed rows with the same token), then one block
 // per vocab row sums its rows in packed-row order.  Rows t==0 go to dfeatures.
 // ---------------------------------------------------------------------------------------------------------
-// Deterministic scatter-add of the token rows into d_w_emb[V,E] in five small, fully parallel kernels:
+// Deterministic scatter-add of the token rows into d_w_emb[V,E], fully parallel:
 //   emb_tok_kernel     token of every packed row t >= 1 and a histogram (integer atomics: order-independent)
-//   emb_scan_kernel    exclusive scan of the histogram -> start[0..V]
-//   emb_place_kernel   each row claims a slot of its token's segment (arbitrary order)
-//   emb_segsort_kernel every segment with > 1 member is put into ascending row order (rank by counting)
-//   emb_reduce8_kernel one block per occurring token sums its rows in that fixed order
+//   emb_scan_kernel    exclusive scan of the histogram -> start[0..V]; tokens that occur more than once are appended
+//                      to a work list
+//   emb_place_kernel   a row whose token occurs once is copied straight to d_w_emb (warp per row); other rows claim a
+//                      slot of their token's segment (arbitrary order)
+//   emb_multi_kernel   persistent blocks walk the work list: the segment's row indices are ranked into ascending
+//                      order in shared memory, then 16 warps sum the rows in that fixed order
+constexpr int EMB_SEG_MAX = 8192;  // longest segment (rows sharing one token, e.g. <start>: one per caption)
 __global__ void __launch_bounds__(256)
 emb_tok_kernel(const __grid_constant__ PackInfo pk, const int64_t* __restrict__ captions, int64_t cap_stride,
                int64_t V, int* __restrict__ tok, int* __restrict__ count, int* flags) {
@@ -503,13 +506,14 @@ emb_tok_kernel(const __grid_constant__ PackInfo pk, const int64_t* __restrict__ 
   tok[i] = (int)tk;
   atomicAdd(&count[tk], 1);
 }
-// exclusive scan of count[0..V) into start[0..V] (and cursor := start), single block: warp-shuffle scan of 1024-wide slabs
+// single block: warp-shuffle scan of 1024-wide slabs; multi[0] = number of listed tokens, multi[1..] = the tokens
 __global__ void __launch_bounds__(1024)
-emb_scan_kernel(const int* __restrict__ count, int V, int* __restrict__ start, int* __restrict__ cursor) {
+emb_scan_kernel(const int* __restrict__ count, int V, int* __restrict__ start, int* __restrict__ cursor,
+                int* __restrict__ multi, int* flags) {
   __shared__ int wsum[32];
   __shared__ int carry_s;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
+  if (threadIdx.x == 0) { carry_s = 0; multi[0] = 0; }
   __syncthreads();
   for (int base = 0; base < V; base += 1024) {
     const int i = base + threadIdx.x;
@@ -523,17 +527,21 @@ emb_scan_kernel(const int* __restrict__ count, int V, int* __restrict__ start, i
     if (lane == 31) wsum[w] = x;
     __syncthreads();
     if (w == 0) {
-      int s = wsum[lane];
+      int sv = wsum[lane];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, s, o);
-        if (lane >= o) s += y;
+        const int y = __shfl_up_sync(0xffffffffu, sv, o);
+        if (lane >= o) sv += y;
       }
-      wsum[lane] = s;  // inclusive scan of the warp totals
+      wsum[lane] = sv;  // inclusive scan of the warp totals
     }
     __syncthreads();
     const int excl = carry_s + (w > 0 ? wsum[w - 1] : 0) + x - c;
-    if (i < V) { start[i] = excl; cursor[i] = excl; }
+    if (i < V) {
+      start[i] = excl;
+      cursor[i] = excl;
+      if (c > 1) multi[1 + atomicAdd(&multi[0], 1)] = i;  // list order is irrelevant: tokens are independent
+    }
     __syncthreads();
     if (threadIdx.x == 0) carry_s += wsum[31];
     __syncthreads();
@@ -541,89 +549,79 @@ emb_scan_kernel(const int* __restrict__ count, int V, int* __restrict__ start, i
   if (threadIdx.x == 0) start[V] = carry_s;
 }
 __global__ void __launch_bounds__(256)
-emb_place_kernel(const int* __restrict__ tok, int n1, int* __restrict__ cursor, int* __restrict__ perm0) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
+emb_place_kernel(const int* __restrict__ tok, int n1, const int* __restrict__ count, int* __restrict__ cursor,
+                 int* __restrict__ perm0, const float* __restrict__ dx1, int E, float* __restrict__ d_w_emb) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);  // one warp per row
+  const int lane = threadIdx.x & 31;
   if (i >= n1) return;
   const int t = tok[i];
-  if (t >= 0) perm0[atomicAdd(&cursor[t], 1)] = i;
-}
-__global__ void __launch_bounds__(256)
-emb_segsort_kernel(const int* __restrict__ start, const int* __restrict__ perm0, int* __restrict__ perm) {
-  const int v = blockIdx.x;
-  const int s0 = start[v], n = start[v + 1] - s0;
-  if (n <= 0) return;
-  if (n == 1) { if (threadIdx.x == 0) perm[s0] = perm0[s0]; return; }
-  for (int a = threadIdx.x; a < n; a += 256) {
-    const int mine = perm0[s0 + a];
-    int rank = 0;
-    for (int b = 0; b < n; ++b) rank += (perm0[s0 + b] < mine);  // row indices are distinct
-    perm[s0 + rank] = mine;
+  if (t < 0) return;
+  if (count[t] == 1) {
+    const float* src = dx1 + (int64_t)i * E;
+    float* dst = d_w_emb + (int64_t)t * E;
+    for (int e = lane * 4; e < E; e += 128) *reinterpret_cast<float4*>(dst + e) = *reinterpret_cast<const float4*>(src + e);
+  } else if (lane == 0) {
+    perm0[atomicAdd(&cursor[t], 1)] = i;
   }
 }
-// One block (8 warps) per vocabulary row that occurs; d_w_emb is pre-zeroed.  Warp w sums rows w, w+8, ... of the
-// token's (sorted) segment with 4 rows x E/128 slabs in flight, then the 8 partials are combined in a fixed order.
-template <int SLABS>
-__global__ void __launch_bounds__(256)
-emb_reduce8_kernel(const float* __restrict__ dx1 /* dx + off[1]*E */, const int* __restrict__ start,
-                   const int* __restrict__ perm, int E, float* __restrict__ d_w_emb) {
-  extern __shared__ float part[];  // [8][E]
-  const int v = blockIdx.x;
-  const int s0 = start[v], s1 = start[v + 1];
-  if (s1 == s0) return;
+__global__ void __launch_bounds__(512)
+emb_multi_kernel(const float* __restrict__ dx1, const int* __restrict__ start, const int* __restrict__ perm0,
+                 int* __restrict__ gsorted, const int* __restrict__ multi, int E, float* __restrict__ d_w_emb) {
+  extern __shared__ int sm_i[];                  // raw[EMB_SEG_MAX] | sorted[EMB_SEG_MAX] | part[16][E]
+  int* raw = sm_i;
+  int* sorted_s = sm_i + EMB_SEG_MAX;
+  float* part = reinterpret_cast<float*>(sm_i + 2 * EMB_SEG_MAX);
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* out = d_w_emb + (int64_t)v * E;
-  if (s1 - s0 == 1) {  // the common case: a plain row copy
-    const float* src = dx1 + (int64_t)perm[s0] * E;
-    for (int e = threadIdx.x * 4; e < E; e += 1024) *reinterpret_cast<float4*>(out + e) = *reinterpret_cast<const float4*>(src + e);
-    return;
-  }
-  float4 acc[SLABS];
-#pragma unroll
-  for (int k = 0; k < SLABS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int i = s0 + w;
-  for (; i + 24 < s1; i += 32) {
-    const float* r0 = dx1 + (int64_t)perm[i] * E + lane * 4;
-    const float* r1 = dx1 + (int64_t)perm[i + 8] * E + lane * 4;
-    const float* r2 = dx1 + (int64_t)perm[i + 16] * E + lane * 4;
-    const float* r3 = dx1 + (int64_t)perm[i + 24] * E + lane * 4;
-    float4 a[SLABS], b[SLABS], c[SLABS], d[SLABS];
-#pragma unroll
-    for (int k = 0; k < SLABS; ++k) {
-      if (k * 128 + lane * 4 < E) {
-        a[k] = *reinterpret_cast<const float4*>(r0 + k * 128);
-        b[k] = *reinterpret_cast<const float4*>(r1 + k * 128);
-        c[k] = *reinterpret_cast<const float4*>(r2 + k * 128);
-        d[k] = *reinterpret_cast<const float4*>(r3 + k * 128);
-      } else {
-        a[k] = b[k] = c[k] = d[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int n_multi = multi[0];
+  for (int li = blockIdx.x; li < n_multi; li += gridDim.x) {
+    const int v = multi[1 + li];
+    const int s0 = start[v];
+    const int n = start[v + 1] - s0;
+    const bool big = n > EMB_SEG_MAX;  // rare: rank straight from global memory into a global scratch segment
+    const int* rawp = big ? perm0 + s0 : raw;
+    int* sorted_w = big ? gsorted + s0 : sorted_s;
+    __syncthreads();  // previous token's shared data no longer in use
+    if (!big) {
+      for (int a = threadIdx.x; a < n; a += 512) raw[a] = perm0[s0 + a];
+      __syncthreads();
+    }
+    for (int a = threadIdx.x; a < n; a += 512) {
+      const int mine = rawp[a];
+      int rank = 0;
+      for (int b = 0; b < n; ++b) rank += (rawp[b] < mine);  // row indices are distinct; broadcast reads
+      sorted_w[rank] = mine;
+    }
+    __syncthreads();
+    const int* sorted = sorted_w;
+    for (int e0 = 0; e0 < E; e0 += 128) {   // lane owns 4 floats of a 128-wide slab; warp w takes rows w, w+16, ...
+      const int e = e0 + lane * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < E) {
+        int i = w;
+        for (; i + 48 < n; i += 64) {
+          const float4 a = *reinterpret_cast<const float4*>(dx1 + (int64_t)sorted[i] * E + e);
+          const float4 b = *reinterpret_cast<const float4*>(dx1 + (int64_t)sorted[i + 16] * E + e);
+          const float4 c = *reinterpret_cast<const float4*>(dx1 + (int64_t)sorted[i + 32] * E + e);
+          const float4 d = *reinterpret_cast<const float4*>(dx1 + (int64_t)sorted[i + 48] * E + e);
+          acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+          acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+          acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+          acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+        }
+        for (; i < n; i += 16) {
+          const float4 a = *reinterpret_cast<const float4*>(dx1 + (int64_t)sorted[i] * E + e);
+          acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        }
+        *reinterpret_cast<float4*>(part + w * E + e) = acc;
       }
     }
+    __syncthreads();
+    for (int e = threadIdx.x; e < E; e += 512) {
+      float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < SLABS; ++k) {
-      acc[k].x += a[k].x; acc[k].y += a[k].y; acc[k].z += a[k].z; acc[k].w += a[k].w;
-      acc[k].x += b[k].x; acc[k].y += b[k].y; acc[k].z += b[k].z; acc[k].w += b[k].w;
-      acc[k].x += c[k].x; acc[k].y += c[k].y; acc[k].z += c[k].z; acc[k].w += c[k].w;
-      acc[k].x += d[k].x; acc[k].y += d[k].y; acc[k].z += d[k].z; acc[k].w += d[k].w;
+      for (int k = 0; k < 16; ++k) t += part[k * E + e];
+      d_w_emb[(int64_t)v * E + e] = t;
     }
-  }
-  for (; i < s1; i += 8) {
-    const float* r0 = dx1 + (int64_t)perm[i] * E + lane * 4;
-#pragma unroll
-    for (int k = 0; k < SLABS; ++k)
-      if (k * 128 + lane * 4 < E) {
-        const float4 a = *reinterpret_cast<const float4*>(r0 + k * 128);
-        acc[k].x += a.x; acc[k].y += a.y; acc[k].z += a.z; acc[k].w += a.w;
-      }
-  }
-#pragma unroll
-  for (int k = 0; k < SLABS; ++k)
-    if (k * 128 + lane * 4 < E) *reinterpret_cast<float4*>(part + w * E + k * 128 + lane * 4) = acc[k];
-  __syncthreads();
-  for (int e = threadIdx.x; e < E; e += 256) {
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t += part[k * E + e];
-    out[e] = t;
   }
 }
 __global__ void __launch_bounds__(256)
@@ -634,7 +632,7 @@ dfeatures_kernel(const float* __restrict__ dx, int bs0, int64_t B, int64_t E, fl
 }
 
 int64_t embed_bwd_ws_bytes(int64_t N, int64_t V) {
-  return ws_bytes_for(N, 4) * 3 + ws_bytes_for(V + 1, 4) * 3;
+  return ws_bytes_for(N, 4) * 3 + ws_bytes_for(V + 1, 4) * 4;
 }
 int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions, int64_t cap_stride,
                    int64_t B, int64_t E, int64_t V, float* dfeatures, float* d_w_emb, void* ws,
@@ -649,31 +647,33 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
   Workspace w(ws, ws_bytes);
   int* tok = w.take<int>(N);
   int* perm0 = w.take<int>(N);
-  int* perm = w.take<int>(N);
+  int* gsorted = w.take<int>(N);
   int* count = w.take<int>(V + 1);
   int* start = w.take<int>(V + 1);
   int* cursor = w.take<int>(V + 1);
+  int* multi = w.take<int>(V + 1);
   if (!w.ok()) { set_error("embed_pack_bwd: workspace too small"); return SNT_EWORKSPACE; }
   SNT_REQUIRE(E % 4 == 0 && E <= 1024, "embed_pack_bwd: E must be a multiple of 4 and <= 1024");
   SNT_REQUIRE(V < (1LL << 31), "embed_pack_bwd: V too large");
   SNT_CUDA(cudaMemsetAsync(d_w_emb, 0, sizeof(float) * (size_t)V * E, st));
   if (n1 <= 0) return SNT_OK;
   SNT_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(V + 1), st));
+  const float* dx1 = dx + (int64_t)pk.off[1] * E;
   emb_tok_kernel<<<nblocks(n1, 256), 256, 0, st>>>(pk, captions, cap_stride, V, tok, count, device_flags());
   SNT_LAUNCH_CHECK("emb_tok_kernel");
-  emb_scan_kernel<<<1, 1024, 0, st>>>(count, (int)V, start, cursor);
+  emb_scan_kernel<<<1, 1024, 0, st>>>(count, (int)V, start, cursor, multi, device_flags());
   SNT_LAUNCH_CHECK("emb_scan_kernel");
-  emb_place_kernel<<<nblocks(n1, 256), 256, 0, st>>>(tok, n1, cursor, perm0);
+  emb_place_kernel<<<nblocks(n1, 8), 256, 0, st>>>(tok, n1, count, cursor, perm0, dx1, (int)E, d_w_emb);
   SNT_LAUNCH_CHECK("emb_place_kernel");
-  emb_segsort_kernel<<<(unsigned)V, 256, 0, st>>>(start, perm0, perm);
-  SNT_LAUNCH_CHECK("emb_segsort_kernel");
-  const float* dx1 = dx + (int64_t)pk.off[1] * E;
-  const size_t sm = (size_t)(8 * E * sizeof(float));
-  const int slabs = (int)((E + 127) / 128);
-  if (slabs <= 2) emb_reduce8_kernel<2><<<(unsigned)V, 256, sm, st>>>(dx1, start, perm, (int)E, d_w_emb);
-  else if (slabs <= 4) emb_reduce8_kernel<4><<<(unsigned)V, 256, sm, st>>>(dx1, start, perm, (int)E, d_w_emb);
-  else emb_reduce8_kernel<8><<<(unsigned)V, 256, sm, st>>>(dx1, start, perm, (int)E, d_w_emb);
-  SNT_LAUNCH_CHECK("emb_reduce8_kernel");
+  const size_t sm = sizeof(int) * 2 * EMB_SEG_MAX + sizeof(float) * 16 * (size_t)E;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SNT_CUDA(cudaFuncSetAttribute(emb_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(int) * 2 * EMB_SEG_MAX + sizeof(float) * 16 * 1024)));
+    attr_set = true;
+  }
+  emb_multi_kernel<<<296, 512, sm, st>>>(dx1, start, perm0, gsorted, multi, (int)E, d_w_emb);
+  SNT_LAUNCH_CHECK("emb_multi_kernel");
   return SNT_OK;
 }
 

@@ -197,6 +197,67 @@ struct LstmBwdEpi {
   }
 };
 
+// ---- backward step, split-K variant: the recurrent contraction dG'_{t+1} . W_hh' runs as a split-K GEMM over all SMs
+// (partials in an L2-resident scratch), and this coalesced pointwise kernel sums the partials in a fixed order and
+// runs the cell backward.  One thread = one packed row x 8 hidden units.
+__global__ void __launch_bounds__(256)
+lstm_bwd_point_kernel(int bs, int bs_next, int H, const float* __restrict__ d_hs, const bf* __restrict__ act,
+                      const float* __restrict__ cs, const float* __restrict__ c_prev,
+                      const float* __restrict__ partial, int splits, int64_t split_stride,
+                      float* __restrict__ dc_state, bf* __restrict__ dg) {
+  const int groups = H >> 3;
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (int64_t)bs * groups) return;
+  const int row = (int)(idx / groups), ju = (int)(idx % groups) * 8;
+  const bool has_next = row < bs_next;
+  const int64_t o1 = (int64_t)row * H + ju;
+  float dhv[8], cv[8], pv[8], sv[8];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(d_hs + o1), b = *reinterpret_cast<const float4*>(d_hs + o1 + 4);
+    dhv[0] = a.x; dhv[1] = a.y; dhv[2] = a.z; dhv[3] = a.w; dhv[4] = b.x; dhv[5] = b.y; dhv[6] = b.z; dhv[7] = b.w;
+    const float4 c0 = *reinterpret_cast<const float4*>(cs + o1), c1 = *reinterpret_cast<const float4*>(cs + o1 + 4);
+    cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { pv[u] = 0.f; sv[u] = 0.f; }
+  if (c_prev) {
+    const float4 a = *reinterpret_cast<const float4*>(c_prev + o1), b = *reinterpret_cast<const float4*>(c_prev + o1 + 4);
+    pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; pv[4] = b.x; pv[5] = b.y; pv[6] = b.z; pv[7] = b.w;
+  }
+  if (has_next) {
+    const float4 a = *reinterpret_cast<const float4*>(dc_state + o1), b = *reinterpret_cast<const float4*>(dc_state + o1 + 4);
+    sv[0] = a.x; sv[1] = a.y; sv[2] = a.z; sv[3] = a.w; sv[4] = b.x; sv[5] = b.y; sv[6] = b.z; sv[7] = b.w;
+    for (int k = 0; k < splits; ++k) {  // fixed order: deterministic
+      const float* p = partial + (int64_t)k * split_stride + o1;
+      const float4 x = __ldcg(reinterpret_cast<const float4*>(p)), y = __ldcg(reinterpret_cast<const float4*>(p + 4));
+      dhv[0] += x.x; dhv[1] += x.y; dhv[2] += x.z; dhv[3] += x.w; dhv[4] += y.x; dhv[5] += y.y; dhv[6] += y.z; dhv[7] += y.w;
+    }
+  }
+  const uint4* a4 = reinterpret_cast<const uint4*>(act + (int64_t)row * 4 * H + 4 * ju);
+  uint32_t a[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const uint4 v = a4[q]; a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w; }
+  float dcn[8];
+  uint32_t go[16];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float2 if_ = unpack_bf2(a[2 * u]), go_ = unpack_bf2(a[2 * u + 1]);
+    const float i_ = if_.x, f_ = if_.y, g_ = go_.x, o_ = go_.y;
+    const float tc_ = tanh_(cv[u]);
+    const float dh = dhv[u];
+    const float dc = sv[u] + dh * o_ * (1.f - tc_ * tc_);
+    go[2 * u] = pack_bf2(dc * g_ * i_ * (1.f - i_), dc * pv[u] * f_ * (1.f - f_));
+    go[2 * u + 1] = pack_bf2(dc * i_ * (1.f - g_ * g_), dh * tc_ * o_ * (1.f - o_));
+    dcn[u] = dc * f_;
+  }
+  float4* sd = reinterpret_cast<float4*>(dc_state + o1);
+  sd[0] = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+  sd[1] = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
+  uint4* gd = reinterpret_cast<uint4*>(dg + (int64_t)row * 4 * H + 4 * ju);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) gd[q] = make_uint4(go[4 * q], go[4 * q + 1], go[4 * q + 2], go[4 * q + 3]);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 struct LstmWs {
   float* bsum; bf* w_ih; bf* w_hh; bf* gx; float* dc_state; float* cpart; float* tmp; float* sws; bool ok;
@@ -302,29 +363,26 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
   const bf* act = (const bf*)gates;
   bf* dg = (bf*)gates + N * 4 * H;
   SNT_CHECK(prep_weights(w, w_ih, w_hh, nullptr, nullptr, In, H, st));
-  CUtensorMap ta, tb;
-  SNT_CHECK(tc::make_operand_tmap(&ta, dg, false, N, 4 * H, 4 * H, tc::BM));
-  SNT_CHECK(tc::make_operand_tmap(&tb, w.w_hh, true, H, 4 * H, H, 64));
+  // split-K keeps all SMs busy on the small per-step contraction; its partials never leave L2
+  const int want_splits = 4;
   for (int t = T - 1; t >= 0; --t) {
     const int bs = pk.off[t + 1] - pk.off[t];
     const int bs_next = t + 1 < T ? pk.off[t + 2] - pk.off[t + 1] : 0;
-    tc::TileSched ts;
-    ts.num_m = (bs + tc::BM - 1) / tc::BM;
-    ts.num_n = (int)((H + 63) / 64);
-    ts.splits = 1;
-    ts.kblocks = (int)((4 * H + tc::BK - 1) / tc::BK);
-    ts.kblocks_per_split = ts.kblocks;
-    ts.a_row0 = pk.off[t + 1];  // dG'_{t+1}; for t = T-1 this is past the tensor (zero fill) and unused
-    ts.b_row0 = 0;
-    LstmBwdEpi e;
-    e.bs = bs; e.bs_next = bs_next; e.H = (int)H;
-    e.d_hs = d_hs + (int64_t)pk.off[t] * H;
-    e.act = act + (int64_t)pk.off[t] * 4 * H;
-    e.cs = cs + (int64_t)pk.off[t] * H;
-    e.c_prev = t > 0 ? cs + (int64_t)pk.off[t - 1] * H : nullptr;
-    e.dc_state = w.dc_state;
-    e.dg = dg + (int64_t)pk.off[t] * 4 * H;
-    SNT_CHECK((tc::launch_gemm_tc<64, false, true, LstmBwdEpi>(ta, tb, ts, e, st, /*pdl=*/t < T - 1)));
+    int used = 1;
+    if (bs_next > 0) {  // partial[s] = dG'_{t+1}[:, K_s] . W_hh'[K_s, :]   (B operand MN-major)
+      const int64_t cap = (int64_t)MAX_SPLITS * 4 * H * (In > H ? In : H);  // floats in w.sws
+      int want = want_splits;
+      while (want > 1 && (int64_t)want * bs_next * H > cap) --want;
+      SNT_CHECK(tc::gemm_tc(false, true, bs_next, H, 4 * H, 1.f, dg + (int64_t)pk.off[t + 1] * 4 * H, 4 * H, w.w_hh, H,
+                            0.f, w.sws, nullptr, H, nullptr, want, w.sws, st, 0, nullptr, /*keep_partials=*/true,
+                            &used));
+    }
+    const int64_t threads = (int64_t)bs * (H / 8);
+    lstm_bwd_point_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+        bs, bs_next, (int)H, d_hs + (int64_t)pk.off[t] * H, act + (int64_t)pk.off[t] * 4 * H,
+        cs + (int64_t)pk.off[t] * H, t > 0 ? cs + (int64_t)pk.off[t - 1] * H : nullptr, w.sws, used,
+        (int64_t)bs_next * H, w.dc_state, dg + (int64_t)pk.off[t] * 4 * H);
+    SNT_LAUNCH_CHECK("lstm_bwd_point_kernel");
   }
   // weight gradients over the whole packed sequence (rows come out interleaved: un-permute on store)
   int s1 = tc::choose_splits(4 * H, In, N, 0), s2 = tc::choose_splits(4 * H, H, N, 0);
