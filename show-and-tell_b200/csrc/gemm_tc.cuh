@@ -45,8 +45,14 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 // Epi must provide:
 //   static constexpr int kWarps            (4 or 8 epilogue warps)
-//   __device__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int epi_warp, int lane) const
+//   struct Pre; __device__ void prefetch(Pre&, int m_blk, int n_blk, int epi_warp, int lane) const
+//       global loads the epilogue will need, issued BEFORE waiting for the accumulator so that their latency
+//       overlaps the TMA/MMA phase (NoPre = nothing to prefetch)
+//   static constexpr int kSmemPerWarp   bytes of shared scratch each epilogue warp gets (16-byte aligned), may be 0
+//   __device__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int epi_warp, int lane, const Pre&,
+//                        uint8_t* warp_smem) const
 // where tmem_rows addresses lane 32*(epi_warp%4), first column of this tile's accumulator.
+struct NoPre {};
 template <int BN, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(128 + 32 * Epi::kWarps, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -59,6 +65,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* epi_smem = smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -174,10 +181,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int rest = tile / ts.num_m;
       const int n_blk = rest % ts.num_n;
       const int split = rest / ts.num_n;
+      typename Epi::Pre pre;
+      epi.prefetch(pre, m_blk, n_blk, ew, lane);
       mbar_wait(&tfull[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t tmem_rows = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)((ew & 3) * 32) << 16);
-      epi.tile(tmem_rows, m_blk, n_blk, split, ew, lane);
+      epi.tile(tmem_rows, m_blk, n_blk, split, ew, lane, pre, epi_smem + ew * Epi::kSmemPerWarp);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -210,7 +219,8 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TileSch
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi>;
   static bool configured = false;  // per instantiation
   if (!configured) {
-    SNT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    SNT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::SMEM_BYTES + Epi::kWarps * Epi::kSmemPerWarp));
     configured = true;
   }
   const int total = ts.num_m * ts.num_n * ts.splits;
@@ -218,7 +228,7 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TileSch
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)min(total, sm_count()));
   cfg.blockDim = dim3(128 + 32 * Epi::kWarps);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.dynamicSmemBytes = C::SMEM_BYTES + Epi::kWarps * Epi::kSmemPerWarp;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -234,6 +244,7 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TileSch
 template <int BN>
 struct PlainEpi {
   static constexpr int kWarps = 4;
+  static constexpr int kSmemPerWarp = 0;
   int M, N;                // valid extent
   float alpha, beta;
   const float* alpha_dev;  // optional device scalar multiplied into alpha (e.g. the incoming dloss)
@@ -244,7 +255,10 @@ struct PlainEpi {
   int64_t split_stride;    // elements between split-K partial slices of C
   int row_perm_h;          // != 0: accumulator row 4*j+g is stored to row g*row_perm_h + j (LSTM gate un-interleave)
 
-  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane) const {
+  using Pre = NoPre;
+  __device__ __forceinline__ void prefetch(Pre&, int, int, int, int) const {}
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane,
+                                       const Pre&, uint8_t*) const {
     const int row = m_blk * BM + (ew & 3) * 32 + lane;
     const bool row_ok = row < M;
     const int drow = row_perm_h ? (row & 3) * row_perm_h + (row >> 2) : row;

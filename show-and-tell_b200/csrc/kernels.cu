@@ -564,10 +564,11 @@ emb_place_kernel(const int* __restrict__ tok, int n1, const int* __restrict__ co
     perm0[atomicAdd(&cursor[t], 1)] = i;
   }
 }
-__global__ void __launch_bounds__(512)
+template <int SLABS>
+__global__ void __launch_bounds__(1024)
 emb_multi_kernel(const float* __restrict__ dx1, const int* __restrict__ start, const int* __restrict__ perm0,
                  int* __restrict__ gsorted, const int* __restrict__ multi, int E, float* __restrict__ d_w_emb) {
-  extern __shared__ int sm_i[];                  // raw[EMB_SEG_MAX] | sorted[EMB_SEG_MAX] | part[16][E]
+  extern __shared__ int sm_i[];                  // raw[EMB_SEG_MAX] | sorted[EMB_SEG_MAX] | part[32][E]
   int* raw = sm_i;
   int* sorted_s = sm_i + EMB_SEG_MAX;
   float* part = reinterpret_cast<float*>(sm_i + 2 * EMB_SEG_MAX);
@@ -582,10 +583,10 @@ emb_multi_kernel(const float* __restrict__ dx1, const int* __restrict__ start, c
     int* sorted_w = big ? gsorted + s0 : sorted_s;
     __syncthreads();  // previous token's shared data no longer in use
     if (!big) {
-      for (int a = threadIdx.x; a < n; a += 512) raw[a] = perm0[s0 + a];
+      for (int a = threadIdx.x; a < n; a += 1024) raw[a] = perm0[s0 + a];
       __syncthreads();
     }
-    for (int a = threadIdx.x; a < n; a += 512) {
+    for (int a = threadIdx.x; a < n; a += 1024) {
       const int mine = rawp[a];
       int rank = 0;
       for (int b = 0; b < n; ++b) rank += (rawp[b] < mine);  // row indices are distinct; broadcast reads
@@ -593,33 +594,44 @@ emb_multi_kernel(const float* __restrict__ dx1, const int* __restrict__ start, c
     }
     __syncthreads();
     const int* sorted = sorted_w;
-    for (int e0 = 0; e0 < E; e0 += 128) {   // lane owns 4 floats of a 128-wide slab; warp w takes rows w, w+16, ...
-      const int e = e0 + lane * 4;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (e < E) {
-        int i = w;
-        for (; i + 48 < n; i += 64) {
-          const float4 a = *reinterpret_cast<const float4*>(dx1 + (int64_t)sorted[i] * E + e);
-          const float4 b = *reinterpret_cast<const float4*>(dx1 + (int64_t)sorted[i + 16] * E + e);
-          const float4 c = *reinterpret_cast<const float4*>(dx1 + (int64_t)sorted[i + 32] * E + e);
-          const float4 d = *reinterpret_cast<const float4*>(dx1 + (int64_t)sorted[i + 48] * E + e);
-          acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-          acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
-          acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
-          acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
-        }
-        for (; i < n; i += 16) {
-          const float4 a = *reinterpret_cast<const float4*>(dx1 + (int64_t)sorted[i] * E + e);
-          acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-        }
-        *reinterpret_cast<float4*>(part + w * E + e) = acc;
+    // warp w sums rows w, w+32, ... (ascending): every lane owns SLABS float4 of the row, 2 rows in flight
+    float4 acc[SLABS];
+#pragma unroll
+    for (int k = 0; k < SLABS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int i = w;
+    for (; i + 32 < n; i += 64) {
+      const float* r0 = dx1 + (int64_t)sorted[i] * E + lane * 4;
+      const float* r1 = dx1 + (int64_t)sorted[i + 32] * E + lane * 4;
+      float4 a[SLABS], b[SLABS];
+#pragma unroll
+      for (int k = 0; k < SLABS; ++k) {
+        const bool in = k * 128 + lane * 4 < E;
+        a[k] = in ? *reinterpret_cast<const float4*>(r0 + k * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b[k] = in ? *reinterpret_cast<const float4*>(r1 + k * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < SLABS; ++k) {
+        acc[k].x += a[k].x; acc[k].y += a[k].y; acc[k].z += a[k].z; acc[k].w += a[k].w;
+        acc[k].x += b[k].x; acc[k].y += b[k].y; acc[k].z += b[k].z; acc[k].w += b[k].w;
       }
     }
-    __syncthreads();
-    for (int e = threadIdx.x; e < E; e += 512) {
-      float t = 0.f;
+    for (; i < n; i += 32) {
+      const float* r0 = dx1 + (int64_t)sorted[i] * E + lane * 4;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) t += part[k * E + e];
+      for (int k = 0; k < SLABS; ++k)
+        if (k * 128 + lane * 4 < E) {
+          const float4 a = *reinterpret_cast<const float4*>(r0 + k * 128);
+          acc[k].x += a.x; acc[k].y += a.y; acc[k].z += a.z; acc[k].w += a.w;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SLABS; ++k)
+      if (k * 128 + lane * 4 < E) *reinterpret_cast<float4*>(part + w * E + k * 128 + lane * 4) = acc[k];
+    __syncthreads();
+    for (int e = threadIdx.x; e < E; e += 1024) {
+      float t = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) t += part[k * E + e];
       d_w_emb[(int64_t)v * E + e] = t;
     }
   }
@@ -665,14 +677,19 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
   SNT_LAUNCH_CHECK("emb_scan_kernel");
   emb_place_kernel<<<nblocks(n1, 8), 256, 0, st>>>(tok, n1, count, cursor, perm0, dx1, (int)E, d_w_emb);
   SNT_LAUNCH_CHECK("emb_place_kernel");
-  const size_t sm = sizeof(int) * 2 * EMB_SEG_MAX + sizeof(float) * 16 * (size_t)E;
+  const size_t sm = sizeof(int) * 2 * EMB_SEG_MAX + sizeof(float) * 32 * (size_t)E;
+  const int max_sm = (int)(sizeof(int) * 2 * EMB_SEG_MAX + sizeof(float) * 32 * 1024);
   static bool attr_set = false;
   if (!attr_set) {
-    SNT_CUDA(cudaFuncSetAttribute(emb_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(sizeof(int) * 2 * EMB_SEG_MAX + sizeof(float) * 16 * 1024)));
+    SNT_CUDA(cudaFuncSetAttribute(emb_multi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_sm));
+    SNT_CUDA(cudaFuncSetAttribute(emb_multi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_sm));
+    SNT_CUDA(cudaFuncSetAttribute(emb_multi_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_sm));
     attr_set = true;
   }
-  emb_multi_kernel<<<296, 512, sm, st>>>(dx1, start, perm0, gsorted, multi, (int)E, d_w_emb);
+  const int slabs = (int)((E + 127) / 128);
+  if (slabs <= 2) emb_multi_kernel<2><<<148, 1024, sm, st>>>(dx1, start, perm0, gsorted, multi, (int)E, d_w_emb);
+  else if (slabs <= 4) emb_multi_kernel<4><<<148, 1024, sm, st>>>(dx1, start, perm0, gsorted, multi, (int)E, d_w_emb);
+  else emb_multi_kernel<8><<<148, 1024, sm, st>>>(dx1, start, perm0, gsorted, multi, (int)E, d_w_emb);
   SNT_LAUNCH_CHECK("emb_multi_kernel");
   return SNT_OK;
 }

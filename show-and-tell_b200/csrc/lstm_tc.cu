@@ -62,6 +62,7 @@ __global__ void unperm_vec_kernel(const float* __restrict__ in, int H, float* __
 // ---- forward step epilogue ---------------------------------------------------------------------------------------------
 struct LstmFwdEpi {
   static constexpr int kWarps = 4;
+  static constexpr int kSmemPerWarp = 0;
   int bs, bs_next, H;
   const bf* gx;         // [bs, 4H]   input projection + biases of this step's rows (bf16), interleaved columns
   const float* c_prev;  // [>=bs, H]  c_{t-1} (NULL at t = 0)
@@ -70,11 +71,38 @@ struct LstmFwdEpi {
   bf* hprev_next;       // [bs_next, H] h_t again, at the packed rows of step t+1 (NULL at the last step)
   bf* act;              // [bs, 4H]   sigma(i), sigma(f), tanh(g), sigma(o), interleaved, kept for BPTT (NULL: skip)
 
-  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane) const {
+  // everything the epilogue reads from global memory for its 128 columns (4 chunks x 8 hidden units)
+  struct Pre {
+    uint4 gx[4][4];   // bf16 input projection, 32 values per chunk
+    float4 cp[4][2];  // c_{t-1}, 8 values per chunk
+  };
+  __device__ __forceinline__ void prefetch(Pre& p, int m_blk, int n_blk, int ew, int lane) const {
+    const int row = m_blk * tc::BM + ew * 32 + lane;
+    if (row >= bs) return;
+    const int H4 = 4 * H;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int col0 = n_blk * 128 + c * 32;
+      if (col0 < H4) {
+        const uint4* g4 = reinterpret_cast<const uint4*>(gx + (int64_t)row * H4 + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) p.gx[c][q] = __ldg(g4 + q);
+        if (c_prev) {
+          const float4* c4 = reinterpret_cast<const float4*>(c_prev + (int64_t)row * H + (col0 >> 2));
+          p.cp[c][0] = c4[0];
+          p.cp[c][1] = c4[1];
+        } else {
+          p.cp[c][0] = p.cp[c][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane,
+                                       const Pre& p, uint8_t*) const {
     const int row = m_blk * tc::BM + ew * 32 + lane;
     const bool ok = row < bs;
     const int H4 = 4 * H;
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int col0 = n_blk * 128 + c * 32;
       if (col0 >= H4) break;  // warp-uniform
@@ -83,24 +111,16 @@ struct LstmFwdEpi {
       tc::tmem_ld_wait();
       if (!ok) continue;
       const int j0 = col0 >> 2;
-      const uint4* g4 = reinterpret_cast<const uint4*>(gx + (int64_t)row * H4 + col0);
       float4 g[8];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {  // 8 bf16 = 2 hidden units per 16-byte load
-        const uint4 v = __ldg(g4 + q);
+        const uint4 v = p.gx[c][q];
         const float2 a = unpack_bf2(v.x), b = unpack_bf2(v.y), c2 = unpack_bf2(v.z), d = unpack_bf2(v.w);
         g[2 * q] = make_float4(a.x, a.y, b.x, b.y);
         g[2 * q + 1] = make_float4(c2.x, c2.y, d.x, d.y);
       }
-      float cp[8];
-      if (c_prev) {
-        const float4 a = *reinterpret_cast<const float4*>(c_prev + (int64_t)row * H + j0);
-        const float4 b = *reinterpret_cast<const float4*>(c_prev + (int64_t)row * H + j0 + 4);
-        cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w; cp[4] = b.x; cp[5] = b.y; cp[6] = b.z; cp[7] = b.w;
-      } else {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) cp[u] = 0.f;
-      }
+      const float cp[8] = {p.cp[c][0].x, p.cp[c][0].y, p.cp[c][0].z, p.cp[c][0].w,
+                           p.cp[c][1].x, p.cp[c][1].y, p.cp[c][1].z, p.cp[c][1].w};
       float cn[8], hn[8];
       uint32_t ap[16];
 #pragma unroll
@@ -133,6 +153,7 @@ struct LstmFwdEpi {
 // ---- backward step epilogue ------------------------------------------------------------------------------------------
 struct LstmBwdEpi {
   static constexpr int kWarps = 4;
+  static constexpr int kSmemPerWarp = 0;
   int bs, bs_next, H;
   const float* d_hs;    // [bs, H]   dL/dh_t from the layer above / the vocab projection
   const bf* act;        // [bs, 4H]  saved activations of step t
@@ -141,7 +162,10 @@ struct LstmBwdEpi {
   float* dc_state;      // [B, H]    in: dL/dc_t carried from step t+1 (rows < bs_next); out: dL/dc_{t-1}
   bf* dg;               // [bs, 4H]  out: gradient w.r.t. the pre-activations, interleaved columns
 
-  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane) const {
+  using Pre = tc::NoPre;
+  __device__ __forceinline__ void prefetch(Pre&, int, int, int, int) const {}
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane,
+                                       const Pre&, uint8_t*) const {
     const int row = m_blk * tc::BM + ew * 32 + lane;
     const bool ok = row < bs;
     const bool has_next = row < bs_next;  // rows that were still alive at step t+1 carry recurrent gradient
@@ -409,11 +433,15 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
 // =====================================================================================================================
 struct ArgmaxEpi {
   static constexpr int kWarps = 8;
+  static constexpr int kSmemPerWarp = 0;
   int M, V;
   const float* bias;
   float2* part;  // [slabs][M]: (max logit, index as int bits)
 
-  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane) const {
+  using Pre = tc::NoPre;
+  __device__ __forceinline__ void prefetch(Pre&, int, int, int, int) const {}
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane,
+                                       const Pre&, uint8_t*) const {
     const int half = ew >> 2;
     const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
     float best = -INFINITY;

@@ -59,12 +59,16 @@ ce_target_logit_kernel(const bf* __restrict__ hs, const bf* __restrict__ w, cons
 // ---- forward epilogue: per (row, 128-column slab) online-softmax partial in the log2 domain ------------------------
 struct CeFwdEpi {
   static constexpr int kWarps = 8;
+  static constexpr int kSmemPerWarp = 0;
   int M;                 // rows
   int V;                 // valid columns
   const float* bias;     // [V]
   float2* part;          // [num_slabs][M] (max2, sum2): sum_j 2^(y_j - max2), y = logit * log2(e)
 
-  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane) const {
+  using Pre = tc::NoPre;
+  __device__ __forceinline__ void prefetch(Pre&, int, int, int, int) const {}
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane,
+                                       const Pre&, uint8_t* wsm) const {
     const int half = ew >> 2;
     const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
     float m = -INFINITY, s = 0.f;
@@ -126,6 +130,7 @@ ce_finish_kernel(const float2* __restrict__ part, int slabs, int64_t N, const fl
 // ---- backward epilogue: dlogits = (2^(y - lse2) - onehot) * scale -> bf16 chunk ------------------------------------
 struct CeBwdEpi {
   static constexpr int kWarps = 8;
+  static constexpr int kSmemPerWarp = 32 * 80;  // 32 rows x (64 B of bf16 + 16 B pad): transpose stage for coalesced stores
   int M;                    // rows in this chunk
   int V;
   const float* bias;        // [V]
@@ -135,7 +140,10 @@ struct CeBwdEpi {
                             // into the consumers' alpha: scaling first would round every target entry the same way)
   int64_t ldo;
 
-  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane) const {
+  using Pre = tc::NoPre;
+  __device__ __forceinline__ void prefetch(Pre&, int, int, int, int) const {}
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane,
+                                       const Pre&, uint8_t* wsm) const {
     const int half = ew >> 2;
     const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
     const bool row_ok = row < M;
@@ -150,7 +158,6 @@ struct CeBwdEpi {
       uint32_t r[32];
       tc::tmem_ld32(tmem_rows + (uint32_t)cofs, r);
       tc::tmem_ld_wait();
-      if (!row_ok) continue;
       const int trel = tgt - col0;
       if (col0 + 32 <= V) {
         uint32_t pk[16];
@@ -169,14 +176,25 @@ struct CeBwdEpi {
           pk[j / 2] = *reinterpret_cast<uint32_t*>(&lo);
           pk[j / 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
         }
-        uint4* dst = reinterpret_cast<uint4*>(orow + col0);
+        // stage the warp's 32 x 64 B through shared memory so that each store instruction writes 8 whole 64-byte row
+        // segments (4 lanes per row) instead of 32 scattered 16-byte pieces
+        uint4* mine = reinterpret_cast<uint4*>(wsm + lane * 80);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) mine[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        __syncwarp();
+        const int row0 = m_blk * tc::BM + (ew & 3) * 32;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + (lane >> 2), cq = lane & 3;
+          const uint4 v = *reinterpret_cast<const uint4*>(wsm + rr * 80 + cq * 16);
+          if (row0 + rr < M) *reinterpret_cast<uint4*>(out + (int64_t)(row0 + rr) * ldo + col0 + cq * 8) = v;
+        }
+        __syncwarp();
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = col0 + j;
-          if (col < V) {
+          if (col < V && row_ok) {
             float p = ex2((__uint_as_float(r[j]) + bias[col]) * LOG2E - l2);
             if (trel == j) p -= 1.f;
             orow[col] = __float2bfloat16_rn(p);
