@@ -129,12 +129,12 @@ static int run_plain_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CU
 int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A,
             int64_t lda, const __nv_bfloat16* B, int64_t ldb, float beta, float* C, __nv_bfloat16* Cb,
             int64_t ldc, const float* bias, int splits, float* split_ws, cudaStream_t st, int row_perm_h,
-            const float* alpha_dev, bool keep_partials, int* splits_used) {
+            const float* alpha_dev, bool keep_partials, int* splits_used, int force_bn) {
   if (M <= 0 || N <= 0) return SNT_OK;
   SNT_REQUIRE(row_perm_h == 0 || M == 4 * (int64_t)row_perm_h, "gemm_tc: row permutation needs M == 4H");
   SNT_REQUIRE(K >= 1 && A && B && (C || Cb), "gemm_tc: bad arguments");
   SNT_REQUIRE(M < (1 << 30) && N < (1 << 30) && K < (1 << 30), "gemm_tc: extent too large");
-  const int bn = pick_bn(M, N);
+  const int bn = (force_bn == 64 || force_bn == 128 || force_bn == 256) ? force_bn : pick_bn(M, N);
   TileSched ts;
   ts.num_m = (int)((M + BM - 1) / BM);
   ts.num_n = (int)((N + bn - 1) / bn);

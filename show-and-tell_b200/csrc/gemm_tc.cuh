@@ -350,7 +350,8 @@ int choose_splits(int64_t M, int64_t N, int64_t K, int bn);
 int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A,
             int64_t lda, const __nv_bfloat16* B, int64_t ldb, float beta, float* C, __nv_bfloat16* Cb,
             int64_t ldc, const float* bias, int splits, float* split_ws, cudaStream_t st, int row_perm_h = 0,
-            const float* alpha_dev = nullptr, bool keep_partials = false, int* splits_used = nullptr);
+            const float* alpha_dev = nullptr, bool keep_partials = false, int* splits_used = nullptr,
+            int force_bn = 0);
 
 }  // namespace tc
 }  // namespace snt

@@ -140,15 +140,20 @@ struct CeBwdEpi {
                             // into the consumers' alpha: scaling first would round every target entry the same way)
   int64_t ldo;
 
-  using Pre = tc::NoPre;
-  __device__ __forceinline__ void prefetch(Pre&, int, int, int, int) const {}
+  struct Pre { float l2; int tgt; };
+  __device__ __forceinline__ void prefetch(Pre& p, int m_blk, int, int ew, int lane) const {
+    const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
+    const bool row_ok = row < M;
+    p.l2 = row_ok ? lse[row] * LOG2E : 0.f;
+    p.tgt = row_ok ? (int)targets[row] : -1;
+  }
   __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane,
-                                       const Pre&, uint8_t* wsm) const {
+                                       const Pre& pre, uint8_t* wsm) const {
     const int half = ew >> 2;
     const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
     const bool row_ok = row < M;
-    const float l2 = row_ok ? lse[row] * LOG2E : 0.f;
-    const int tgt = row_ok ? (int)targets[row] : -1;
+    const float l2 = pre.l2;
+    const int tgt = pre.tgt;
     bf* orow = out + (int64_t)row * ldo;
 #pragma unroll 1
     for (int c = 0; c < CE_BN / 64; ++c) {
@@ -364,6 +369,14 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
   SNT_CHECK(cast_bf16(w_out, w.wb, V * H, st));
   CUtensorMap tb;
   SNT_CHECK(tc::make_operand_tmap(&tb, w.wb, false, V, H, H, CE_BN));
+  // tile width for dW_out: whichever of 256 / 128 wastes less of its last wave
+  int dw_bn = 0;
+  if (H >= 256) {
+    const int64_t sms = tc::sm_count(), mt = (V + 127) / 128;
+    const int64_t t256 = mt * ((H + 255) / 256), t128 = mt * ((H + 127) / 128);
+    const double c256 = (double)((t256 + sms - 1) / sms) * 2.0, c128 = (double)((t128 + sms - 1) / sms) * 1.15;
+    dw_bn = c128 < c256 ? 128 : 256;
+  }
   for (int64_t r0 = 0; r0 < N; r0 += w.R) {
     const int64_t r = N - r0 < w.R ? N - r0 : w.R;
     const float acc = r0 > 0 ? 1.f : 0.f;
@@ -382,27 +395,10 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
     if (sp < 1) sp = 1;
     SNT_CHECK(tc::gemm_tc(false, true, r, H, V, scale, w.dl, w.Vp, w.wb, H, 0.f, d_hs + r0 * H, nullptr, H, nullptr, sp,
                           w.sws, st, 0, dloss));
-    // dW_out[V,H] += dlogits^T[V,r] . Hs[r,H]   (both operands MN-major).  ceil(V/128) x (H/256) tiles rarely fill
-    // whole waves: the row tiles that fill complete waves run unsplit, the few left over are split along K so they
-    // occupy all SMs instead of a nearly empty last wave.
-    {
-      const int64_t n_tiles = (H + 255) / 256, m_tiles = (V + 127) / 128;
-      const int64_t sms = tc::sm_count();
-      int64_t m_main = m_tiles;
-      if (H >= 256 && m_tiles * n_tiles > sms && (m_tiles * n_tiles) % sms != 0 && (m_tiles * n_tiles) % sms < sms / 2)
-        m_main = (m_tiles * n_tiles / sms) * sms / n_tiles;
-      const int64_t v_main = m_main < m_tiles ? m_main * 128 : V;
-      SNT_CHECK(tc::gemm_tc(true, true, v_main, H, r, scale, w.dl, w.Vp, hs_b + r0 * H, H, acc, d_w_out, nullptr, H,
-                            nullptr, 1, nullptr, st, 0, dloss));
-      if (v_main < V) {
-        const int64_t v_tail = V - v_main;  // <= 1024 rows by construction when sms <= 296
-        int sp = (int)(sms / (((v_tail + 127) / 128) * n_tiles));
-        if (sp > MAX_SPLITS) sp = MAX_SPLITS;
-        if (v_tail > 1024) sp = 1;
-        SNT_CHECK(tc::gemm_tc(true, true, v_tail, H, r, scale, w.dl + v_main, w.Vp, hs_b + r0 * H, H, acc,
-                              d_w_out + v_main * H, nullptr, H, nullptr, sp, w.sws, st, 0, dloss));
-      }
-    }
+    // dW_out[V,H] += dlogits^T[V,r] . Hs[r,H]   (both operands MN-major).  ceil(V/128) x (H/BN) tiles rarely fill whole
+    // waves; 128-wide tiles give the finer granularity (316 tiles = 3 short rounds instead of 2 long ones at V=10000).
+    SNT_CHECK(tc::gemm_tc(true, true, V, H, r, scale, w.dl, w.Vp, hs_b + r0 * H, H, acc, d_w_out, nullptr, H, nullptr, 1,
+                          nullptr, st, 0, dloss, false, nullptr, /*force_bn=*/dw_bn));
     SNT_CHECK(colsum_bf16(w.dl, r, V, w.Vp, acc, w.db, w.cpart, st));
   }
   scale_vec_kernel<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(w.db, V, scale, dloss, d_b_out);
