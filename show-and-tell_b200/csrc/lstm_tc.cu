@@ -13,6 +13,8 @@
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 
+#include <stdlib.h>
+
 namespace snt {
 namespace bf16 {
 
@@ -20,17 +22,15 @@ typedef __nv_bfloat16 bf;
 constexpr int MAX_SPLITS = 16;
 constexpr float LOG2E_F = 1.4426950408889634f;
 
-__device__ __forceinline__ float ex2f_(float x) {
+// Gate non-linearities on the SFU: ONE MUFU.TANH per value (tanh.approx.f32, max relative error 2^-11 — below the
+// bf16 rounding (2^-9) applied to every activation that leaves the epilogue).  The exp2 + reciprocal formulation costs
+// two MUFU ops per value and made the 10-transcendental-per-unit gate epilogue MUFU-bound (16 lanes/clk/SM).
+__device__ __forceinline__ float tanh_(float x) {
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float sigm(float x) { return __fdividef(1.f, 1.f + ex2f_(-x * LOG2E_F)); }
-__device__ __forceinline__ float tanh_(float x) {
-  const float e = ex2f_(-2.f * LOG2E_F * fabsf(x));  // in (0,1]: no overflow
-  const float t = __fdividef(1.f - e, 1.f + e);
-  return copysignf(t, x);
-}
+__device__ __forceinline__ float sigm(float x) { return fmaf(0.5f, tanh_(0.5f * x), 0.5f); }
 __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -221,6 +221,507 @@ struct LstmBwdEpi {
   }
 };
 
+// =====================================================================================================================
+// Persistent forward recurrence: ONE cooperative launch runs all T steps.  CTA (m_blk, n_blk) owns 128 batch rows x
+// 32 hidden units (128 interleaved gate columns) for the whole sequence:
+//   * its W_hh' slice [128, H] is TMA-loaded into shared memory once and stays resident; c_t stays in registers,
+//   * per step only h_{t-1}[128, H] streams in (TMA, 4-stage ring), tcgen05.mma accumulates into one of two TMEM
+//     accumulators, 16 epilogue warps (one 32-row x 32-column chunk each) run the gate math,
+//   * sequences are independent, so step t+1 of a row block depends only on the num_n CTAs of the SAME row block.
+//     They synchronise through global arrival counters, one per (row block, step, 64-unit k-block): a consumer
+//     starts fetching k-block kb of h_t as soon as the two CTAs that produce it have published, so the exchange
+//     overlaps the stragglers' epilogues.  No grid-wide barrier, no relaunch.
+//   * the epilogue publishes h_t (the only thing other CTAs wait for) first; c_t and the saved activations are
+//     stored after the release, off the critical path.
+// h_t is written with generic stores and read back by other CTAs through TMA (async proxy): writers execute
+// fence.proxy.async + __threadfence before the release, the reader fences again after its acquire.
+// =====================================================================================================================
+constexpr int PF_STAGES = 4;
+constexpr int PF_EPI_WARPS = 16;
+constexpr int PF_THREADS = 128 + 32 * PF_EPI_WARPS;
+constexpr int PF_FLAGS_PER_STEP = 8;  // k-blocks of 64 hidden units (H <= 512)
+
+struct PersistFwdParams {
+  int H, T, num_n;
+  const bf* gx; float* cs; bf* hs; bf* hprev; bf* act;
+  int* flags;  // [num_m0][T][PF_FLAGS_PER_STEP] arrival counters, zeroed before the launch
+#ifdef SNT_LSTM_DBG
+  long long* dbg;  // [T][8] clock64 stamps of one block
+#endif
+};
+#ifdef SNT_LSTM_DBG
+#define DBG_STAMP(t, k) do { if (blockIdx.x == SNT_DBG_BLOCK) p.dbg[(t) * 8 + (k)] = clock64(); } while (0)
+#else
+#define DBG_STAMP(t, k) do {} while (0)
+#endif
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(PF_THREADS, 1)
+lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ PackInfo pk, const PersistFwdParams p) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int KB = (p.H + BK - 1) / BK;                 // k-blocks of the contraction (<= 8)
+  uint8_t* sW = smem;                                 // KB x 16 KB, resident
+  uint8_t* sA = smem + KB * 16384;                    // PF_STAGES x 16 KB ring
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + PF_STAGES * 16384);
+  uint64_t* empty = full + PF_STAGES;
+  uint64_t* wbar = empty + PF_STAGES;
+  uint64_t* tfull = wbar + 1;                         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x % p.num_n, m_blk = blockIdx.x / p.num_n;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < PF_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(wbar, 1);
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tfull[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // number of steps this row block is alive (batch_sizes is non-increasing)
+  int t_end = 0;
+  while (t_end < p.T && m_blk * BM < pk.off[t_end + 1] - pk.off[t_end]) ++t_end;
+
+  // step 0 needs no contraction: h_{-1} = 0, so the recurrent term vanishes and the epilogue starts from Gx' alone
+  if (warp == 0) {
+    // ================= TMA producer (lane 0 issues, lanes 0..KB-1 poll one k-block counter each) =================
+    int stage = 0;
+    uint32_t phase = 0;
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, (uint32_t)(KB * 16384));
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * 16384, &tmB, wbar, kb * BK, n_blk * 128);
+    }
+    const int need = min(2, p.num_n - 2 * lane);  // CTAs that produce the 64 hidden units of k-block `lane`
+    for (int t = 1; t < t_end; ++t) {
+      const int* f = p.flags + ((int64_t)m_blk * p.T + (t - 1)) * PF_FLAGS_PER_STEP;
+      int kb = 0;
+      const long long t0 = clock64();
+      while (kb < KB) {
+        const int v = lane < KB ? ld_acquire_gpu(f + lane) : 0;
+        const unsigned waiting = __ballot_sync(0xffffffffu, lane < KB && v < need);
+        const int ready = waiting ? __ffs((int)waiting) - 1 : KB;  // k-blocks [0, ready) are published
+        if (ready <= kb) {
+          if (clock64() - t0 > SNT_MBAR_TIMEOUT_CYCLES) {
+            if (lane == 0) printf("snt: lstm persistent flag timeout block %d step %d\n", (int)blockIdx.x, t);
+            __trap();
+          }
+          continue;
+        }
+        if (lane == 0) {
+          if (kb == 0) DBG_STAMP(t, 0);
+          fence_proxy_async_all();
+          for (int k = kb; k < ready; ++k) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], 16384);
+            tma_load_2d(sA + stage * 16384, &tmA, &full[stage], k * BK, pk.off[t] + m_blk * BM);
+            if (++stage == PF_STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (ready == KB) DBG_STAMP(t, 1);
+        }
+        kb = ready;
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ================= MMA issuer =================
+      constexpr uint32_t idesc = make_idesc_bf16(BM, 128, false, false);
+      mbar_wait(wbar, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 1; t < t_end; ++t) {
+        // accumulator (t & 1) is free: its previous reader (step t-2's epilogue) finished before h_{t-1} could exist
+        const uint32_t tmem_d = tmem_base + (uint32_t)((t & 1) * 128);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          if (kb == 0) DBG_STAMP(t, 2);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * 16384);
+          const uint32_t b_addr = smem_u32(sW + kb * 16384);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_d, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
+                      idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == PF_STAGES) { stage = 0; phase ^= 1; }
+        }
+        DBG_STAMP(t, 3);
+        umma_commit(&tfull[t & 1]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= gate epilogue: warp -> (TMEM lane quadrant q, 32-column chunk c) =================
+    const int q = warp & 3, c = (warp - 4) >> 2;
+    const int row = m_blk * BM + q * 32 + lane;
+    const int H = p.H, H4 = 4 * p.H;
+    const int col0 = n_blk * 128 + c * 32;  // first interleaved gate column of this thread's 8 hidden units
+    const int j0 = col0 >> 2;
+    const bool col_ok = col0 < H4;
+    const bool stamp = threadIdx.x == 128;
+    float creg[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) creg[u] = 0.f;
+    uint4 gxv[4];
+    if (col_ok && t_end > 0 && row < pk.off[1]) {
+      const uint4* g4 = reinterpret_cast<const uint4*>(p.gx + (int64_t)row * H4 + col0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gxv[k] = __ldg(g4 + k);
+    }
+    for (int t = 0; t < t_end; ++t) {
+      const int bs = pk.off[t + 1] - pk.off[t];
+      const int bs_next = t + 1 < p.T ? pk.off[t + 2] - pk.off[t + 1] : 0;
+      const bool ok = col_ok && row < bs;
+      uint32_t r[32];
+      if (t > 0) {
+        // tfull[a] completes once per use of accumulator a: steps 1,3,5,.. for a = 1 and 2,4,6,.. for a = 0
+        const int a = t & 1;
+        mbar_wait(&tfull[a], (uint32_t)(((t >> 1) & 1) ^ (a ^ 1)));
+        if (stamp) DBG_STAMP(t, 4);
+        tcgen05_fence_after();
+        tmem_ld32(tmem_base + (uint32_t)(a * 128 + c * 32) + ((uint32_t)(q * 32) << 16), r);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) r[k] = 0u;
+      }
+      float cn[8];
+      uint32_t ap[16];
+      if (ok) {
+        float hn[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 8 bf16 = 2 hidden units per 16-byte load
+          const uint4 v = gxv[k];
+          const float2 a0 = unpack_bf2(v.x), a1 = unpack_bf2(v.y), b0 = unpack_bf2(v.z), b1 = unpack_bf2(v.w);
+          const float gi[2][4] = {{a0.x, a0.y, a1.x, a1.y}, {b0.x, b0.y, b1.x, b1.y}};
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int u = 2 * k + e;
+            const float i_ = sigm(__uint_as_float(r[4 * u]) + gi[e][0]);
+            const float f_ = sigm(__uint_as_float(r[4 * u + 1]) + gi[e][1]);
+            const float g_ = tanh_(__uint_as_float(r[4 * u + 2]) + gi[e][2]);
+            const float o_ = sigm(__uint_as_float(r[4 * u + 3]) + gi[e][3]);
+            cn[u] = f_ * creg[u] + i_ * g_;
+            hn[u] = o_ * tanh_(cn[u]);
+            creg[u] = cn[u];
+            ap[2 * u] = pack_bf2(i_, f_);
+            ap[2 * u + 1] = pack_bf2(g_, o_);
+          }
+        }
+        // publish h_t first: it is all the other CTAs of this row block wait for
+        const uint4 hv = make_uint4(pack_bf2(hn[0], hn[1]), pack_bf2(hn[2], hn[3]), pack_bf2(hn[4], hn[5]),
+                                    pack_bf2(hn[6], hn[7]));
+        if (row < bs_next) *reinterpret_cast<uint4*>(p.hprev + ((int64_t)pk.off[t + 1] + row) * H + j0) = hv;
+        *reinterpret_cast<uint4*>(p.hs + ((int64_t)pk.off[t] + row) * H + j0) = hv;
+      }
+      if (stamp) DBG_STAMP(t, 5);
+      if (t + 1 < t_end) {
+        fence_proxy_async_all();  // generic-proxy writes -> visible to other CTAs' TMA reads
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (stamp) DBG_STAMP(t, 6);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
+        if (threadIdx.x == 128)
+          atomicAdd(p.flags + ((int64_t)m_blk * p.T + t) * PF_FLAGS_PER_STEP + (n_blk >> 1), 1);
+        if (stamp) DBG_STAMP(t, 7);
+      }
+      // off the critical path: c_t and the activations kept for BPTT, then next step's input projection
+      if (ok) {
+        float4* cd = reinterpret_cast<float4*>(p.cs + ((int64_t)pk.off[t] + row) * H + j0);
+        cd[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        cd[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+        if (p.act) {  // training only
+          uint4* ad = reinterpret_cast<uint4*>(p.act + ((int64_t)pk.off[t] + row) * H4 + col0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ad[k] = make_uint4(ap[4 * k], ap[4 * k + 1], ap[4 * k + 2], ap[4 * k + 3]);
+        }
+      }
+      if (col_ok && t + 1 < t_end && row < bs_next) {
+        const uint4* g4 = reinterpret_cast<const uint4*>(p.gx + ((int64_t)pk.off[t + 1] + row) * H4 + col0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gxv[k] = __ldg(g4 + k);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// =====================================================================================================================
+// Persistent BPTT recurrence, the mirror image of the forward kernel: CTA (m_blk, n_blk) owns 128 batch rows x 32 hidden
+// units for all T steps, going backward in time.
+//   * resident in shared memory: the [32 units, 4H] slice of W_hh'^T (K-major, 128 KB at H = 512); dL/dc stays in
+//     registers,
+//   * per step the CTA streams dG'_{t+1}[128 rows, 4H] (the pre-activation gradients all num_n CTAs of the row block
+//     produced one step earlier) through a TMA ring into tcgen05.mma (M = 128, N = 32), accumulating the recurrent
+//     dL/dh_t for its 32 units in TMEM; 16 epilogue warps add dL/dh_t from above, run the cell backward and publish
+//     dG'_t (bf16) — the A operand of step t-1 and later of the weight-gradient GEMMs,
+//   * same release/acquire counters as the forward kernel, one per (row block, step, producer CTA): k-blocks
+//     2n, 2n+1 of dG'_{t+1} are fetched as soon as CTA n has published them.
+// =====================================================================================================================
+constexpr int PB_STAGES = 5;
+constexpr int PB_FLAGS_PER_STEP = 16;  // producer CTAs per row block (H <= 512)
+
+struct PersistBwdParams {
+  int H, T, num_n;
+  const float* d_hs; const bf* act; const float* cs; bf* dg;
+  int* flags;  // [num_m0][T][PB_FLAGS_PER_STEP]
+#ifdef SNT_LSTM_DBG
+  long long* dbg;
+#endif
+};
+
+// W_hh (fp32, gate-major rows g*H + j, [4H, H]) -> bf16 W^T with interleaved contraction index: out[n][4j + g]
+__global__ void __launch_bounds__(256)
+perm_transpose_bf16_kernel(const float* __restrict__ w, int H, bf* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, r0 = blockIdx.y * 32;  // r = gate-major source row
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, n = n0 + tx;
+    tile[i][tx] = (r < 4 * H && n < H) ? w[(int64_t)r * H + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i, r = r0 + tx;
+    if (n < H && r < 4 * H) {
+      const int g = r / H, j = r - g * H;
+      out[(int64_t)n * 4 * H + 4 * j + g] = __float2bfloat16_rn(tile[tx][i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PF_THREADS, 1)
+lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ PackInfo pk, const PersistBwdParams p) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int KB = (4 * p.H) / BK;                      // k-blocks of the contraction over interleaved gate columns
+  uint8_t* sW = smem;                                 // KB x 4 KB (32 units x 64 k), resident
+  uint8_t* sA = smem + KB * 4096;                     // PB_STAGES x 16 KB ring
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + PB_STAGES * 16384);
+  uint64_t* empty = full + PB_STAGES;
+  uint64_t* wbar = empty + PB_STAGES;
+  uint64_t* tfull = wbar + 1;                         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x % p.num_n, m_blk = blockIdx.x / p.num_n;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < PB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(wbar, 1);
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tfull[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this row block is alive for steps [0, t_end); going backward it starts at t_end - 1.  Step index s counts from
+  // there: t = t_end - 1 - s.  s = 0 has no recurrent term (no row of the block is alive at t + 1).
+  int t_end = 0;
+  while (t_end < p.T && m_blk * BM < pk.off[t_end + 1] - pk.off[t_end]) ++t_end;
+
+  if (warp == 0) {
+    // ================= TMA producer (lane 0 issues, lanes 0..num_n-1 poll one producer counter each) =================
+    int stage = 0;
+    uint32_t phase = 0;
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, (uint32_t)(KB * 4096));
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * 4096, &tmB, wbar, kb * BK, n_blk * 32);
+    }
+    for (int s = 1; s < t_end; ++s) {
+      const int t = t_end - 1 - s;
+      const int* f = p.flags + ((int64_t)m_blk * p.T + (t + 1)) * PB_FLAGS_PER_STEP;
+      int kb = 0;
+      const long long t0 = clock64();
+      while (kb < KB) {
+        const int v = lane < p.num_n ? ld_acquire_gpu(f + lane) : 0;
+        const unsigned waiting = __ballot_sync(0xffffffffu, lane < p.num_n && v < 1);
+        const int ready = waiting ? 2 * (__ffs((int)waiting) - 1) : KB;  // CTA n publishes k-blocks 2n, 2n+1
+        if (ready <= kb) {
+          if (clock64() - t0 > SNT_MBAR_TIMEOUT_CYCLES) {
+            if (lane == 0) printf("snt: lstm bwd persistent flag timeout block %d step %d\n", (int)blockIdx.x, t);
+            __trap();
+          }
+          continue;
+        }
+        if (lane == 0) {
+          if (kb == 0) DBG_STAMP(s, 0);
+          fence_proxy_async_all();
+          for (int k = kb; k < ready; ++k) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], 16384);
+            tma_load_2d(sA + stage * 16384, &tmA, &full[stage], k * BK, pk.off[t + 1] + m_blk * BM);
+            if (++stage == PB_STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (ready == KB) DBG_STAMP(s, 1);
+        }
+        kb = ready;
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ================= MMA issuer =================
+      constexpr uint32_t idesc = make_idesc_bf16(BM, 32, false, false);
+      mbar_wait(wbar, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 1; s < t_end; ++s) {
+        const uint32_t tmem_d = tmem_base + (uint32_t)((s & 1) * 32);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          if (kb == 0) DBG_STAMP(s, 2);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * 16384);
+          const uint32_t b_addr = smem_u32(sW + kb * 4096);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_d, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
+                      idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == PB_STAGES) { stage = 0; phase ^= 1; }
+        }
+        DBG_STAMP(s, 3);
+        umma_commit(&tfull[s & 1]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= cell-backward epilogue: warp -> (TMEM lane quadrant q, 8-unit chunk c) =================
+    const int q = warp & 3, c = (warp - 4) >> 2;
+    const int row = m_blk * BM + q * 32 + lane;
+    const int H = p.H, H4 = 4 * p.H;
+    const int j0 = n_blk * 32 + c * 8;
+    const bool stamp = threadIdx.x == 128;
+    float dcreg[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dcreg[u] = 0.f;
+    // inputs of one step for this thread's (row, 8 units)
+    float4 dh4[2], c4[2], p4[2];
+    uint4 a4[4];
+    auto load_inputs = [&](int t) {
+      const int bs = pk.off[t + 1] - pk.off[t];
+      if (row < bs) {
+        const int64_t o1 = ((int64_t)pk.off[t] + row) * H + j0;
+        dh4[0] = *reinterpret_cast<const float4*>(p.d_hs + o1);
+        dh4[1] = *reinterpret_cast<const float4*>(p.d_hs + o1 + 4);
+        c4[0] = *reinterpret_cast<const float4*>(p.cs + o1);
+        c4[1] = *reinterpret_cast<const float4*>(p.cs + o1 + 4);
+        if (t > 0) {
+          const int64_t o0 = ((int64_t)pk.off[t - 1] + row) * H + j0;
+          p4[0] = *reinterpret_cast<const float4*>(p.cs + o0);
+          p4[1] = *reinterpret_cast<const float4*>(p.cs + o0 + 4);
+        } else {
+          p4[0] = p4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const uint4* ap = reinterpret_cast<const uint4*>(p.act + ((int64_t)pk.off[t] + row) * H4 + 4 * j0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a4[k] = ap[k];
+      }
+    };
+    if (t_end > 0) load_inputs(t_end - 1);
+    for (int s = 0; s < t_end; ++s) {
+      const int t = t_end - 1 - s;
+      const int bs = pk.off[t + 1] - pk.off[t];
+      const int bs_next = t + 1 < p.T ? pk.off[t + 2] - pk.off[t + 1] : 0;
+      const bool ok = row < bs;
+      const bool has_next = row < bs_next;  // rows still alive at step t+1 carry recurrent gradient
+      uint32_t r[8];
+      if (s > 0) {
+        const int a = s & 1;
+        mbar_wait(&tfull[a], (uint32_t)(((s >> 1) & 1) ^ (a ^ 1)));
+        if (stamp) DBG_STAMP(s, 4);
+        tcgen05_fence_after();
+        tmem_ld8(tmem_base + (uint32_t)(a * 32 + c * 8) + ((uint32_t)(q * 32) << 16), r);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = 0u;
+      }
+      if (ok) {
+        const float dhv[8] = {dh4[0].x, dh4[0].y, dh4[0].z, dh4[0].w, dh4[1].x, dh4[1].y, dh4[1].z, dh4[1].w};
+        const float cv[8] = {c4[0].x, c4[0].y, c4[0].z, c4[0].w, c4[1].x, c4[1].y, c4[1].z, c4[1].w};
+        const float pv[8] = {p4[0].x, p4[0].y, p4[0].z, p4[0].w, p4[1].x, p4[1].y, p4[1].z, p4[1].w};
+        const uint32_t a[16] = {a4[0].x, a4[0].y, a4[0].z, a4[0].w, a4[1].x, a4[1].y, a4[1].z, a4[1].w,
+                                a4[2].x, a4[2].y, a4[2].z, a4[2].w, a4[3].x, a4[3].y, a4[3].z, a4[3].w};
+        uint32_t go[16];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float2 if_ = unpack_bf2(a[2 * u]), go_ = unpack_bf2(a[2 * u + 1]);
+          const float i_ = if_.x, f_ = if_.y, g_ = go_.x, o_ = go_.y;
+          const float tc_ = tanh_(cv[u]);
+          const float dh = dhv[u] + (has_next ? __uint_as_float(r[u]) : 0.f);
+          const float dc = dcreg[u] + dh * o_ * (1.f - tc_ * tc_);
+          go[2 * u] = pack_bf2(dc * g_ * i_ * (1.f - i_), dc * pv[u] * f_ * (1.f - f_));
+          go[2 * u + 1] = pack_bf2(dc * i_ * (1.f - g_ * g_), dh * tc_ * o_ * (1.f - o_));
+          dcreg[u] = dc * f_;
+        }
+        uint4* gd = reinterpret_cast<uint4*>(p.dg + ((int64_t)pk.off[t] + row) * H4 + 4 * j0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gd[k] = make_uint4(go[4 * k], go[4 * k + 1], go[4 * k + 2], go[4 * k + 3]);
+      }
+      if (stamp) DBG_STAMP(s, 5);
+      if (s + 1 < t_end) {
+        fence_proxy_async_all();  // generic-proxy writes -> visible to other CTAs' TMA reads
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (stamp) DBG_STAMP(s, 6);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
+        if (threadIdx.x == 128) atomicAdd(p.flags + ((int64_t)m_blk * p.T + t) * PB_FLAGS_PER_STEP + n_blk, 1);
+        if (stamp) DBG_STAMP(s, 7);
+        load_inputs(t - 1);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
 // ---- backward step, split-K variant: the recurrent contraction dG'_{t+1} . W_hh' runs as a split-K GEMM over all SMs
 // (partials in an L2-resident scratch), and this coalesced pointwise kernel sums the partials in a fixed order and
 // runs the cell backward.  One thread = one packed row x 8 hidden units.
@@ -284,7 +785,7 @@ lstm_bwd_point_kernel(int bs, int bs_next, int H, const float* __restrict__ d_hs
 
 // ---------------------------------------------------------------------------------------------------------------------
 struct LstmWs {
-  float* bsum; bf* w_ih; bf* w_hh; bf* gx; float* dc_state; float* cpart; float* tmp; float* sws; bool ok;
+  float* bsum; bf* w_ih; bf* w_hh; bf* w_hh_t; bf* gx; float* dc_state; float* cpart; float* tmp; float* sws; int* flags; bool ok;
 };
 static int64_t csb_partials(int64_t R, int64_t C) { return ((R + 255) / 256) * C; }
 static LstmWs carve(void* ws, int64_t ws_bytes, int64_t N, int64_t B, int64_t In, int64_t H) {
@@ -298,13 +799,28 @@ static LstmWs carve(void* ws, int64_t ws_bytes, int64_t N, int64_t B, int64_t In
   r.cpart = w.take<float>(csb_partials(N, 4 * H));
   r.tmp = w.take<float>(4 * H);
   r.sws = w.take<float>(MAX_SPLITS * 4 * H * (In > H ? In : H));
+  r.flags = w.take<int>(((B + 127) / 128) * SNT_MAX_T * PB_FLAGS_PER_STEP);
+  r.w_hh_t = w.take<bf>(4 * H * H);
   r.ok = w.ok();
   return r;
 }
 int64_t lstm_ws_bytes(int64_t N, int64_t B, int64_t In, int64_t H) {
   return 2 * ws_bytes_for(4 * H, 4) + ws_bytes_for(4 * H * In, 2) + ws_bytes_for(4 * H * H, 2) +
          ws_bytes_for(N * 4 * H, 2) + ws_bytes_for(B * H, 4) + ws_bytes_for(csb_partials(N, 4 * H), 4) +
-         ws_bytes_for(MAX_SPLITS * 4 * H * (In > H ? In : H), 4);
+         ws_bytes_for(MAX_SPLITS * 4 * H * (In > H ? In : H), 4) + ws_bytes_for(((B + 127) / 128) * SNT_MAX_T * PB_FLAGS_PER_STEP, 4) + ws_bytes_for(4 * H * H, 2);
+}
+
+// the persistent kernels need every CTA co-resident (cooperative launch) and ~200 KB of shared memory
+static void persist_caps(int* coop, int* max_smem) {
+  static int c = -1, m = 0;
+  if (c < 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&c, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&m, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  }
+  *coop = c;
+  *max_smem = m;
 }
 
 static int prep_weights(const LstmWs& w, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
@@ -351,6 +867,52 @@ int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const flo
   CUtensorMap ta, tb;
   SNT_CHECK(tc::make_operand_tmap(&ta, hp_b, false, N, H, H, tc::BM));
   SNT_CHECK(tc::make_operand_tmap(&tb, w.w_hh, false, 4 * H, H, H, 128));
+  {
+    // persistent path: every (row block, column block) CTA must be co-resident (cooperative launch) and the W_hh'
+    // slice must fit in shared memory next to the h ring
+    const int num_m0 = (int)((B + tc::BM - 1) / tc::BM), num_n = (int)((4 * H + 127) / 128);
+    const int KB = (int)((H + tc::BK - 1) / tc::BK);
+    const size_t smem = (size_t)(KB + PF_STAGES) * 16384 + 1024 + 256;
+    int coop = 0, max_smem = 0;
+    persist_caps(&coop, &max_smem);
+    if (coop == 1 && !getenv("SNT_NO_PERSISTENT") && (int64_t)num_m0 * num_n <= tc::sm_count() &&
+        smem <= (size_t)max_smem && KB <= PF_FLAGS_PER_STEP && w.flags != nullptr) {
+      SNT_CUDA(cudaFuncSetAttribute(lstm_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SNT_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)num_m0 * T * PF_FLAGS_PER_STEP, st));
+      PersistFwdParams pp;
+      pp.H = (int)H; pp.T = T; pp.num_n = num_n; pp.gx = w.gx; pp.cs = cs; pp.hs = hs_b; pp.hprev = hp_b; pp.act = act;
+      pp.flags = w.flags;
+#ifdef SNT_LSTM_DBG
+      static long long* dbg_dev = nullptr;
+      if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * SNT_MAX_T * 8);
+      cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * SNT_MAX_T * 8, st);
+      pp.dbg = dbg_dev;
+#endif
+      PackInfo pkc = pk;
+      void* args[] = {(void*)&ta, (void*)&tb, (void*)&pkc, (void*)&pp};
+      count_launch();
+      SNT_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_fwd_persistent_kernel, dim3((unsigned)(num_m0 * num_n)),
+                                           dim3(PF_THREADS), args, smem, st));
+#ifdef SNT_LSTM_DBG
+      {
+        static int printed = 0;
+        if (printed++ == 3) {
+          long long h[SNT_MAX_T * 8];
+          cudaStreamSynchronize(st);
+          cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+          const long long t0 = h[5];
+          fprintf(stderr, "[lstm dbg] block %d: step: flag0_seen tma_issued first_full mma_issued tfull_seen h_stored fenced flag_set (cycles since step-0 start)\n", SNT_DBG_BLOCK);
+          for (int t = 0; t < T; ++t) {
+            fprintf(stderr, "[lstm dbg] %2d:", t);
+            for (int k = 0; k < 8; ++k) fprintf(stderr, " %8lld", h[t * 8 + k] - t0);
+            fprintf(stderr, "\n");
+          }
+        }
+      }
+#endif
+      return SNT_OK;
+    }
+  }
   for (int t = 0; t < T; ++t) {
     const int bs = pk.off[t + 1] - pk.off[t];
     const int bs_next = t + 1 < T ? pk.off[t + 2] - pk.off[t + 1] : 0;
@@ -387,9 +949,60 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
   const bf* act = (const bf*)gates;
   bf* dg = (bf*)gates + N * 4 * H;
   SNT_CHECK(prep_weights(w, w_ih, w_hh, nullptr, nullptr, In, H, st));
+  bool persistent = false;
+  {
+    const int num_m0 = (int)((B + tc::BM - 1) / tc::BM), num_n = (int)(H / 32);
+    const int KB = (int)(4 * H / tc::BK);
+    const size_t smem = (size_t)KB * 4096 + (size_t)PB_STAGES * 16384 + 1024 + 256;
+    int coop = 0, max_smem = 0;
+    persist_caps(&coop, &max_smem);
+    if (coop == 1 && !getenv("SNT_NO_PERSISTENT") && H % 32 == 0 && num_n <= PB_FLAGS_PER_STEP &&
+        (int64_t)num_m0 * num_n <= tc::sm_count() && smem <= (size_t)max_smem && w.flags && w.w_hh_t) {
+      perm_transpose_bf16_kernel<<<dim3((unsigned)((H + 31) / 32), (unsigned)((4 * H + 31) / 32)), 256, 0, st>>>(
+          w_hh, (int)H, w.w_hh_t);
+      SNT_LAUNCH_CHECK("perm_transpose_bf16_kernel");
+      CUtensorMap ta, tb;
+      SNT_CHECK(tc::make_operand_tmap(&ta, dg, false, N, 4 * H, 4 * H, tc::BM));
+      SNT_CHECK(tc::make_operand_tmap(&tb, w.w_hh_t, false, H, 4 * H, 4 * H, 32));
+      SNT_CUDA(cudaFuncSetAttribute(lstm_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SNT_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)num_m0 * T * PB_FLAGS_PER_STEP, st));
+      PersistBwdParams pp;
+      pp.H = (int)H; pp.T = T; pp.num_n = num_n; pp.d_hs = d_hs; pp.act = act; pp.cs = cs; pp.dg = dg;
+      pp.flags = w.flags;
+#ifdef SNT_LSTM_DBG
+      static long long* dbg_dev = nullptr;
+      if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * SNT_MAX_T * 8);
+      cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * SNT_MAX_T * 8, st);
+      pp.dbg = dbg_dev;
+#endif
+      PackInfo pkc = pk;
+      void* args[] = {(void*)&ta, (void*)&tb, (void*)&pkc, (void*)&pp};
+      count_launch();
+      SNT_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_persistent_kernel, dim3((unsigned)(num_m0 * num_n)),
+                                           dim3(PF_THREADS), args, smem, st));
+#ifdef SNT_LSTM_DBG
+      {
+        static int printed = 0;
+        if (printed++ == 3) {
+          long long h[SNT_MAX_T * 8];
+          cudaStreamSynchronize(st);
+          cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+          const long long t0 = h[5];
+          fprintf(stderr, "[lstm bwd dbg] block %d: s: flag0_seen tma_issued first_full mma_issued tfull_seen dg_stored fenced flag_set\n", SNT_DBG_BLOCK);
+          for (int t = 0; t < T; ++t) {
+            fprintf(stderr, "[lstm bwd dbg] %2d:", t);
+            for (int k = 0; k < 8; ++k) fprintf(stderr, " %8lld", h[t * 8 + k] - t0);
+            fprintf(stderr, "\n");
+          }
+        }
+      }
+#endif
+      persistent = true;
+    }
+  }
   // split-K keeps all SMs busy on the small per-step contraction; its partials never leave L2
   const int want_splits = 4;
-  for (int t = T - 1; t >= 0; --t) {
+  for (int t = T - 1; t >= 0 && !persistent; --t) {
     const int bs = pk.off[t + 1] - pk.off[t];
     const int bs_next = t + 1 < T ? pk.off[t + 2] - pk.off[t + 1] : 0;
     int used = 1;
