@@ -55,9 +55,14 @@ int linear_nt(const float* a, const float* w, const float* bias, int64_t M, int6
   bf* ab = wk.take<bf>(M * K);
   bf* wb = wk.take<bf>(N * K);
   if (!wk.ok()) { set_error("bf16 linear: workspace too small"); return SNT_EWORKSPACE; }
+  wk.take<bf>(M * pad8(N));
+  float* sws = wk.take<float>(MAX_SPLITS * N * K);  // shared with wgrad_tn's split-K scratch
   SNT_CHECK(cast_bf16(a, ab, M * K, st));
   SNT_CHECK(cast_bf16(w, wb, N * K, st));
-  return tc::gemm_tc(false, false, M, N, K, 1.f, ab, K, wb, K, 0.f, y, nullptr, N, bias, 1, nullptr, st);
+  // few output tiles (8 x 2 at B=1024, E=256) but a long contraction: split K over the idle SMs
+  int splits = sws ? tc::choose_splits(M, N, K, 0) : 1;
+  while (splits > 1 && (int64_t)splits * M > (int64_t)MAX_SPLITS * K) --splits;
+  return tc::gemm_tc(false, false, M, N, K, 1.f, ab, K, wb, K, 0.f, y, nullptr, N, bias, splits, sws, st);
 }
 
 int wgrad_tn(const float* dy, const float* a, int64_t M, int64_t N, int64_t K, float* dw, void* ws,

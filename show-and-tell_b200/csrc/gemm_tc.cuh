@@ -243,8 +243,9 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TileSch
 // ---- the plain epilogue: C = alpha*acc + bias[col] + beta*C, fp32 and/or bf16 out, optional split-K slices ----
 template <int BN>
 struct PlainEpi {
-  static constexpr int kWarps = 4;
-  static constexpr int kSmemPerWarp = 0;
+  static constexpr int kWarps = BN >= 128 ? 8 : 4;
+  static constexpr int kPitch = 80;  // bytes per staged row: 64 of data (16 fp32 / 32 bf16) + 16 of padding
+  static constexpr int kSmemPerWarp = 32 * kPitch;
   int M, N;                // valid extent
   float alpha, beta;
   const float* alpha_dev;  // optional device scalar multiplied into alpha (e.g. the incoming dloss)
@@ -257,71 +258,103 @@ struct PlainEpi {
 
   using Pre = NoPre;
   __device__ __forceinline__ void prefetch(Pre&, int, int, int, int) const {}
-  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane,
-                                       const Pre&, uint8_t*) const {
-    const int row = m_blk * BM + (ew & 3) * 32 + lane;
-    const bool row_ok = row < M;
-    const int drow = row_perm_h ? (row & 3) * row_perm_h + (row >> 2) : row;
-    const float a = alpha_dev ? alpha * alpha_dev[0] : alpha;
-    float* crow = C ? C + (int64_t)split * split_stride + (int64_t)drow * ldc : nullptr;
-    __nv_bfloat16* brow = Cb ? Cb + (int64_t)drow * ldc : nullptr;
-    const bool bias_al = !bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
-    const bool vec_ok = crow && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && bias_al;
-    const bool bvec_ok = !crow && brow && ((ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0) && bias_al;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int col0 = n_blk * BN + c * 32;
-      if (col0 >= N) break;  // warp-uniform
-      uint32_t r[32];
-      tmem_ld32(tmem_rows + (uint32_t)(c * 32), r);
-      tmem_ld_wait();
-      if (!row_ok) continue;
-      if (vec_ok && col0 + 32 <= N) {
-        float4* dst = reinterpret_cast<float4*>(crow + col0);
-        float4 o[8];
-        if (beta != 0.f) {  // all loads first: a load placed after a (possibly aliasing) store cannot be hoisted
+  // Accumulator rows live one per lane, so a direct store makes every instruction touch 32 different rows (16 bytes
+  // each).  Full 32-column chunks are instead transposed through a per-warp shared-memory stage (row pitch padded
+  // against bank conflicts) and written as whole 64-byte row segments (two rounds per chunk for fp32); the beta read of
+  // C happens in the same coalesced pattern.
+  struct Ctx {
+    int row0, n_blk, split, lane;
+    float a;
+    bool vec_ok, bvec_ok;
+    uint32_t wsa;
+  };
+  // one 32-column chunk of this warp's 32 accumulator rows
+  __device__ __forceinline__ void chunk(const Ctx& x, const uint32_t (&r)[32], int c) const {
+    const int col0 = x.n_blk * BN + c * 32;
+    if (col0 >= N) return;  // warp-uniform
+    const int lane = x.lane;
+    const float a = x.a;
+    const bool full = col0 + 32 <= N;
+    float4 bv[8];
+    if (bias && full && (x.vec_ok || x.bvec_ok)) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) o[q] = __ldcg(dst + q);
-        }
+      for (int q = 0; q < 8; ++q) bv[q] = __ldg(reinterpret_cast<const float4*>(bias + col0) + q);
+    } else {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int j = q * 4;
-          float4 v;
-          v.x = a * __uint_as_float(r[j]);
-          v.y = a * __uint_as_float(r[j + 1]);
-          v.z = a * __uint_as_float(r[j + 2]);
-          v.w = a * __uint_as_float(r[j + 3]);
-          if (bias) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-          }
-          if (beta != 0.f) {
-            v.x += beta * o[q].x; v.y += beta * o[q].y; v.z += beta * o[q].z; v.w += beta * o[q].w;
-          }
-          dst[q] = v;
-          if (brow) {
-            brow[col0 + j] = __float2bfloat16_rn(v.x);
-            brow[col0 + j + 1] = __float2bfloat16_rn(v.y);
-            brow[col0 + j + 2] = __float2bfloat16_rn(v.z);
-            brow[col0 + j + 3] = __float2bfloat16_rn(v.w);
-          }
-        }
-      } else if (bvec_ok && col0 + 32 <= N) {  // bf16-only output: 4 x 16-byte stores per 32 columns
-        uint4* dst = reinterpret_cast<uint4*>(brow + col0);
+      for (int q = 0; q < 8; ++q) bv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (x.vec_ok && full) {
+      float* cbase = C + (int64_t)x.split * split_stride + col0;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {  // 16 columns (64 bytes per row) per round
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const int j = q * 8 + h * 2;
-            float v0 = a * __uint_as_float(r[j]), v1 = a * __uint_as_float(r[j + 1]);
-            if (bias) { v0 += bias[col0 + j]; v1 += bias[col0 + j + 1]; }
-            __nv_bfloat162 t = __floats2bfloat162_rn(v0, v1);
-            pk[h] = *reinterpret_cast<uint32_t*>(&t);
-          }
-          dst[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          const int j = hf * 16 + q * 4;
+          const float4 b4 = bv[hf * 4 + q];
+          sts128(x.wsa + lane * kPitch + q * 16, __float_as_uint(fmaf(a, __uint_as_float(r[j]), b4.x)),
+                 __float_as_uint(fmaf(a, __uint_as_float(r[j + 1]), b4.y)),
+                 __float_as_uint(fmaf(a, __uint_as_float(r[j + 2]), b4.z)),
+                 __float_as_uint(fmaf(a, __uint_as_float(r[j + 3]), b4.w)));
         }
-      } else {
+        __syncwarp();
+        float4* dst[4];
+        float4 o[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int grow = x.row0 + it * 8 + (lane >> 2);
+          const int dr = row_perm_h ? (grow & 3) * row_perm_h + (grow >> 2) : grow;
+          dst[it] = grow < M ? reinterpret_cast<float4*>(cbase + (int64_t)dr * ldc + hf * 16) + (lane & 3) : nullptr;
+        }
+        if (beta != 0.f) {  // all loads first: a load placed after a (possibly aliasing) store cannot be hoisted
+#pragma unroll
+          for (int it = 0; it < 4; ++it) o[it] = dst[it] ? __ldcg(dst[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const uint4 u = lds128(x.wsa + (it * 8 + (lane >> 2)) * kPitch + (lane & 3) * 16);
+          float4 v = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+          if (beta != 0.f) {
+            v.x += beta * o[it].x; v.y += beta * o[it].y; v.z += beta * o[it].z; v.w += beta * o[it].w;
+          }
+          if (dst[it]) *dst[it] = v;
+        }
+        __syncwarp();
+      }
+    } else if (x.bvec_ok && full) {  // bf16-only output
+      const float bf_[32] = {bv[0].x, bv[0].y, bv[0].z, bv[0].w, bv[1].x, bv[1].y, bv[1].z, bv[1].w,
+                             bv[2].x, bv[2].y, bv[2].z, bv[2].w, bv[3].x, bv[3].y, bv[3].z, bv[3].w,
+                             bv[4].x, bv[4].y, bv[4].z, bv[4].w, bv[5].x, bv[5].y, bv[5].z, bv[5].w,
+                             bv[6].x, bv[6].y, bv[6].z, bv[6].w, bv[7].x, bv[7].y, bv[7].z, bv[7].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int j = q * 8 + h * 2;
+          __nv_bfloat162 t = __floats2bfloat162_rn(fmaf(a, __uint_as_float(r[j]), bf_[j]),
+                                                   fmaf(a, __uint_as_float(r[j + 1]), bf_[j + 1]));
+          pk[h] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        sts128(x.wsa + lane * kPitch + q * 16, pk[0], pk[1], pk[2], pk[3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + (lane >> 2), cq = lane & 3;
+        const int grow = x.row0 + rr;
+        const uint4 v = lds128(x.wsa + rr * kPitch + cq * 16);
+        if (grow < M) {
+          const int dr = row_perm_h ? (grow & 3) * row_perm_h + (grow >> 2) : grow;
+          *reinterpret_cast<uint4*>(Cb + (int64_t)dr * ldc + col0 + cq * 8) = v;
+        }
+      }
+      __syncwarp();
+    } else {
+      const int row = x.row0 + lane;
+      if (row < M) {
+        const int drow = row_perm_h ? (row & 3) * row_perm_h + (row >> 2) : row;
+        float* crow = C ? C + (int64_t)x.split * split_stride + (int64_t)drow * ldc : nullptr;
+        __nv_bfloat16* brow = Cb ? Cb + (int64_t)drow * ldc : nullptr;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = col0 + j;
@@ -336,6 +369,34 @@ struct PlainEpi {
           }
         }
       }
+    }
+  }
+  // Each epilogue warp owns kChunks consecutive 32-column chunks of its lane quadrant; the TMEM load of chunk c+1 is in
+  // flight while chunk c is converted, staged and stored (two register buffers, loop unrolled by two).
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane,
+                                       const Pre&, uint8_t* wsm) const {
+    Ctx x;
+    x.row0 = m_blk * BM + (ew & 3) * 32;
+    x.n_blk = n_blk; x.split = split; x.lane = lane;
+    x.a = alpha_dev ? alpha * alpha_dev[0] : alpha;
+    const bool bias_al = !bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
+    x.vec_ok = C && !Cb && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && bias_al &&
+               ((split_stride & 3) == 0);
+    x.bvec_ok = !C && Cb && ((ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0) && bias_al;
+    x.wsa = smem_u32(wsm);
+    constexpr int kChunks = BN / 32 / (kWarps / 4);
+    static_assert(kChunks % 2 == 0, "chunk loop is unrolled by two");
+    const int c0 = (ew >> 2) * kChunks;
+    uint32_t ra[32], rb[32];
+    tmem_ld32(tmem_rows + (uint32_t)(c0 * 32), ra);
+#pragma unroll 1
+    for (int c = 0; c < kChunks; c += 2) {
+      tmem_ld_wait();
+      tmem_ld32(tmem_rows + (uint32_t)((c0 + c + 1) * 32), rb);
+      chunk(x, ra, c0 + c);
+      tmem_ld_wait();
+      if (c + 2 < kChunks) tmem_ld32(tmem_rows + (uint32_t)((c0 + c + 2) * 32), ra);
+      chunk(x, rb, c0 + c + 1);
     }
   }
 };

@@ -489,8 +489,10 @@ int bn_bwd(const float* dout, const float* yhat, const float* rstd, const float*
 //                      to a work list
 //   emb_place_kernel   a row whose token occurs once is copied straight to d_w_emb (warp per row); other rows claim a
 //                      slot of their token's segment (arbitrary order)
-//   emb_multi_kernel   persistent blocks walk the work list: the segment's row indices are ranked into ascending
-//                      order in shared memory, then 16 warps sum the rows in that fixed order
+//   emb_small_kernel   segments of 2..32 rows: one warp per token ranks the row indices with shuffles and adds the rows
+//                      in ascending order
+//   emb_multi_kernel   longer segments: persistent blocks walk the work list, the segment's row indices are ranked into
+//                      ascending order in shared memory, then 32 warps sum the rows in that fixed order
 constexpr int EMB_SEG_MAX = 8192;  // longest segment (rows sharing one token, e.g. <start>: one per caption)
 __global__ void __launch_bounds__(256)
 emb_tok_kernel(const __grid_constant__ PackInfo pk, const int64_t* __restrict__ captions, int64_t cap_stride,
@@ -506,14 +508,17 @@ emb_tok_kernel(const __grid_constant__ PackInfo pk, const int64_t* __restrict__ 
   tok[i] = (int)tk;
   atomicAdd(&count[tk], 1);
 }
-// single block: warp-shuffle scan of 1024-wide slabs; multi[0] = number of listed tokens, multi[1..] = the tokens
+// single block: warp-shuffle scan of 1024-wide slabs.  Tokens that occur more than once go to one of two work lists
+// (warp-aggregated appends; list order is irrelevant, tokens are independent): small[0] / multi[0] = entries,
+// small[1..] = tokens with 2..EMB_SMALL_MAX rows (one warp each), multi[1..] = longer segments (one block each).
+constexpr int EMB_SMALL_MAX = 32;
 __global__ void __launch_bounds__(1024)
 emb_scan_kernel(const int* __restrict__ count, int V, int* __restrict__ start, int* __restrict__ cursor,
-                int* __restrict__ multi, int* flags) {
+                int* __restrict__ multi, int* __restrict__ small, int* flags) {
   __shared__ int wsum[32];
   __shared__ int carry_s;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { carry_s = 0; multi[0] = 0; }
+  if (threadIdx.x == 0) { carry_s = 0; multi[0] = 0; small[0] = 0; }
   __syncthreads();
   for (int base = 0; base < V; base += 1024) {
     const int i = base + threadIdx.x;
@@ -540,7 +545,21 @@ emb_scan_kernel(const int* __restrict__ count, int V, int* __restrict__ start, i
     if (i < V) {
       start[i] = excl;
       cursor[i] = excl;
-      if (c > 1) multi[1 + atomicAdd(&multi[0], 1)] = i;  // list order is irrelevant: tokens are independent
+    }
+    const bool is_small = c > 1 && c <= EMB_SMALL_MAX, is_big = c > EMB_SMALL_MAX;
+    const unsigned ms = __ballot_sync(0xffffffffu, is_small), mb = __ballot_sync(0xffffffffu, is_big);
+    const unsigned lt = (1u << lane) - 1u;
+    if (ms) {
+      int b0 = 0;
+      if (lane == 0) b0 = atomicAdd(&small[0], __popc(ms));
+      b0 = __shfl_sync(0xffffffffu, b0, 0);
+      if (is_small) small[1 + b0 + __popc(ms & lt)] = i;
+    }
+    if (mb) {
+      int b0 = 0;
+      if (lane == 0) b0 = atomicAdd(&multi[0], __popc(mb));
+      b0 = __shfl_sync(0xffffffffu, b0, 0);
+      if (is_big) multi[1 + b0 + __popc(mb & lt)] = i;
     }
     __syncthreads();
     if (threadIdx.x == 0) carry_s += wsum[31];
@@ -562,6 +581,41 @@ emb_place_kernel(const int* __restrict__ tok, int n1, const int* __restrict__ co
     for (int e = lane * 4; e < E; e += 128) *reinterpret_cast<float4*>(dst + e) = *reinterpret_cast<const float4*>(src + e);
   } else if (lane == 0) {
     perm0[atomicAdd(&cursor[t], 1)] = i;
+  }
+}
+// segments of 2..32 rows: ONE WARP per token, no block-wide synchronisation.  Lane i holds row index i of the segment,
+// ranks it against the others with shuffles, and the warp then adds the rows in ascending row order (deterministic).
+template <int SLABS>
+__global__ void __launch_bounds__(256)
+emb_small_kernel(const float* __restrict__ dx1, const int* __restrict__ start, const int* __restrict__ perm0,
+                 const int* __restrict__ small, int E, float* __restrict__ d_w_emb) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+  const int n_small = small[0];
+  for (int li = gw; li < n_small; li += nw) {
+    const int v = small[1 + li];
+    const int s0 = start[v];
+    const int n = start[v + 1] - s0;  // 2..32
+    const int mine = lane < n ? perm0[s0 + lane] : 0x7fffffff;
+    int rank = 0;
+    for (int b = 0; b < n; ++b) rank += (__shfl_sync(0xffffffffu, mine, b) < mine);  // row indices are distinct
+    float4 acc[SLABS];
+#pragma unroll
+    for (int k = 0; k < SLABS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < n; ++r) {
+      const unsigned who = __ballot_sync(0xffffffffu, lane < n && rank == r);
+      const int idx = __shfl_sync(0xffffffffu, mine, __ffs((int)who) - 1);
+      const float* src = dx1 + (int64_t)idx * E + lane * 4;
+#pragma unroll
+      for (int k = 0; k < SLABS; ++k)
+        if (k * 128 + lane * 4 < E) {
+          const float4 a = *reinterpret_cast<const float4*>(src + k * 128);
+          acc[k].x += a.x; acc[k].y += a.y; acc[k].z += a.z; acc[k].w += a.w;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SLABS; ++k)
+      if (k * 128 + lane * 4 < E) *reinterpret_cast<float4*>(d_w_emb + (int64_t)v * E + k * 128 + lane * 4) = acc[k];
   }
 }
 template <int SLABS>
@@ -644,7 +698,7 @@ dfeatures_kernel(const float* __restrict__ dx, int bs0, int64_t B, int64_t E, fl
 }
 
 int64_t embed_bwd_ws_bytes(int64_t N, int64_t V) {
-  return ws_bytes_for(N, 4) * 3 + ws_bytes_for(V + 1, 4) * 4;
+  return ws_bytes_for(N, 4) * 3 + ws_bytes_for(V + 1, 4) * 5;
 }
 int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions, int64_t cap_stride,
                    int64_t B, int64_t E, int64_t V, float* dfeatures, float* d_w_emb, void* ws,
@@ -664,6 +718,7 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
   int* start = w.take<int>(V + 1);
   int* cursor = w.take<int>(V + 1);
   int* multi = w.take<int>(V + 1);
+  int* small = w.take<int>(V + 1);
   if (!w.ok()) { set_error("embed_pack_bwd: workspace too small"); return SNT_EWORKSPACE; }
   SNT_REQUIRE(E % 4 == 0 && E <= 1024, "embed_pack_bwd: E must be a multiple of 4 and <= 1024");
   SNT_REQUIRE(V < (1LL << 31), "embed_pack_bwd: V too large");
@@ -673,7 +728,7 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
   const float* dx1 = dx + (int64_t)pk.off[1] * E;
   emb_tok_kernel<<<nblocks(n1, 256), 256, 0, st>>>(pk, captions, cap_stride, V, tok, count, device_flags());
   SNT_LAUNCH_CHECK("emb_tok_kernel");
-  emb_scan_kernel<<<1, 1024, 0, st>>>(count, (int)V, start, cursor, multi, device_flags());
+  emb_scan_kernel<<<1, 1024, 0, st>>>(count, (int)V, start, cursor, multi, small, device_flags());
   SNT_LAUNCH_CHECK("emb_scan_kernel");
   emb_place_kernel<<<nblocks(n1, 8), 256, 0, st>>>(tok, n1, count, cursor, perm0, dx1, (int)E, d_w_emb);
   SNT_LAUNCH_CHECK("emb_place_kernel");
@@ -687,6 +742,11 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
     attr_set = true;
   }
   const int slabs = (int)((E + 127) / 128);
+  const int sgrid = 4 * 148;  // persistent warps walk the small-segment list
+  if (slabs <= 2) emb_small_kernel<2><<<sgrid, 256, 0, st>>>(dx1, start, perm0, small, (int)E, d_w_emb);
+  else if (slabs <= 4) emb_small_kernel<4><<<sgrid, 256, 0, st>>>(dx1, start, perm0, small, (int)E, d_w_emb);
+  else emb_small_kernel<8><<<sgrid, 256, 0, st>>>(dx1, start, perm0, small, (int)E, d_w_emb);
+  SNT_LAUNCH_CHECK("emb_small_kernel");
   if (slabs <= 2) emb_multi_kernel<2><<<148, 1024, sm, st>>>(dx1, start, perm0, gsorted, multi, (int)E, d_w_emb);
   else if (slabs <= 4) emb_multi_kernel<4><<<148, 1024, sm, st>>>(dx1, start, perm0, gsorted, multi, (int)E, d_w_emb);
   else emb_multi_kernel<8><<<148, 1024, sm, st>>>(dx1, start, perm0, gsorted, multi, (int)E, d_w_emb);

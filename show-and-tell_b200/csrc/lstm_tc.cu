@@ -20,7 +20,6 @@ namespace bf16 {
 
 typedef __nv_bfloat16 bf;
 constexpr int MAX_SPLITS = 16;
-constexpr float LOG2E_F = 1.4426950408889634f;
 
 // Gate non-linearities on the SFU: ONE MUFU.TANH per value (tanh.approx.f32, max relative error 2^-11 — below the
 // bf16 rounding (2^-9) applied to every activation that leaves the epilogue).  The exp2 + reciprocal formulation costs
@@ -233,10 +232,10 @@ struct LstmBwdEpi {
 //     overlaps the stragglers' epilogues.  No grid-wide barrier, no relaunch.
 //   * the epilogue publishes h_t (the only thing other CTAs wait for) first; c_t and the saved activations are
 //     stored after the release, off the critical path.
-// h_t is written with generic stores and read back by other CTAs through TMA (async proxy): writers execute
-// fence.proxy.async + __threadfence before the release, the reader fences again after its acquire.
+// h_t is written with generic stores and read back by other CTAs through TMA (async proxy): see publish_fence().
+// With clusters (CL = 4) the CL CTAs that share a row block take turns issuing each k-block as ONE multicast TMA.
 // =====================================================================================================================
-constexpr int PF_STAGES = 4;
+constexpr int PF_STAGES = 6;
 constexpr int PF_EPI_WARPS = 16;
 constexpr int PF_THREADS = 128 + 32 * PF_EPI_WARPS;
 constexpr int PF_FLAGS_PER_STEP = 8;  // k-blocks of 64 hidden units (H <= 512)
@@ -250,17 +249,27 @@ struct PersistFwdParams {
 #endif
 };
 #ifdef SNT_LSTM_DBG
-#define DBG_STAMP(t, k) do { if (blockIdx.x == SNT_DBG_BLOCK) p.dbg[(t) * 8 + (k)] = clock64(); } while (0)
+#define DBG_STAMP(t, k) do { if (blockIdx.x == SNT_DBG_BLOCK) p.dbg[(t) * 12 + (k)] = clock64(); } while (0)
 #else
 #define DBG_STAMP(t, k) do {} while (0)
 #endif
 
+// Publishing global data that other CTAs will fetch with TMA (async proxy): the writer orders its generic-proxy stores
+// before later async-proxy accesses with ONE proxy fence restricted to the global space, then releases at gpu scope.
+// The consumer's TMA is issued behind the acquire load of the counter (control dependency), i.e. after the fence in
+// causality order.  (The unrestricted fence.proxy.async measured ~1.8k cycles per step on the writer and ~3k on the
+// reader side of this kernel; the .global form ~150.)
+__device__ __forceinline__ void publish_fence() {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
+template <int CL>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                            const __grid_constant__ PackInfo pk, const PersistFwdParams p) {
@@ -285,7 +294,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && elect_one()) {
-    for (int i = 0; i < PF_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < PF_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
     mbar_init(wbar, 1);
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
@@ -297,8 +306,11 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast traffic
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
 
   // number of steps this row block is alive (batch_sizes is non-increasing)
   int t_end = 0;
@@ -331,11 +343,13 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         }
         if (lane == 0) {
           if (kb == 0) DBG_STAMP(t, 0);
-          fence_proxy_async_all();
           for (int k = kb; k < ready; ++k) {
-            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_wait(&empty[stage], phase ^ 1);  // released by every CTA of the cluster
             mbar_arrive_expect_tx(&full[stage], 16384);
-            tma_load_2d(sA + stage * 16384, &tmA, &full[stage], k * BK, pk.off[t] + m_blk * BM);
+            if (CL == 1)
+              tma_load_2d(sA + stage * 16384, &tmA, &full[stage], k * BK, pk.off[t] + m_blk * BM);
+            else if ((uint32_t)(k % CL) == crank)  // one L2 read feeds the CL CTAs that share this row block
+              tma_load_2d_mc(sA + stage * 16384, &tmA, &full[stage], k * BK, pk.off[t] + m_blk * BM, CMASK);
             if (++stage == PF_STAGES) { stage = 0; phase ^= 1; }
           }
           if (ready == KB) DBG_STAMP(t, 1);
@@ -364,7 +378,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16(tmem_d, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
                       idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty[stage]);
+          if (CL == 1) umma_commit(&empty[stage]); else umma_commit_mc(&empty[stage], CMASK);
           if (++stage == PF_STAGES) { stage = 0; phase ^= 1; }
         }
         DBG_STAMP(t, 3);
@@ -438,8 +452,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       }
       if (stamp) DBG_STAMP(t, 5);
       if (t + 1 < t_end) {
-        fence_proxy_async_all();  // generic-proxy writes -> visible to other CTAs' TMA reads
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        publish_fence();
         if (stamp) DBG_STAMP(t, 6);
         asm volatile("bar.sync 1, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
         if (threadIdx.x == 128)
@@ -467,6 +480,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 256);
@@ -485,7 +499,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 //   * same release/acquire counters as the forward kernel, one per (row block, step, producer CTA): k-blocks
 //     2n, 2n+1 of dG'_{t+1} are fetched as soon as CTA n has published them.
 // =====================================================================================================================
-constexpr int PB_STAGES = 5;
+constexpr int PB_STAGES = 6;
 constexpr int PB_FLAGS_PER_STEP = 16;  // producer CTAs per row block (H <= 512)
 
 struct PersistBwdParams {
@@ -517,6 +531,7 @@ perm_transpose_bf16_kernel(const float* __restrict__ w, int H, bf* __restrict__ 
   }
 }
 
+template <int CL>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                            const __grid_constant__ PackInfo pk, const PersistBwdParams p) {
@@ -541,7 +556,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && elect_one()) {
-    for (int i = 0; i < PB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < PB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
     mbar_init(wbar, 1);
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
@@ -553,8 +568,11 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast traffic
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
 
   // this row block is alive for steps [0, t_end); going backward it starts at t_end - 1.  Step index s counts from
   // there: t = t_end - 1 - s.  s = 0 has no recurrent term (no row of the block is alive at t + 1).
@@ -587,11 +605,13 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         }
         if (lane == 0) {
           if (kb == 0) DBG_STAMP(s, 0);
-          fence_proxy_async_all();
           for (int k = kb; k < ready; ++k) {
-            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_wait(&empty[stage], phase ^ 1);  // released by every CTA of the cluster
             mbar_arrive_expect_tx(&full[stage], 16384);
-            tma_load_2d(sA + stage * 16384, &tmA, &full[stage], k * BK, pk.off[t + 1] + m_blk * BM);
+            if (CL == 1)
+              tma_load_2d(sA + stage * 16384, &tmA, &full[stage], k * BK, pk.off[t + 1] + m_blk * BM);
+            else if ((uint32_t)(k % CL) == crank)
+              tma_load_2d_mc(sA + stage * 16384, &tmA, &full[stage], k * BK, pk.off[t + 1] + m_blk * BM, CMASK);
             if (++stage == PB_STAGES) { stage = 0; phase ^= 1; }
           }
           if (ready == KB) DBG_STAMP(s, 1);
@@ -619,7 +639,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16(tmem_d, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
                       idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty[stage]);
+          if (CL == 1) umma_commit(&empty[stage]); else umma_commit_mc(&empty[stage], CMASK);
           if (++stage == PB_STAGES) { stage = 0; phase ^= 1; }
         }
         DBG_STAMP(s, 3);
@@ -703,8 +723,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       }
       if (stamp) DBG_STAMP(s, 5);
       if (s + 1 < t_end) {
-        fence_proxy_async_all();  // generic-proxy writes -> visible to other CTAs' TMA reads
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        publish_fence();
         if (stamp) DBG_STAMP(s, 6);
         asm volatile("bar.sync 1, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
         if (threadIdx.x == 128) atomicAdd(p.flags + ((int64_t)m_blk * p.T + t) * PB_FLAGS_PER_STEP + n_blk, 1);
@@ -716,6 +735,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 64);
@@ -823,6 +843,67 @@ static void persist_caps(int* coop, int* max_smem) {
   *max_smem = m;
 }
 
+// Launch a persistent recurrence kernel.  All CTAs must be co-resident (the row-block counters are spin-waited), so
+// the launch is cooperative; with cluster > 1 the num_n CTAs of a row block are grouped into clusters that share
+// their TMA loads by multicast.  Returns the cluster size used through *cluster_used (0: could not launch).
+template <class Params>
+static int launch_persistent(void (*k1)(CUtensorMap, CUtensorMap, PackInfo, Params),
+                             void (*k4)(CUtensorMap, CUtensorMap, PackInfo, Params), int ctas, int num_n, size_t smem,
+                             const CUtensorMap& ta, const CUtensorMap& tb, const PackInfo& pk, const Params& pp,
+                             cudaStream_t st) {
+  static int mode = -1;  // per instantiation: 4 = clusters of 4 fit, 1 = no clusters
+  // Measured on B200 (profiles/r01_lstm_persistent_timeline.txt): clusters of 4 with multicast loads do not shorten the
+  // per-step exchange (L2 already serves the 4 unicast requests of a line from one fill), and cooperative + cluster
+  // launches fail under ncu, so the default is plain cooperative; SNT_PERSIST_CLUSTER=4 opts in.
+  const char* env = getenv("SNT_PERSIST_CLUSTER");
+  int want = env ? atoi(env) : 1;
+  if (num_n % 4 != 0 || want != 4) want = 1;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const int cl = (want == 4 && mode != 1) ? 4 : 1;
+    auto kern = cl == 4 ? k4 : k1;
+    SNT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(PF_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)cl;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cl > 1 ? 2 : 1;
+    if (cl > 1 && mode < 0) {  // first use: do that many clusters fit at once?
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters * cl < ctas) {
+        cudaGetLastError();
+        mode = 1;
+        continue;
+      }
+    }
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, pk, pp);
+    if (e == cudaSuccess) {
+#ifdef SNT_LSTM_DBG
+      if (mode < 0) fprintf(stderr, "[lstm dbg] persistent launch: cluster %d\n", cl);
+#endif
+      if (mode < 0) mode = cl;
+      count_launch();
+      return SNT_OK;
+    }
+    if (cl > 1) {  // cluster + cooperative refused on this driver: fall back to plain cooperative
+      cudaGetLastError();
+      mode = 1;
+      continue;
+    }
+    return check_cuda(e, "persistent LSTM launch");
+  }
+  set_error("persistent LSTM launch failed");
+  return SNT_EINVAL;
+}
+
 static int prep_weights(const LstmWs& w, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                         int64_t In, int64_t H, cudaStream_t st) {
   perm_rows_bf16_kernel<<<(unsigned)(4 * H), 128, 0, st>>>(w_ih, (int)H, (int)In, w.w_ih);
@@ -877,34 +958,31 @@ int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const flo
     persist_caps(&coop, &max_smem);
     if (coop == 1 && !getenv("SNT_NO_PERSISTENT") && (int64_t)num_m0 * num_n <= tc::sm_count() &&
         smem <= (size_t)max_smem && KB <= PF_FLAGS_PER_STEP && w.flags != nullptr) {
-      SNT_CUDA(cudaFuncSetAttribute(lstm_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       SNT_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)num_m0 * T * PF_FLAGS_PER_STEP, st));
       PersistFwdParams pp;
       pp.H = (int)H; pp.T = T; pp.num_n = num_n; pp.gx = w.gx; pp.cs = cs; pp.hs = hs_b; pp.hprev = hp_b; pp.act = act;
       pp.flags = w.flags;
 #ifdef SNT_LSTM_DBG
       static long long* dbg_dev = nullptr;
-      if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * SNT_MAX_T * 8);
-      cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * SNT_MAX_T * 8, st);
+      if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * SNT_MAX_T * 12);
+      cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * SNT_MAX_T * 12, st);
       pp.dbg = dbg_dev;
 #endif
-      PackInfo pkc = pk;
-      void* args[] = {(void*)&ta, (void*)&tb, (void*)&pkc, (void*)&pp};
-      count_launch();
-      SNT_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_fwd_persistent_kernel, dim3((unsigned)(num_m0 * num_n)),
-                                           dim3(PF_THREADS), args, smem, st));
+      SNT_CHECK(launch_persistent<PersistFwdParams>(lstm_fwd_persistent_kernel<1>, lstm_fwd_persistent_kernel<4>,
+                                                    num_m0 * num_n, num_n, smem, ta, tb, pk, pp, st));
 #ifdef SNT_LSTM_DBG
       {
         static int printed = 0;
         if (printed++ == 3) {
-          long long h[SNT_MAX_T * 8];
+          long long h[SNT_MAX_T * 12];
           cudaStreamSynchronize(st);
           cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
           const long long t0 = h[5];
+          fprintf(stderr, "cols 8: after reader fence, 9: after writer proxy fence\n");
           fprintf(stderr, "[lstm dbg] block %d: step: flag0_seen tma_issued first_full mma_issued tfull_seen h_stored fenced flag_set (cycles since step-0 start)\n", SNT_DBG_BLOCK);
           for (int t = 0; t < T; ++t) {
             fprintf(stderr, "[lstm dbg] %2d:", t);
-            for (int k = 0; k < 8; ++k) fprintf(stderr, " %8lld", h[t * 8 + k] - t0);
+            for (int k = 0; k < 12; ++k) fprintf(stderr, " %8lld", h[t * 12 + k] > 0 ? h[t * 12 + k] - t0 : -1);
             fprintf(stderr, "\n");
           }
         }
@@ -964,34 +1042,31 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
       CUtensorMap ta, tb;
       SNT_CHECK(tc::make_operand_tmap(&ta, dg, false, N, 4 * H, 4 * H, tc::BM));
       SNT_CHECK(tc::make_operand_tmap(&tb, w.w_hh_t, false, H, 4 * H, 4 * H, 32));
-      SNT_CUDA(cudaFuncSetAttribute(lstm_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       SNT_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)num_m0 * T * PB_FLAGS_PER_STEP, st));
       PersistBwdParams pp;
       pp.H = (int)H; pp.T = T; pp.num_n = num_n; pp.d_hs = d_hs; pp.act = act; pp.cs = cs; pp.dg = dg;
       pp.flags = w.flags;
 #ifdef SNT_LSTM_DBG
       static long long* dbg_dev = nullptr;
-      if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * SNT_MAX_T * 8);
-      cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * SNT_MAX_T * 8, st);
+      if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * SNT_MAX_T * 12);
+      cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * SNT_MAX_T * 12, st);
       pp.dbg = dbg_dev;
 #endif
-      PackInfo pkc = pk;
-      void* args[] = {(void*)&ta, (void*)&tb, (void*)&pkc, (void*)&pp};
-      count_launch();
-      SNT_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_persistent_kernel, dim3((unsigned)(num_m0 * num_n)),
-                                           dim3(PF_THREADS), args, smem, st));
+      SNT_CHECK(launch_persistent<PersistBwdParams>(lstm_bwd_persistent_kernel<1>, lstm_bwd_persistent_kernel<4>,
+                                                    num_m0 * num_n, num_n, smem, ta, tb, pk, pp, st));
 #ifdef SNT_LSTM_DBG
       {
         static int printed = 0;
         if (printed++ == 3) {
-          long long h[SNT_MAX_T * 8];
+          long long h[SNT_MAX_T * 12];
           cudaStreamSynchronize(st);
           cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
           const long long t0 = h[5];
+          fprintf(stderr, "cols 8: after reader fence, 9: after writer proxy fence\n");
           fprintf(stderr, "[lstm bwd dbg] block %d: s: flag0_seen tma_issued first_full mma_issued tfull_seen dg_stored fenced flag_set\n", SNT_DBG_BLOCK);
           for (int t = 0; t < T; ++t) {
             fprintf(stderr, "[lstm bwd dbg] %2d:", t);
-            for (int k = 0; k < 8; ++k) fprintf(stderr, " %8lld", h[t * 8 + k] - t0);
+            for (int k = 0; k < 12; ++k) fprintf(stderr, " %8lld", h[t * 12 + k] > 0 ? h[t * 12 + k] - t0 : -1);
             fprintf(stderr, "\n");
           }
         }

@@ -79,12 +79,17 @@ struct CeFwdEpi {
       if (col0 >= V) break;  // warp-uniform
       uint32_t r[32];
       tc::tmem_ld32(tmem_rows + (uint32_t)cofs, r);
+      float4 bv[8];  // bias of the chunk, fetched while the TMEM load is in flight
+      if (col0 + 32 <= V) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) bv[q] = __ldg(reinterpret_cast<const float4*>(bias + col0) + q);
+      }
       tc::tmem_ld_wait();
       float y[32];
       if (col0 + 32 <= V) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
+          const float4 b = bv[j >> 2];
           y[j] = (__uint_as_float(r[j]) + b.x) * LOG2E;
           y[j + 1] = (__uint_as_float(r[j + 1]) + b.y) * LOG2E;
           y[j + 2] = (__uint_as_float(r[j + 2]) + b.z) * LOG2E;
@@ -162,13 +167,18 @@ struct CeBwdEpi {
       if (col0 >= V) break;  // warp-uniform
       uint32_t r[32];
       tc::tmem_ld32(tmem_rows + (uint32_t)cofs, r);
+      float4 bv[8];  // bias of the chunk, fetched while the TMEM load is in flight
+      if (col0 + 32 <= V) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) bv[q] = __ldg(reinterpret_cast<const float4*>(bias + col0) + q);
+      }
       tc::tmem_ld_wait();
       const int trel = tgt - col0;
       if (col0 + 32 <= V) {
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
+          const float4 b = bv[j >> 2];
           float p0 = ex2((__uint_as_float(r[j]) + b.x) * LOG2E - l2);
           float p1 = ex2((__uint_as_float(r[j + 1]) + b.y) * LOG2E - l2);
           float p2 = ex2((__uint_as_float(r[j + 2]) + b.z) * LOG2E - l2);
@@ -183,15 +193,15 @@ struct CeBwdEpi {
         }
         // stage the warp's 32 x 64 B through shared memory so that each store instruction writes 8 whole 64-byte row
         // segments (4 lanes per row) instead of 32 scattered 16-byte pieces
-        uint4* mine = reinterpret_cast<uint4*>(wsm + lane * 80);
+        const uint32_t wsa = tc::smem_u32(wsm);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) mine[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) tc::sts128(wsa + lane * 80 + q * 16, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         __syncwarp();
         const int row0 = m_blk * tc::BM + (ew & 3) * 32;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int rr = it * 8 + (lane >> 2), cq = lane & 3;
-          const uint4 v = *reinterpret_cast<const uint4*>(wsm + rr * 80 + cq * 16);
+          const uint4 v = tc::lds128(wsa + rr * 80 + cq * 16);
           if (row0 + rr < M) *reinterpret_cast<uint4*>(out + (int64_t)(row0 + rr) * ldo + col0 + cq * 8) = v;
         }
         __syncwarp();
