@@ -653,21 +653,23 @@ emb_multi_kernel(const float* __restrict__ dx1, const int* __restrict__ start, c
 #pragma unroll
     for (int k = 0; k < SLABS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     int i = w;
-    for (; i + 32 < n; i += 64) {
-      const float* r0 = dx1 + (int64_t)sorted[i] * E + lane * 4;
-      const float* r1 = dx1 + (int64_t)sorted[i + 32] * E + lane * 4;
-      float4 a[SLABS], b[SLABS];
+    for (; i + 96 < n; i += 128) {  // 4 rows in flight per warp, added in ascending order
+      const float* rp[4];
 #pragma unroll
-      for (int k = 0; k < SLABS; ++k) {
-        const bool in = k * 128 + lane * 4 < E;
-        a[k] = in ? *reinterpret_cast<const float4*>(r0 + k * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-        b[k] = in ? *reinterpret_cast<const float4*>(r1 + k * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int u = 0; u < 4; ++u) rp[u] = dx1 + (int64_t)sorted[i + 32 * u] * E + lane * 4;
+      float4 a[4][SLABS];
 #pragma unroll
-      for (int k = 0; k < SLABS; ++k) {
-        acc[k].x += a[k].x; acc[k].y += a[k].y; acc[k].z += a[k].z; acc[k].w += a[k].w;
-        acc[k].x += b[k].x; acc[k].y += b[k].y; acc[k].z += b[k].z; acc[k].w += b[k].w;
-      }
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < SLABS; ++k)
+          a[u][k] = (k * 128 + lane * 4 < E) ? *reinterpret_cast<const float4*>(rp[u] + k * 128)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < SLABS; ++k) {
+          acc[k].x += a[u][k].x; acc[k].y += a[u][k].y; acc[k].z += a[u][k].z; acc[k].w += a[u][k].w;
+        }
     }
     for (; i < n; i += 32) {
       const float* r0 = dx1 + (int64_t)sorted[i] * E + lane * 4;

@@ -114,18 +114,35 @@ struct CeFwdEpi {
   }
 };
 
-// lse[n] = ln2 * (M + log2 sum_k s_k 2^(m_k - M)); nll[n] = lse - tl
-__global__ void __launch_bounds__(256)
+// lse[n] = ln2 * (M + log2 sum_k s_k 2^(m_k - M)); nll[n] = lse - tl.  One thread per row, one pass (online merge of
+// the slab partials, 4 loads in flight); small blocks so that ~200 of them cover a 12k-row batch.
+__global__ void __launch_bounds__(64)
 ce_finish_kernel(const float2* __restrict__ part, int slabs, int64_t N, const float* __restrict__ tl,
                  float* __restrict__ lse, float* __restrict__ nll) {
-  const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t row = (int64_t)blockIdx.x * 64 + threadIdx.x;
   if (row >= N) return;
-  float M = -INFINITY;
-  for (int k = 0; k < slabs; ++k) M = fmaxf(M, part[(int64_t)k * N + row].x);
-  float S = 0.f;
-  for (int k = 0; k < slabs; ++k) {
+  float M = -INFINITY, S = 0.f;
+  int k = 0;
+  for (; k + 4 <= slabs; k += 4) {
+    float2 p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = part[(int64_t)(k + i) * N + row];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (p[i].y > 0.f) {
+        const float mn = fmaxf(M, p[i].x);
+        S = S * exp2f(M - mn) + p[i].y * exp2f(p[i].x - mn);
+        M = mn;
+      }
+    }
+  }
+  for (; k < slabs; ++k) {
     const float2 p = part[(int64_t)k * N + row];
-    if (p.y > 0.f) S += p.y * exp2f(p.x - M);
+    if (p.y > 0.f) {
+      const float mn = fmaxf(M, p.x);
+      S = S * exp2f(M - mn) + p.y * exp2f(p.x - mn);
+      M = mn;
+    }
   }
   const float l = (M + log2f(S)) * LN2;
   lse[row] = l;
@@ -152,70 +169,90 @@ struct CeBwdEpi {
     p.l2 = row_ok ? lse[row] * LOG2E : 0.f;
     p.tgt = row_ok ? (int)targets[row] : -1;
   }
+  // one 32-column chunk: softmax - onehot from the accumulator registers, bf16, staged through shared memory so that each
+  // store instruction writes 8 whole 64-byte row segments (4 lanes per row) instead of 32 scattered 16-byte pieces
+  __device__ __forceinline__ void chunk(const uint32_t (&r)[32], const float4 (&bv)[8], int col0, int row0, int lane,
+                                        float l2, int tgt, uint32_t wsa) const {
+    const int trel = tgt - col0;
+    if (col0 + 32 <= V) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = bv[j >> 2];
+        float p0 = ex2((__uint_as_float(r[j]) + b.x) * LOG2E - l2);
+        float p1 = ex2((__uint_as_float(r[j + 1]) + b.y) * LOG2E - l2);
+        float p2 = ex2((__uint_as_float(r[j + 2]) + b.z) * LOG2E - l2);
+        float p3 = ex2((__uint_as_float(r[j + 3]) + b.w) * LOG2E - l2);
+        if (trel == j) p0 -= 1.f;
+        if (trel == j + 1) p1 -= 1.f;
+        if (trel == j + 2) p2 -= 1.f;
+        if (trel == j + 3) p3 -= 1.f;
+        __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
+        pk[j / 2] = *reinterpret_cast<uint32_t*>(&lo);
+        pk[j / 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tc::sts128(wsa + lane * 80 + q * 16, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + (lane >> 2), cq = lane & 3;
+        const uint4 v = tc::lds128(wsa + rr * 80 + cq * 16);
+        if (row0 + rr < M) *reinterpret_cast<uint4*>(out + (int64_t)(row0 + rr) * ldo + col0 + cq * 8) = v;
+      }
+      __syncwarp();
+    } else if (row0 + lane < M) {
+      bf* orow = out + (int64_t)(row0 + lane) * ldo;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = col0 + j;
+        if (col < V) {
+          float p = ex2((__uint_as_float(r[j]) + bias[col]) * LOG2E - l2);
+          if (trel == j) p -= 1.f;
+          orow[col] = __float2bfloat16_rn(p);
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void load_bias(float4 (&bv)[8], int col0) const {
+    if (col0 + 32 <= V) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) bv[q] = __ldg(reinterpret_cast<const float4*>(bias + col0) + q);
+    }
+  }
+  // 4 chunks per warp; the TMEM load and the bias fetch of chunk c+1 are in flight while chunk c is processed
   __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane,
                                        const Pre& pre, uint8_t* wsm) const {
     const int half = ew >> 2;
-    const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
-    const bool row_ok = row < M;
-    const float l2 = pre.l2;
-    const int tgt = pre.tgt;
-    bf* orow = out + (int64_t)row * ldo;
+    const int row0 = m_blk * tc::BM + (ew & 3) * 32;
+    const uint32_t wsa = tc::smem_u32(wsm);
+    const int cbase = half * (CE_BN / 2);
+    const int colb = n_blk * CE_BN + cbase;
+    constexpr int NCH = CE_BN / 64;
+    static_assert(NCH % 2 == 0, "chunk loop is unrolled by two");
+    uint32_t ra[32], rb[32];
+    float4 ba[8], bb[8];
+    if (colb >= V) return;  // warp-uniform
+    tc::tmem_ld32(tmem_rows + (uint32_t)cbase, ra);
+    load_bias(ba, colb);
 #pragma unroll 1
-    for (int c = 0; c < CE_BN / 64; ++c) {
-      const int cofs = half * (CE_BN / 2) + c * 32;
-      const int col0 = n_blk * CE_BN + cofs;
+    for (int c = 0; c < NCH; c += 2) {
+      const int col0 = colb + c * 32;
       if (col0 >= V) break;  // warp-uniform
-      uint32_t r[32];
-      tc::tmem_ld32(tmem_rows + (uint32_t)cofs, r);
-      float4 bv[8];  // bias of the chunk, fetched while the TMEM load is in flight
-      if (col0 + 32 <= V) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) bv[q] = __ldg(reinterpret_cast<const float4*>(bias + col0) + q);
-      }
       tc::tmem_ld_wait();
-      const int trel = tgt - col0;
-      if (col0 + 32 <= V) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b = bv[j >> 2];
-          float p0 = ex2((__uint_as_float(r[j]) + b.x) * LOG2E - l2);
-          float p1 = ex2((__uint_as_float(r[j + 1]) + b.y) * LOG2E - l2);
-          float p2 = ex2((__uint_as_float(r[j + 2]) + b.z) * LOG2E - l2);
-          float p3 = ex2((__uint_as_float(r[j + 3]) + b.w) * LOG2E - l2);
-          if (trel == j) p0 -= 1.f;
-          if (trel == j + 1) p1 -= 1.f;
-          if (trel == j + 2) p2 -= 1.f;
-          if (trel == j + 3) p3 -= 1.f;
-          __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
-          pk[j / 2] = *reinterpret_cast<uint32_t*>(&lo);
-          pk[j / 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
-        }
-        // stage the warp's 32 x 64 B through shared memory so that each store instruction writes 8 whole 64-byte row
-        // segments (4 lanes per row) instead of 32 scattered 16-byte pieces
-        const uint32_t wsa = tc::smem_u32(wsm);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tc::sts128(wsa + lane * 80 + q * 16, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        __syncwarp();
-        const int row0 = m_blk * tc::BM + (ew & 3) * 32;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rr = it * 8 + (lane >> 2), cq = lane & 3;
-          const uint4 v = tc::lds128(wsa + rr * 80 + cq * 16);
-          if (row0 + rr < M) *reinterpret_cast<uint4*>(out + (int64_t)(row0 + rr) * ldo + col0 + cq * 8) = v;
-        }
-        __syncwarp();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col < V && row_ok) {
-            float p = ex2((__uint_as_float(r[j]) + bias[col]) * LOG2E - l2);
-            if (trel == j) p -= 1.f;
-            orow[col] = __float2bfloat16_rn(p);
-          }
-        }
+      const bool more1 = col0 + 32 < V;
+      if (more1) {
+        tc::tmem_ld32(tmem_rows + (uint32_t)(cbase + (c + 1) * 32), rb);
+        load_bias(bb, col0 + 32);
       }
+      chunk(ra, ba, col0, row0, lane, pre.l2, pre.tgt, wsa);
+      if (!more1) break;
+      tc::tmem_ld_wait();
+      if (c + 2 < NCH && col0 + 64 < V) {
+        tc::tmem_ld32(tmem_rows + (uint32_t)(cbase + (c + 2) * 32), ra);
+        load_bias(ba, col0 + 64);
+      }
+      chunk(rb, bb, col0 + 32, row0, lane, pre.l2, pre.tgt, wsa);
     }
   }
 };
@@ -363,9 +400,28 @@ int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const i
   CeFwdEpi e;
   e.M = (int)N; e.V = (int)V; e.bias = b_out; e.part = w.part;
   SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeFwdEpi>(ta, tb, ts, e, st)));
-  ce_finish_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w.part, w.slabs, N, w.tl, lse, w.nll);
+  ce_finish_kernel<<<(unsigned)((N + 63) / 64), 64, 0, st>>>(w.part, w.slabs, N, w.tl, lse, w.nll);
   SNT_LAUNCH_CHECK("ce_finish_kernel");
   return reduce_sum(w.nll, N, 1.0f / (float)N, loss, st);
+}
+
+// Side stream for the bandwidth-bound column sums (d_b_out): they read the same L2-resident dlogits chunk as the two
+// tensor-core contractions but need almost no SM resources, so they run next to them instead of after them.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream() {
+  static SideStream tab[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& x = tab[dev];
+  if (!x.s) {
+    if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming);
+  }
+  return &x;
 }
 
 int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, const float* lse,
@@ -387,9 +443,11 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
     const double c256 = (double)((t256 + sms - 1) / sms) * 2.0, c128 = (double)((t128 + sms - 1) / sms) * 1.15;
     dw_bn = c128 < c256 ? 128 : 256;
   }
+  SideStream* side = side_stream();
   for (int64_t r0 = 0; r0 < N; r0 += w.R) {
     const int64_t r = N - r0 < w.R ? N - r0 : w.R;
     const float acc = r0 > 0 ? 1.f : 0.f;
+    if (side && r0 > 0) SNT_CUDA(cudaStreamWaitEvent(st, side->join, 0));  // previous chunk's column sums have read dl
     CUtensorMap ta;
     SNT_CHECK(tc::make_operand_tmap(&ta, hs_b + r0 * H, false, r, H, H, tc::BM));
     tc::TileSched ts;
@@ -398,6 +456,12 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
     e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;
     e.out = w.dl; e.ldo = w.Vp;
     SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeBwdEpi>(ta, tb, ts, e, st)));
+    if (side) {
+      SNT_CUDA(cudaEventRecord(side->fork, st));
+      SNT_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+      SNT_CHECK(colsum_bf16(w.dl, r, V, w.Vp, acc, w.db, w.cpart, side->s));
+      SNT_CUDA(cudaEventRecord(side->join, side->s));
+    }
     // dHs[r,H] = dlogits[r,V] . W_out[V,H]      (B operand MN-major)
     int sp = tc::choose_splits(r, H, V, 0);
     if (sp > MAX_SPLITS) sp = MAX_SPLITS;
@@ -409,8 +473,9 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
     // waves; 128-wide tiles give the finer granularity (316 tiles = 3 short rounds instead of 2 long ones at V=10000).
     SNT_CHECK(tc::gemm_tc(true, true, V, H, r, scale, w.dl, w.Vp, hs_b + r0 * H, H, acc, d_w_out, nullptr, H, nullptr, 1,
                           nullptr, st, 0, dloss, false, nullptr, /*force_bn=*/dw_bn));
-    SNT_CHECK(colsum_bf16(w.dl, r, V, w.Vp, acc, w.db, w.cpart, st));
+    if (!side) SNT_CHECK(colsum_bf16(w.dl, r, V, w.Vp, acc, w.db, w.cpart, st));
   }
+  if (side) SNT_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   scale_vec_kernel<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(w.db, V, scale, dloss, d_b_out);
   SNT_LAUNCH_CHECK("scale_vec_kernel");
   return SNT_OK;
