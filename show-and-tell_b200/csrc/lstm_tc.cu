@@ -488,24 +488,28 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 }
 
 // =====================================================================================================================
-// Persistent BPTT recurrence, the mirror image of the forward kernel: CTA (m_blk, n_blk) owns 128 batch rows x 32 hidden
-// units for all T steps, going backward in time.
-//   * resident in shared memory: the [32 units, 4H] slice of W_hh'^T (K-major, 128 KB at H = 512); dL/dc stays in
-//     registers,
-//   * per step the CTA streams dG'_{t+1}[128 rows, 4H] (the pre-activation gradients all num_n CTAs of the row block
-//     produced one step earlier) through a TMA ring into tcgen05.mma (M = 128, N = 32), accumulating the recurrent
-//     dL/dh_t for its 32 units in TMEM; 16 epilogue warps add dL/dh_t from above, run the cell backward and publish
-//     dG'_t (bf16) — the A operand of step t-1 and later of the weight-gradient GEMMs,
-//   * same release/acquire counters as the forward kernel, one per (row block, step, producer CTA): k-blocks
-//     2n, 2n+1 of dG'_{t+1} are fetched as soon as CTA n has published them.
+// Persistent BPTT recurrence.  Per step and 128-row block the contraction is dL/dh_t[128, H] = dG'_{t+1}[128, 4H] . W_hh'
+// (K = 4H).  A CTA that owned whole output columns would have to stream the full 4H-wide dG'_{t+1} every step (512 KB at
+// H = 512: measured 15-20k cycles per step, bound by TMA latency x ring depth), so the work is split over K as well:
+//   CTA (m_blk, nq, ks), ns = H/128, ns*ns CTAs per row block:
+//     * resident in shared memory: W_hh'^T[units 128nq..+128, gate columns 512ks..+512]  (128 KB, K-major),
+//     * per step it streams only dG'_{t+1}[128 rows, 512ks..+512] (128 KB) into tcgen05.mma (M = N = 128) and writes the
+//       fp32 partial tile P[128, 128] to an L2-resident scratch (phase 1),
+//     * phase 2: it owns the final 128/ns units [128nq + ks*128/ns, ..) of that tile: sums the ns partial slices in a
+//       fixed order (deterministic), adds dL/dh_t from above, runs the cell backward (dL/dc carried in registers) and
+//       publishes dG'_t (bf16) - the A operand of step t-1 and later of the weight-gradient GEMMs.
+//   Two release/acquire counters per (row block, step, CTA): "partial written" and "dG' published" (publish_fence()).
 // =====================================================================================================================
 constexpr int PB_STAGES = 6;
-constexpr int PB_FLAGS_PER_STEP = 16;  // producer CTAs per row block (H <= 512)
+constexpr int PB_FLAGS_PER_STEP = 16;  // CTAs per row block (ns * ns, ns <= 4)
+constexpr int PB_PART_FLOATS = 128 * 128;
 
 struct PersistBwdParams {
-  int H, T, num_n;
+  int H, T, ns;
   const float* d_hs; const bf* act; const float* cs; bf* dg;
-  int* flags;  // [num_m0][T][PB_FLAGS_PER_STEP]
+  float* part;   // [num_m0][ns*ns][2][128*128] partial dL/dh tiles: [finalizer slice][8-unit group][row][8]
+  int* dgflag;   // [num_m0][T][PB_FLAGS_PER_STEP]
+  int* pflag;    // [num_m0][T][PB_FLAGS_PER_STEP]
 #ifdef SNT_LSTM_DBG
   long long* dbg;
 #endif
@@ -531,16 +535,18 @@ perm_transpose_bf16_kernel(const float* __restrict__ w, int H, bf* __restrict__ 
   }
 }
 
-template <int CL>
+template <int NS>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                            const __grid_constant__ PackInfo pk, const PersistBwdParams p) {
   using namespace tc;
+  constexpr int KB = 8;             // 512 gate columns per K-split
+  constexpr int WS = 128 / NS;      // units this CTA finalises
+  constexpr int UG = WS / 32;       // groups of 8 units per epilogue thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int KB = (4 * p.H) / BK;                      // k-blocks of the contraction over interleaved gate columns
-  uint8_t* sW = smem;                                 // KB x 4 KB (32 units x 64 k), resident
-  uint8_t* sA = smem + KB * 4096;                     // PB_STAGES x 16 KB ring
+  uint8_t* sW = smem;                                 // KB x 16 KB, resident
+  uint8_t* sA = smem + KB * 16384;                    // PB_STAGES x 16 KB ring
   uint64_t* full = reinterpret_cast<uint64_t*>(sA + PB_STAGES * 16384);
   uint64_t* empty = full + PB_STAGES;
   uint64_t* wbar = empty + PB_STAGES;
@@ -549,53 +555,53 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int n_blk = blockIdx.x % p.num_n, m_blk = blockIdx.x / p.num_n;
+  const int rank = blockIdx.x % (NS * NS), m_blk = blockIdx.x / (NS * NS);
+  const int nq = rank / NS, ks = rank % NS;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && elect_one()) {
-    for (int i = 0; i < PB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
+    for (int i = 0; i < PB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(wbar, 1);
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 64);
+    tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast traffic
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
-  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
 
   // this row block is alive for steps [0, t_end); going backward it starts at t_end - 1.  Step index s counts from
   // there: t = t_end - 1 - s.  s = 0 has no recurrent term (no row of the block is alive at t + 1).
   int t_end = 0;
   while (t_end < p.T && m_blk * BM < pk.off[t_end + 1] - pk.off[t_end]) ++t_end;
+  float* my_part = p.part + ((int64_t)m_blk * (NS * NS) + rank) * 2 * PB_PART_FLOATS;
 
   if (warp == 0) {
-    // ================= TMA producer (lane 0 issues, lanes 0..num_n-1 poll one producer counter each) =================
+    // ============ TMA producer (lane 0 issues; lanes 0..NS-1 poll the CTAs that publish this K range) ============
     int stage = 0;
     uint32_t phase = 0;
     if (lane == 0) {
-      mbar_arrive_expect_tx(wbar, (uint32_t)(KB * 4096));
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * 4096, &tmB, wbar, kb * BK, n_blk * 32);
+      mbar_arrive_expect_tx(wbar, (uint32_t)(KB * 16384));
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * 16384, &tmB, wbar, 512 * ks + kb * BK, 128 * nq);
     }
     for (int s = 1; s < t_end; ++s) {
       const int t = t_end - 1 - s;
-      const int* f = p.flags + ((int64_t)m_blk * p.T + (t + 1)) * PB_FLAGS_PER_STEP;
+      // gate columns 512ks + 64kb.. are units 128ks + 16kb..: finalised by CTA (nq' = ks, ks' = kb * NS / 8)
+      const int* f = p.dgflag + ((int64_t)m_blk * p.T + (t + 1)) * PB_FLAGS_PER_STEP + ks * NS;
       int kb = 0;
       const long long t0 = clock64();
       while (kb < KB) {
-        const int v = lane < p.num_n ? ld_acquire_gpu(f + lane) : 0;
-        const unsigned waiting = __ballot_sync(0xffffffffu, lane < p.num_n && v < 1);
-        const int ready = waiting ? 2 * (__ffs((int)waiting) - 1) : KB;  // CTA n publishes k-blocks 2n, 2n+1
+        const int v = lane < NS ? ld_acquire_gpu(f + lane) : 0;
+        const unsigned waiting = __ballot_sync(0xffffffffu, lane < NS && v < 1);
+        const int ready = waiting ? (KB / NS) * (__ffs((int)waiting) - 1) : KB;
         if (ready <= kb) {
           if (clock64() - t0 > SNT_MBAR_TIMEOUT_CYCLES) {
             if (lane == 0) printf("snt: lstm bwd persistent flag timeout block %d step %d\n", (int)blockIdx.x, t);
@@ -606,12 +612,9 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         if (lane == 0) {
           if (kb == 0) DBG_STAMP(s, 0);
           for (int k = kb; k < ready; ++k) {
-            mbar_wait(&empty[stage], phase ^ 1);  // released by every CTA of the cluster
+            mbar_wait(&empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full[stage], 16384);
-            if (CL == 1)
-              tma_load_2d(sA + stage * 16384, &tmA, &full[stage], k * BK, pk.off[t + 1] + m_blk * BM);
-            else if ((uint32_t)(k % CL) == crank)
-              tma_load_2d_mc(sA + stage * 16384, &tmA, &full[stage], k * BK, pk.off[t + 1] + m_blk * BM, CMASK);
+            tma_load_2d(sA + stage * 16384, &tmA, &full[stage], 512 * ks + k * BK, pk.off[t + 1] + m_blk * BM);
             if (++stage == PB_STAGES) { stage = 0; phase ^= 1; }
           }
           if (ready == KB) DBG_STAMP(s, 1);
@@ -623,23 +626,23 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   } else if (warp == 1) {
     if (elect_one()) {
       // ================= MMA issuer =================
-      constexpr uint32_t idesc = make_idesc_bf16(BM, 32, false, false);
+      constexpr uint32_t idesc = make_idesc_bf16(BM, 128, false, false);
       mbar_wait(wbar, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int s = 1; s < t_end; ++s) {
-        const uint32_t tmem_d = tmem_base + (uint32_t)((s & 1) * 32);
+        const uint32_t tmem_d = tmem_base + (uint32_t)((s & 1) * 128);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full[stage], phase);
           if (kb == 0) DBG_STAMP(s, 2);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * 16384);
-          const uint32_t b_addr = smem_u32(sW + kb * 4096);
+          const uint32_t b_addr = smem_u32(sW + kb * 16384);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16(tmem_d, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
                       idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          if (CL == 1) umma_commit(&empty[stage]); else umma_commit_mc(&empty[stage], CMASK);
+          umma_commit(&empty[stage]);
           if (++stage == PB_STAGES) { stage = 0; phase ^= 1; }
         }
         DBG_STAMP(s, 3);
@@ -647,98 +650,155 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       }
     }
   } else if (warp >= 4) {
-    // ================= cell-backward epilogue: warp -> (TMEM lane quadrant q, 8-unit chunk c) =================
+    // ================= epilogue =================
+    // phase 1 (TMEM -> scratch) uses the TMEM mapping: warp -> (lane quadrant q, 32-column chunk c), thread = one row.
+    // phase 2 (cell backward) re-maps threads so that global accesses coalesce: warp wi owns rows 8wi..8wi+7, the 4
+    // lanes of a row own interleaved unit pairs {8k + 2j, 8k + 2j + 1}, so one store instruction writes 64 contiguous
+    // bytes of dG' per row (and one scratch load reads 256 contiguous bytes).
     const int q = warp & 3, c = (warp - 4) >> 2;
-    const int row = m_blk * BM + q * 32 + lane;
+    const int row_l1 = q * 32 + lane;
+    const int wi = warp - 4, j = lane & 3;
+    const int row_l = wi * 8 + (lane >> 2);
+    const int row = m_blk * BM + row_l;
     const int H = p.H, H4 = 4 * p.H;
-    const int j0 = n_blk * 32 + c * 8;
+    const int u0 = 128 * nq + WS * ks;  // first unit this CTA finalises
+    constexpr int KP = WS / 8;          // 8-unit groups in this CTA's slice
     const bool stamp = threadIdx.x == 128;
-    float dcreg[8];
+    float dcreg[UG][8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) dcreg[u] = 0.f;
-    // inputs of one step for this thread's (row, 8 units)
-    float4 dh4[2], c4[2], p4[2];
+    for (int g = 0; g < UG; ++g)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dcreg[g][u] = 0.f;
+    // inputs of one step for this thread's row and the 4 unit pairs k = 4g..4g+3
+    float2 dh2[4], c2[4], p2[4];
     uint4 a4[4];
-    auto load_inputs = [&](int t) {
+    auto load_inputs = [&](int t, int g) {
       const int bs = pk.off[t + 1] - pk.off[t];
       if (row < bs) {
-        const int64_t o1 = ((int64_t)pk.off[t] + row) * H + j0;
-        dh4[0] = *reinterpret_cast<const float4*>(p.d_hs + o1);
-        dh4[1] = *reinterpret_cast<const float4*>(p.d_hs + o1 + 4);
-        c4[0] = *reinterpret_cast<const float4*>(p.cs + o1);
-        c4[1] = *reinterpret_cast<const float4*>(p.cs + o1 + 4);
-        if (t > 0) {
-          const int64_t o0 = ((int64_t)pk.off[t - 1] + row) * H + j0;
-          p4[0] = *reinterpret_cast<const float4*>(p.cs + o0);
-          p4[1] = *reinterpret_cast<const float4*>(p.cs + o0 + 4);
-        } else {
-          p4[0] = p4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const uint4* ap = reinterpret_cast<const uint4*>(p.act + ((int64_t)pk.off[t] + row) * H4 + 4 * j0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) a4[k] = ap[k];
+        for (int kk = 0; kk < 4; ++kk) {
+          const int u = u0 + 8 * (4 * g + kk) + 2 * j;
+          const int64_t o1 = ((int64_t)pk.off[t] + row) * H + u;
+          dh2[kk] = *reinterpret_cast<const float2*>(p.d_hs + o1);
+          c2[kk] = *reinterpret_cast<const float2*>(p.cs + o1);
+          p2[kk] = t > 0 ? *reinterpret_cast<const float2*>(p.cs + ((int64_t)pk.off[t - 1] + row) * H + u)
+                         : make_float2(0.f, 0.f);
+          a4[kk] = *reinterpret_cast<const uint4*>(p.act + ((int64_t)pk.off[t] + row) * H4 + 4 * u);
+        }
       }
     };
-    if (t_end > 0) load_inputs(t_end - 1);
+    if (t_end > 0) load_inputs(t_end - 1, 0);
     for (int s = 0; s < t_end; ++s) {
       const int t = t_end - 1 - s;
       const int bs = pk.off[t + 1] - pk.off[t];
       const int bs_next = t + 1 < p.T ? pk.off[t + 2] - pk.off[t + 1] : 0;
       const bool ok = row < bs;
       const bool has_next = row < bs_next;  // rows still alive at step t+1 carry recurrent gradient
-      uint32_t r[8];
+      const int par = s & 1;
+      const int* pf = p.pflag + ((int64_t)m_blk * p.T + t) * PB_FLAGS_PER_STEP;
       if (s > 0) {
-        const int a = s & 1;
-        mbar_wait(&tfull[a], (uint32_t)(((s >> 1) & 1) ^ (a ^ 1)));
+        // ---- phase 1: this K-split's partial tile, chunk c (32 units of the 128-unit tile) -> scratch ----
+        mbar_wait(&tfull[par], (uint32_t)(((s >> 1) & 1) ^ (par ^ 1)));
         if (stamp) DBG_STAMP(s, 4);
         tcgen05_fence_after();
-        tmem_ld8(tmem_base + (uint32_t)(a * 32 + c * 8) + ((uint32_t)(q * 32) << 16), r);
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t)(par * 128 + c * 32) + ((uint32_t)(q * 32) << 16), r);
         tmem_ld_wait();
         tcgen05_fence_before();
-      } else {
+        {
+          const int x0 = 32 * c;  // tile column -> (finalizer slice, 8-unit group inside the slice)
+          float* base = my_part + (int64_t)par * PB_PART_FLOATS +
+                        (((int64_t)(x0 / WS) * KP + (x0 % WS) / 8) * 128 + row_l1) * 8;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = 0u;
-      }
-      if (ok) {
-        const float dhv[8] = {dh4[0].x, dh4[0].y, dh4[0].z, dh4[0].w, dh4[1].x, dh4[1].y, dh4[1].z, dh4[1].w};
-        const float cv[8] = {c4[0].x, c4[0].y, c4[0].z, c4[0].w, c4[1].x, c4[1].y, c4[1].z, c4[1].w};
-        const float pv[8] = {p4[0].x, p4[0].y, p4[0].z, p4[0].w, p4[1].x, p4[1].y, p4[1].z, p4[1].w};
-        const uint32_t a[16] = {a4[0].x, a4[0].y, a4[0].z, a4[0].w, a4[1].x, a4[1].y, a4[1].z, a4[1].w,
-                                a4[2].x, a4[2].y, a4[2].z, a4[2].w, a4[3].x, a4[3].y, a4[3].z, a4[3].w};
-        uint32_t go[16];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float2 if_ = unpack_bf2(a[2 * u]), go_ = unpack_bf2(a[2 * u + 1]);
-          const float i_ = if_.x, f_ = if_.y, g_ = go_.x, o_ = go_.y;
-          const float tc_ = tanh_(cv[u]);
-          const float dh = dhv[u] + (has_next ? __uint_as_float(r[u]) : 0.f);
-          const float dc = dcreg[u] + dh * o_ * (1.f - tc_ * tc_);
-          go[2 * u] = pack_bf2(dc * g_ * i_ * (1.f - i_), dc * pv[u] * f_ * (1.f - f_));
-          go[2 * u + 1] = pack_bf2(dc * i_ * (1.f - g_ * g_), dh * tc_ * o_ * (1.f - o_));
-          dcreg[u] = dc * f_;
+          for (int kk = 0; kk < 4; ++kk) {
+            float4* dst = reinterpret_cast<float4*>(base + (int64_t)kk * 128 * 8);
+            __stcg(dst, make_float4(__uint_as_float(r[8 * kk]), __uint_as_float(r[8 * kk + 1]),
+                                    __uint_as_float(r[8 * kk + 2]), __uint_as_float(r[8 * kk + 3])));
+            __stcg(dst + 1, make_float4(__uint_as_float(r[8 * kk + 4]), __uint_as_float(r[8 * kk + 5]),
+                                        __uint_as_float(r[8 * kk + 6]), __uint_as_float(r[8 * kk + 7])));
+          }
         }
-        uint4* gd = reinterpret_cast<uint4*>(p.dg + ((int64_t)pk.off[t] + row) * H4 + 4 * j0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) gd[k] = make_uint4(go[4 * k], go[4 * k + 1], go[4 * k + 2], go[4 * k + 3]);
+        if (stamp) DBG_STAMP(s, 5);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
+        if (threadIdx.x == 128) atomicAdd(const_cast<int*>(pf) + rank, 1);
+        if (stamp) DBG_STAMP(s, 6);
+        // ---- wait for the NS partials of this N tile (CTAs nq*NS .. nq*NS+NS-1) ----
+        if (warp == 4) {
+          const long long t0 = clock64();
+          for (;;) {
+            const int v = lane < NS ? ld_acquire_gpu(pf + nq * NS + lane) : 1;
+            if (__all_sync(0xffffffffu, v >= 1)) break;
+            if (clock64() - t0 > SNT_MBAR_TIMEOUT_CYCLES) {
+              if (lane == 0) printf("snt: lstm bwd partial timeout block %d step %d\n", (int)blockIdx.x, t);
+              __trap();
+            }
+          }
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
+        if (stamp) DBG_STAMP(s, 7);
       }
-      if (stamp) DBG_STAMP(s, 5);
+      // ---- phase 2: final dL/dh for this CTA's units, cell backward, publish dG'_t ----
+#pragma unroll
+      for (int g = 0; g < UG; ++g) {
+        if (g > 0) load_inputs(t, g);
+        if (ok) {
+          float2 rec[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) rec[kk] = make_float2(0.f, 0.f);
+          if (s > 0 && has_next) {
+            float2 x[NS][4];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+              const float* src = p.part + (((int64_t)m_blk * (NS * NS) + nq * NS + k) * 2 + par) * PB_PART_FLOATS +
+                                 (((int64_t)ks * KP + 4 * g) * 128 + row_l) * 8 + 2 * j;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) x[k][kk] = __ldcg(reinterpret_cast<const float2*>(src + (int64_t)kk * 128 * 8));
+            }
+#pragma unroll
+            for (int k = 0; k < NS; ++k)  // fixed order: deterministic
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) { rec[kk].x += x[k][kk].x; rec[kk].y += x[k][kk].y; }
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t a[4] = {a4[kk].x, a4[kk].y, a4[kk].z, a4[kk].w};
+            const float dhv[2] = {dh2[kk].x + rec[kk].x, dh2[kk].y + rec[kk].y};
+            const float cv[2] = {c2[kk].x, c2[kk].y}, pv[2] = {p2[kk].x, p2[kk].y};
+            uint32_t go[4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float2 if_ = unpack_bf2(a[2 * e]), go_ = unpack_bf2(a[2 * e + 1]);
+              const float i_ = if_.x, f_ = if_.y, g_ = go_.x, o_ = go_.y;
+              const float tc_ = tanh_(cv[e]);
+              const float dh = dhv[e];
+              const float dc = dcreg[g][2 * kk + e] + dh * o_ * (1.f - tc_ * tc_);
+              go[2 * e] = pack_bf2(dc * g_ * i_ * (1.f - i_), dc * pv[e] * f_ * (1.f - f_));
+              go[2 * e + 1] = pack_bf2(dc * i_ * (1.f - g_ * g_), dh * tc_ * o_ * (1.f - o_));
+              dcreg[g][2 * kk + e] = dc * f_;
+            }
+            const int u = u0 + 8 * (4 * g + kk) + 2 * j;
+            *reinterpret_cast<uint4*>(p.dg + ((int64_t)pk.off[t] + row) * H4 + 4 * u) = make_uint4(go[0], go[1], go[2], go[3]);
+          }
+        }
+      }
+      if (stamp) DBG_STAMP(s, 8);
       if (s + 1 < t_end) {
         publish_fence();
-        if (stamp) DBG_STAMP(s, 6);
         asm volatile("bar.sync 1, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
-        if (threadIdx.x == 128) atomicAdd(p.flags + ((int64_t)m_blk * p.T + t) * PB_FLAGS_PER_STEP + n_blk, 1);
-        if (stamp) DBG_STAMP(s, 7);
-        load_inputs(t - 1);
+        if (threadIdx.x == 128)
+          atomicAdd(p.dgflag + ((int64_t)m_blk * p.T + t) * PB_FLAGS_PER_STEP + rank, 1);
+        if (stamp) DBG_STAMP(s, 9);
+        load_inputs(t - 1, 0);
       }
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -805,7 +865,7 @@ lstm_bwd_point_kernel(int bs, int bs_next, int H, const float* __restrict__ d_hs
 
 // ---------------------------------------------------------------------------------------------------------------------
 struct LstmWs {
-  float* bsum; bf* w_ih; bf* w_hh; bf* w_hh_t; bf* gx; float* dc_state; float* cpart; float* tmp; float* sws; int* flags; bool ok;
+  float* bsum; bf* w_ih; bf* w_hh; bf* w_hh_t; bf* gx; float* dc_state; float* cpart; float* tmp; float* sws; int* flags; float* part; bool ok;
 };
 static int64_t csb_partials(int64_t R, int64_t C) { return ((R + 255) / 256) * C; }
 static LstmWs carve(void* ws, int64_t ws_bytes, int64_t N, int64_t B, int64_t In, int64_t H) {
@@ -819,15 +879,17 @@ static LstmWs carve(void* ws, int64_t ws_bytes, int64_t N, int64_t B, int64_t In
   r.cpart = w.take<float>(csb_partials(N, 4 * H));
   r.tmp = w.take<float>(4 * H);
   r.sws = w.take<float>(MAX_SPLITS * 4 * H * (In > H ? In : H));
-  r.flags = w.take<int>(((B + 127) / 128) * SNT_MAX_T * PB_FLAGS_PER_STEP);
+  r.flags = w.take<int>(((B + 127) / 128) * SNT_MAX_T * PB_FLAGS_PER_STEP * 2);
   r.w_hh_t = w.take<bf>(4 * H * H);
+  r.part = w.take<float>(((B + 127) / 128) * PB_FLAGS_PER_STEP * 2 * PB_PART_FLOATS);
   r.ok = w.ok();
   return r;
 }
 int64_t lstm_ws_bytes(int64_t N, int64_t B, int64_t In, int64_t H) {
   return 2 * ws_bytes_for(4 * H, 4) + ws_bytes_for(4 * H * In, 2) + ws_bytes_for(4 * H * H, 2) +
          ws_bytes_for(N * 4 * H, 2) + ws_bytes_for(B * H, 4) + ws_bytes_for(csb_partials(N, 4 * H), 4) +
-         ws_bytes_for(MAX_SPLITS * 4 * H * (In > H ? In : H), 4) + ws_bytes_for(((B + 127) / 128) * SNT_MAX_T * PB_FLAGS_PER_STEP, 4) + ws_bytes_for(4 * H * H, 2);
+         ws_bytes_for(MAX_SPLITS * 4 * H * (In > H ? In : H), 4) + ws_bytes_for(((B + 127) / 128) * SNT_MAX_T * PB_FLAGS_PER_STEP * 2, 4) + ws_bytes_for(4 * H * H, 2) +
+         ws_bytes_for(((B + 127) / 128) * PB_FLAGS_PER_STEP * 2 * PB_PART_FLOATS, 4);
 }
 
 // the persistent kernels need every CTA co-resident (cooperative launch) and ~200 KB of shared memory
@@ -857,7 +919,7 @@ static int launch_persistent(void (*k1)(CUtensorMap, CUtensorMap, PackInfo, Para
   // launches fail under ncu, so the default is plain cooperative; SNT_PERSIST_CLUSTER=4 opts in.
   const char* env = getenv("SNT_PERSIST_CLUSTER");
   int want = env ? atoi(env) : 1;
-  if (num_n % 4 != 0 || want != 4) want = 1;
+  if (num_n % 4 != 0 || want != 4 || k4 == nullptr) want = 1;
   for (int attempt = 0; attempt < 2; ++attempt) {
     const int cl = (want == 4 && mode != 1) ? 4 : 1;
     auto kern = cl == 4 ? k4 : k1;
@@ -1029,31 +1091,36 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
   SNT_CHECK(prep_weights(w, w_ih, w_hh, nullptr, nullptr, In, H, st));
   bool persistent = false;
   {
-    const int num_m0 = (int)((B + tc::BM - 1) / tc::BM), num_n = (int)(H / 32);
-    const int KB = (int)(4 * H / tc::BK);
-    const size_t smem = (size_t)KB * 4096 + (size_t)PB_STAGES * 16384 + 1024 + 256;
+    const int num_m0 = (int)((B + tc::BM - 1) / tc::BM);
+    const int ns = (int)(H / 128);  // K-splits = N tiles; ns*ns CTAs per row block
+    const size_t smem = (size_t)(8 + PB_STAGES) * 16384 + 1024 + 256;
     int coop = 0, max_smem = 0;
     persist_caps(&coop, &max_smem);
-    if (coop == 1 && !getenv("SNT_NO_PERSISTENT") && H % 32 == 0 && num_n <= PB_FLAGS_PER_STEP &&
-        (int64_t)num_m0 * num_n <= tc::sm_count() && smem <= (size_t)max_smem && w.flags && w.w_hh_t) {
+    if (coop == 1 && !getenv("SNT_NO_PERSISTENT") && (H == 256 || H == 512) &&
+        (int64_t)num_m0 * ns * ns <= tc::sm_count() && smem <= (size_t)max_smem && w.flags && w.w_hh_t && w.part) {
       perm_transpose_bf16_kernel<<<dim3((unsigned)((H + 31) / 32), (unsigned)((4 * H + 31) / 32)), 256, 0, st>>>(
           w_hh, (int)H, w.w_hh_t);
       SNT_LAUNCH_CHECK("perm_transpose_bf16_kernel");
       CUtensorMap ta, tb;
       SNT_CHECK(tc::make_operand_tmap(&ta, dg, false, N, 4 * H, 4 * H, tc::BM));
-      SNT_CHECK(tc::make_operand_tmap(&tb, w.w_hh_t, false, H, 4 * H, 4 * H, 32));
-      SNT_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)num_m0 * T * PB_FLAGS_PER_STEP, st));
+      SNT_CHECK(tc::make_operand_tmap(&tb, w.w_hh_t, false, H, 4 * H, 4 * H, 128));
+      const size_t nflags = (size_t)num_m0 * T * PB_FLAGS_PER_STEP;
+      SNT_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(int) * 2 * nflags, st));
       PersistBwdParams pp;
-      pp.H = (int)H; pp.T = T; pp.num_n = num_n; pp.d_hs = d_hs; pp.act = act; pp.cs = cs; pp.dg = dg;
-      pp.flags = w.flags;
+      pp.H = (int)H; pp.T = T; pp.ns = ns; pp.d_hs = d_hs; pp.act = act; pp.cs = cs; pp.dg = dg;
+      pp.part = w.part; pp.dgflag = w.flags; pp.pflag = w.flags + nflags;
 #ifdef SNT_LSTM_DBG
       static long long* dbg_dev = nullptr;
       if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * SNT_MAX_T * 12);
       cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * SNT_MAX_T * 12, st);
       pp.dbg = dbg_dev;
 #endif
-      SNT_CHECK(launch_persistent<PersistBwdParams>(lstm_bwd_persistent_kernel<1>, lstm_bwd_persistent_kernel<4>,
-                                                    num_m0 * num_n, num_n, smem, ta, tb, pk, pp, st));
+      if (ns == 4)
+        SNT_CHECK(launch_persistent<PersistBwdParams>(lstm_bwd_persistent_kernel<4>, nullptr, num_m0 * ns * ns, 1, smem,
+                                                      ta, tb, pk, pp, st));
+      else
+        SNT_CHECK(launch_persistent<PersistBwdParams>(lstm_bwd_persistent_kernel<2>, nullptr, num_m0 * ns * ns, 1, smem,
+                                                      ta, tb, pk, pp, st));
 #ifdef SNT_LSTM_DBG
       {
         static int printed = 0;
@@ -1061,12 +1128,11 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
           long long h[SNT_MAX_T * 12];
           cudaStreamSynchronize(st);
           cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
-          const long long t0 = h[5];
-          fprintf(stderr, "cols 8: after reader fence, 9: after writer proxy fence\n");
-          fprintf(stderr, "[lstm bwd dbg] block %d: s: flag0_seen tma_issued first_full mma_issued tfull_seen dg_stored fenced flag_set\n", SNT_DBG_BLOCK);
+          const long long t0 = h[8];
+          fprintf(stderr, "[lstm bwd dbg] block %d: s: ready0_seen tma_issued first_full mma_issued tfull_seen part_stored pflag_set parts_ready dg_stored dgflag_set\n", SNT_DBG_BLOCK);
           for (int t = 0; t < T; ++t) {
             fprintf(stderr, "[lstm bwd dbg] %2d:", t);
-            for (int k = 0; k < 12; ++k) fprintf(stderr, " %8lld", h[t * 12 + k] > 0 ? h[t * 12 + k] - t0 : -1);
+            for (int k = 0; k < 10; ++k) fprintf(stderr, " %8lld", h[t * 12 + k] > 0 ? h[t * 12 + k] - t0 : -1);
             fprintf(stderr, "\n");
           }
         }

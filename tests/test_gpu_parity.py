@@ -196,7 +196,8 @@ def _oracle_case(B, E, H, V, L, seed, lengths=None):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-@pytest.mark.parametrize("B,E,H,V,L", [(64, 64, 128, 1000, 1), (48, 32, 64, 517, 2), (200, 256, 512, 2000, 1)])
+@pytest.mark.parametrize("B,E,H,V,L", [(64, 64, 128, 1000, 1), (48, 32, 64, 517, 2), (200, 256, 512, 2000, 1),
+                                         (150, 64, 256, 600, 2), (300, 128, 512, 1200, 2)])
 def test_train_step_vs_oracle(prec, B, E, H, V, L):
     params, b, targets = _oracle_case(B, E, H, V, L, seed=B + L)
     r = O.train_step(O.cast_params(params, np.float64), b["features"].astype(np.float64), b["captions"],
