@@ -52,46 +52,121 @@ def train_flops(B, N, c=CFG):
 
 
 class ClockSampler:
+    """SM clock / power / throttle reasons of this rank's GPU, sampled DURING the timed region.
+
+    In-process NVML (the library behind nvidia-smi) from a background thread, every 100 ms: a `nvidia-smi -lms 50`
+    subprocess per rank was measured to stretch a 2-GPU step from 1.56 ms to 7.4 ms (its query loop contends with
+    kernel launches), which made the sampled run unrepresentative.  Falls back to one `nvidia-smi -lms 200`
+    subprocess when pynvml is missing."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    PERIOD_S = 0.1
 
     def __init__(self, device_index):
         self.idx = device_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.rows = []          # (sm_mhz, max_mhz, power_w, reasons bitmask)
+        self.thread = None
+        self.stop_flag = False
         self.p = None
+        self.f = None
+        self.source = None
+
+    def _nvml_loop(self, nv, h):
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), float(mx), float(pw), int(rs)))
+            except Exception:
+                pass
+            time.sleep(self.PERIOD_S)
+
+    def _nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+        return nv, nv.nvmlDeviceGetHandleByIndex(phys)
+
+    def open_manual(self):
+        """N > 1: no polling thread (see bench main); sample_once() is called while the GPU is under load."""
+        try:
+            self._nv, self._h = self._nvml()
+            self._mx = self._nv.nvmlDeviceGetMaxClockInfo(self._h, self._nv.NVML_CLOCK_SM)
+            self.thread = "manual"
+            self.source = "nvml (in-process, on-demand samples right after the timed region)"
+        except Exception:
+            self.thread = None
+
+    def sample_once(self):
+        if self.thread != "manual":
+            return
+        nv, h = self._nv, self._h
+        try:
+            rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(self._mx),
+                              nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(rs)))
+        except Exception:
+            pass
 
     def start(self):
         try:
+            import threading
+            nv, h = self._nvml()
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            self.source = "nvml (in-process, 100 ms)"
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                       "-lms", "50", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "200", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi -lms 200"
         except OSError:
             self.p = None
 
     def stop(self):
-        if self.p is not None:
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        sm, mx, pw, reasons = [], [], [], set()
+        if self.thread is not None:
+            self.stop_flag = True
+            if self.thread != "manual":
+                self.thread.join(timeout=2)
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            for a, b, c, r in self.rows:
+                sm.append(a); mx.append(b); pw.append(c)
+                for n in names:
+                    if r & bits[n]:
+                        reasons.add(n)
+        elif self.p is not None:
             self.p.terminate()
             try:
                 self.p.wait(timeout=5)
             except subprocess.TimeoutExpired:
                 self.p.kill()
-        self.f.flush()
-        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
-        os.unlink(self.f.name)
-        sm, mx, pw, reasons = [], [], [], set()
-        for r in rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.strip().lower() == "active":
-                    reasons.add(name)
+            self.f.flush()
+            rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+            os.unlink(self.f.name)
+            for r in rows:
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                except (ValueError, IndexError):
+                    continue
+                for name, v in zip(names, r[4:8]):
+                    if v.strip().lower() == "active":
+                        reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
         loaded = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
         return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": float(max(pw))}
+                "samples": len(sm), "power_w_max": float(max(pw)), "source": self.source}
 
 
 def make_global_batch(world, c=CFG, seed=1):
@@ -275,18 +350,41 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     sampler = ClockSampler(local)
-    sampler.start()
     L = snt._lib.lib()
-    L.snt_launch_count(1)
-    t_res = timed(step_resident, args.steps)
-    launches = int(L.snt_launch_count(0))
-    # keep the same step running so that nvidia-smi (50 ms period) sees the loaded clocks
-    t_end = time.time() + max(0.0, 1.5 - t_res)
-    while time.time() < t_end:
-        step_resident()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    clocks["sampled_over"] = "timed region + continuation of the same step to >= 1.5 s"
+    if world == 1:
+        # one GPU: NVML is polled from a background thread for the whole timed region (no measurable effect on the step)
+        sampler.start()
+        L.snt_launch_count(1)
+        t_res = timed(step_resident, args.steps)
+        launches = int(L.snt_launch_count(0))
+        # keep the same step running so that the 100 ms poll sees the loaded clocks
+        n_extra = int(np.ceil(max(0.0, 1.5 - t_res) / max(t_res / args.steps, 1e-6)))
+        for _ in range(n_extra):
+            step_resident()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        clocks["sampled_over"] = "timed region + continuation of the same step to >= 1.5 s"
+    else:
+        # N > 1: any NVML / nvidia-smi polling while the ranks exchange gradients stretches the step 3-6x (measured:
+        # 1.56 ms -> 4.5-9.8 ms at N=2), so the clocks are sampled on demand while the GPU is busy with the SAME step
+        # immediately after the timed region, never inside it.  Step counts are identical on
+        # every rank (a wall-clock loop would issue different numbers of all-reduces per rank and hang).
+        sampler.open_manual()
+        L.snt_launch_count(1)
+        t_res = timed(step_resident, args.steps)
+        launches = int(L.snt_launch_count(0))
+        for _ in range(4):
+            for _ in range(5):
+                step_resident()
+            sampler.sample_once()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        clocks["sampled_over"] = "20 more steps of the same load right after the timed region (polling inside it perturbs multi-GPU steps)"
+    if os.environ.get("SNT_BENCH_DEBUG"):
+        t2 = timed(step_resident, args.steps)
+        if rank == 0:
+            print(f"[dbg] resident again, no clock sampler: {t2 / args.steps * 1e3:.3f} ms/step "
+                  f"(with sampler {t_res / args.steps * 1e3:.3f})", file=sys.stderr)
 
     # per-stage GPU time: CUDA events around every C-ABI call of 10 more real steps (rank 0's stream)
     stages = None

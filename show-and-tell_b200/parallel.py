@@ -51,10 +51,23 @@ class GradAllReducer:
         if names is None:
             self.finish()
             return
+        self._reduce_group(tensors)
         for n, t in zip(names, tensors):
-            self.pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
             self.order.append(n)
             self.bytes += t.numel() * t.element_size()
+
+    def _reduce_group(self, tensors):
+        """One asynchronous SUM all-reduce per readiness group.  On NCCL the group's tensors are coalesced into a
+        single launch (ncclGroupStart/End): one kernel instead of one per tensor next to the BPTT kernels."""
+        tensors = list(tensors)
+        if len(tensors) > 1 and dist.get_backend(self.group) == "nccl" and hasattr(dist, "_coalescing_manager"):
+            with dist._coalescing_manager(group=self.group, device=tensors[0].device, async_ops=True) as cm:
+                for t in tensors:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self.pending.append(cm)
+        else:
+            for t in tensors:
+                self.pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def finish(self):
         for w in self.pending:
@@ -79,10 +92,17 @@ class DataParallelStep:
         self.m = [torch.zeros_like(p) for p in self.params]
         self.v = [torch.zeros_like(p) for p in self.params]
         self.t = 0
+        self._inflight = []   # events of the last steps (world > 1): bounds how far the host runs ahead
 
     def step(self, inputs, captions, lengths, targets, n_tokens_global=None):
         """inputs: pooled[B,2048] when an encoder is attached, else features[B,E].  Returns this rank's share
         of the global mean loss (sum over ranks = global-batch loss)."""
+        if self.world > 1 and self.params and self.params[0].is_cuda:
+            # Gradients are consumed on NCCL's stream, so the caching allocator can recycle their blocks only once
+            # that work has completed.  A host that runs many steps ahead keeps asking for fresh blocks (cudaMalloc
+            # synchronises the device); two steps of run-ahead hide all launch latency and keep the pool steady.
+            if len(self._inflight) >= 2:
+                self._inflight.pop(0).synchronize()
         for p in self.params:
             p.grad = None
         n_local = int(sum(lengths))
@@ -91,13 +111,17 @@ class DataParallelStep:
         loss = self.decoder.loss(feats, captions, lengths, targets, grad_scale=scale)
         loss.backward()
         if self.world > 1 and self.encoder is not None:   # head gradients: final only after the decoder's backward
-            for p in self.encoder.parameters():
-                if p.requires_grad and p.grad is not None:
-                    dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group)
+            hg = [p.grad for p in self.encoder.parameters() if p.requires_grad and p.grad is not None]
+            self.reducer._reduce_group(hg)
+            self.reducer.finish()
         if self.optimizer:
             self.t += 1
             live = [(p.data, p.grad.contiguous(), m, v) for p, m, v in zip(self.params, self.m, self.v)
                     if p.grad is not None]
             ops.clamp_adam_multi_([x[0] for x in live], [x[1] for x in live], [x[2] for x in live],
                                   [x[3] for x in live], self.t, self.lr, self.betas, self.eps, self.grad_clip)
+        if self.world > 1 and self.params and self.params[0].is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._inflight.append(ev)
         return loss.detach()
