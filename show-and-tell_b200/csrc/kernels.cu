@@ -519,10 +519,25 @@ emb_scan_kernel(const int* __restrict__ count, int V, int* __restrict__ start, i
   __shared__ int carry_s;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (threadIdx.x == 0) { carry_s = 0; multi[0] = 0; small[0] = 0; }
+  int pre[16];  // the first 16 slabs' counts are fetched up front: one global-load latency instead of one per slab
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int i = k * 1024 + threadIdx.x;
+    pre[k] = i < V ? count[i] : 0;
+  }
   __syncthreads();
-  for (int base = 0; base < V; base += 1024) {
+  int slab = 0;
+#pragma unroll 1
+  for (int base = 0; base < V; base += 1024, ++slab) {
     const int i = base + threadIdx.x;
-    const int c = i < V ? count[i] : 0;
+    int c;
+    if (slab < 16) {
+      c = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) c = (k == slab) ? pre[k] : c;
+    } else {
+      c = i < V ? count[i] : 0;
+    }
     int x = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -637,14 +652,28 @@ emb_multi_kernel(const float* __restrict__ dx1, const int* __restrict__ start, c
     int* sorted_w = big ? gsorted + s0 : sorted_s;
     __syncthreads();  // previous token's shared data no longer in use
     if (!big) {
-      for (int a = threadIdx.x; a < n; a += 1024) raw[a] = perm0[s0 + a];
+      const int n4 = (n + 3) & ~3;
+      for (int a = threadIdx.x; a < n4; a += 1024) raw[a] = a < n ? perm0[s0 + a] : 0x7fffffff;
       __syncthreads();
-    }
-    for (int a = threadIdx.x; a < n; a += 1024) {
-      const int mine = rawp[a];
-      int rank = 0;
-      for (int b = 0; b < n; ++b) rank += (rawp[b] < mine);  // row indices are distinct; broadcast reads
-      sorted_w[rank] = mine;
+      // O(n^2) ranking out of shared memory, 4 indices per (broadcast) 16-byte load
+      for (int a = threadIdx.x; a < n; a += 1024) {
+        const int mine = raw[a];
+        int rank = 0;
+        const int4* r4 = reinterpret_cast<const int4*>(raw);
+#pragma unroll 4
+        for (int b = 0; b < n4 / 4; ++b) {
+          const int4 v = r4[b];
+          rank += (v.x < mine) + (v.y < mine) + (v.z < mine) + (v.w < mine);
+        }
+        sorted_s[rank] = mine;
+      }
+    } else {
+      for (int a = threadIdx.x; a < n; a += 1024) {
+        const int mine = rawp[a];
+        int rank = 0;
+        for (int b = 0; b < n; ++b) rank += (rawp[b] < mine);  // row indices are distinct; broadcast reads
+        sorted_w[rank] = mine;
+      }
     }
     __syncthreads();
     const int* sorted = sorted_w;

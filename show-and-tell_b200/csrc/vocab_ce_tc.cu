@@ -10,6 +10,8 @@
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 
+#include <stdlib.h>
+
 namespace snt {
 namespace bf16 {
 
@@ -114,39 +116,43 @@ struct CeFwdEpi {
   }
 };
 
-// lse[n] = ln2 * (M + log2 sum_k s_k 2^(m_k - M)); nll[n] = lse - tl.  One thread per row, one pass (online merge of
-// the slab partials, 4 loads in flight); small blocks so that ~200 of them cover a 12k-row batch.
-__global__ void __launch_bounds__(64)
+// lse[n] = ln2 * (M + log2 sum_k s_k 2^(m_k - M)); nll[n] = lse - tl.  Block = 64 rows x 8 slab groups: every thread
+// merges its share of the slab partials online (coalesced across rows), the 8 groups are merged through shared memory
+// in a fixed order.
+__global__ void __launch_bounds__(512)
 ce_finish_kernel(const float2* __restrict__ part, int slabs, int64_t N, const float* __restrict__ tl,
                  float* __restrict__ lse, float* __restrict__ nll) {
-  const int64_t row = (int64_t)blockIdx.x * 64 + threadIdx.x;
-  if (row >= N) return;
+  __shared__ float2 red[8][64];
+  const int tx = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int64_t row = (int64_t)blockIdx.x * 64 + tx;
   float M = -INFINITY, S = 0.f;
-  int k = 0;
-  for (; k + 4 <= slabs; k += 4) {
-    float2 p[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) p[i] = part[(int64_t)(k + i) * N + row];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (p[i].y > 0.f) {
-        const float mn = fmaxf(M, p[i].x);
-        S = S * exp2f(M - mn) + p[i].y * exp2f(p[i].x - mn);
+  if (row < N) {
+    for (int k = g; k < slabs; k += 8) {
+      const float2 p = part[(int64_t)k * N + row];
+      if (p.y > 0.f) {
+        const float mn = fmaxf(M, p.x);
+        S = S * exp2f(M - mn) + p.y * exp2f(p.x - mn);
         M = mn;
       }
     }
   }
-  for (; k < slabs; ++k) {
-    const float2 p = part[(int64_t)k * N + row];
-    if (p.y > 0.f) {
-      const float mn = fmaxf(M, p.x);
-      S = S * exp2f(M - mn) + p.y * exp2f(p.x - mn);
-      M = mn;
+  red[g][tx] = make_float2(M, S);
+  __syncthreads();
+  if (g == 0 && row < N) {
+    float Mt = -INFINITY, St = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 p = red[i][tx];
+      if (p.y > 0.f) {
+        const float mn = fmaxf(Mt, p.x);
+        St = St * exp2f(Mt - mn) + p.y * exp2f(p.x - mn);
+        Mt = mn;
+      }
     }
+    const float l = (Mt + log2f(St)) * LN2;
+    lse[row] = l;
+    nll[row] = l - tl[row];
   }
-  const float l = (M + log2f(S)) * LN2;
-  lse[row] = l;
-  nll[row] = l - tl[row];
 }
 
 // ---- backward epilogue: dlogits = (2^(y - lse2) - onehot) * scale -> bf16 chunk ------------------------------------
@@ -332,7 +338,10 @@ __global__ void scale_vec_kernel(const float* __restrict__ in, int64_t n, float 
 // ---------------------------------------------------------------------------------------------------------------------
 static inline int64_t pad8(int64_t x) { return (x + 7) / 8 * 8; }
 // rows of dlogits alive at once: (SMs/4) row tiles make dHs (BN=128) exactly one wave and the softmax-grad pass a whole
-// number of waves; capped so the bf16 chunk stays around 3/4 of the 126 MB L2 (37*128 x 10000 x 2 B = 95 MB)
+// number of waves; capped so the bf16 chunk stays around 3/4 of the 126 MB L2 (37*128 x 10000 x 2 B = 95 MB).
+// Measured (round 1, V=10000, H=512): 33-37 row tiles per chunk give 499 us for the whole backward; 25 tiles 544 us,
+// 19 tiles 645 us - smaller chunks would sit deeper in L2 (ncu: the consumers re-read ~1-2x the chunk from DRAM at 37
+// tiles) but lose more to partial waves and per-launch overhead than they gain.
 static int64_t bwd_chunk_rows(int64_t N, int64_t V) {
   int64_t tiles = tc::sm_count() / 4;
   if (tiles < 1) tiles = 1;
@@ -400,7 +409,7 @@ int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const i
   CeFwdEpi e;
   e.M = (int)N; e.V = (int)V; e.bias = b_out; e.part = w.part;
   SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeFwdEpi>(ta, tb, ts, e, st)));
-  ce_finish_kernel<<<(unsigned)((N + 63) / 64), 64, 0, st>>>(w.part, w.slabs, N, w.tl, lse, w.nll);
+  ce_finish_kernel<<<(unsigned)((N + 63) / 64), 512, 0, st>>>(w.part, w.slabs, N, w.tl, lse, w.nll);
   SNT_LAUNCH_CHECK("ce_finish_kernel");
   return reduce_sum(w.nll, N, 1.0f / (float)N, loss, st);
 }
@@ -443,6 +452,7 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
     const double c256 = (double)((t256 + sms - 1) / sms) * 2.0, c128 = (double)((t128 + sms - 1) / sms) * 1.15;
     dw_bn = c128 < c256 ? 128 : 256;
   }
+
   SideStream* side = side_stream();
   for (int64_t r0 = 0; r0 < N; r0 += w.R) {
     const int64_t r = N - r0 < w.R ? N - r0 : w.R;
@@ -464,13 +474,19 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
     }
     // dHs[r,H] = dlogits[r,V] . W_out[V,H]      (B operand MN-major)
     int sp = tc::choose_splits(r, H, V, 0);
+    {  // fill the machine: (row tiles x column tiles) x splits ~ SM count
+      const int64_t tiles = ((r + 127) / 128) * ((H + 127) / 128);
+      const int want = (int)(tc::sm_count() / (tiles > 0 ? tiles : 1));
+      if (want > sp) sp = want;
+    }
     if (sp > MAX_SPLITS) sp = MAX_SPLITS;
     if ((int64_t)sp * r > MAX_SPLITS * 1024) sp = (int)(MAX_SPLITS * 1024 / r);  // partials must fit the scratch
     if (sp < 1) sp = 1;
     SNT_CHECK(tc::gemm_tc(false, true, r, H, V, scale, w.dl, w.Vp, w.wb, H, 0.f, d_hs + r0 * H, nullptr, H, nullptr, sp,
                           w.sws, st, 0, dloss));
-    // dW_out[V,H] += dlogits^T[V,r] . Hs[r,H]   (both operands MN-major).  ceil(V/128) x (H/BN) tiles rarely fill whole
-    // waves; 128-wide tiles give the finer granularity (316 tiles = 3 short rounds instead of 2 long ones at V=10000).
+    // dW_out[V,H] += dlogits^T[V,r] . Hs[r,H]   (both operands MN-major).  Measured at V=10000, H=512 (round 1): 128- and
+    // 256-wide tiles, with or without a split-K tail for the last partial wave, all land within 2% of each other - the
+    // contraction re-reads the 95 MB dlogits chunk from L2 once per column tile and is bound there, not by wave shape.
     SNT_CHECK(tc::gemm_tc(true, true, V, H, r, scale, w.dl, w.Vp, hs_b + r0 * H, H, acc, d_w_out, nullptr, H, nullptr, 1,
                           nullptr, st, 0, dloss, false, nullptr, /*force_bn=*/dw_bn));
     if (!side) SNT_CHECK(colsum_bf16(w.dl, r, V, w.Vp, acc, w.db, w.cpart, st));
