@@ -35,6 +35,7 @@ import torch
 
 CFG = dict(B=1024, E=256, H=512, V=10000, L=1, POOLED=2048)          # BASELINE.json configs[1]
 GREEDY_B = 4096                                                       # BASELINE.json configs[2]
+EXTRA_WARMUP_MULTI_GPU = 120                                          # untimed steps added to --warmup when N > 1
 
 
 def load_peaks():
@@ -369,6 +370,12 @@ def main():
         # 1.56 ms -> 4.5-9.8 ms at N=2), so the clocks are sampled on demand while the GPU is busy with the SAME step
         # immediately after the timed region, never inside it.  Step counts are identical on
         # every rank (a wall-clock loop would issue different numbers of all-reduces per rank and hang).
+        # Multi-GPU steps need a much longer warm-up than W: measured at N=2, successive blocks of 30 steps take 5.7,
+        # 3.6, 2.7 and then a steady 1.56 ms per step (the caching allocator keeps growing its pool while gradient
+        # blocks are still held by NCCL's stream, NCCL sets up its channels lazily).  EXTRA_WARMUP more untimed steps
+        # (identical on every rank) put the timed region in the steady state a training run lives in.
+        for _ in range(EXTRA_WARMUP_MULTI_GPU):
+            step_resident()
         sampler.open_manual()
         L.snt_launch_count(1)
         t_res = timed(step_resident, args.steps)
@@ -463,6 +470,7 @@ def main():
                                    "batch 1024 per GPU (BASELINE configs[1]; N>1 = configs[4] weak-scaled)",
                        "global_batch": total_caps, "tokens_per_rank": n_tok, "max_len": int(max(lengths)),
                        "parallelism": f"dp{world}", "precision_mode": args.prec,
+                       "extra_warmup_steps": EXTRA_WARMUP_MULTI_GPU if world > 1 else 0,
                        "l2": "no explicit flush: each step streams ~0.6 GB of activations/weights (> 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": "captions/s", "ms_per_step": t_e2e / args.steps * 1e3,
                     "h2d_bytes_per_step": int(pooled_h.numel() * 4 + caps_h.numel() * 8 + tg_h.numel() * 8),
