@@ -368,58 +368,79 @@ int argmax_gather(const float* logits, int64_t B, int64_t V, int64_t ld, const f
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// a2: BatchNorm1d over the batch (models.py:17,28; momentum 0.01).  Block = 32 features x 32 row-lanes.
+// a2: BatchNorm1d over the batch (models.py:17,28; momentum 0.01).
+// Block = 8 features x 128 row-lanes (E/8 blocks: 32 at E=256).  A warp covers 4 rows x 8 features = four whole 32-byte
+// sectors per load; each thread keeps its first BN_CACHE rows in registers, so for B <= 1024 the batch is read from
+// global memory once (statistics are still two-pass: mean first, then centred squares).  Column sums are reduced over
+// the 128 row-lanes through shared memory in a fixed order.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+constexpr int BN_FEATS = 8, BN_LANES = 128, BN_CACHE = 8;
+__device__ __forceinline__ float bn_block_sum(float v, float (*red)[BN_FEATS], int tx, int ty) {
+  // a warp holds 4 rows x 8 features: fold the 4 rows with two shuffles, then the 32 warps through shared memory
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  __syncthreads();  // previous use of red[] is over
+  if ((threadIdx.x & 31) < BN_FEATS) red[threadIdx.x >> 5][tx] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < BN_LANES / 4; ++i) t += red[i][tx];  // same order in every thread: deterministic
+  return t;
+}
+__global__ void __launch_bounds__(BN_FEATS * BN_LANES)
 bn_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
               float* __restrict__ running_mean, float* __restrict__ running_var, int training, float momentum,
               float eps, int B, int E, float* __restrict__ out, float* __restrict__ yhat,
               float* __restrict__ rstd_out) {
-  __shared__ float red[32][33];
-  __shared__ float s_mean[32], s_rstd[32];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int e = blockIdx.x * 32 + tx;
+  __shared__ float red[BN_LANES / 4][BN_FEATS];
+  const int tx = threadIdx.x & (BN_FEATS - 1), ty = threadIdx.x / BN_FEATS;
+  const int e = blockIdx.x * BN_FEATS + tx;
   const bool ok = e < E;
+  float v[BN_CACHE];
+#pragma unroll
+  for (int k = 0; k < BN_CACHE; ++k) {
+    const int r = ty + BN_LANES * k;
+    v[k] = (ok && r < B) ? y[(int64_t)r * E + e] : 0.f;
+  }
+  float mu, rs;
   if (training) {
     float s = 0.f;
-    if (ok) for (int r = ty; r < B; r += 32) s += y[(int64_t)r * E + e];
-    red[ty][tx] = s;
-    __syncthreads();
-    if (ty == 0) {
-      float t = 0.f;
-      for (int i = 0; i < 32; ++i) t += red[i][tx];
-      s_mean[tx] = t / (float)B;
-    }
-    __syncthreads();
-    const float mu = s_mean[tx];
+#pragma unroll
+    for (int k = 0; k < BN_CACHE; ++k) s += v[k];
+    if (ok) for (int r = ty + BN_LANES * BN_CACHE; r < B; r += BN_LANES) s += y[(int64_t)r * E + e];
+    mu = bn_block_sum(s, red, tx, ty) / (float)B;
     float q = 0.f;
-    if (ok) for (int r = ty; r < B; r += 32) { float d = y[(int64_t)r * E + e] - mu; q += d * d; }
-    __syncthreads();
-    red[ty][tx] = q;
-    __syncthreads();
-    if (ty == 0) {
-      float t = 0.f;
-      for (int i = 0; i < 32; ++i) t += red[i][tx];
-      const float var = t / (float)B;
-      s_rstd[tx] = rsqrtf(var + eps);
-      if (ok) {
-        const float unbiased = B > 1 ? t / (float)(B - 1) : var;
-        running_mean[e] = (1.f - momentum) * running_mean[e] + momentum * mu;
-        running_var[e] = (1.f - momentum) * running_var[e] + momentum * unbiased;
-      }
+#pragma unroll
+    for (int k = 0; k < BN_CACHE; ++k) {
+      const float d = v[k] - mu;
+      if (ty + BN_LANES * k < B) q += d * d;
     }
-    __syncthreads();
-  } else {
+    if (ok) for (int r = ty + BN_LANES * BN_CACHE; r < B; r += BN_LANES) { const float d = y[(int64_t)r * E + e] - mu; q += d * d; }
+    const float t = bn_block_sum(q, red, tx, ty);
+    const float var = t / (float)B;
+    rs = rsqrtf(var + eps);
     if (ty == 0 && ok) {
-      s_mean[tx] = running_mean[e];
-      s_rstd[tx] = rsqrtf(running_var[e] + eps);
+      const float unbiased = B > 1 ? t / (float)(B - 1) : var;
+      running_mean[e] = (1.f - momentum) * running_mean[e] + momentum * mu;
+      running_var[e] = (1.f - momentum) * running_var[e] + momentum * unbiased;
     }
-    __syncthreads();
+  } else {
+    mu = ok ? running_mean[e] : 0.f;
+    rs = ok ? rsqrtf(running_var[e] + eps) : 0.f;
   }
   if (!ok) return;
-  const float mu = s_mean[tx], rs = s_rstd[tx], ga = gamma[e], be = beta[e];
+  const float ga = gamma[e], be = beta[e];
   if (ty == 0) rstd_out[e] = rs;
-  for (int r = ty; r < B; r += 32) {
+#pragma unroll
+  for (int k = 0; k < BN_CACHE; ++k) {
+    const int r = ty + BN_LANES * k;
+    if (r < B) {
+      const float yh = (v[k] - mu) * rs;
+      yhat[(int64_t)r * E + e] = yh;
+      out[(int64_t)r * E + e] = yh * ga + be;
+    }
+  }
+  for (int r = ty + BN_LANES * BN_CACHE; r < B; r += BN_LANES) {
     const float yh = (y[(int64_t)r * E + e] - mu) * rs;
     yhat[(int64_t)r * E + e] = yh;
     out[(int64_t)r * E + e] = yh * ga + be;
@@ -428,52 +449,59 @@ bn_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, cons
 int bn_fwd(const float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
            int training, float momentum, float eps, int64_t B, int64_t E, float* out, float* yhat,
            float* rstd, cudaStream_t st) {
-  bn_fwd_kernel<<<nblocks(E, 32), 1024, 0, st>>>(y, gamma, beta, running_mean, running_var, training, momentum,
-                                                 eps, (int)B, (int)E, out, yhat, rstd);
+  bn_fwd_kernel<<<nblocks(E, BN_FEATS), BN_FEATS * BN_LANES, 0, st>>>(y, gamma, beta, running_mean, running_var,
+                                                                     training, momentum, eps, (int)B, (int)E, out,
+                                                                     yhat, rstd);
   SNT_LAUNCH_CHECK("bn_fwd_kernel");
   return SNT_OK;
 }
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(BN_FEATS * BN_LANES)
 bn_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ yhat, const float* __restrict__ rstd,
               const float* __restrict__ gamma, int training, int B, int E, float* __restrict__ dy,
               float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float red1[32][33], red2[32][33];
-  __shared__ float s_sum[32], s_dot[32];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int e = blockIdx.x * 32 + tx;
+  __shared__ float red[BN_LANES / 4][BN_FEATS];
+  const int tx = threadIdx.x & (BN_FEATS - 1), ty = threadIdx.x / BN_FEATS;
+  const int e = blockIdx.x * BN_FEATS + tx;
   const bool ok = e < E;
-  float s = 0.f, d = 0.f;
-  if (ok)
-    for (int r = ty; r < B; r += 32) {
-      const float g = dout[(int64_t)r * E + e];
-      s += g;
-      d += g * yhat[(int64_t)r * E + e];
-    }
-  red1[ty][tx] = s;
-  red2[ty][tx] = d;
-  __syncthreads();
-  if (ty == 0) {
-    float a = 0.f, c = 0.f;
-    for (int i = 0; i < 32; ++i) { a += red1[i][tx]; c += red2[i][tx]; }
-    s_sum[tx] = a;
-    s_dot[tx] = c;
-    if (ok) { dbeta[e] = a; dgamma[e] = c; }
+  float g[BN_CACHE], h[BN_CACHE];
+#pragma unroll
+  for (int k = 0; k < BN_CACHE; ++k) {
+    const int r = ty + BN_LANES * k;
+    const bool in = ok && r < B;
+    g[k] = in ? dout[(int64_t)r * E + e] : 0.f;
+    h[k] = in ? yhat[(int64_t)r * E + e] : 0.f;
   }
-  __syncthreads();
+  float s = 0.f, d = 0.f;
+#pragma unroll
+  for (int k = 0; k < BN_CACHE; ++k) { s += g[k]; d += g[k] * h[k]; }
+  if (ok)
+    for (int r = ty + BN_LANES * BN_CACHE; r < B; r += BN_LANES) {
+      const float gg = dout[(int64_t)r * E + e];
+      s += gg;
+      d += gg * yhat[(int64_t)r * E + e];
+    }
+  const float ssum = bn_block_sum(s, red, tx, ty);
+  const float sdot = bn_block_sum(d, red, tx, ty);
   if (!ok) return;
+  if (ty == 0) { dbeta[e] = ssum; dgamma[e] = sdot; }
   const float ga = gamma[e], rs = rstd[e];
-  const float ms = s_sum[tx] / (float)B, md = s_dot[tx] / (float)B;
-  for (int r = ty; r < B; r += 32) {
+  const float ms = ssum / (float)B, md = sdot / (float)B;
+#pragma unroll
+  for (int k = 0; k < BN_CACHE; ++k) {
+    const int r = ty + BN_LANES * k;
+    if (r < B) dy[(int64_t)r * E + e] = training ? ga * rs * (g[k] - ms - h[k] * md) : ga * rs * g[k];
+  }
+  for (int r = ty + BN_LANES * BN_CACHE; r < B; r += BN_LANES) {
     const int64_t i = (int64_t)r * E + e;
-    const float g = dout[i];
-    dy[i] = training ? ga * rs * (g - ms - yhat[i] * md) : ga * rs * g;
+    const float gg = dout[i];
+    dy[i] = training ? ga * rs * (gg - ms - yhat[i] * md) : ga * rs * gg;
   }
 }
 int bn_bwd(const float* dout, const float* yhat, const float* rstd, const float* gamma, int training,
            int64_t B, int64_t E, float* dy, float* dgamma, float* dbeta, cudaStream_t st) {
-  bn_bwd_kernel<<<nblocks(E, 32), 1024, 0, st>>>(dout, yhat, rstd, gamma, training, (int)B, (int)E, dy, dgamma,
-                                                 dbeta);
+  bn_bwd_kernel<<<nblocks(E, BN_FEATS), BN_FEATS * BN_LANES, 0, st>>>(dout, yhat, rstd, gamma, training, (int)B,
+                                                                     (int)E, dy, dgamma, dbeta);
   SNT_LAUNCH_CHECK("bn_bwd_kernel");
   return SNT_OK;
 }
@@ -491,9 +519,7 @@ int bn_bwd(const float* dout, const float* yhat, const float* rstd, const float*
 //                      slot of their token's segment (arbitrary order)
 //   emb_small_kernel   segments of 2..32 rows: one warp per token ranks the row indices with shuffles and adds the rows
 //                      in ascending order
-//   emb_multi_kernel   longer segments: persistent blocks walk the work list, the segment's row indices are ranked into
-//                      ascending order in shared memory, then 32 warps sum the rows in that fixed order
-constexpr int EMB_SEG_MAX = 8192;  // longest segment (rows sharing one token, e.g. <start>: one per caption)
+//   emb_sort/chunk/final  longer segments (see below)
 __global__ void __launch_bounds__(256)
 emb_tok_kernel(const __grid_constant__ PackInfo pk, const int64_t* __restrict__ captions, int64_t cap_stride,
                int64_t V, int* __restrict__ tok, int* __restrict__ count, int* flags) {
@@ -516,9 +542,10 @@ __global__ void __launch_bounds__(1024)
 emb_scan_kernel(const int* __restrict__ count, int V, int* __restrict__ start, int* __restrict__ cursor,
                 int* __restrict__ multi, int* __restrict__ small, int* flags) {
   __shared__ int wsum[32];
-  __shared__ int carry_s;
+  __shared__ int carry_s, n_small_s, n_multi_s;  // list lengths live in shared memory: a global atomic round trip per
+                                                 // warp and slab (~2 us each) used to dominate this kernel
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { carry_s = 0; multi[0] = 0; small[0] = 0; }
+  if (threadIdx.x == 0) { carry_s = 0; n_small_s = 0; n_multi_s = 0; }
   int pre[16];  // the first 16 slabs' counts are fetched up front: one global-load latency instead of one per slab
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
@@ -566,13 +593,13 @@ emb_scan_kernel(const int* __restrict__ count, int V, int* __restrict__ start, i
     const unsigned lt = (1u << lane) - 1u;
     if (ms) {
       int b0 = 0;
-      if (lane == 0) b0 = atomicAdd(&small[0], __popc(ms));
+      if (lane == 0) b0 = atomicAdd(&n_small_s, __popc(ms));
       b0 = __shfl_sync(0xffffffffu, b0, 0);
       if (is_small) small[1 + b0 + __popc(ms & lt)] = i;
     }
     if (mb) {
       int b0 = 0;
-      if (lane == 0) b0 = atomicAdd(&multi[0], __popc(mb));
+      if (lane == 0) b0 = atomicAdd(&n_multi_s, __popc(mb));
       b0 = __shfl_sync(0xffffffffu, b0, 0);
       if (is_big) multi[1 + b0 + __popc(mb & lt)] = i;
     }
@@ -580,7 +607,7 @@ emb_scan_kernel(const int* __restrict__ count, int V, int* __restrict__ start, i
     if (threadIdx.x == 0) carry_s += wsum[31];
     __syncthreads();
   }
-  if (threadIdx.x == 0) start[V] = carry_s;
+  if (threadIdx.x == 0) { start[V] = carry_s; small[0] = n_small_s; multi[0] = n_multi_s; }
 }
 __global__ void __launch_bounds__(256)
 emb_place_kernel(const int* __restrict__ tok, int n1, const int* __restrict__ count, int* __restrict__ cursor,
@@ -617,15 +644,29 @@ emb_small_kernel(const float* __restrict__ dx1, const int* __restrict__ start, c
     float4 acc[SLABS];
 #pragma unroll
     for (int k = 0; k < SLABS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // lane r of `sorted` holds the r-th smallest row index
+    int sorted = 0;
     for (int r = 0; r < n; ++r) {
       const unsigned who = __ballot_sync(0xffffffffu, lane < n && rank == r);
       const int idx = __shfl_sync(0xffffffffu, mine, __ffs((int)who) - 1);
-      const float* src = dx1 + (int64_t)idx * E + lane * 4;
+      if (lane == r) sorted = idx;
+    }
+    for (int r0 = 0; r0 < n; r0 += 4) {  // 4 rows in flight (a dependent round of scattered loads costs ~2 us)
+      float4 a[4][SLABS];
 #pragma unroll
-      for (int k = 0; k < SLABS; ++k)
-        if (k * 128 + lane * 4 < E) {
-          const float4 a = *reinterpret_cast<const float4*>(src + k * 128);
-          acc[k].x += a.x; acc[k].y += a.y; acc[k].z += a.z; acc[k].w += a.w;
+      for (int u = 0; u < 4; ++u) {
+        const int idx = __shfl_sync(0xffffffffu, sorted, (r0 + u) & 31);
+        const float* src = dx1 + (int64_t)idx * E + lane * 4;
+#pragma unroll
+        for (int k = 0; k < SLABS; ++k)
+          a[u][k] = (r0 + u < n && k * 128 + lane * 4 < E) ? *reinterpret_cast<const float4*>(src + k * 128)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)  // ascending row order
+#pragma unroll
+        for (int k = 0; k < SLABS; ++k) {
+          acc[k].x += a[u][k].x; acc[k].y += a[u][k].y; acc[k].z += a[u][k].z; acc[k].w += a[u][k].w;
         }
     }
 #pragma unroll
@@ -633,66 +674,161 @@ emb_small_kernel(const float* __restrict__ dx1, const int* __restrict__ start, c
       if (k * 128 + lane * 4 < E) *reinterpret_cast<float4*>(d_w_emb + (int64_t)v * E + k * 128 + lane * 4) = acc[k];
   }
 }
-template <int SLABS>
+// Longer segments, three short kernels so that one frequent token (e.g. <start>: one row per caption) is spread over
+// the machine instead of over one block.  A dependent round of scattered global loads costs ~2 us here, so every kernel
+// issues all of a thread's loads in one round:
+//   emb_sort_kernel   persistent blocks walk the work list and rank the segment's row indices into ascending order with
+//                     a bitmap over all packed rows in shared memory (set bits, prefix popcount: O(n + N/32)) -> gsorted;
+//                     reserve ceil(n/8) chunk slots
+//   emb_chunk_kernel  one warp per chunk of 8 consecutive sorted rows, all 8 rows in flight -> partial[slot][E]
+//   emb_final_kernel  one block per token: 32 warps add contiguous runs of chunk partials, then the 32 warp sums are
+//                     added in warp order -> d_w_emb[v]
+// Every sum runs in a fixed order: deterministic.
+constexpr int EMB_CHUNK = 8;
+constexpr int EMB_BITMAP_WORDS = 8192;  // rows covered by the shared-memory bitmap: 262144
+struct EmbChunkLists {
+  int* counter;    // [1] chunk slots reserved so far
+  int* chunk_pos;  // [slots] first position in gsorted
+  int* chunk_cnt;  // [slots] rows in the chunk (1..8)
+  int* tok_base;   // [n_multi] first slot of work-list entry li
+};
 __global__ void __launch_bounds__(1024)
-emb_multi_kernel(const float* __restrict__ dx1, const int* __restrict__ start, const int* __restrict__ perm0,
-                 int* __restrict__ gsorted, const int* __restrict__ multi, int E, float* __restrict__ d_w_emb) {
-  extern __shared__ int sm_i[];                  // raw[EMB_SEG_MAX] | sorted[EMB_SEG_MAX] | part[32][E]
-  int* raw = sm_i;
-  int* sorted_s = sm_i + EMB_SEG_MAX;
-  float* part = reinterpret_cast<float*>(sm_i + 2 * EMB_SEG_MAX);
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+emb_sort_kernel(const int* __restrict__ start, const int* __restrict__ perm0, int* __restrict__ gsorted,
+                const int* __restrict__ multi, int n1, EmbChunkLists cl) {
+  __shared__ unsigned bitmap[EMB_BITMAP_WORDS];
+  __shared__ int wpre[EMB_BITMAP_WORDS / 8];  // exclusive prefix of popcounts, one entry per 8 words
+  __shared__ int wsum[32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int words = (n1 + 31) >> 5;
   const int n_multi = multi[0];
   for (int li = blockIdx.x; li < n_multi; li += gridDim.x) {
     const int v = multi[1 + li];
     const int s0 = start[v];
     const int n = start[v + 1] - s0;
-    const bool big = n > EMB_SEG_MAX;  // rare: rank straight from global memory into a global scratch segment
-    const int* rawp = big ? perm0 + s0 : raw;
-    int* sorted_w = big ? gsorted + s0 : sorted_s;
     __syncthreads();  // previous token's shared data no longer in use
-    if (!big) {
-      const int n4 = (n + 3) & ~3;
-      for (int a = threadIdx.x; a < n4; a += 1024) raw[a] = a < n ? perm0[s0 + a] : 0x7fffffff;
+    if (words <= EMB_BITMAP_WORDS) {
+      for (int i = threadIdx.x; i < words; i += 1024) bitmap[i] = 0u;
       __syncthreads();
-      // O(n^2) ranking out of shared memory, 4 indices per (broadcast) 16-byte load
       for (int a = threadIdx.x; a < n; a += 1024) {
-        const int mine = raw[a];
-        int rank = 0;
-        const int4* r4 = reinterpret_cast<const int4*>(raw);
-#pragma unroll 4
-        for (int b = 0; b < n4 / 4; ++b) {
-          const int4 v = r4[b];
-          rank += (v.x < mine) + (v.y < mine) + (v.z < mine) + (v.w < mine);
-        }
-        sorted_s[rank] = mine;
+        const int idx = perm0[s0 + a];
+        atomicOr(&bitmap[idx >> 5], 1u << (idx & 31));
       }
-    } else {
+      __syncthreads();
+      // thread t owns words 8t..8t+7: block-wide exclusive scan of their popcounts
+      int mine = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = threadIdx.x * 8 + k;
+        mine += i < words ? __popc(bitmap[i]) : 0;
+      }
+      int x = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) wsum[w] = x;
+      __syncthreads();
+      if (w == 0) {
+        int sv = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, sv, o);
+          if (lane >= o) sv += y;
+        }
+        wsum[lane] = sv;
+      }
+      __syncthreads();
+      wpre[threadIdx.x] = (w > 0 ? wsum[w - 1] : 0) + x - mine;
+      __syncthreads();
       for (int a = threadIdx.x; a < n; a += 1024) {
-        const int mine = rawp[a];
+        const int idx = perm0[s0 + a];
+        const int wd = idx >> 5;
+        int rank = wpre[wd >> 3];
+        for (int k = wd & ~7; k < wd; ++k) rank += __popc(bitmap[k]);
+        rank += __popc(bitmap[wd] & ((1u << (idx & 31)) - 1u));
+        gsorted[s0 + rank] = idx;
+      }
+    } else {  // more packed rows than the bitmap covers: rank straight from global memory, O(n^2)
+      for (int a = threadIdx.x; a < n; a += 1024) {
+        const int mine = perm0[s0 + a];
         int rank = 0;
-        for (int b = 0; b < n; ++b) rank += (rawp[b] < mine);  // row indices are distinct; broadcast reads
-        sorted_w[rank] = mine;
+        for (int b = 0; b < n; ++b) rank += (perm0[s0 + b] < mine);
+        gsorted[s0 + rank] = mine;
       }
     }
+    const int nc = (n + EMB_CHUNK - 1) / EMB_CHUNK;
+    if (threadIdx.x == 0) {
+      s_base = atomicAdd(cl.counter, nc);  // slot order across tokens is irrelevant: tokens are independent
+      cl.tok_base[li] = s_base;
+    }
     __syncthreads();
-    const int* sorted = sorted_w;
-    // warp w sums rows w, w+32, ... (ascending): every lane owns SLABS float4 of the row, 2 rows in flight
+    for (int k = threadIdx.x; k < nc; k += 1024) {
+      cl.chunk_pos[s_base + k] = s0 + k * EMB_CHUNK;
+      cl.chunk_cnt[s_base + k] = min(EMB_CHUNK, n - k * EMB_CHUNK);
+    }
+  }
+}
+template <int SLABS>
+__global__ void __launch_bounds__(256)
+emb_chunk_kernel(const float* __restrict__ dx1, const int* __restrict__ gsorted, EmbChunkLists cl, int E,
+                 float* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+  const int n_chunks = cl.counter[0];
+  for (int ci = gw; ci < n_chunks; ci += nw) {
+    const int pos = cl.chunk_pos[ci], cnt = cl.chunk_cnt[ci];
+    const int mine = lane < cnt ? gsorted[pos + lane] : 0;
+    float4 a[EMB_CHUNK][SLABS];
+#pragma unroll
+    for (int u = 0; u < EMB_CHUNK; ++u) {  // all rows of the chunk in flight at once
+      const int idx = __shfl_sync(0xffffffffu, mine, u);
+      const float* src = dx1 + (int64_t)idx * E + lane * 4;
+#pragma unroll
+      for (int k = 0; k < SLABS; ++k)
+        a[u][k] = (u < cnt && k * 128 + lane * 4 < E) ? *reinterpret_cast<const float4*>(src + k * 128)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float4 acc[SLABS];
 #pragma unroll
     for (int k = 0; k < SLABS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int i = w;
-    for (; i + 96 < n; i += 128) {  // 4 rows in flight per warp, added in ascending order
-      const float* rp[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) rp[u] = dx1 + (int64_t)sorted[i + 32 * u] * E + lane * 4;
+    for (int u = 0; u < EMB_CHUNK; ++u)  // ascending row order
+#pragma unroll
+      for (int k = 0; k < SLABS; ++k) {
+        acc[k].x += a[u][k].x; acc[k].y += a[u][k].y; acc[k].z += a[u][k].z; acc[k].w += a[u][k].w;
+      }
+#pragma unroll
+    for (int k = 0; k < SLABS; ++k)
+      if (k * 128 + lane * 4 < E) *reinterpret_cast<float4*>(partial + (int64_t)ci * E + k * 128 + lane * 4) = acc[k];
+  }
+}
+template <int SLABS>
+__global__ void __launch_bounds__(1024)
+emb_final_kernel(const float* __restrict__ partial, const int* __restrict__ start, const int* __restrict__ multi,
+                 EmbChunkLists cl, int E, float* __restrict__ d_w_emb) {
+  extern __shared__ float part_s[];  // [32][E]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n_multi = multi[0];
+  for (int li = blockIdx.x; li < n_multi; li += gridDim.x) {
+    const int v = multi[1 + li];
+    const int nc = (start[v + 1] - start[v] + EMB_CHUNK - 1) / EMB_CHUNK;
+    const int per = (nc + 31) / 32;  // warp w adds chunk partials [w*per, (w+1)*per) in slot order
+    const int c0 = w * per, c1 = min(nc, c0 + per);
+    const float* src = partial + (int64_t)cl.tok_base[li] * E + lane * 4;
+    float4 acc[SLABS];
+#pragma unroll
+    for (int k = 0; k < SLABS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = c0; c < c1; c += 4) {
       float4 a[4][SLABS];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int k = 0; k < SLABS; ++k)
-          a[u][k] = (k * 128 + lane * 4 < E) ? *reinterpret_cast<const float4*>(rp[u] + k * 128)
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          a[u][k] = (c + u < c1 && k * 128 + lane * 4 < E)
+                        ? *reinterpret_cast<const float4*>(src + (int64_t)(c + u) * E + k * 128)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -700,23 +836,15 @@ emb_multi_kernel(const float* __restrict__ dx1, const int* __restrict__ start, c
           acc[k].x += a[u][k].x; acc[k].y += a[u][k].y; acc[k].z += a[u][k].z; acc[k].w += a[u][k].w;
         }
     }
-    for (; i < n; i += 32) {
-      const float* r0 = dx1 + (int64_t)sorted[i] * E + lane * 4;
-#pragma unroll
-      for (int k = 0; k < SLABS; ++k)
-        if (k * 128 + lane * 4 < E) {
-          const float4 a = *reinterpret_cast<const float4*>(r0 + k * 128);
-          acc[k].x += a.x; acc[k].y += a.y; acc[k].z += a.z; acc[k].w += a.w;
-        }
-    }
+    __syncthreads();  // previous token's part_s no longer in use
 #pragma unroll
     for (int k = 0; k < SLABS; ++k)
-      if (k * 128 + lane * 4 < E) *reinterpret_cast<float4*>(part + w * E + k * 128 + lane * 4) = acc[k];
+      if (k * 128 + lane * 4 < E) *reinterpret_cast<float4*>(part_s + w * E + k * 128 + lane * 4) = acc[k];
     __syncthreads();
     for (int e = threadIdx.x; e < E; e += 1024) {
       float t = 0.f;
 #pragma unroll 8
-      for (int k = 0; k < 32; ++k) t += part[k * E + e];
+      for (int k = 0; k < 32; ++k) t += part_s[k * E + e];
       d_w_emb[(int64_t)v * E + e] = t;
     }
   }
@@ -728,8 +856,11 @@ dfeatures_kernel(const float* __restrict__ dx, int bs0, int64_t B, int64_t E, fl
   dfeat[i] = (i / E) < bs0 ? dx[i] : 0.f;
 }
 
+static int64_t emb_chunk_slots(int64_t N) { return N / EMB_CHUNK + N / (EMB_SMALL_MAX + 1) + 2; }  // sum ceil(n_i/8)
 int64_t embed_bwd_ws_bytes(int64_t N, int64_t V) {
-  return ws_bytes_for(N, 4) * 3 + ws_bytes_for(V + 1, 4) * 5;
+  // E is not known here: the chunk partials are sized for the largest supported row (E = 1024)
+  return ws_bytes_for(N, 4) * 3 + ws_bytes_for(V + 1, 4) * 6 + ws_bytes_for(emb_chunk_slots(N), 4) * 2 +
+         ws_bytes_for(emb_chunk_slots(N) * 1024, 4) + ws_bytes_for(4, 4);
 }
 int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions, int64_t cap_stride,
                    int64_t B, int64_t E, int64_t V, float* dfeatures, float* d_w_emb, void* ws,
@@ -750,12 +881,19 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
   int* cursor = w.take<int>(V + 1);
   int* multi = w.take<int>(V + 1);
   int* small = w.take<int>(V + 1);
+  EmbChunkLists cl;
+  cl.tok_base = w.take<int>(V + 1);
+  cl.chunk_pos = w.take<int>(emb_chunk_slots(N));
+  cl.chunk_cnt = w.take<int>(emb_chunk_slots(N));
+  float* partial = w.take<float>(emb_chunk_slots(N) * 1024);
+  cl.counter = w.take<int>(4);
   if (!w.ok()) { set_error("embed_pack_bwd: workspace too small"); return SNT_EWORKSPACE; }
   SNT_REQUIRE(E % 4 == 0 && E <= 1024, "embed_pack_bwd: E must be a multiple of 4 and <= 1024");
   SNT_REQUIRE(V < (1LL << 31), "embed_pack_bwd: V too large");
   SNT_CUDA(cudaMemsetAsync(d_w_emb, 0, sizeof(float) * (size_t)V * E, st));
   if (n1 <= 0) return SNT_OK;
   SNT_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(V + 1), st));
+  SNT_CUDA(cudaMemsetAsync(cl.counter, 0, sizeof(int) * 4, st));
   const float* dx1 = dx + (int64_t)pk.off[1] * E;
   emb_tok_kernel<<<nblocks(n1, 256), 256, 0, st>>>(pk, captions, cap_stride, V, tok, count, device_flags());
   SNT_LAUNCH_CHECK("emb_tok_kernel");
@@ -763,25 +901,33 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
   SNT_LAUNCH_CHECK("emb_scan_kernel");
   emb_place_kernel<<<nblocks(n1, 8), 256, 0, st>>>(tok, n1, count, cursor, perm0, dx1, (int)E, d_w_emb);
   SNT_LAUNCH_CHECK("emb_place_kernel");
-  const size_t sm = sizeof(int) * 2 * EMB_SEG_MAX + sizeof(float) * 32 * (size_t)E;
-  const int max_sm = (int)(sizeof(int) * 2 * EMB_SEG_MAX + sizeof(float) * 32 * 1024);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SNT_CUDA(cudaFuncSetAttribute(emb_multi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_sm));
-    SNT_CUDA(cudaFuncSetAttribute(emb_multi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_sm));
-    SNT_CUDA(cudaFuncSetAttribute(emb_multi_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_sm));
-    attr_set = true;
-  }
   const int slabs = (int)((E + 127) / 128);
-  const int sgrid = 4 * 148;  // persistent warps walk the small-segment list
+  const int sgrid = 4 * 148;  // persistent warps walk the work lists
   if (slabs <= 2) emb_small_kernel<2><<<sgrid, 256, 0, st>>>(dx1, start, perm0, small, (int)E, d_w_emb);
   else if (slabs <= 4) emb_small_kernel<4><<<sgrid, 256, 0, st>>>(dx1, start, perm0, small, (int)E, d_w_emb);
   else emb_small_kernel<8><<<sgrid, 256, 0, st>>>(dx1, start, perm0, small, (int)E, d_w_emb);
   SNT_LAUNCH_CHECK("emb_small_kernel");
-  if (slabs <= 2) emb_multi_kernel<2><<<148, 1024, sm, st>>>(dx1, start, perm0, gsorted, multi, (int)E, d_w_emb);
-  else if (slabs <= 4) emb_multi_kernel<4><<<148, 1024, sm, st>>>(dx1, start, perm0, gsorted, multi, (int)E, d_w_emb);
-  else emb_multi_kernel<8><<<148, 1024, sm, st>>>(dx1, start, perm0, gsorted, multi, (int)E, d_w_emb);
-  SNT_LAUNCH_CHECK("emb_multi_kernel");
+  emb_sort_kernel<<<148, 1024, 0, st>>>(start, perm0, gsorted, multi, n1, cl);
+  SNT_LAUNCH_CHECK("emb_sort_kernel");
+  if (slabs <= 2) emb_chunk_kernel<2><<<sgrid, 256, 0, st>>>(dx1, gsorted, cl, (int)E, partial);
+  else if (slabs <= 4) emb_chunk_kernel<4><<<sgrid, 256, 0, st>>>(dx1, gsorted, cl, (int)E, partial);
+  else emb_chunk_kernel<8><<<sgrid, 256, 0, st>>>(dx1, gsorted, cl, (int)E, partial);
+  SNT_LAUNCH_CHECK("emb_chunk_kernel");
+  {
+    const size_t fsm = sizeof(float) * 32 * (size_t)E;  // <= 128 KB at E = 1024
+    static bool attr_set = false;
+    if (!attr_set) {
+      const int max_sm = (int)(sizeof(float) * 32 * 1024);
+      SNT_CUDA(cudaFuncSetAttribute(emb_final_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_sm));
+      SNT_CUDA(cudaFuncSetAttribute(emb_final_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_sm));
+      SNT_CUDA(cudaFuncSetAttribute(emb_final_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_sm));
+      attr_set = true;
+    }
+    if (slabs <= 2) emb_final_kernel<2><<<148, 1024, fsm, st>>>(partial, start, multi, cl, (int)E, d_w_emb);
+    else if (slabs <= 4) emb_final_kernel<4><<<148, 1024, fsm, st>>>(partial, start, multi, cl, (int)E, d_w_emb);
+    else emb_final_kernel<8><<<148, 1024, fsm, st>>>(partial, start, multi, cl, (int)E, d_w_emb);
+  }
+  SNT_LAUNCH_CHECK("emb_final_kernel");
   return SNT_OK;
 }
 
