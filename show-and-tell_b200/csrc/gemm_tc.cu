@@ -129,7 +129,7 @@ static int run_plain_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CU
 int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A,
             int64_t lda, const __nv_bfloat16* B, int64_t ldb, float beta, float* C, __nv_bfloat16* Cb,
             int64_t ldc, const float* bias, int splits, float* split_ws, cudaStream_t st, int row_perm_h,
-            const float* alpha_dev, bool keep_partials, int* splits_used, int force_bn) {
+            const float* alpha_dev, bool keep_partials, int* splits_used, int force_bn, int n_fastest) {
   if (M <= 0 || N <= 0) return SNT_OK;
   SNT_REQUIRE(row_perm_h == 0 || M == 4 * (int64_t)row_perm_h, "gemm_tc: row permutation needs M == 4H");
   SNT_REQUIRE(K >= 1 && A && B && (C || Cb), "gemm_tc: bad arguments");
@@ -146,6 +146,7 @@ int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, 
   ts.splits = splits;
   ts.a_row0 = 0;
   ts.b_row0 = 0;
+  ts.n_fastest = n_fastest;
   CUtensorMap ta, tb;
   SNT_CHECK(make_operand_tmap(&ta, A, a_mn, M, K, lda, BM));
   SNT_CHECK(make_operand_tmap(&tb, B, b_mn, N, K, ldb, bn));

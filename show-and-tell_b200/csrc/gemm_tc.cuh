@@ -22,19 +22,36 @@ constexpr int BM = 128;  // tile rows = TMEM lanes
 constexpr int BK = 64;   // 64 bf16 = 128 B = one swizzle row
 
 struct TileSched {
-  int num_m, num_n, splits;  // tile grid; tile id = (split * num_n + n) * num_m + m
+  int num_m, num_n, splits;  // tile grid; tile id = (split * num_n + n) * num_m + m, or with n_fastest
+                             // (split * num_m + m) * num_n + n: the CTAs of one wave then share few A row panels (each is
+                             // fetched from DRAM once and served to its num_n column tiles out of L2)
+  int n_fastest;
   int kblocks;               // total K blocks of BK
   int kblocks_per_split;
   int a_row0, b_row0;        // coordinate offsets into the M / N extents of the tensor maps
 };
 
-template <int BN>
+__device__ __forceinline__ void decode_tile(const TileSched& ts, int tile, int& m_blk, int& n_blk, int& split) {
+  if (ts.n_fastest) {
+    n_blk = tile % ts.num_n;
+    const int rest = tile / ts.num_n;
+    m_blk = rest % ts.num_m;
+    split = rest / ts.num_m;
+  } else {
+    m_blk = tile % ts.num_m;
+    const int rest = tile / ts.num_m;
+    n_blk = rest % ts.num_n;
+    split = rest / ts.num_n;
+  }
+}
+
+template <int BN, int STAGES_OVERRIDE = 0>
 struct Cfg {
   static_assert(BN == 64 || BN == 128 || BN == 256, "BN must be 64, 128 or 256");
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = STAGES_OVERRIDE ? STAGES_OVERRIDE : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (128, 256 or 512 columns)
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
@@ -44,7 +61,8 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Epi must provide:
-//   static constexpr int kWarps            (4 or 8 epilogue warps)
+//   static constexpr int kWarps            (4, 8 or 16 epilogue warps)
+//   static constexpr int kStages           (TMA ring depth; 0 = the default for BN)
 //   struct Pre; __device__ void prefetch(Pre&, int m_blk, int n_blk, int epi_warp, int lane) const
 //       global loads the epilogue will need, issued BEFORE waiting for the accumulator so that their latency
 //       overlaps the TMA/MMA phase (NoPre = nothing to prefetch)
@@ -57,7 +75,7 @@ template <int BN, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(128 + 32 * Epi::kWarps, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TileSched ts, const Epi epi) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, Epi::kStages>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -105,10 +123,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile % ts.num_m;
-        const int rest = tile / ts.num_m;
-        const int n_blk = rest % ts.num_n;
-        const int split = rest / ts.num_n;
+        int m_blk, n_blk, split;
+        decode_tile(ts, tile, m_blk, n_blk, split);
         const int kb0 = split * ts.kblocks_per_split;
         const int kb1 = min(kb0 + ts.kblocks_per_split, ts.kblocks);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -143,7 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int split = (tile / ts.num_m) / ts.num_n;
+        const int split = tile / (ts.num_m * ts.num_n);
         const int kb0 = split * ts.kblocks_per_split;
         const int kb1 = min(kb0 + ts.kblocks_per_split, ts.kblocks);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -177,10 +193,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t acc_phase = 0;
     pdl_wait();  // the epilogue may read tensors written by the preceding kernel (C for beta, Gx, lse, ...)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = tile % ts.num_m;
-      const int rest = tile / ts.num_m;
-      const int n_blk = rest % ts.num_n;
-      const int split = rest / ts.num_n;
+      int m_blk, n_blk, split;
+      decode_tile(ts, tile, m_blk, n_blk, split);
       typename Epi::Pre pre;
       epi.prefetch(pre, m_blk, n_blk, ew, lane);
       mbar_wait(&tfull[acc], acc_phase);
@@ -215,7 +229,7 @@ int sm_count();
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TileSched& ts, const Epi& epi,
                    cudaStream_t st, bool pdl = false) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, Epi::kStages>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi>;
   static bool configured = false;  // per instantiation
   if (!configured) {
@@ -244,6 +258,7 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TileSch
 template <int BN>
 struct PlainEpi {
   static constexpr int kWarps = BN >= 128 ? 8 : 4;
+  static constexpr int kStages = 0;
   static constexpr int kPitch = 80;  // bytes per staged row: 64 of data (16 fp32 / 32 bf16) + 16 of padding
   static constexpr int kSmemPerWarp = 32 * kPitch;
   int M, N;                // valid extent
@@ -412,7 +427,7 @@ int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, 
             int64_t lda, const __nv_bfloat16* B, int64_t ldb, float beta, float* C, __nv_bfloat16* Cb,
             int64_t ldc, const float* bias, int splits, float* split_ws, cudaStream_t st, int row_perm_h = 0,
             const float* alpha_dev = nullptr, bool keep_partials = false, int* splits_used = nullptr,
-            int force_bn = 0);
+            int force_bn = 0, int n_fastest = 0);
 
 }  // namespace tc
 }  // namespace snt

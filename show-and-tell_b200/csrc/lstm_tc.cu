@@ -61,6 +61,7 @@ __global__ void unperm_vec_kernel(const float* __restrict__ in, int H, float* __
 // ---- forward step epilogue ---------------------------------------------------------------------------------------------
 struct LstmFwdEpi {
   static constexpr int kWarps = 4;
+  static constexpr int kStages = 0;
   static constexpr int kSmemPerWarp = 0;
   int bs, bs_next, H;
   const bf* gx;         // [bs, 4H]   input projection + biases of this step's rows (bf16), interleaved columns
@@ -152,6 +153,7 @@ struct LstmFwdEpi {
 // ---- backward step epilogue ------------------------------------------------------------------------------------------
 struct LstmBwdEpi {
   static constexpr int kWarps = 4;
+  static constexpr int kStages = 0;
   static constexpr int kSmemPerWarp = 0;
   int bs, bs_next, H;
   const float* d_hs;    // [bs, H]   dL/dh_t from the layer above / the vocab projection
@@ -1060,6 +1062,7 @@ int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const flo
     ts.num_m = (bs + tc::BM - 1) / tc::BM;
     ts.num_n = (int)((4 * H + 127) / 128);
     ts.splits = 1;
+    ts.n_fastest = 0;
     ts.kblocks = (int)((H + tc::BK - 1) / tc::BK);
     ts.kblocks_per_split = ts.kblocks;
     ts.a_row0 = pk.off[t];
@@ -1187,6 +1190,7 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
 // =====================================================================================================================
 struct ArgmaxEpi {
   static constexpr int kWarps = 8;
+  static constexpr int kStages = 0;
   static constexpr int kSmemPerWarp = 0;
   int M, V;
   const float* bias;
@@ -1319,6 +1323,7 @@ int greedy_decode(const float* features, const float* w_emb, int L, const float*
       ts.num_m = (int)((B + tc::BM - 1) / tc::BM);
       ts.num_n = (int)((4 * H + 127) / 128);
       ts.splits = 1;
+    ts.n_fastest = 0;
       ts.kblocks = (int)((H + tc::BK - 1) / tc::BK);
       ts.kblocks_per_split = ts.kblocks;
       ts.a_row0 = 0;
@@ -1334,6 +1339,7 @@ int greedy_decode(const float* features, const float* w_emb, int L, const float*
     ts.num_m = (int)((B + tc::BM - 1) / tc::BM);
     ts.num_n = (int)((V + 255) / 256);
     ts.splits = 1;
+    ts.n_fastest = 0;
     ts.kblocks = (int)((H + tc::BK - 1) / tc::BK);
     ts.kblocks_per_split = ts.kblocks;
     ts.a_row0 = 0;

@@ -61,6 +61,7 @@ ce_target_logit_kernel(const bf* __restrict__ hs, const bf* __restrict__ w, cons
 // ---- forward epilogue: per (row, 128-column slab) online-softmax partial in the log2 domain ------------------------
 struct CeFwdEpi {
   static constexpr int kWarps = 8;
+  static constexpr int kStages = 0;
   static constexpr int kSmemPerWarp = 0;
   int M;                 // rows
   int V;                 // valid columns
@@ -156,8 +157,10 @@ ce_finish_kernel(const float2* __restrict__ part, int slabs, int64_t N, const fl
 }
 
 // ---- backward epilogue: dlogits = (2^(y - lse2) - onehot) * scale -> bf16 chunk ------------------------------------
-struct CeBwdEpi {
-  static constexpr int kWarps = 8;
+template <int W>
+struct CeBwdEpiT {
+  static constexpr int kWarps = W;
+  static constexpr int kStages = W == 16 ? 3 : 0;  // 16 staging buffers (40 KB) fit next to 3 ring stages
   static constexpr int kSmemPerWarp = 32 * 80;  // 32 rows x (64 B of bf16 + 16 B pad): transpose stage for coalesced stores
   int M;                    // rows in this chunk
   int V;
@@ -232,6 +235,21 @@ struct CeBwdEpi {
     const int half = ew >> 2;
     const int row0 = m_blk * tc::BM + (ew & 3) * 32;
     const uint32_t wsa = tc::smem_u32(wsm);
+    if (W == 16) {  // 16 warps x 2 chunks, no register double-buffering: latency is hidden by warps instead
+      const int cb = half * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = n_blk * CE_BN + cb + c * 32;
+        if (col0 >= V) break;  // warp-uniform
+        uint32_t r[32];
+        float4 b8[8];
+        tc::tmem_ld32(tmem_rows + (uint32_t)(cb + c * 32), r);
+        load_bias(b8, col0);
+        tc::tmem_ld_wait();
+        chunk(r, b8, col0, row0, lane, pre.l2, pre.tgt, wsa);
+      }
+      return;
+    }
     const int cbase = half * (CE_BN / 2);
     const int colb = n_blk * CE_BN + cbase;
     constexpr int NCH = CE_BN / 64;
@@ -262,6 +280,8 @@ struct CeBwdEpi {
     }
   }
 };
+
+typedef CeBwdEpiT<8> CeBwdEpi;
 
 // ---- column sums of a bf16 matrix (for d_b_out), deterministic two pass -----------------------------------------------
 constexpr int CSB_ROWS = 256;
@@ -383,6 +403,7 @@ static int make_sched(int64_t M, int64_t Ncols, int64_t K, tc::TileSched* ts) {
   ts->num_m = (int)((M + tc::BM - 1) / tc::BM);
   ts->num_n = (int)((Ncols + CE_BN - 1) / CE_BN);
   ts->splits = 1;
+  ts->n_fastest = 0;
   ts->kblocks = (int)((K + tc::BK - 1) / tc::BK);
   ts->kblocks_per_split = ts->kblocks;
   ts->a_row0 = 0;
@@ -462,10 +483,19 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
     SNT_CHECK(tc::make_operand_tmap(&ta, hs_b + r0 * H, false, r, H, H, tc::BM));
     tc::TileSched ts;
     make_sched(r, V, H, &ts);
-    CeBwdEpi e;
-    e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;
-    e.out = w.dl; e.ldo = w.Vp;
-    SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeBwdEpi>(ta, tb, ts, e, st)));
+    // 16 epilogue warps (2 chunks each) hide the TMEM-load / staging / store latencies better than 8 warps with register
+    // double-buffering: 58 -> 51 us per chunk pass (measured); SNT_CEBWD_W8 selects the 8-warp variant.
+    if (!getenv("SNT_CEBWD_W8")) {
+      CeBwdEpiT<16> e;
+      e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;
+      e.out = w.dl; e.ldo = w.Vp;
+      SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeBwdEpiT<16>>(ta, tb, ts, e, st)));
+    } else {
+      CeBwdEpi e;
+      e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;
+      e.out = w.dl; e.ldo = w.Vp;
+      SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeBwdEpi>(ta, tb, ts, e, st)));
+    }
     if (side) {
       SNT_CUDA(cudaEventRecord(side->fork, st));
       SNT_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
@@ -487,8 +517,11 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
     // dW_out[V,H] += dlogits^T[V,r] . Hs[r,H]   (both operands MN-major).  Measured at V=10000, H=512 (round 1): 128- and
     // 256-wide tiles, with or without a split-K tail for the last partial wave, all land within 2% of each other - the
     // contraction re-reads the 95 MB dlogits chunk from L2 once per column tile and is bound there, not by wave shape.
+    // Column tiles of one vocabulary panel are scheduled next to each other (n_fastest): a wave then touches 37 panels
+    // of dlogits instead of 79+, each panel is fetched once and its other column tiles hit L2.
     SNT_CHECK(tc::gemm_tc(true, true, V, H, r, scale, w.dl, w.Vp, hs_b + r0 * H, H, acc, d_w_out, nullptr, H, nullptr, 1,
-                          nullptr, st, 0, dloss, false, nullptr, /*force_bn=*/dw_bn));
+                          nullptr, st, 0, dloss, false, nullptr, /*force_bn=*/dw_bn,
+                          /*n_fastest=*/1));
     if (!side) SNT_CHECK(colsum_bf16(w.dl, r, V, w.Vp, acc, w.db, w.cpart, st));
   }
   if (side) SNT_CUDA(cudaStreamWaitEvent(st, side->join, 0));
