@@ -38,20 +38,7 @@ __device__ __forceinline__ float2 unpack_bf2(uint32_t u) {
   return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
 }
 
-// ---- weight preparation: fp32 gate-major rows -> bf16 unit-interleaved rows ------------------------------------------
-__global__ void __launch_bounds__(128)
-perm_rows_bf16_kernel(const float* __restrict__ w, int H, int cols, bf* __restrict__ out) {
-  const int rp = blockIdx.x;  // 4*j + g
-  const int src = (rp & 3) * H + (rp >> 2);
-  for (int c = threadIdx.x; c < cols; c += 128) out[(int64_t)rp * cols + c] = __float2bfloat16_rn(w[(int64_t)src * cols + c]);
-}
-__global__ void perm_bias_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh, int H,
-                                 float* __restrict__ out) {
-  const int rp = blockIdx.x * blockDim.x + threadIdx.x;
-  if (rp >= 4 * H) return;
-  const int src = (rp & 3) * H + (rp >> 2);
-  out[rp] = b_ih[src] + b_hh[src];
-}
+// ---- weight preparation lives in lstm_prep_kernel (below) ----------------------------------------------------------
 __global__ void unperm_vec_kernel(const float* __restrict__ in, int H, float* __restrict__ out) {
   const int rp = blockIdx.x * blockDim.x + threadIdx.x;
   if (rp >= 4 * H) return;
@@ -517,26 +504,6 @@ struct PersistBwdParams {
 #endif
 };
 
-// W_hh (fp32, gate-major rows g*H + j, [4H, H]) -> bf16 W^T with interleaved contraction index: out[n][4j + g]
-__global__ void __launch_bounds__(256)
-perm_transpose_bf16_kernel(const float* __restrict__ w, int H, bf* __restrict__ out) {
-  __shared__ float tile[32][33];
-  const int n0 = blockIdx.x * 32, r0 = blockIdx.y * 32;  // r = gate-major source row
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int i = ty; i < 32; i += 8) {
-    const int r = r0 + i, n = n0 + tx;
-    tile[i][tx] = (r < 4 * H && n < H) ? w[(int64_t)r * H + n] : 0.f;
-  }
-  __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int n = n0 + i, r = r0 + tx;
-    if (n < H && r < 4 * H) {
-      const int g = r / H, j = r - g * H;
-      out[(int64_t)n * 4 * H + 4 * j + g] = __float2bfloat16_rn(tile[tx][i]);
-    }
-  }
-}
-
 template <int NS>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -968,17 +935,87 @@ static int launch_persistent(void (*k1)(CUtensorMap, CUtensorMap, PackInfo, Para
   return SNT_EINVAL;
 }
 
+// One launch prepares everything a recurrence call needs: bf16 unit-interleaved W_ih' / W_hh' rows, the summed and
+// interleaved bias, the transposed W_hh'^T of the persistent BPTT kernel, and the cleared regions (h_{-1}, arrival
+// counters).  Sections are laid out back to back over blockIdx.x; a pointer that is NULL drops its section.
+struct PrepJob {
+  const float* w_ih; const float* w_hh; const float* b_ih; const float* b_hh;
+  int H, In;
+  bf* o_ih; bf* o_hh; float* o_bias; bf* o_hh_t;
+  uint4* zero[2]; int64_t zero_n16[2];  // regions to clear, in 16-byte units
+  int nA, nB, nC, nD;                   // blocks per section
+};
+__global__ void __launch_bounds__(256)
+lstm_prep_kernel(const PrepJob j) {
+  __shared__ float tile[32][33];
+  int b = blockIdx.x;
+  const int H = j.H;
+  if (b < j.nA) {  // row rp = 4*unit + gate of the interleaved weights
+    const int rp = b, src = (rp & 3) * H + (rp >> 2);
+    if (j.o_ih)
+      for (int c = threadIdx.x; c < j.In; c += 256)
+        j.o_ih[(int64_t)rp * j.In + c] = __float2bfloat16_rn(j.w_ih[(int64_t)src * j.In + c]);
+    if (j.o_hh)
+      for (int c = threadIdx.x; c < H; c += 256)
+        j.o_hh[(int64_t)rp * H + c] = __float2bfloat16_rn(j.w_hh[(int64_t)src * H + c]);
+    return;
+  }
+  b -= j.nA;
+  if (b < j.nB) {  // 32 x 32 tile of W_hh -> W^T with interleaved contraction index: out[n][4j + g]
+    const int tiles_n = (H + 31) / 32;
+    const int n0 = (b % tiles_n) * 32, r0 = (b / tiles_n) * 32;  // r = gate-major source row
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+      const int r = r0 + i, n = n0 + tx;
+      tile[i][tx] = (r < 4 * H && n < H) ? j.w_hh[(int64_t)r * H + n] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int n = n0 + i, r = r0 + tx;
+      if (n < H && r < 4 * H) {
+        const int g = r / H, u = r - g * H;
+        j.o_hh_t[(int64_t)n * 4 * H + 4 * u + g] = __float2bfloat16_rn(tile[tx][i]);
+      }
+    }
+    return;
+  }
+  b -= j.nB;
+  if (b < j.nC) {
+    const int rp = b * 256 + threadIdx.x;
+    if (rp < 4 * H) {
+      const int src = (rp & 3) * H + (rp >> 2);
+      j.o_bias[rp] = j.b_ih[src] + j.b_hh[src];
+    }
+    return;
+  }
+  b -= j.nC;
+  for (int k = 0; k < 2; ++k)
+    for (int64_t i = (int64_t)b * 256 + threadIdx.x; i < j.zero_n16[k]; i += (int64_t)j.nD * 256)
+      j.zero[k][i] = make_uint4(0u, 0u, 0u, 0u);
+}
+// zero0/zero1: optional regions to clear (byte counts are rounded up to 16: callers pass padded workspace regions)
+static int prep_launch(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int64_t In, int64_t H,
+                       bf* o_ih, bf* o_hh, float* o_bias, bf* o_hh_t, void* zero0, int64_t zero0_bytes, void* zero1,
+                       int64_t zero1_bytes, cudaStream_t st) {
+  PrepJob j;
+  j.w_ih = w_ih; j.w_hh = w_hh; j.b_ih = b_ih; j.b_hh = b_hh; j.H = (int)H; j.In = (int)In;
+  j.o_ih = o_ih; j.o_hh = o_hh; j.o_bias = (b_ih && b_hh) ? o_bias : nullptr; j.o_hh_t = o_hh_t;
+  j.zero[0] = (uint4*)zero0; j.zero_n16[0] = zero0 ? (zero0_bytes + 15) / 16 : 0;
+  j.zero[1] = (uint4*)zero1; j.zero_n16[1] = zero1 ? (zero1_bytes + 15) / 16 : 0;
+  j.nA = (o_ih || o_hh) ? (int)(4 * H) : 0;
+  j.nB = o_hh_t ? (int)(((H + 31) / 32) * ((4 * H + 31) / 32)) : 0;
+  j.nC = j.o_bias ? (int)((4 * H + 255) / 256) : 0;
+  const int64_t z = j.zero_n16[0] + j.zero_n16[1];
+  j.nD = z > 0 ? (int)(z / 1024 + 1 > 128 ? 128 : z / 1024 + 1) : 0;
+  const int total = j.nA + j.nB + j.nC + j.nD;
+  if (total == 0) return SNT_OK;
+  lstm_prep_kernel<<<(unsigned)total, 256, 0, st>>>(j);
+  SNT_LAUNCH_CHECK("lstm_prep_kernel");
+  return SNT_OK;
+}
 static int prep_weights(const LstmWs& w, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                         int64_t In, int64_t H, cudaStream_t st) {
-  perm_rows_bf16_kernel<<<(unsigned)(4 * H), 128, 0, st>>>(w_ih, (int)H, (int)In, w.w_ih);
-  SNT_LAUNCH_CHECK("perm_rows_bf16_kernel");
-  perm_rows_bf16_kernel<<<(unsigned)(4 * H), 128, 0, st>>>(w_hh, (int)H, (int)H, w.w_hh);
-  SNT_LAUNCH_CHECK("perm_rows_bf16_kernel");
-  if (b_ih) {
-    perm_bias_kernel<<<(unsigned)((4 * H + 255) / 256), 256, 0, st>>>(b_ih, b_hh, (int)H, w.bsum);
-    SNT_LAUNCH_CHECK("perm_bias_kernel");
-  }
-  return SNT_OK;
+  return prep_launch(w_ih, w_hh, b_ih, b_hh, In, H, w.w_ih, w.w_hh, w.bsum, nullptr, nullptr, 0, nullptr, 0, st);
 }
 
 #define SNT_REQ8(v, what)                                                                               \
@@ -1004,11 +1041,13 @@ int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const flo
   bf* hs_b = (bf*)hs;
   bf* hp_b = (bf*)hprev;
   bf* act = (bf*)gates;
-  SNT_CHECK(prep_weights(w, w_ih, w_hh, b_ih, b_hh, In, H, st));
+  // one launch: interleaved bf16 weights + bias, h_{-1} = 0 (first B rows of hprev), cleared arrival counters
+  SNT_CHECK(prep_launch(w_ih, w_hh, b_ih, b_hh, In, H, w.w_ih, w.w_hh, w.bsum, nullptr, hp_b,
+                        (int64_t)sizeof(bf) * B * H, w.flags,
+                        w.flags ? (int64_t)sizeof(int) * ((B + tc::BM - 1) / tc::BM) * T * PF_FLAGS_PER_STEP : 0, st));
   // the input projection of every timestep as ONE tensor-core contraction: Gx' = x . W_ih'^T + (b_ih + b_hh)'
   SNT_CHECK(tc::gemm_tc(false, false, N, 4 * H, In, 1.f, (const bf*)x, In, w.w_ih, In, 0.f, nullptr, w.gx, 4 * H,
                         w.bsum, 1, nullptr, st));
-  SNT_CUDA(cudaMemsetAsync(hp_b, 0, sizeof(bf) * (size_t)B * H, st));  // h_{-1} = 0
   CUtensorMap ta, tb;
   SNT_CHECK(tc::make_operand_tmap(&ta, hp_b, false, N, H, H, tc::BM));
   SNT_CHECK(tc::make_operand_tmap(&tb, w.w_hh, false, 4 * H, H, H, 128));
@@ -1022,7 +1061,6 @@ int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const flo
     persist_caps(&coop, &max_smem);
     if (coop == 1 && !getenv("SNT_NO_PERSISTENT") && (int64_t)num_m0 * num_n <= tc::sm_count() &&
         smem <= (size_t)max_smem && KB <= PF_FLAGS_PER_STEP && w.flags != nullptr) {
-      SNT_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(int) * (size_t)num_m0 * T * PF_FLAGS_PER_STEP, st));
       PersistFwdParams pp;
       pp.H = (int)H; pp.T = T; pp.num_n = num_n; pp.gx = w.gx; pp.cs = cs; pp.hs = hs_b; pp.hprev = hp_b; pp.act = act;
       pp.flags = w.flags;
@@ -1091,24 +1129,25 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
   if (!w.ok) { set_error("bf16 lstm_bwd: workspace too small"); return SNT_EWORKSPACE; }
   const bf* act = (const bf*)gates;
   bf* dg = (bf*)gates + N * 4 * H;
-  SNT_CHECK(prep_weights(w, w_ih, w_hh, nullptr, nullptr, In, H, st));
   bool persistent = false;
   {
     const int num_m0 = (int)((B + tc::BM - 1) / tc::BM);
     const int ns = (int)(H / 128);  // K-splits = N tiles; ns*ns CTAs per row block
     const size_t smem = (size_t)(8 + PB_STAGES) * 16384 + 1024 + 256;
+    const size_t nflags = (size_t)num_m0 * T * PB_FLAGS_PER_STEP;
     int coop = 0, max_smem = 0;
     persist_caps(&coop, &max_smem);
-    if (coop == 1 && !getenv("SNT_NO_PERSISTENT") && (H == 256 || H == 512) &&
-        (int64_t)num_m0 * ns * ns <= tc::sm_count() && smem <= (size_t)max_smem && w.flags && w.w_hh_t && w.part) {
-      perm_transpose_bf16_kernel<<<dim3((unsigned)((H + 31) / 32), (unsigned)((4 * H + 31) / 32)), 256, 0, st>>>(
-          w_hh, (int)H, w.w_hh_t);
-      SNT_LAUNCH_CHECK("perm_transpose_bf16_kernel");
+    const bool can_persist = coop == 1 && !getenv("SNT_NO_PERSISTENT") && (H == 256 || H == 512) &&
+                             (int64_t)num_m0 * ns * ns <= tc::sm_count() && smem <= (size_t)max_smem && w.flags &&
+                             w.w_hh_t && w.part;
+    // one launch: W_ih' (for dX), and either W_hh'^T + cleared counters (persistent) or W_hh' (per-step path)
+    SNT_CHECK(prep_launch(w_ih, w_hh, nullptr, nullptr, In, H, w.w_ih, can_persist ? nullptr : w.w_hh, nullptr,
+                          can_persist ? w.w_hh_t : nullptr, can_persist ? w.flags : nullptr,
+                          (int64_t)sizeof(int) * 2 * nflags, nullptr, 0, st));
+    if (can_persist) {
       CUtensorMap ta, tb;
       SNT_CHECK(tc::make_operand_tmap(&ta, dg, false, N, 4 * H, 4 * H, tc::BM));
       SNT_CHECK(tc::make_operand_tmap(&tb, w.w_hh_t, false, H, 4 * H, 4 * H, 128));
-      const size_t nflags = (size_t)num_m0 * T * PB_FLAGS_PER_STEP;
-      SNT_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(int) * 2 * nflags, st));
       PersistBwdParams pp;
       pp.H = (int)H; pp.T = T; pp.ns = ns; pp.d_hs = d_hs; pp.act = act; pp.cs = cs; pp.dg = dg;
       pp.part = w.part; pp.dgflag = w.flags; pp.pflag = w.flags + nflags;
