@@ -266,6 +266,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # all-reduce CTAs are placed first when SMs free up
         dist.init_process_group("nccl", device_id=dev)
     c = CFG
     peaks = load_peaks()
@@ -388,6 +389,16 @@ def main():
         clocks = sampler.stop()
         clocks["sampled_over"] = "20 more steps of the same load right after the timed region (polling inside it perturbs multi-GPU steps)"
     if os.environ.get("SNT_BENCH_DEBUG"):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        barrier()
+        evs[0].record()
+        for i in range(args.steps):
+            step_resident()
+            evs[i + 1].record()
+        barrier()
+        if rank == 0:
+            per = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+            print("[dbg] per-step ms: " + " ".join(f"{x:.2f}" for x in per), file=sys.stderr)
         t2 = timed(step_resident, args.steps)
         if rank == 0:
             print(f"[dbg] resident again, no clock sampler: {t2 / args.steps * 1e3:.3f} ms/step "

@@ -43,6 +43,12 @@ int snt_device_query(int device, int* sm_count, int* cc, int64_t* smem_optin);
 int snt_read_flags(int* flags_out, int reset, void* stream);
 /* Number of CUDA kernels this library has launched in this process (optionally resetting the counter). */
 int64_t snt_launch_count(int reset);
+/* Persistent tensor-core kernels normally launch one CTA per SM.  `n` > 0 leaves that many SMs free (grids shrink, tiles
+ * are redistributed) so that concurrently running kernels of another stream - the NCCL gradient all-reduce of the
+ * data-parallel step (train.py:43-44's DataParallel replaced by one process per GPU) - always find room and neither
+ * stall nor push CTAs of these kernels into a second wave.  Returns the previous value.  Host-side, takes effect for
+ * launches issued after the call. */
+int snt_set_sm_reserve(int n);
 
 /* ---- generic dense contractions (exported for the head, the drop-in Linear and unit tests) --------
  * C[M,N] = alpha * opA(A) . opB(B) + beta * C + bias[N]   (bias may be NULL), row-major C with ldc.

@@ -28,6 +28,7 @@ SIGNATURES = {
     "snt_device_query": (_int, [_int, C.POINTER(_int), C.POINTER(_int), C.POINTER(_i64)]),
     "snt_read_flags": (_int, [C.POINTER(_int), _int, _vp]),
     "snt_launch_count": (_i64, [_int]),
+    "snt_set_sm_reserve": (_int, [_int]),
     "snt_gemm_f32": (_int, [_int, _int, _i64, _i64, _i64, _f32, _vp, _i64, _vp, _i64, _f32, _vp, _i64, _vp, _vp]),
     "snt_gemm_bf16": (_int, [_int, _int, _i64, _i64, _i64, _f32, _vp, _i64, _vp, _i64, _f32, _vp, _i64, _int, _vp, _vp]),
     "snt_cast_bf16": (_int, [_vp, _vp, _i64, _vp]),

@@ -3,6 +3,8 @@
 // and split-K selection, the deterministic split-K reduction and the exported snt_gemm_bf16.
 #include "gemm_tc.cuh"
 
+#include <atomic>
+
 #include <cudaTypedefs.h>
 #include <mutex>
 
@@ -35,6 +37,13 @@ int sm_count() {
   }
   return n;
 }
+
+static std::atomic<int> g_sm_reserve{0};
+int grid_sms() {
+  const int n = sm_count() - g_sm_reserve.load();
+  return n < 1 ? 1 : n;
+}
+int set_sm_reserve(int n) { return g_sm_reserve.exchange(n < 0 ? 0 : n); }
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
                    int box_outer) {
@@ -178,6 +187,8 @@ int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, 
 
 }  // namespace tc
 }  // namespace snt
+
+extern "C" int snt_set_sm_reserve(int n) { return snt::tc::set_sm_reserve(n); }
 
 // C[M,N] = alpha*op(A).op(B) + beta*C + bias.  transA=0: A [M,K]; 1: A [K,M].  transB=0: B [K,N]; 1: B [N,K].
 extern "C" int snt_gemm_bf16(int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,

@@ -225,6 +225,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t inner, int64_t ou
 int make_operand_tmap(CUtensorMap* out, const void* base, bool mn_major, int64_t rows, int64_t K, int64_t ld,
                       int box_rows);
 int sm_count();
+int grid_sms();  // SMs a persistent grid may occupy: sm_count() minus the reserve set through snt_set_sm_reserve()
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TileSched& ts, const Epi& epi,
@@ -240,7 +241,7 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TileSch
   const int total = ts.num_m * ts.num_n * ts.splits;
   if (total <= 0) return SNT_OK;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)min(total, sm_count()));
+  cfg.gridDim = dim3((unsigned)min(total, grid_sms()));
   cfg.blockDim = dim3(128 + 32 * Epi::kWarps);
   cfg.dynamicSmemBytes = C::SMEM_BYTES + Epi::kWarps * Epi::kSmemPerWarp;
   cfg.stream = st;

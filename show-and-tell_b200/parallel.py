@@ -12,11 +12,13 @@ Greedy decode shards the batch with no communication at all.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import _lib, ops
 
 
 def strided_shard(n_rows, world, rank):
@@ -45,16 +47,39 @@ class GradAllReducer:
         self.group = group
         self.pending = []
         self.order = []     # names in the order they were reduced (introspection / tests)
+        self.groups = []    # (names, number of handles in self.pending) per readiness group of the current step
         self.bytes = 0
+        self.defer = False  # True: the end-of-backward call does not wait; the owner waits group by group
+        self.sm_reserve = int(os.environ.get("SNT_SM_RESERVE", "16"))
+        self.reserved = False
 
     def __call__(self, names, tensors):
         if names is None:
-            self.finish()
+            if not self.defer:
+                self.finish()
             return
+        if not self.groups and tensors and tensors[0].is_cuda and self.sm_reserve > 0:
+            # first collective of this backward: from here on an all-reduce kernel may be running next to the BPTT /
+            # embedding / head kernels, so the persistent GEMM grids leave it some SMs (see snt_set_sm_reserve)
+            _lib.lib().snt_set_sm_reserve(self.sm_reserve)
+            self.reserved = True
+        n0 = len(self.pending)
         self._reduce_group(tensors)
+        self.groups.append((list(names), len(self.pending) - n0))
         for n, t in zip(names, tensors):
             self.order.append(n)
             self.bytes += t.numel() * t.element_size()
+
+    def wait_groups(self, count):
+        """Make the current stream wait for the first `count` still-pending readiness groups; returns their names."""
+        names = []
+        for _ in range(min(count, len(self.groups))):
+            g, k = self.groups.pop(0)
+            for w in self.pending[:k]:
+                w.wait()
+            self.pending = self.pending[k:]
+            names += g
+        return names
 
     def _reduce_group(self, tensors):
         """One asynchronous SUM all-reduce per readiness group.  On NCCL the group's tensors are coalesced into a
@@ -73,6 +98,10 @@ class GradAllReducer:
         for w in self.pending:
             w.wait()
         self.pending = []
+        self.groups = []
+        if self.reserved:
+            _lib.lib().snt_set_sm_reserve(0)
+            self.reserved = False
 
 
 class DataParallelStep:
@@ -93,33 +122,58 @@ class DataParallelStep:
         self.v = [torch.zeros_like(p) for p in self.params]
         self.t = 0
         self._inflight = []   # events of the last steps (world > 1): bounds how far the host runs ahead
+        self.max_run_ahead = 16
+
+    def _reduce_named(self, grads):
+        self.reducer(["encoder.%d" % i for i in range(len(grads))], grads)
 
     def step(self, inputs, captions, lengths, targets, n_tokens_global=None):
         """inputs: pooled[B,2048] when an encoder is attached, else features[B,E].  Returns this rank's share
         of the global mean loss (sum over ranks = global-batch loss)."""
         if self.world > 1 and self.params and self.params[0].is_cuda:
             # Gradients are consumed on NCCL's stream, so the caching allocator can recycle their blocks only once
-            # that work has completed.  A host that runs many steps ahead keeps asking for fresh blocks (cudaMalloc
-            # synchronises the device); two steps of run-ahead hide all launch latency and keep the pool steady.
-            if len(self._inflight) >= 2:
+            # that work has completed: an unbounded host run-ahead keeps the pool growing.  The bound is generous
+            # (16 steps) on purpose: with only 2 steps of queued work every host-side hiccup (measured: sporadic
+            # 5-70 ms pauses of the Python thread) stalls the GPUs of ALL ranks through the next all-reduce.
+            if len(self._inflight) >= self.max_run_ahead:
                 self._inflight.pop(0).synchronize()
         for p in self.params:
             p.grad = None
         n_local = int(sum(lengths))
         scale = 1.0 if (self.world == 1 or n_tokens_global is None) else n_local / float(n_tokens_global)
         feats = self.encoder.forward_pooled(inputs) if self.encoder is not None else inputs
+        if self.reducer is not None:
+            self.reducer.defer = self.optimizer          # with the optimizer attached, step() waits group by group
         loss = self.decoder.loss(feats, captions, lengths, targets, grad_scale=scale)
         loss.backward()
-        if self.world > 1 and self.encoder is not None:   # head gradients: final only after the decoder's backward
-            hg = [p.grad for p in self.encoder.parameters() if p.requires_grad and p.grad is not None]
-            self.reducer._reduce_group(hg)
-            self.reducer.finish()
+        late = set()
+        if self.world > 1:
+            # Readiness order: linear.*, lstm.* (per layer), embed.weight, then the head.  The last two finish only at
+            # the very end of backward, so their all-reduce cannot hide behind it; the optimizer therefore first updates
+            # the parameters whose gradients are already reduced (70 % of the bytes) while those two are on the wire.
+            n_early = max(0, len(self.reducer.groups) - 1) if self.optimizer else 0
+            if self.encoder is not None:                 # head gradients: final only after the decoder's backward
+                hg = [p.grad for p in self.encoder.parameters() if p.requires_grad and p.grad is not None]
+                if hg:
+                    self._reduce_named(hg)
+            if self.optimizer:
+                self.reducer.wait_groups(n_early)
+                late = {id(p) for n, p in self.decoder.named_parameters() if n == "embed.weight"}
+                if self.encoder is not None:
+                    late |= {id(p) for p in self.encoder.parameters()}
+            else:
+                self.reducer.finish()
         if self.optimizer:
             self.t += 1
-            live = [(p.data, p.grad.contiguous(), m, v) for p, m, v in zip(self.params, self.m, self.v)
-                    if p.grad is not None]
-            ops.clamp_adam_multi_([x[0] for x in live], [x[1] for x in live], [x[2] for x in live],
-                                  [x[3] for x in live], self.t, self.lr, self.betas, self.eps, self.grad_clip)
+            live = [(p, p.grad.contiguous(), m, v) for p, m, v in zip(self.params, self.m, self.v) if p.grad is not None]
+            first = [x for x in live if id(x[0]) not in late]
+            last = [x for x in live if id(x[0]) in late]
+            for part in (first, last):
+                if part is last and self.world > 1:
+                    self.reducer.finish()                # embed.weight / head gradients have landed
+                if part:
+                    ops.clamp_adam_multi_([x[0].data for x in part], [x[1] for x in part], [x[2] for x in part],
+                                          [x[3] for x in part], self.t, self.lr, self.betas, self.eps, self.grad_clip)
         if self.world > 1 and self.params and self.params[0].is_cuda:
             ev = torch.cuda.Event()
             ev.record()

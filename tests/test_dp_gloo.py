@@ -57,6 +57,18 @@ def _worker(rank, world, port, q):
     for g in groups:                       # the order ops._DecoderLoss.backward reports gradients in
         red(g, [named[n].grad for n in g])
     red(None, None)                        # end of backward: wait for the collectives
+    # deferred mode (what DataParallelStep uses with its optimizer): the end-of-backward call does not wait, the owner
+    # waits for the early groups first, updates their parameters, then for the rest
+    t1, t2, t3 = torch.ones(5), torch.ones(7), torch.ones(3)
+    red2 = parallel.GradAllReducer()
+    red2.defer = True
+    red2(["a"], [t1])
+    red2(["b", "c"], [t2, t3])
+    red2(None, None)
+    assert len(red2.groups) == 2 and len(red2.pending) >= 2
+    assert red2.wait_groups(1) == ["a"] and float(t1[0]) == world and len(red2.groups) == 1
+    red2.finish()
+    assert float(t2[0]) == world and float(t3[0]) == world and not red2.pending and not red2.groups
     tot = loss.detach().clone()
     dist.all_reduce(tot)
     if rank == 0:
