@@ -438,9 +438,13 @@ def main():
     if rank == 0:
         top = stages[0]
         roof = {"bound": top.get("bound"), "achieved": top.get("achieved"), "peak": top.get("peak"),
-                "unit": top.get("unit"), "frac": top.get("frac"), "traffic": None,
-                "kernel": top["stage"] + " (largest share of the step; tcgen05 GEMMs gemm_tc_kernel<256,CeBwdEpi> + "
-                          "dHs/dW_out gemm_tc_kernel<PlainEpi> per L2-resident chunk)" if top["stage"] == "snt_vocab_ce_bwd"
+                "unit": top.get("unit"), "frac": top.get("frac"),
+                # dram__bytes_read.sum + dram__bytes_write.sum of the stage's nine tensor-core launches, one ncu --set
+                # full capture (profiles/r01_ncu_hot_kernels.txt); null for any other stage
+                "traffic": 1.0035e9 if top["stage"] == "snt_vocab_ce_bwd" else None,
+                "traffic_unit": "bytes per step (ncu, profiles/r01_ncu_hot_kernels.txt)",
+                "kernel": top["stage"] + " (largest share of the step; tcgen05 GEMMs gemm_tc_kernel<256,CeBwdEpiT<16>> + "
+                          "dHs/dW_out gemm_tc_kernel<128,PlainEpi> per 37-row-tile chunk)" if top["stage"] == "snt_vocab_ce_bwd"
                           else top["stage"],
                 "us_per_step": top["us_per_step"], "share_of_step": top["us_per_step"] / (t_res / args.steps * 1e6),
                 "algorithmic_work_per_step": top.get("algorithmic_work"),
