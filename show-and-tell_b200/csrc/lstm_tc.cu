@@ -51,12 +51,15 @@ struct LstmFwdEpi {
   static constexpr int kStages = 0;
   static constexpr int kSmemPerWarp = 0;
   int bs, bs_next, H;
-  const bf* gx;         // [bs, 4H]   input projection + biases of this step's rows (bf16), interleaved columns
+  const bf* gx;         // [bs, 4H]   input projection + biases of this step's rows (bf16), interleaved columns;
+                        //            NULL: the contraction already covers [x | h] (greedy decode) and only `bias` is added
+  const float* bias;    // [4H]       interleaved b_ih + b_hh, used when gx == NULL
   const float* c_prev;  // [>=bs, H]  c_{t-1} (NULL at t = 0)
   float* cs;            // [bs, H]    c_t
-  bf* hs;               // [bs, H]    h_t (layer output rows of this step)
-  bf* hprev_next;       // [bs_next, H] h_t again, at the packed rows of step t+1 (NULL at the last step)
+  bf* hs;               // [bs, ldh]  h_t (layer output rows of this step)
+  bf* hprev_next;       // [bs_next, ldn] h_t again: the packed rows of step t+1 / the next layer's input (NULL: skip)
   bf* act;              // [bs, 4H]   sigma(i), sigma(f), tanh(g), sigma(o), interleaved, kept for BPTT (NULL: skip)
+  int ldh, ldn;         // row pitches of hs / hprev_next in elements
 
   // everything the epilogue reads from global memory for its 128 columns (4 chunks x 8 hidden units)
   struct Pre {
@@ -71,9 +74,18 @@ struct LstmFwdEpi {
     for (int c = 0; c < 4; ++c) {
       const int col0 = n_blk * 128 + c * 32;
       if (col0 < H4) {
-        const uint4* g4 = reinterpret_cast<const uint4*>(gx + (int64_t)row * H4 + col0);
+        if (gx) {
+          const uint4* g4 = reinterpret_cast<const uint4*>(gx + (int64_t)row * H4 + col0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) p.gx[c][q] = __ldg(g4 + q);
+          for (int q = 0; q < 4; ++q) p.gx[c][q] = __ldg(g4 + q);
+        } else {  // bias only, packed to the same bf16 layout as a Gx' row would have
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * q));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * q + 4));
+            p.gx[c][q] = make_uint4(pack_bf2(b0.x, b0.y), pack_bf2(b0.z, b0.w), pack_bf2(b1.x, b1.y), pack_bf2(b1.z, b1.w));
+          }
+        }
         if (c_prev) {
           const float4* c4 = reinterpret_cast<const float4*>(c_prev + (int64_t)row * H + (col0 >> 2));
           p.cp[c][0] = c4[0];
@@ -126,8 +138,8 @@ struct LstmFwdEpi {
       cd[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
       const uint4 hv = make_uint4(pack_bf2(hn[0], hn[1]), pack_bf2(hn[2], hn[3]), pack_bf2(hn[4], hn[5]),
                                   pack_bf2(hn[6], hn[7]));
-      *reinterpret_cast<uint4*>(hs + (int64_t)row * H + j0) = hv;
-      if (row < bs_next) *reinterpret_cast<uint4*>(hprev_next + (int64_t)row * H + j0) = hv;
+      *reinterpret_cast<uint4*>(hs + (int64_t)row * ldh + j0) = hv;
+      if (row < bs_next) *reinterpret_cast<uint4*>(hprev_next + (int64_t)row * ldn + j0) = hv;
       if (act) {  // training only
         uint4* ad = reinterpret_cast<uint4*>(act + (int64_t)row * H4 + col0);
 #pragma unroll
@@ -942,6 +954,7 @@ struct PrepJob {
   const float* w_ih; const float* w_hh; const float* b_ih; const float* b_hh;
   int H, In;
   bf* o_ih; bf* o_hh; float* o_bias; bf* o_hh_t;
+  int ld_ih, ld_hh;                     // row pitches of o_ih / o_hh (In / H, or In + H for the concatenated [W_ih'|W_hh'])
   uint4* zero[2]; int64_t zero_n16[2];  // regions to clear, in 16-byte units
   int nA, nB, nC, nD;                   // blocks per section
 };
@@ -954,10 +967,10 @@ lstm_prep_kernel(const PrepJob j) {
     const int rp = b, src = (rp & 3) * H + (rp >> 2);
     if (j.o_ih)
       for (int c = threadIdx.x; c < j.In; c += 256)
-        j.o_ih[(int64_t)rp * j.In + c] = __float2bfloat16_rn(j.w_ih[(int64_t)src * j.In + c]);
+        j.o_ih[(int64_t)rp * j.ld_ih + c] = __float2bfloat16_rn(j.w_ih[(int64_t)src * j.In + c]);
     if (j.o_hh)
       for (int c = threadIdx.x; c < H; c += 256)
-        j.o_hh[(int64_t)rp * H + c] = __float2bfloat16_rn(j.w_hh[(int64_t)src * H + c]);
+        j.o_hh[(int64_t)rp * j.ld_hh + c] = __float2bfloat16_rn(j.w_hh[(int64_t)src * H + c]);
     return;
   }
   b -= j.nA;
@@ -996,8 +1009,9 @@ lstm_prep_kernel(const PrepJob j) {
 // zero0/zero1: optional regions to clear (byte counts are rounded up to 16: callers pass padded workspace regions)
 static int prep_launch(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int64_t In, int64_t H,
                        bf* o_ih, bf* o_hh, float* o_bias, bf* o_hh_t, void* zero0, int64_t zero0_bytes, void* zero1,
-                       int64_t zero1_bytes, cudaStream_t st) {
+                       int64_t zero1_bytes, cudaStream_t st, int64_t ld_ih = 0, int64_t ld_hh = 0) {
   PrepJob j;
+  j.ld_ih = (int)(ld_ih ? ld_ih : In); j.ld_hh = (int)(ld_hh ? ld_hh : H);
   j.w_ih = w_ih; j.w_hh = w_hh; j.b_ih = b_ih; j.b_hh = b_hh; j.H = (int)H; j.In = (int)In;
   j.o_ih = o_ih; j.o_hh = o_hh; j.o_bias = (b_ih && b_hh) ? o_bias : nullptr; j.o_hh_t = o_hh_t;
   j.zero[0] = (uint4*)zero0; j.zero_n16[0] = zero0 ? (zero0_bytes + 15) / 16 : 0;
@@ -1112,6 +1126,7 @@ int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const flo
     e.cs = cs + (int64_t)pk.off[t] * H;
     e.hs = hs_b + (int64_t)pk.off[t] * H;
     e.hprev_next = bs_next > 0 ? hp_b + (int64_t)pk.off[t + 1] * H : nullptr;
+    e.bias = nullptr; e.ldh = (int)H; e.ldn = (int)H;
     e.act = act + (int64_t)pk.off[t] * 4 * H;
     SNT_CHECK((tc::launch_gemm_tc<128, false, false, LstmFwdEpi>(ta, tb, ts, e, st, /*pdl=*/t > 0)));
   }
@@ -1267,7 +1282,7 @@ struct ArgmaxEpi {
 // one warp per row: first global maximum over the slab partials, id out, next input = bf16(W_emb[id])
 __global__ void __launch_bounds__(256)
 argmax_finish_kernel(const float2* __restrict__ part, int slabs, int64_t B, const float* __restrict__ w_emb, int E,
-                     int64_t* __restrict__ ids, int64_t ids_stride, bf* __restrict__ x_next) {
+                     int64_t* __restrict__ ids, int64_t ids_stride, bf* __restrict__ x_next, int64_t ldx) {
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -1291,17 +1306,30 @@ argmax_finish_kernel(const float2* __restrict__ part, int slabs, int64_t B, cons
     uint2 o;
     o.x = pack_bf2(v.x, v.y);
     o.y = pack_bf2(v.z, v.w);
-    *reinterpret_cast<uint2*>(x_next + row * E + e) = o;
+    *reinterpret_cast<uint2*>(x_next + row * ldx + e) = o;
   }
 }
 
+// fp32 [rows, cols] -> bf16 rows of pitch ld (the [x | h] operand buffers of the decode loop)
+__global__ void __launch_bounds__(256)
+cast_rows_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, bf* __restrict__ dst, int64_t ld) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int64_t r = i / cols, c = i % cols;
+  dst[r * ld + c] = __float2bfloat16_rn(src[i]);
+}
+
+// Per layer the step's two contractions (input projection and recurrence) are ONE GEMM over the concatenated operand
+// [x_s | h_{s-1}] (K = in + H) against [W_ih' | W_hh']: the gate epilogue writes h_s straight into the h half of the
+// next step's operand buffer (and into the x half of the next layer's), argmax_finish writes the next token's embedding
+// into the x half, and the vocab projection reads h_s in place through a strided tensor map - no copies, no Gx' buffer.
 int64_t greedy_ws_bytes(int64_t B, int64_t E, int64_t H, int64_t V, int L) {
   const int64_t slabs = ((V + 255) / 256) * 2;
-  int64_t b = ws_bytes_for(B * E, 2) + ws_bytes_for(V * H, 2) + ws_bytes_for(B * 4 * H, 2) + ws_bytes_for(slabs * B, 8);
+  int64_t b = ws_bytes_for(V * H, 2) + ws_bytes_for(slabs * B, 8);
   for (int k = 0; k < L; ++k) {
     const int64_t in = k == 0 ? E : H;
-    b += 2 * ws_bytes_for(B * H, 2) + ws_bytes_for(B * H, 4) + ws_bytes_for(4 * H, 4) + ws_bytes_for(4 * H * in, 2) +
-         ws_bytes_for(4 * H * H, 2);
+    b += 2 * ws_bytes_for(B * (in + H), 2) + ws_bytes_for(B * H, 4) + ws_bytes_for(4 * H, 4) +
+         ws_bytes_for(4 * H * (in + H), 2);
   }
   return b;
 }
@@ -1315,64 +1343,66 @@ int greedy_decode(const float* features, const float* w_emb, int L, const float*
   SNT_REQUIRE(B < (1LL << 31) && V < (1LL << 31), "greedy_decode: extent too large");
   const int slabs = (int)((V + 255) / 256) * 2;
   Workspace w(ws, ws_bytes);
-  bf* x = w.take<bf>(B * E);
   bf* wout = w.take<bf>(V * H);
-  bf* gx = w.take<bf>(B * 4 * H);
   float2* part = w.take<float2>((int64_t)slabs * B);
-  bf *h[SNT_MAX_LAYERS][2], *wih[SNT_MAX_LAYERS], *whh[SNT_MAX_LAYERS];
+  bf *cat[SNT_MAX_LAYERS][2], *wcat[SNT_MAX_LAYERS];
   float *c[SNT_MAX_LAYERS], *bsum[SNT_MAX_LAYERS];
+  int64_t kin[SNT_MAX_LAYERS];
   for (int k = 0; k < L; ++k) {
-    const int64_t in = k == 0 ? E : H;
-    h[k][0] = w.take<bf>(B * H);
-    h[k][1] = w.take<bf>(B * H);
+    kin[k] = k == 0 ? E : H;
+    cat[k][0] = w.take<bf>(B * (kin[k] + H));
+    cat[k][1] = w.take<bf>(B * (kin[k] + H));
     c[k] = w.take<float>(B * H);
     bsum[k] = w.take<float>(4 * H);
-    wih[k] = w.take<bf>(4 * H * in);
-    whh[k] = w.take<bf>(4 * H * H);
+    wcat[k] = w.take<bf>(4 * H * (kin[k] + H));
   }
   if (!w.ok()) { set_error("bf16 greedy_decode: workspace too small"); return SNT_EWORKSPACE; }
   SNT_CHECK(cast_bf16(w_out, wout, V * H, st));
-  SNT_CHECK(cast_bf16(features, x, B * E, st));
-  CUtensorMap th[SNT_MAX_LAYERS][2], tw[SNT_MAX_LAYERS], tout_a[2], tout_b;
+  CUtensorMap ta[SNT_MAX_LAYERS][2], tw[SNT_MAX_LAYERS], tout_a[2], tout_b;
   for (int k = 0; k < L; ++k) {
-    const int64_t in = k == 0 ? E : H;
-    LstmWs lw;
-    lw.w_ih = wih[k]; lw.w_hh = whh[k]; lw.bsum = bsum[k];
-    SNT_CHECK(prep_weights(lw, w_ih[k], w_hh[k], b_ih[k], b_hh[k], in, H, st));
+    const int64_t ld = kin[k] + H;
+    // [W_ih' | W_hh'] interleaved rows + summed bias; the step-0 operand buffer starts as zeros (h_{-1} = 0)
+    SNT_CHECK(prep_launch(w_ih[k], w_hh[k], b_ih[k], b_hh[k], kin[k], H, wcat[k], wcat[k] + kin[k], bsum[k], nullptr,
+                          cat[k][0], (int64_t)sizeof(bf) * B * ld, nullptr, 0, st, ld, ld));
     if (h0) {
-      SNT_CHECK(cast_bf16(h0 + (int64_t)k * B * H, h[k][0], B * H, st));
+      cast_rows_kernel<<<(unsigned)((B * H + 255) / 256), 256, 0, st>>>(h0 + (int64_t)k * B * H, B, H, cat[k][0] + kin[k], ld);
+      SNT_LAUNCH_CHECK("cast_rows_kernel");
       SNT_CUDA(cudaMemcpyAsync(c[k], c0 + (int64_t)k * B * H, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, st));
     } else {
-      SNT_CUDA(cudaMemsetAsync(h[k][0], 0, sizeof(bf) * B * H, st));
       SNT_CUDA(cudaMemsetAsync(c[k], 0, sizeof(float) * B * H, st));
     }
-    for (int q = 0; q < 2; ++q) SNT_CHECK(tc::make_operand_tmap(&th[k][q], h[k][q], false, B, H, H, tc::BM));
-    SNT_CHECK(tc::make_operand_tmap(&tw[k], whh[k], false, 4 * H, H, H, 128));
+    for (int q = 0; q < 2; ++q) SNT_CHECK(tc::make_operand_tmap(&ta[k][q], cat[k][q], false, B, ld, ld, tc::BM));
+    SNT_CHECK(tc::make_operand_tmap(&tw[k], wcat[k], false, 4 * H, ld, ld, 128));
   }
-  for (int q = 0; q < 2; ++q) SNT_CHECK(tc::make_operand_tmap(&tout_a[q], h[L - 1][q], false, B, H, H, tc::BM));
+  cast_rows_kernel<<<(unsigned)((B * E + 255) / 256), 256, 0, st>>>(features, B, E, cat[0][0], E + H);
+  SNT_LAUNCH_CHECK("cast_rows_kernel");
+  {
+    const int64_t ld = kin[L - 1] + H;
+    for (int q = 0; q < 2; ++q)
+      SNT_CHECK(tc::make_operand_tmap(&tout_a[q], cat[L - 1][q] + kin[L - 1], false, B, H, ld, tc::BM));
+  }
   SNT_CHECK(tc::make_operand_tmap(&tout_b, wout, false, V, H, H, 256));
   for (int s = 0; s < steps; ++s) {
-    const int cur = s & 1, nxt = cur ^ 1;  // h[k][cur] = h_{s-1}, h[k][nxt] = h_s
-    const bf* inp = x;
-    int64_t in = E;
+    const int cur = s & 1, nxt = cur ^ 1;  // cat[k][cur] = [input_s | h_{s-1}]; h_s goes to cat[k][nxt]
     for (int k = 0; k < L; ++k) {
-      SNT_CHECK(tc::gemm_tc(false, false, B, 4 * H, in, 1.f, inp, in, wih[k], in, 0.f, nullptr, gx, 4 * H, bsum[k], 1,
-                            nullptr, st));
+      const int64_t ld = kin[k] + H;
       tc::TileSched ts;
       ts.num_m = (int)((B + tc::BM - 1) / tc::BM);
       ts.num_n = (int)((4 * H + 127) / 128);
       ts.splits = 1;
-    ts.n_fastest = 0;
-      ts.kblocks = (int)((H + tc::BK - 1) / tc::BK);
+      ts.n_fastest = 0;
+      ts.kblocks = (int)((ld + tc::BK - 1) / tc::BK);
       ts.kblocks_per_split = ts.kblocks;
       ts.a_row0 = 0;
       ts.b_row0 = 0;
       LstmFwdEpi e;
-      e.bs = (int)B; e.bs_next = 0; e.H = (int)H; e.gx = gx; e.c_prev = c[k]; e.cs = c[k];
-      e.hs = h[k][nxt]; e.hprev_next = nullptr; e.act = nullptr;
-      SNT_CHECK((tc::launch_gemm_tc<128, false, false, LstmFwdEpi>(th[k][cur], tw[k], ts, e, st, true)));
-      inp = h[k][nxt];
-      in = H;
+      e.bs = (int)B; e.H = (int)H; e.gx = nullptr; e.bias = bsum[k]; e.c_prev = c[k]; e.cs = c[k];
+      e.hs = cat[k][nxt] + kin[k]; e.ldh = (int)ld;
+      e.hprev_next = k + 1 < L ? cat[k + 1][cur] : nullptr;  // this step's input of the next layer
+      e.bs_next = k + 1 < L ? (int)B : 0;
+      e.ldn = k + 1 < L ? (int)(kin[k + 1] + H) : 0;
+      e.act = nullptr;
+      SNT_CHECK((tc::launch_gemm_tc<128, false, false, LstmFwdEpi>(ta[k][cur], tw[k], ts, e, st, true)));
     }
     tc::TileSched ts;
     ts.num_m = (int)((B + tc::BM - 1) / tc::BM);
@@ -1386,7 +1416,8 @@ int greedy_decode(const float* features, const float* w_emb, int L, const float*
     ArgmaxEpi e;
     e.M = (int)B; e.V = (int)V; e.bias = b_out; e.part = part;
     SNT_CHECK((tc::launch_gemm_tc<256, false, false, ArgmaxEpi>(tout_a[nxt], tout_b, ts, e, st, true)));
-    argmax_finish_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(part, slabs, B, w_emb, (int)E, ids + s, steps, x);
+    argmax_finish_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(part, slabs, B, w_emb, (int)E, ids + s, steps,
+                                                                   cat[0][nxt], E + H);
     SNT_LAUNCH_CHECK("argmax_finish_kernel");
   }
   return SNT_OK;
