@@ -50,6 +50,7 @@ class GradAllReducer:
         self.groups = []    # (names, number of handles in self.pending) per readiness group of the current step
         self.bytes = 0
         self.defer = False  # True: the end-of-backward call does not wait; the owner waits group by group
+        self.coalesce = True
         self.sm_reserve = int(os.environ.get("SNT_SM_RESERVE", "16"))
         self.reserved = False
 
@@ -85,7 +86,8 @@ class GradAllReducer:
         """One asynchronous SUM all-reduce per readiness group.  On NCCL the group's tensors are coalesced into a
         single launch (ncclGroupStart/End): one kernel instead of one per tensor next to the BPTT kernels."""
         tensors = list(tensors)
-        if len(tensors) > 1 and dist.get_backend(self.group) == "nccl" and hasattr(dist, "_coalescing_manager"):
+        if (self.coalesce and len(tensors) > 1 and dist.get_backend(self.group) == "nccl"
+                and hasattr(dist, "_coalescing_manager")):
             with dist._coalescing_manager(group=self.group, device=tensors[0].device, async_ops=True) as cm:
                 for t in tensors:
                     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
@@ -109,8 +111,21 @@ class DataParallelStep:
     train.py:137-146 for the models.py pair, per rank.  world == 1 needs no process group."""
 
     def __init__(self, encoder, decoder, group=None, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_clip=0.1,
-                 optimizer=True):
+                 optimizer=True, cuda_graph=False, graph_after=3):
+        """cuda_graph=True: once the same (input tensors, lengths) signature has been stepped `graph_after` times
+        eagerly, forward + backward (+ gradient all-reduce) are captured into a CUDA graph and replayed from then on:
+        one graph launch instead of ~60 kernel launches and ~20 C-ABI calls.  The host needs ~1.0 ms to enqueue an eager
+        step (measured), which is what bounds a multi-GPU step; the optimizer stays outside the graph (its
+        bias-correction scalars change every step).  Signatures that never repeat (real, ragged batches) stay eager."""
         self.encoder, self.decoder = encoder, decoder
+        self.cuda_graph, self.graph_after = cuda_graph, graph_after
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 \
+                and not os.environ.get("SNT_GRAPH_MULTI"):
+            # Round 1: a 2-GPU run with NCCL collectives inside the captured graph hung once in two tries (the other
+            # try ran at 1.52 ms/step against 1.57 eager), so multi-GPU steps stay eager unless SNT_GRAPH_MULTI=1.
+            self.cuda_graph = False
+        self._graphs, self._seen = {}, {}
+        self.replayed_kernels = 0   # kernels executed through graph replays (snt_launch_count only sees eager launches)
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.group = group
         self.reducer = GradAllReducer(group) if self.world > 1 else None
@@ -127,54 +142,100 @@ class DataParallelStep:
     def _reduce_named(self, grads):
         self.reducer(["encoder.%d" % i for i in range(len(grads))], grads)
 
+    def _fwd_bwd(self, inputs, captions, lengths, targets, n_tokens_global, staged):
+        """forward + backward + gradient all-reduce launches.  staged=True (eager, optimizer attached): returns with the
+        late groups still in flight; otherwise every collective has been waited for on the current stream."""
+        n_local = int(sum(lengths))
+        scale = 1.0 if (self.world == 1 or n_tokens_global is None) else n_local / float(n_tokens_global)
+        feats = self.encoder.forward_pooled(inputs) if self.encoder is not None else inputs
+        if self.reducer is not None:
+            self.reducer.defer = staged
+        loss = self.decoder.loss(feats, captions, lengths, targets, grad_scale=scale)
+        loss.backward()
+        if self.world > 1:
+            # Readiness order: linear.*, lstm.* (per layer), embed.weight, then the head.  The last two finish only at
+            # the very end of backward, so their all-reduce cannot hide behind it; the optimizer therefore first updates
+            # the parameters whose gradients are already reduced (70 % of the bytes) while those two are on the wire.
+            n_early = max(0, len(self.reducer.groups) - 1) if staged else 0
+            if self.encoder is not None:                 # head gradients: final only after the decoder's backward
+                hg = [p.grad for p in self.encoder.parameters() if p.requires_grad and p.grad is not None]
+                if hg:
+                    self._reduce_named(hg)
+            if staged:
+                self.reducer.wait_groups(n_early)
+            else:
+                self.reducer.finish()
+        return loss
+
+    def _adam(self, late):
+        self.t += 1
+        live = [(p, p.grad.contiguous(), m, v) for p, m, v in zip(self.params, self.m, self.v) if p.grad is not None]
+        first = [x for x in live if id(x[0]) not in late]
+        last = [x for x in live if id(x[0]) in late]
+        for part in (first, last):
+            if part is last and self.world > 1:
+                self.reducer.finish()                # embed.weight / head gradients have landed
+            if part:
+                ops.clamp_adam_multi_([x[0].data for x in part], [x[1] for x in part], [x[2] for x in part],
+                                      [x[3] for x in part], self.t, self.lr, self.betas, self.eps, self.grad_clip)
+
+    def _graph_step(self, key, inputs, captions, lengths, targets, n_tokens_global):
+        ent = self._graphs.get(key)
+        if ent is None:
+            g = torch.cuda.CUDAGraph()
+            for p in self.params:
+                p.grad = None                            # the captured backward allocates the (then static) gradients
+            if self.reducer is not None:
+                self.reducer.coalesce = False            # plain per-tensor collectives inside the capture
+            torch.cuda.synchronize()
+            n0 = int(_lib.lib().snt_launch_count(0))
+            # thread_local: CUDA calls of other threads (e.g. NCCL's watchdog) must not invalidate this capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                loss = self._fwd_bwd(inputs, captions, lengths, targets, n_tokens_global, staged=False)
+            kernels = int(_lib.lib().snt_launch_count(0)) - n0   # launches recorded into the graph (not executed yet)
+            if self.reducer is not None:
+                self.reducer.coalesce = True
+            # keep the captured tensors alive; the gradients written by a replay are THIS capture's tensors
+            ent = self._graphs[key] = (g, loss, [p.grad for p in self.params], kernels, (inputs, captions, targets))
+        ent[0].replay()
+        for p, gr in zip(self.params, ent[2]):
+            p.grad = gr
+        self.replayed_kernels += ent[3]
+        return ent[1]
+
     def step(self, inputs, captions, lengths, targets, n_tokens_global=None):
         """inputs: pooled[B,2048] when an encoder is attached, else features[B,E].  Returns this rank's share
         of the global mean loss (sum over ranks = global-batch loss)."""
-        if self.world > 1 and self.params and self.params[0].is_cuda:
+        cuda = bool(self.params) and self.params[0].is_cuda
+        if self.world > 1 and cuda:
             # Gradients are consumed on NCCL's stream, so the caching allocator can recycle their blocks only once
             # that work has completed: an unbounded host run-ahead keeps the pool growing.  The bound is generous
             # (16 steps) on purpose: with only 2 steps of queued work every host-side hiccup (measured: sporadic
             # 5-70 ms pauses of the Python thread) stalls the GPUs of ALL ranks through the next all-reduce.
             if len(self._inflight) >= self.max_run_ahead:
                 self._inflight.pop(0).synchronize()
-        for p in self.params:
-            p.grad = None
-        n_local = int(sum(lengths))
-        scale = 1.0 if (self.world == 1 or n_tokens_global is None) else n_local / float(n_tokens_global)
-        feats = self.encoder.forward_pooled(inputs) if self.encoder is not None else inputs
-        if self.reducer is not None:
-            self.reducer.defer = self.optimizer          # with the optimizer attached, step() waits group by group
-        loss = self.decoder.loss(feats, captions, lengths, targets, grad_scale=scale)
-        loss.backward()
+        key = None
+        if self.cuda_graph and cuda:
+            key = (inputs.data_ptr(), captions.data_ptr(), targets.data_ptr(), tuple(int(x) for x in lengths),
+                   n_tokens_global, tuple(inputs.shape), tuple(captions.shape))
+            self._seen[key] = self._seen.get(key, 0) + 1
+            if key not in self._graphs and self._seen[key] <= self.graph_after:
+                key = None
         late = set()
-        if self.world > 1:
-            # Readiness order: linear.*, lstm.* (per layer), embed.weight, then the head.  The last two finish only at
-            # the very end of backward, so their all-reduce cannot hide behind it; the optimizer therefore first updates
-            # the parameters whose gradients are already reduced (70 % of the bytes) while those two are on the wire.
-            n_early = max(0, len(self.reducer.groups) - 1) if self.optimizer else 0
-            if self.encoder is not None:                 # head gradients: final only after the decoder's backward
-                hg = [p.grad for p in self.encoder.parameters() if p.requires_grad and p.grad is not None]
-                if hg:
-                    self._reduce_named(hg)
-            if self.optimizer:
-                self.reducer.wait_groups(n_early)
+        if key is not None:
+            loss = self._graph_step(key, inputs, captions, lengths, targets, n_tokens_global)
+        else:
+            for p in self.params:
+                p.grad = None
+            staged = bool(self.optimizer) and self.world > 1
+            loss = self._fwd_bwd(inputs, captions, lengths, targets, n_tokens_global, staged)
+            if staged:
                 late = {id(p) for n, p in self.decoder.named_parameters() if n == "embed.weight"}
                 if self.encoder is not None:
                     late |= {id(p) for p in self.encoder.parameters()}
-            else:
-                self.reducer.finish()
         if self.optimizer:
-            self.t += 1
-            live = [(p, p.grad.contiguous(), m, v) for p, m, v in zip(self.params, self.m, self.v) if p.grad is not None]
-            first = [x for x in live if id(x[0]) not in late]
-            last = [x for x in live if id(x[0]) in late]
-            for part in (first, last):
-                if part is last and self.world > 1:
-                    self.reducer.finish()                # embed.weight / head gradients have landed
-                if part:
-                    ops.clamp_adam_multi_([x[0].data for x in part], [x[1] for x in part], [x[2] for x in part],
-                                          [x[3] for x in part], self.t, self.lr, self.betas, self.eps, self.grad_clip)
-        if self.world > 1 and self.params and self.params[0].is_cuda:
+            self._adam(late)
+        if self.world > 1 and cuda:
             ev = torch.cuda.Event()
             ev.record()
             self._inflight.append(ev)
