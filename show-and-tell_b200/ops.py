@@ -29,6 +29,24 @@ def _act_dtype(prec):
 def batch_sizes_from_lengths(lengths, max_steps=None):
     """`lengths` as the reference passes them (list of ints sorted descending, data_loader.py:50) ->
     int32 batch_sizes[T] of the packed sequence (what pack_padded_sequence computes at models.py:51)."""
+    key = (tuple(lengths) if isinstance(lengths, (list, tuple)) else None, max_steps)
+    if key[0] is not None:
+        hit = _BS_CACHE.get(key)
+        if hit is not None:
+            return hit
+    bs = _batch_sizes_from_lengths(lengths, max_steps)
+    if key[0] is not None:
+        if len(_BS_CACHE) > 64:
+            _BS_CACHE.clear()
+        bs.setflags(write=False)
+        _BS_CACHE[key] = bs
+    return bs
+
+
+_BS_CACHE = {}   # lengths tuple -> batch_sizes (the same validation + numpy pass costs ~140 us per call otherwise)
+
+
+def _batch_sizes_from_lengths(lengths, max_steps=None):
     l = np.asarray([int(x) for x in lengths], dtype=np.int64)
     if l.ndim != 1 or l.size == 0:
         raise RuntimeError("lengths must be a non-empty 1-D sequence")
