@@ -93,3 +93,16 @@ def test_gemm_bf16_tcgen05(M, N, K, tA, tB):
 def test_gemm_bf16_out_bf16(M, N, K):
     err = _bf16_case(M, N, K, 0, 1, True, 5)
     assert err < 4e-3, err
+
+
+def test_gemm_bf16_with_sm_reserve():
+    """snt_set_sm_reserve shrinks the persistent grids (tiles are redistributed over fewer CTAs); results are unchanged
+    bit for bit, and the previous value is returned."""
+    L = _lib()
+    base = _bf16_case(12851, 2048, 256, 0, 1, False, 11)
+    assert L.lib().snt_set_sm_reserve(16) == 0
+    try:
+        assert _bf16_case(12851, 2048, 256, 0, 1, False, 11) == base
+        assert _bf16_case(1024, 10000, 512, 1, 0, False, 12) < 5e-5
+    finally:
+        assert L.lib().snt_set_sm_reserve(0) == 16
