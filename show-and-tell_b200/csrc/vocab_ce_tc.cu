@@ -26,38 +26,6 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// ---- target logit: tl[n] = Hs[n,:] . W[target[n],:] + b[target[n]]  (one warp per row) ---------------------------
-__global__ void __launch_bounds__(256)
-ce_target_logit_kernel(const bf* __restrict__ hs, const bf* __restrict__ w, const float* __restrict__ bias,
-                       const int64_t* __restrict__ targets, int64_t N, int H, int64_t V, float* __restrict__ tl,
-                       int* flags) {
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= N) return;
-  const int64_t t = targets[row];
-  if (t < 0 || t >= V) {
-    if (lane == 0) { atomicOr(flags, 2); tl[row] = 0.f; }
-    return;
-  }
-  const bf* a = hs + row * H;
-  const bf* b = w + t * H;
-  float acc = 0.f;
-  for (int k = lane * 8; k < H; k += 256) {  // H % 8 == 0
-    const uint4 va = *reinterpret_cast<const uint4*>(a + k);
-    const uint4 vb = *reinterpret_cast<const uint4*>(b + k);
-    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&va);
-    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&vb);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 fa = __bfloat1622float2(pa[i]), fb = __bfloat1622float2(pb[i]);
-      acc = fmaf(fa.x, fb.x, acc);
-      acc = fmaf(fa.y, fb.y, acc);
-    }
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) tl[row] = acc + bias[t];
-}
-
 // ---- forward epilogue: per (row, 128-column slab) online-softmax partial in the log2 domain ------------------------
 struct CeFwdEpi {
   static constexpr int kWarps = 8;
@@ -67,11 +35,18 @@ struct CeFwdEpi {
   int V;                 // valid columns
   const float* bias;     // [V]
   float2* part;          // [num_slabs][M] (max2, sum2): sum_j 2^(y_j - max2), y = logit * log2(e)
+  const int64_t* targets;  // [M]
+  float* tl;             // [M] out: logit of the target class, picked out of the accumulator by the one thread whose
+                         // chunk holds it (rows with an out-of-range target are left alone; ce_finish flags them)
 
-  using Pre = tc::NoPre;
-  __device__ __forceinline__ void prefetch(Pre&, int, int, int, int) const {}
+  struct Pre { int tgt; };
+  __device__ __forceinline__ void prefetch(Pre& p, int m_blk, int, int ew, int lane) const {
+    const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
+    int64_t t = row < M ? targets[row] : -1;
+    p.tgt = (t >= 0 && t < V) ? (int)t : -1;
+  }
   __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int split, int ew, int lane,
-                                       const Pre&, uint8_t* wsm) const {
+                                       const Pre& pre, uint8_t* wsm) const {
     const int half = ew >> 2;
     const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
     float m = -INFINITY, s = 0.f;
@@ -88,6 +63,16 @@ struct CeFwdEpi {
         for (int q = 0; q < 8; ++q) bv[q] = __ldg(reinterpret_cast<const float4*>(bias + col0) + q);
       }
       tc::tmem_ld_wait();
+      {
+        const int trel = pre.tgt - col0;
+        const bool hit = pre.tgt >= 0 && trel >= 0 && trel < 32;
+        if (__any_sync(0xffffffffu, hit)) {  // ~10 % of the chunks: some row of the warp has its target in here
+          float v = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v = (trel == j) ? __uint_as_float(r[j]) : v;
+          if (hit) tl[row] = v + __ldg(bias + pre.tgt);
+        }
+      }
       float y[32];
       if (col0 + 32 <= V) {
 #pragma unroll
@@ -117,13 +102,17 @@ struct CeFwdEpi {
   }
 };
 
-// lse[n] = ln2 * (M + log2 sum_k s_k 2^(m_k - M)); nll[n] = lse - tl.  Block = 64 rows x 8 slab groups: every thread
-// merges its share of the slab partials online (coalesced across rows), the 8 groups are merged through shared memory
-// in a fixed order.
+// lse[n] = ln2 * (M + log2 sum_k s_k 2^(m_k - M)); nll[n] = lse - tl; loss = mean(nll).  Block = 64 rows x 8 slab
+// groups: every thread merges its share of the slab partials online (coalesced across rows), the 8 groups are merged
+// through shared memory in a fixed order.  Each block leaves the sum of its 64 nll values in block_sum[]; the block that
+// takes the last ticket adds those in index order (deterministic) and writes the mean - no separate reduction launch.
 __global__ void __launch_bounds__(512)
 ce_finish_kernel(const float2* __restrict__ part, int slabs, int64_t N, const float* __restrict__ tl,
-                 float* __restrict__ lse, float* __restrict__ nll) {
+                 const int64_t* __restrict__ targets, int64_t V, float* __restrict__ lse, float* __restrict__ block_sum,
+                 int* __restrict__ ticket, float inv_n, float* __restrict__ loss, int* flags) {
   __shared__ float2 red[8][64];
+  __shared__ float wred[16];
+  __shared__ int s_last;
   const int tx = threadIdx.x & 63, g = threadIdx.x >> 6;
   const int64_t row = (int64_t)blockIdx.x * 64 + tx;
   float M = -INFINITY, S = 0.f;
@@ -139,6 +128,7 @@ ce_finish_kernel(const float2* __restrict__ part, int slabs, int64_t N, const fl
   }
   red[g][tx] = make_float2(M, S);
   __syncthreads();
+  float nll = 0.f;
   if (g == 0 && row < N) {
     float Mt = -INFINITY, St = 0.f;
 #pragma unroll
@@ -152,7 +142,37 @@ ce_finish_kernel(const float2* __restrict__ part, int slabs, int64_t N, const fl
     }
     const float l = (Mt + log2f(St)) * LN2;
     lse[row] = l;
-    nll[row] = l - tl[row];
+    const int64_t t = targets[row];
+    const bool valid = t >= 0 && t < V;
+    if (!valid) atomicOr(flags, 2);
+    nll = l - (valid ? tl[row] : 0.f);
+  }
+  // block sum of the 64 nll values (threads 0..63 = warps 0 and 1), fixed order
+  if (g == 0) {
+    const float w = warp_sum(nll);
+    if ((tx & 31) == 0) wred[tx >> 5] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    block_sum[blockIdx.x] = wred[0] + wred[1];
+    __threadfence();
+    s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 512) t += __ldcg(block_sum + i);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) tot += wred[i];
+      loss[0] = tot * inv_n;
+      *ticket = 0;  // self-resetting
+    }
   }
 }
 
@@ -411,6 +431,18 @@ static int make_sched(int64_t M, int64_t Ncols, int64_t K, tc::TileSched* ts) {
   return SNT_OK;
 }
 
+// self-resetting ticket counter of ce_finish_kernel's last-block reduction (one per device, allocated once)
+static int* ce_ticket() {
+  static int* tab[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!tab[dev]) {
+    if (cudaMalloc(&tab[dev], sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(tab[dev], 0, sizeof(int));
+  }
+  return tab[dev];
+}
+
 int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, int64_t N,
                  int64_t H, int64_t V, float* lse, float* loss, void* ws, int64_t ws_bytes, cudaStream_t st) {
   if (H % 8 != 0) { set_error("bf16 mode: H=%lld must be a multiple of 8", (long long)H); return SNT_EUNSUPPORTED; }
@@ -419,20 +451,21 @@ int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const i
   if (!w.ok) { set_error("bf16 vocab_ce_fwd: workspace too small"); return SNT_EWORKSPACE; }
   const bf* hs_b = (const bf*)hs;
   SNT_CHECK(cast_bf16(w_out, w.wb, V * H, st));
-  ce_target_logit_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(hs_b, w.wb, b_out, targets, N, (int)H, V, w.tl,
-                                                                 device_flags());
-  SNT_LAUNCH_CHECK("ce_target_logit_kernel");
   CUtensorMap ta, tb;
   SNT_CHECK(tc::make_operand_tmap(&ta, hs_b, false, N, H, H, tc::BM));
   SNT_CHECK(tc::make_operand_tmap(&tb, w.wb, false, V, H, H, CE_BN));
   tc::TileSched ts;
   make_sched(N, V, H, &ts);
   CeFwdEpi e;
-  e.M = (int)N; e.V = (int)V; e.bias = b_out; e.part = w.part;
+  e.M = (int)N; e.V = (int)V; e.bias = b_out; e.part = w.part; e.targets = targets; e.tl = w.tl;
   SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeFwdEpi>(ta, tb, ts, e, st)));
-  ce_finish_kernel<<<(unsigned)((N + 63) / 64), 512, 0, st>>>(w.part, w.slabs, N, w.tl, lse, w.nll);
+  int* ticket = ce_ticket();
+  if (!ticket) { set_error("vocab_ce_fwd: could not allocate the reduction ticket"); return SNT_EINVAL; }
+  // w.nll doubles as the per-block partial sums (ceil(N/64) <= N floats)
+  ce_finish_kernel<<<(unsigned)((N + 63) / 64), 512, 0, st>>>(w.part, w.slabs, N, w.tl, targets, V, lse, w.nll, ticket,
+                                                             1.0f / (float)N, loss, device_flags());
   SNT_LAUNCH_CHECK("ce_finish_kernel");
-  return reduce_sum(w.nll, N, 1.0f / (float)N, loss, st);
+  return SNT_OK;
 }
 
 // Side stream for the bandwidth-bound column sums (d_b_out): they read the same L2-resident dlogits chunk as the two
