@@ -83,10 +83,22 @@ extern "C" int snt_head_bwd(int prec, const float* dfeatures, const float* poole
   float* part = w.take<float>(colsum_partial_count(B, E));
   if (!w.ok()) { set_error("snt_head_bwd: workspace too small"); return SNT_EWORKSPACE; }
   SNT_CHECK(bn_bwd(dfeatures, yhat, rstd, gamma, training, B, E, dy, d_gamma, d_beta, st));
+  // d_b_fc = column sums of dy: on the side stream, next to the weight-gradient contraction that reads the same dy
+  SideStream* side = side_stream();
+  if (side) {
+    SNT_CUDA(cudaEventRecord(side->fork, st));
+    SNT_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+    SNT_CHECK(colsum(dy, B, E, E, 0.f, d_b_fc, part, side->s));
+    SNT_CUDA(cudaEventRecord(side->join, side->s));
+  }
   if (prec == SNT_PREC_BF16) {
     SNT_CHECK(bf16::wgrad_tn(dy, pooled, B, E, K, d_w_fc, (char*)ws + w.used, ws_bytes - w.used, st));
   } else {
     SNT_CHECK(gemm_f32(1, 0, E, K, B, 1.f, dy, E, pooled, K, 0.f, d_w_fc, K, nullptr, st));
+  }
+  if (side) {
+    SNT_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    return SNT_OK;
   }
   return colsum(dy, B, E, E, 0.f, d_b_fc, part, st);
 }

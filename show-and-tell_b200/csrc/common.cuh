@@ -21,6 +21,15 @@ int check_cuda(cudaError_t e, const char* what);
 // Validates batch_sizes (positive, non-increasing, T in range) and fills PackInfo.
 int make_pack(const int32_t* batch_sizes, int T, PackInfo* out);
 int* device_flags();  // sticky device-side flag word
+
+// Side stream (one per device) for small bandwidth-bound kernels - column sums of a gradient matrix - that read the same
+// data as a tensor-core contraction but need almost no SM resources: they run next to it instead of after it.  Usage:
+// record `fork` on the main stream, make `s` wait for it, launch, record `join` on `s`, make the main stream wait.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream();  // NULL if the stream could not be created
 void count_launch();   // bumps the process-wide kernel-launch counter (snt_launch_count)
 
 #define SNT_CHECK(expr)                                  \

@@ -57,6 +57,19 @@ int* device_flags() {
   return flags[dev];
 }
 
+SideStream* side_stream() {
+  static SideStream tab[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& x = tab[dev];
+  if (!x.s) {
+    if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming);
+  }
+  return &x;
+}
+
 }  // namespace snt
 
 using namespace snt;

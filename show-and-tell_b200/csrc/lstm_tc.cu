@@ -1219,6 +1219,16 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
         (int64_t)bs_next * H, w.dc_state, dg + (int64_t)pk.off[t] * 4 * H);
     SNT_LAUNCH_CHECK("lstm_bwd_point_kernel");
   }
+  // bias gradient = column sums of dG': bandwidth-bound, runs on the side stream next to the weight-gradient GEMMs
+  SideStream* side = side_stream();
+  if (side) {
+    SNT_CUDA(cudaEventRecord(side->fork, st));
+    SNT_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+    SNT_CHECK(colsum_bf16(dg, N, 4 * H, 4 * H, 0.f, w.tmp, w.cpart, side->s));
+    unperm_vec_kernel<<<(unsigned)((4 * H + 255) / 256), 256, 0, side->s>>>(w.tmp, (int)H, d_bias);
+    SNT_LAUNCH_CHECK("unperm_vec_kernel");
+    SNT_CUDA(cudaEventRecord(side->join, side->s));
+  }
   // weight gradients over the whole packed sequence (rows come out interleaved: un-permute on store)
   int s1 = tc::choose_splits(4 * H, In, N, 0), s2 = tc::choose_splits(4 * H, H, N, 0);
   if (s1 > MAX_SPLITS) s1 = MAX_SPLITS;
@@ -1227,12 +1237,15 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
                         nullptr, s1, w.sws, st, (int)H));
   SNT_CHECK(tc::gemm_tc(true, true, 4 * H, H, N, 1.f, dg, 4 * H, (const bf*)hprev, H, 0.f, d_w_hh, nullptr, H,
                         nullptr, s2, w.sws, st, (int)H));
-  SNT_CHECK(colsum_bf16(dg, N, 4 * H, 4 * H, 0.f, w.tmp, w.cpart, st));
-  unperm_vec_kernel<<<(unsigned)((4 * H + 255) / 256), 256, 0, st>>>(w.tmp, (int)H, d_bias);
-  SNT_LAUNCH_CHECK("unperm_vec_kernel");
+  if (!side) {
+    SNT_CHECK(colsum_bf16(dg, N, 4 * H, 4 * H, 0.f, w.tmp, w.cpart, st));
+    unperm_vec_kernel<<<(unsigned)((4 * H + 255) / 256), 256, 0, st>>>(w.tmp, (int)H, d_bias);
+    SNT_LAUNCH_CHECK("unperm_vec_kernel");
+  }
   if (dx)
     SNT_CHECK(tc::gemm_tc(false, true, N, In, 4 * H, 1.f, dg, 4 * H, w.w_ih, In, 0.f, dx, nullptr, In, nullptr, 1,
                           nullptr, st));
+  if (side) SNT_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   return SNT_OK;
 }
 

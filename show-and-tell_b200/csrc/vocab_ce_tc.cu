@@ -468,25 +468,6 @@ int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const i
   return SNT_OK;
 }
 
-// Side stream for the bandwidth-bound column sums (d_b_out): they read the same L2-resident dlogits chunk as the two
-// tensor-core contractions but need almost no SM resources, so they run next to them instead of after them.
-struct SideStream {
-  cudaStream_t s = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-};
-static SideStream* side_stream() {
-  static SideStream tab[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  SideStream& x = tab[dev];
-  if (!x.s) {
-    if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming);
-  }
-  return &x;
-}
-
 int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, const float* lse,
                  const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
                  float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
