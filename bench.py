@@ -452,7 +452,7 @@ def main():
                 "unit": top.get("unit"), "frac": top.get("frac"),
                 # dram__bytes_read.sum + dram__bytes_write.sum of the stage's nine tensor-core launches, one ncu --set
                 # full capture (profiles/r01_ncu_hot_kernels.txt); null for any other stage
-                "traffic": 1.0035e9 if top["stage"] == "snt_vocab_ce_bwd" else None,
+                "traffic": 7.6840e+08 if top["stage"] == "snt_vocab_ce_bwd" else None,
                 "traffic_unit": "bytes per step (ncu, profiles/r01_ncu_hot_kernels.txt)",
                 "kernel": top["stage"] + " (largest share of the step; tcgen05 GEMMs gemm_tc_kernel<256,CeBwdEpiT<16>> + "
                           "dHs/dW_out gemm_tc_kernel<128,PlainEpi> per 37-row-tile chunk)" if top["stage"] == "snt_vocab_ce_bwd"
