@@ -226,11 +226,22 @@ class DataParallelStep:
             if key not in self._graphs and self._seen[key] <= self.graph_after:
                 key = None
         late = set()
+        loss = None
         if key is not None:
-            loss = self._graph_step(key, inputs, captions, lengths, targets, n_tokens_global)
-        else:
+            try:
+                loss = self._graph_step(key, inputs, captions, lengths, targets, n_tokens_global)
+            except Exception as e:   # capture refused (driver / allocator state): stay eager from now on, loudly
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the training step failed ({e!r}); continuing with eager launches")
+                self.cuda_graph = False
+                self._graphs.pop(key, None)
+                torch.cuda.synchronize()
+                key = None
+        if key is None:
             for p in self.params:
                 p.grad = None
+            if self.reducer is not None:
+                self.reducer.coalesce = True
             staged = bool(self.optimizer) and self.world > 1
             loss = self._fwd_bwd(inputs, captions, lengths, targets, n_tokens_global, staged)
             if staged:
