@@ -192,6 +192,10 @@ class DataParallelStep:
             if self.reducer is not None:
                 self.reducer.coalesce = False            # plain per-tensor collectives inside the capture
             torch.cuda.synchronize()
+            if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+                # the AccumulateGrad nodes were created by the eager steps on the default stream; the capture runs on
+                # torch's capture stream: intended, and verified bit-identical (tests/test_gpu_parity.py)
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
             n0 = int(_lib.lib().snt_launch_count(0))
             # thread_local: CUDA calls of other threads (e.g. NCCL's watchdog) must not invalidate this capture
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
