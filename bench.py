@@ -457,10 +457,14 @@ def main():
                 "kernel": top["stage"] + " (largest share of the step; tcgen05 GEMMs gemm_tc_kernel<256,CeBwdEpiT<16>> + "
                           "dHs/dW_out gemm_tc_kernel<128,PlainEpi> per 37-row-tile chunk)" if top["stage"] == "snt_vocab_ce_bwd"
                           else top["stage"],
-                "us_per_step": top["us_per_step"], "share_of_step": top["us_per_step"] / (t_res / args.steps * 1e6),
+                "us_per_step": top["us_per_step"],
+                # share of the summed per-stage GPU time of the same (eager) profiling steps - comparable with the
+                # kernel shares of the ncu launch list in profiles/
+                "share_of_step": top["us_per_step"] / max(sum(e["us_per_step"] for e in stages), 1e-9),
                 "algorithmic_work_per_step": top.get("algorithmic_work"),
                 "peak_source": f"{peaks['src']} (MEASURED_PEAKS.json: sustained bf16 for a stage inside a long step)",
-                "timing": "CUDA events around the C-ABI call on the launching stream, mean of 10 steps"}
+                "timing": "CUDA events around the C-ABI call on the launching stream, mean of 10 eagerly launched steps "
+                          "(the timed region itself replays forward+backward as one CUDA graph on one GPU)"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import torch_port as TP   # bench's cpu_baseline leg: the checker timed, never shipped
