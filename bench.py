@@ -358,6 +358,18 @@ def main():
 
     for _ in range(args.warmup):
         step_resident()
+    if os.environ.get("SNT_BENCH_GC", "freeze") == "freeze":
+        # Everything allocated so far (torch, modules, CUDA graph, NCCL state) is long-lived: move it to the permanent
+        # generation so that the cyclic collector's full passes stay short.  A full collection over the whole heap in
+        # the middle of a multi-GPU run pauses one rank's host thread for tens of ms and, through the next all-reduce,
+        # every GPU of the job.
+        import gc
+        gc.collect()
+        gc.freeze()
+    elif os.environ.get("SNT_BENCH_GC") == "off":
+        import gc
+        gc.collect()
+        gc.disable()
     sampler = ClockSampler(local)
     L = snt._lib.lib()
     if world == 1:
