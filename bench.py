@@ -268,10 +268,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # all-reduce CTAs are placed first when SMs free up
-        # keep gradient blocks referenced until the collective is done instead of record_stream(): with record_stream the
-        # caching allocator keeps re-growing its pool (measured at N=2: median step 1.57 ms with frequent 3-70 ms stalls
-        # vs a steady 1.43 ms with this setting)
-        os.environ.setdefault("TORCH_NCCL_AVOID_RECORD_STREAMS", "1")
+
         dist.init_process_group("nccl", device_id=dev)
     c = CFG
     peaks = load_peaks()

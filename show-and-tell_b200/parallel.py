@@ -10,9 +10,8 @@ N_rank / N_global, so the summed gradients equal the global-batch gradients.  Th
 uses per-shard batch statistics (as torch DDP / DataParallel replicas would); decoder-only steps are exact.
 Greedy decode shards the batch with no communication at all.
 
-Launch the ranks with TORCH_NCCL_AVOID_RECORD_STREAMS=1 (and TORCH_NCCL_HIGH_PRIORITY=1), as bench.py does: gradients
-are handed to NCCL's stream every step, and the default record_stream() bookkeeping makes the caching allocator re-grow
-its pool again and again (measured at 2 GPUs: frequent 3-70 ms stalls, median step 1.57 ms instead of 1.43 ms).
+Launch the ranks with TORCH_NCCL_HIGH_PRIORITY=1, as bench.py does (the all-reduce CTAs are then placed first when SMs
+free up).
 """
 from __future__ import annotations
 
