@@ -4,6 +4,7 @@
 #include "gemm_tc.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 
 #include <cudaTypedefs.h>
 #include <mutex>
@@ -119,6 +120,12 @@ template <int BN, bool A_MN, bool B_MN>
 static int run_plain(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, int64_t M, int64_t N,
                      float alpha, float beta, float* C, __nv_bfloat16* Cb, int64_t ldc, const float* bias,
                      int64_t split_stride, cudaStream_t st, int perm, const float* adev) {
+  if (BN == 256 && ts.kblocks_per_split <= 8 && !getenv("SNT_NO_WIDE_EPI")) {  // short K: epilogue-bound
+    PlainEpi<256, true> e;
+    e.M = (int)M; e.N = (int)N; e.alpha = alpha; e.beta = beta; e.C = C; e.Cb = Cb; e.ldc = ldc; e.bias = bias;
+    e.split_stride = split_stride; e.row_perm_h = perm; e.alpha_dev = adev;
+    return launch_gemm_tc<256, A_MN, B_MN, PlainEpi<256, true>>(ta, tb, ts, e, st);
+  }
   PlainEpi<BN> e;
   e.M = (int)M; e.N = (int)N; e.alpha = alpha; e.beta = beta; e.C = C; e.Cb = Cb; e.ldc = ldc; e.bias = bias;
   e.split_stride = split_stride; e.row_perm_h = perm; e.alpha_dev = adev;

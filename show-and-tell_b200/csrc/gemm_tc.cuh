@@ -256,10 +256,13 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TileSch
 }
 
 // ---- the plain epilogue: C = alpha*acc + bias[col] + beta*C, fp32 and/or bf16 out, optional split-K slices ----
-template <int BN>
+// WIDE (BN = 256 only): 16 epilogue warps and a 3-stage ring, for short contractions whose tiles finish their MMAs faster
+// than 8 warps can drain 128 x 256 outputs (e.g. the input projection Gx' with K = 256).
+template <int BN, bool WIDE = false>
 struct PlainEpi {
-  static constexpr int kWarps = BN >= 128 ? 8 : 4;
-  static constexpr int kStages = 0;
+  static_assert(!WIDE || BN == 256, "the wide epilogue is a BN = 256 variant");
+  static constexpr int kWarps = WIDE ? 16 : (BN >= 128 ? 8 : 4);
+  static constexpr int kStages = WIDE ? 3 : 0;
   static constexpr int kPitch = 80;  // bytes per staged row: 64 of data (16 fp32 / 32 bf16) + 16 of padding
   static constexpr int kSmemPerWarp = 32 * kPitch;
   int M, N;                // valid extent
@@ -403,6 +406,16 @@ struct PlainEpi {
     constexpr int kChunks = BN / 32 / (kWarps / 4);
     static_assert(kChunks % 2 == 0, "chunk loop is unrolled by two");
     const int c0 = (ew >> 2) * kChunks;
+    if (WIDE) {  // 16 warps hide the latencies by themselves: one register buffer, no software pipelining
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_rows + (uint32_t)((c0 + c) * 32), r);
+        tmem_ld_wait();
+        chunk(x, r, c0 + c);
+      }
+      return;
+    }
     uint32_t ra[32], rb[32];
     tmem_ld32(tmem_rows + (uint32_t)(c0 * 32), ra);
 #pragma unroll 1
