@@ -257,6 +257,11 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    t_start = time.time()
+
+    def phase(name):
+        if os.environ.get("SNT_BENCH_DEBUG"):
+            print(f"[dbg] rank {rank} +{time.time() - t_start:6.1f}s {name}", file=sys.stderr, flush=True)
 
     import torch.distributed as dist
     import show_and_tell_b200 as snt
@@ -353,8 +358,10 @@ def main():
         barrier()
         return max_over_ranks(e0.elapsed_time(e1) * 1e-3)
 
+    phase("warm-up")
     for _ in range(args.warmup):
         step_resident()
+    phase("warm-up done")
     if os.environ.get("SNT_BENCH_GC", "freeze") == "freeze":
         # Everything allocated so far (torch, modules, CUDA graph, NCCL state) is long-lived: move it to the permanent
         # generation so that the cyclic collector's full passes stay short.  A full collection over the whole heap in
@@ -422,6 +429,7 @@ def main():
             print(f"[dbg] resident again, no clock sampler: {t2 / args.steps * 1e3:.3f} ms/step "
                   f"(with sampler {t_res / args.steps * 1e3:.3f})", file=sys.stderr)
 
+    phase("timed region done; stage profile")
     # per-stage GPU time: CUDA events around every C-ABI call of 10 more real steps (rank 0's stream)
     stages = None
     graph_mode, stepper.cuda_graph = stepper.cuda_graph, False   # the per-call events need eager C-ABI calls
@@ -440,10 +448,13 @@ def main():
                       file=sys.stderr)
             print(f"[stages] sum {tot:.1f} us/step", file=sys.stderr)
     stepper.cuda_graph = graph_mode
+    phase("stage profile done; e2e pre-steps")
 
     for _ in range(8):            # both host-buffer slots get captured (graph mode) before the timed region
         step_e2e()
+    phase("e2e pre-steps done; e2e timed")
     t_e2e = timed(step_e2e, args.steps)
+    phase("e2e timed done")
     loss_val = step_e2e()
     loss_ev.synchronize()
     loss_val = float(loss_host[0])
@@ -521,9 +532,12 @@ def main():
             "algorithmic_flops_per_step": flops_step, "loss": loss_val, **extra,
         }
         print(json.dumps(line), flush=True)
+    phase("line printed; teardown")
+    stepper.close()   # graphs holding NCCL collectives must be released before barrier()/destroy_process_group()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    phase("exit")
 
 
 if __name__ == "__main__":
