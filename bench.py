@@ -9,7 +9,9 @@ precomputed pooled 2048-d features -> gather/concat/pack -> LSTM -> vocab Linear
 BPTT -> (N>1: gradient all-reduce overlapped with BPTT) -> clip_gradient + Adam.  Per GPU: B=1024 captions
 (weak scaling; global batch 1024*N sorted by length and sharded by strided rows).
 
-value  : captions/s, inputs resident in HBM, CUDA events, max over ranks.
+value  : captions/s, inputs resident in HBM, CUDA events, max over ranks.  Forward + backward (+ all-reduces) are
+         replayed as one CUDA graph once the fixed benchmark batch has been stepped twice eagerly (--no-graph: eager
+         launches); the optimizer launch stays outside the graph.
 e2e    : the same step through the public module API with HOST (pinned) inputs: H2D copies of that step's
          pooled features / captions / targets and a D2H read of the loss inside the timed region.
 roofline: the dominant kernel (the tcgen05 vocab-projection contraction) timed alone with CUDA events.
