@@ -6,9 +6,12 @@
 //   forward step t : TMEM = h_{t-1}[bs_t,H] . W_hh'^T ; epilogue adds the batched input projection Gx'[t]
 //                    (one tcgen05 GEMM over all timesteps), applies sigma/tanh, writes c_t, h_t (bf16, also as next
 //                    step's A operand) and the bf16 activations kept for BPTT.
-//   backward step t: TMEM = dG'_{t+1}[bs_{t+1},4H] . W_hh' ; epilogue adds dL/dh_t, runs the cell backward and
-//                    writes dG'_t as bf16 — the A operand of step t-1 and of the weight-gradient GEMMs.
-// Steps are chained with programmatic dependent launch, so each step's prologue overlaps its predecessor's tail.
+//   backward step t: dG'_{t+1}[bs_{t+1},4H] . W_hh' as a split-K contraction, then a coalesced pointwise kernel that sums
+//                    the partials, adds dL/dh_t, runs the cell backward and writes dG'_t as bf16 — the A operand of
+//                    step t-1 and of the weight-gradient GEMMs.  (A variant with the cell backward fused into the GEMM
+//                    epilogue was measured slower at both B=1024/H=512 and B=2048/H=1024 and removed.)
+// Forward steps are chained with programmatic dependent launch, so each step's prologue overlaps its predecessor's tail.
+// At H <= 512 both directions run as ONE persistent cooperative kernel each (further down).
 #include "bf16.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -144,78 +147,6 @@ struct LstmFwdEpi {
         uint4* ad = reinterpret_cast<uint4*>(act + (int64_t)row * H4 + col0);
 #pragma unroll
         for (int q = 0; q < 4; ++q) ad[q] = make_uint4(ap[4 * q], ap[4 * q + 1], ap[4 * q + 2], ap[4 * q + 3]);
-      }
-    }
-  }
-};
-
-// ---- backward step epilogue ------------------------------------------------------------------------------------------
-struct LstmBwdEpi {
-  static constexpr int kWarps = 4;
-  static constexpr int kStages = 0;
-  static constexpr int kSmemPerWarp = 0;
-  int bs, bs_next, H;
-  const float* d_hs;    // [bs, H]   dL/dh_t from the layer above / the vocab projection
-  const bf* act;        // [bs, 4H]  saved activations of step t
-  const float* cs;      // [bs, H]   c_t
-  const float* c_prev;  // [>=bs, H] c_{t-1} (NULL at t = 0)
-  float* dc_state;      // [B, H]    in: dL/dc_t carried from step t+1 (rows < bs_next); out: dL/dc_{t-1}
-  bf* dg;               // [bs, 4H]  out: gradient w.r.t. the pre-activations, interleaved columns
-
-  using Pre = tc::NoPre;
-  __device__ __forceinline__ void prefetch(Pre&, int, int, int, int) const {}
-  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane,
-                                       const Pre&, uint8_t*) const {
-    const int row = m_blk * tc::BM + ew * 32 + lane;
-    const bool ok = row < bs;
-    const bool has_next = row < bs_next;  // rows that were still alive at step t+1 carry recurrent gradient
-    const int H4 = 4 * H;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      const int j0 = n_blk * 64 + c * 32;
-      if (j0 >= H) break;  // warp-uniform
-      uint32_t r[32];
-      tc::tmem_ld32(tmem_rows + (uint32_t)(c * 32), r);
-      tc::tmem_ld_wait();
-      if (!ok) continue;
-#pragma unroll
-      for (int sub = 0; sub < 4; ++sub) {
-        const int ju = j0 + sub * 8;
-        if (ju < H) {
-          const int64_t o1 = (int64_t)row * H + ju;
-          const float4 dh0 = *reinterpret_cast<const float4*>(d_hs + o1), dh1 = *reinterpret_cast<const float4*>(d_hs + o1 + 4);
-          const float4 c0 = *reinterpret_cast<const float4*>(cs + o1), c1 = *reinterpret_cast<const float4*>(cs + o1 + 4);
-          float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, s0 = p0, s1 = p0;
-          if (c_prev) { p0 = *reinterpret_cast<const float4*>(c_prev + o1); p1 = *reinterpret_cast<const float4*>(c_prev + o1 + 4); }
-          if (has_next) { s0 = *reinterpret_cast<const float4*>(dc_state + o1); s1 = *reinterpret_cast<const float4*>(dc_state + o1 + 4); }
-          const uint4* a4 = reinterpret_cast<const uint4*>(act + (int64_t)row * H4 + 4 * ju);
-          uint32_t a[16];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) { const uint4 v = a4[q]; a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w; }
-          const float dhv[8] = {dh0.x, dh0.y, dh0.z, dh0.w, dh1.x, dh1.y, dh1.z, dh1.w};
-          const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-          const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-          const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          float dcn[8];
-          uint32_t go[16];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float2 if_ = unpack_bf2(a[2 * u]), go_ = unpack_bf2(a[2 * u + 1]);
-            const float i_ = if_.x, f_ = if_.y, g_ = go_.x, o_ = go_.y;
-            const float tc_ = tanh_(cv[u]);
-            const float dh = dhv[u] + (has_next ? __uint_as_float(r[sub * 8 + u]) : 0.f);
-            const float dc = sv[u] + dh * o_ * (1.f - tc_ * tc_);
-            go[2 * u] = pack_bf2(dc * g_ * i_ * (1.f - i_), dc * pv[u] * f_ * (1.f - f_));
-            go[2 * u + 1] = pack_bf2(dc * i_ * (1.f - g_ * g_), dh * tc_ * o_ * (1.f - o_));
-            dcn[u] = dc * f_;
-          }
-          float4* sd = reinterpret_cast<float4*>(dc_state + o1);
-          sd[0] = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
-          sd[1] = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
-          uint4* gd = reinterpret_cast<uint4*>(dg + (int64_t)row * H4 + 4 * ju);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) gd[q] = make_uint4(go[4 * q], go[4 * q + 1], go[4 * q + 2], go[4 * q + 3]);
-        }
       }
     }
   }
@@ -1027,11 +958,6 @@ static int prep_launch(const float* w_ih, const float* w_hh, const float* b_ih, 
   SNT_LAUNCH_CHECK("lstm_prep_kernel");
   return SNT_OK;
 }
-static int prep_weights(const LstmWs& w, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                        int64_t In, int64_t H, cudaStream_t st) {
-  return prep_launch(w_ih, w_hh, b_ih, b_hh, In, H, w.w_ih, w.w_hh, w.bsum, nullptr, nullptr, 0, nullptr, 0, st);
-}
-
 #define SNT_REQ8(v, what)                                                                               \
   do {                                                                                                  \
     if ((v) % 8 != 0) {                                                                                 \
