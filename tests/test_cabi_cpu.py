@@ -69,6 +69,23 @@ def test_batch_sizes_from_lengths(snt):
     assert f(l).tolist() == bs.tolist()
 
 
+def test_batch_sizes_cache_is_transparent(snt):
+    """Repeated `lengths` lists hit a small host-side cache: same values, validation still raises, callers cannot
+    corrupt the cached array, and the SM-reserve knob of the C ABI round-trips without a GPU."""
+    f = snt.ops.batch_sizes_from_lengths
+    a = f([5, 3, 3, 1])
+    b = f([5, 3, 3, 1])
+    assert a is b and a.tolist() == [4, 3, 3, 1, 1] and not a.flags.writeable
+    assert f((5, 3, 3, 1)).tolist() == a.tolist()
+    assert f([5, 3, 3, 1], max_steps=7).tolist() == a.tolist()
+    with pytest.raises(RuntimeError):
+        f([5, 3, 3, 1], max_steps=4)
+    with pytest.raises(RuntimeError):
+        f([3, 5])
+    L = snt._lib.lib()
+    assert L.snt_set_sm_reserve(12) == 0 and L.snt_set_sm_reserve(0) == 12
+
+
 def test_no_cpu_fallback(snt):
     dec = snt.DecoderRNN(8, 16, 23, 1)
     feats, caps = torch.randn(2, 8), torch.ones(2, 3, dtype=torch.int64)
