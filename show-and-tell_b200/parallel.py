@@ -126,9 +126,13 @@ class DataParallelStep:
         group."""
         self.encoder, self.decoder = encoder, decoder
         self.cuda_graph, self.graph_after = cuda_graph, graph_after
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 \
-                and os.environ.get("SNT_GRAPH_MULTI", "1") == "0":
-            self.cuda_graph = False   # opt-out: eager launches on multi-GPU jobs
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            # Graph replay with the collectives inside was validated at 2 and 4 GPUs in round 1; the 8-GPU runs of that
+            # round used eager launches, so larger jobs stay eager unless SNT_GRAPH_MULTI=1 asks for replay explicitly
+            # (SNT_GRAPH_MULTI=0: always eager).
+            mode = os.environ.get("SNT_GRAPH_MULTI", "auto")
+            if mode == "0" or (mode != "1" and dist.get_world_size(group) > 4):
+                self.cuda_graph = False
         self._graphs, self._seen = {}, {}
         self.replayed_kernels = 0   # kernels executed through graph replays (snt_launch_count only sees eager launches)
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
