@@ -143,6 +143,13 @@ int snt_greedy_decode(int prec, const float* features, const float* w_emb, int L
                       int64_t B, int64_t E, int64_t H, int64_t V, int steps, int64_t* ids,
                       void* ws, int64_t ws_bytes, void* stream);
 
+/* ---- f4  the caller-side tail of sample(): words before the first <end>  (eval.py:101-109) ---------------
+ * lengths[b] = position of the first `end_id` in ids[b, 0..steps) (= steps when there is none), i.e. the
+ * number of words eval.py keeps.  ids_out[B,steps] (optional; may alias ids) = ids with every position
+ * >= lengths[b] replaced by pad_id.  At least one of lengths / ids_out must be given. */
+int snt_caption_trim(const int64_t* ids, int64_t B, int steps, int64_t end_id, int64_t pad_id,
+                     int32_t* lengths, int64_t* ids_out, void* stream);
+
 /* ---- a11  clip_gradient (clamp to +-grad_clip) + Adam  (train.py:88-91,145-146) -------------------------
  * In-place on p, m, v; g is read only.  `step` is the 1-based count after this update.
  * grad_clip <= 0 disables the clamp.  grad_scale multiplies g first (1/world for averaged DP grads).

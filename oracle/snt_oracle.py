@@ -300,6 +300,27 @@ def greedy_sample(params, features, states=None, steps=SAMPLE_STEPS, forced_ids=
 
 
 # --------------------------------------------------------------------------------------
+# caller-side tail of sample()  (eval.py:101-109)
+# --------------------------------------------------------------------------------------
+def trim_captions(ids, end_id=2, pad_id=0):
+    """eval.py:103-109: for every sampled row, the words kept are those before the first `<end>`
+    (`if word == '<end>': break`); a row without `<end>` keeps all its words.  -> (ids with the dropped positions
+    replaced by pad_id, lengths[B] int32 = number of words kept).  <end> = 2, <pad> = 0: preprocess.py:75-78."""
+    ids = np.asarray(ids, dtype=np.int64)
+    out = np.full_like(ids, pad_id)
+    lengths = np.zeros(ids.shape[0], dtype=np.int32)
+    for b, sentence_ids in enumerate(ids):
+        kept = []
+        for word_id in sentence_ids:
+            if word_id == end_id:
+                break
+            kept.append(word_id)
+        lengths[b] = len(kept)
+        out[b, :len(kept)] = kept
+    return out, lengths
+
+
+# --------------------------------------------------------------------------------------
 # clip + Adam  (train.py:88-91 clip_gradient clamps each grad to +-grad_clip; train.py:56 optim.Adam)
 # --------------------------------------------------------------------------------------
 def clamp_adam(p, g, m, v, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_clip=0.1):

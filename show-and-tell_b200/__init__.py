@@ -6,4 +6,6 @@ whose own name is not a valid Python identifier).
 from . import _lib, ops, synthetic  # noqa: F401
 from .models import DecoderRNN, EncoderCNN  # noqa: F401
 
-__all__ = ["EncoderCNN", "DecoderRNN", "ops", "synthetic"]
+from .trainer import CaptionModel, Trainer, evaluation  # noqa: F401
+
+__all__ = ["EncoderCNN", "DecoderRNN", "CaptionModel", "Trainer", "evaluation", "ops", "synthetic"]

@@ -386,3 +386,13 @@ extern "C" int snt_greedy_decode(int prec, const float* features, const float* w
   }
   return SNT_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// f4: words before the first <end> (eval.py:101-109)
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int snt_caption_trim(const int64_t* ids, int64_t B, int steps, int64_t end_id, int64_t pad_id,
+                                int32_t* lengths, int64_t* ids_out, void* stream) {
+  SNT_REQUIRE(B >= 0 && steps >= 0, "snt_caption_trim: bad sizes");
+  SNT_REQUIRE(B == 0 || steps == 0 || (ids && (lengths || ids_out)), "snt_caption_trim: NULL pointer");
+  return caption_trim(ids, B, steps, end_id, pad_id, lengths, ids_out, (cudaStream_t)stream);
+}

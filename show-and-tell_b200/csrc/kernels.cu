@@ -1053,4 +1053,42 @@ int clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, double l
   return SNT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// f4: the caller-side tail of sample() (eval.py:101-109): a caption is the words before the first <end>.
+// One warp per caption; a row of `steps` ids is scanned 32 at a time, the first hit ends the caption.
+// HBM-bound (8 or 16 bytes per token), latency-trivial: it exists so that eval needs ONE device->host copy of
+// (ids, lengths) instead of a Python loop over every word of every caption.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+caption_trim_kernel(const int64_t* __restrict__ ids, int64_t B, int steps, int64_t end_id, int64_t pad_id,
+                    int32_t* __restrict__ lengths, int64_t* ids_out) {
+  const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;  // whole warps leave together: the ballots below always see a full warp
+  const int lane = threadIdx.x & 31;
+  const int64_t* row = ids + b * steps;
+  int len = steps;
+  for (int s0 = 0; s0 < steps; s0 += 32) {
+    const int s = s0 + lane;
+    const bool hit = s < steps && row[s] == end_id;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m != 0u) { len = s0 + __ffs((int)m) - 1; break; }  // warp-uniform
+  }
+  if (lane == 0 && lengths != nullptr) lengths[b] = len;
+  if (ids_out != nullptr) {
+    int64_t* orow = ids_out + b * steps;
+    // in-place use (ids_out == ids) is safe: every lane has finished reading the row at the last ballot
+    for (int s = lane; s < steps; s += 32) {
+      const int64_t v = s < len ? row[s] : pad_id;
+      orow[s] = v;
+    }
+  }
+}
+int caption_trim(const int64_t* ids, int64_t B, int steps, int64_t end_id, int64_t pad_id, int32_t* lengths,
+                 int64_t* ids_out, cudaStream_t st) {
+  if (B <= 0 || steps <= 0) return SNT_OK;
+  caption_trim_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(ids, B, steps, end_id, pad_id, lengths, ids_out);
+  SNT_LAUNCH_CHECK("caption_trim_kernel");
+  return SNT_OK;
+}
+
 }  // namespace snt

@@ -55,4 +55,9 @@ int clamp_adam_multi(int count, float* const* p, const float* const* g, float* c
                      const int64_t* n, double lr, double beta1, double beta2, double eps, float grad_clip,
                      float grad_scale, int64_t step, cudaStream_t st);
 
+// lengths[b] = index of the first end_id in ids[b,0..steps) (steps if none); ids_out (optional, may alias ids) = ids with
+// everything from that position on replaced by pad_id
+int caption_trim(const int64_t* ids, int64_t B, int steps, int64_t end_id, int64_t pad_id, int32_t* lengths,
+                 int64_t* ids_out, cudaStream_t st);
+
 }  // namespace snt

@@ -112,3 +112,10 @@ class DecoderRNN(nn.Module):
         ids = ops.greedy(features, self.embed.weight, self._lstm_weights(), self.linear.weight, self.linear.bias,
                          states, ops.SAMPLE_STEPS, precision or self.sample_precision)
         return ids.squeeze()
+
+    def sample_trimmed(self, features, states=None, precision=None, end_id=2, pad_id=0):
+        """sample() followed by eval.py:101-109's "words before the first <end>" rule on the device:
+        -> (ids[B,20] with everything from the first <end> on replaced by <pad>, lengths[B] int32)."""
+        ids = ops.greedy(features, self.embed.weight, self._lstm_weights(), self.linear.weight, self.linear.bias,
+                         states, ops.SAMPLE_STEPS, precision or self.sample_precision)
+        return ops.trim_captions(ids, end_id, pad_id)

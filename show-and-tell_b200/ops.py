@@ -359,6 +359,28 @@ def greedy(features, w_emb, lstm_w, w_out, b_out, states=None, steps=SAMPLE_STEP
     return ids
 
 
+@torch.no_grad()
+def trim_captions(ids, end_id=2, pad_id=0, return_ids=True):
+    """The caller-side tail of sample() (eval.py:101-109) on the device: -> (ids_trimmed[B,S] int64 or None,
+    lengths[B] int32) where lengths[b] = position of the first `end_id` in ids[b] (S if none) = the number of words
+    eval.py keeps, and ids_trimmed has every later position replaced by `pad_id`.  `end_id`/`pad_id` default to the
+    reference vocabulary's <end> = 2 / <pad> = 0 (preprocess.py:75-78)."""
+    require_cuda(ids)
+    if ids.dtype != torch.int64:
+        raise RuntimeError("trim_captions needs int64 ids (what sample() returns)")
+    squeeze = ids.dim() == 1                       # sample() squeezes a batch of one (models.py:66)
+    ids2 = (ids.unsqueeze(0) if squeeze else ids).contiguous()
+    if ids2.dim() != 2:
+        raise RuntimeError("trim_captions expects ids of shape [B,S] (or [S])")
+    B, S = ids2.shape
+    lengths = torch.empty(B, dtype=torch.int32, device=ids2.device)
+    out = torch.empty_like(ids2) if return_ids else None
+    call("snt_caption_trim", ptr(ids2), B, int(S), int(end_id), int(pad_id), ptr(lengths), ptr(out), stream_ptr())
+    if squeeze and out is not None:
+        out = out.squeeze(0)
+    return out, lengths
+
+
 # ---------------------------------------------------------------------------------------------------------
 # clip_gradient + Adam
 # ---------------------------------------------------------------------------------------------------------

@@ -163,7 +163,12 @@ class DataParallelStep:
         late groups still in flight; otherwise every collective has been waited for on the current stream."""
         n_local = int(sum(lengths))
         scale = 1.0 if (self.world == 1 or n_tokens_global is None) else n_local / float(n_tokens_global)
-        feats = self.encoder.forward_pooled(inputs) if self.encoder is not None else inputs
+        if self.encoder is None:
+            feats = inputs
+        elif inputs.dim() == 4:                          # images through the frozen cuDNN trunk (models.py:25-29)
+            feats = self.encoder(inputs)
+        else:
+            feats = self.encoder.forward_pooled(inputs)
         if self.reducer is not None:
             self.reducer.defer = staged
         loss = self.decoder.loss(feats, captions, lengths, targets, grad_scale=scale)
@@ -224,7 +229,8 @@ class DataParallelStep:
         return ent[1]
 
     def step(self, inputs, captions, lengths, targets, n_tokens_global=None):
-        """inputs: pooled[B,2048] when an encoder is attached, else features[B,E].  Returns this rank's share
+        """inputs: pooled[B,2048] (or images[B,3,H,W] for an encoder with its backbone) when an encoder is attached,
+        else features[B,E].  Returns this rank's share
         of the global mean loss (sum over ranks = global-batch loss)."""
         cuda = bool(self.params) and self.params[0].is_cuda
         if self.world > 1 and cuda:

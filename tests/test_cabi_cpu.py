@@ -47,6 +47,8 @@ def test_abi_version_and_error_string(snt):
     assert rc == -1 and b"prec" in l.snt_last_error()
     assert l.snt_lstm_workspace_bytes(0, 100, 10, 8, 16) > 0
     assert l.snt_lstm_workspace_bytes(5, 100, 10, 8, 16) == -1
+    assert l.snt_caption_trim(None, 4, 20, 2, 0, None, None, None) == -1 and b"NULL" in l.snt_last_error()
+    assert l.snt_caption_trim(None, 0, 20, 2, 0, None, None, None) == 0      # empty batch: nothing to launch
     bs = (ctypes.c_int32 * 3)(2, 3, 1)   # not non-increasing
     rc = l.snt_embed_pack_fwd(None, None, None, 4, ctypes.cast(bs, ctypes.c_void_p), 3, 8, 10, None, None, None)
     assert rc == -1 and b"non-increasing" in l.snt_last_error()

@@ -105,3 +105,23 @@ def test_torch_port_matches_reference(name):
         assert rel(p.grad.numpy(), g[f"f32.grad.{k}"]) < 1e-5, k
     ids = dec.eval().sample(f).numpy()
     np.testing.assert_array_equal(ids, g["f32.greedy_ids"])
+
+
+def test_trim_captions_follows_eval_loop():
+    """eval.py:101-109 with a stand-in vocabulary: join the words before '<end>'."""
+    idx2word = {0: "<pad>", 1: "<start>", 2: "<end>", 3: "<unk>", 4: "a", 5: "dog", 6: "runs"}
+    ids = np.array([[4, 5, 6, 2, 4, 2], [2, 4, 4, 4, 4, 4], [4, 5, 4, 5, 4, 5], [1, 4, 3, 6, 5, 2]], dtype=np.int64)
+    sentences = []
+    for sentence_ids in ids:                      # the reference's loop, verbatim in structure
+        sampled_caption = []
+        for word_id in sentence_ids:
+            word = idx2word[int(word_id)]
+            if word == "<end>":
+                break
+            sampled_caption.append(word)
+        sentences.append(" ".join(sampled_caption))
+    out, lengths = O.trim_captions(ids)
+    assert lengths.tolist() == [3, 0, 6, 5]
+    for b in range(len(ids)):
+        assert " ".join(idx2word[int(w)] for w in out[b, :lengths[b]]) == sentences[b]
+        assert (out[b, lengths[b]:] == 0).all()
