@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _rel(a, b):
-    return float((a.double() - b.double()).norm() / b.double().norm())
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm() / b.norm())
 
 
 def test_trunk_feed_and_prefetch_loader():
