@@ -17,6 +17,8 @@ e2e    : the same step through the public module API with HOST (pinned) inputs: 
 roofline: the dominant kernel (the tcgen05 vocab-projection contraction) timed alone with CUDA events.
 cpu_baseline / --impl reference: the reference's CPU composition (oracle/torch_port.py, pinned to the
          reference's golden vectors) timed on this box's host cores.
+gpu_torch_reference: the same torch.nn composition on THIS GPU (cuDNN LSTM, cuBLAS, ATen; fp32, TF32 and bf16 autocast),
+         SURVEY.md §8(d)(ii) — timed in a child process after the timed regions; a reported baseline only.
 """
 from __future__ import annotations
 
@@ -205,6 +207,43 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def gpu_torch_reference_child(device_index):
+    """Child process of `gpu_torch_reference`: prints one JSON object."""
+    import show_and_tell_b200 as snt
+    from oracle import torch_port as TP   # a reported baseline (the reference's composition), never the product
+    c = CFG
+    dev = torch.device("cuda", device_index)
+    torch.cuda.set_device(dev)
+    b = snt.synthetic.make_batch(c["B"], c["V"], embed=c["E"], seed=1, pooled_dim=c["POOLED"])
+    b["targets"] = snt.synthetic.pack_host(b["captions"], b["lengths"])
+    out = {"unit": "captions/s",
+           "what": "torch.nn composition of the same train step (head, decoder, CE, backward, clip, Adam) on this GPU, "
+                   f"torch {torch.__version__}: cuDNN LSTM, cuBLAS, ATen kernels; CUDA events, 10 steps after 3 warm-up"}
+    for name, tf32, amp in (("fp32", False, False), ("tf32", True, False), ("bf16_autocast", True, True)):
+        try:
+            cps, dt, loss = TP.time_full_train_on(dev, c["B"], c["E"], c["H"], c["V"], c["L"], b, steps=10, warmup=3,
+                                                  tf32=tf32, autocast_bf16=amp)
+            out[name] = {"value": cps, "ms_per_step": dt * 1e3, "loss": loss}
+        except Exception as e:   # noqa: BLE001
+            out[name] = {"error": repr(e)[:300]}
+    print(json.dumps(out), flush=True)
+
+
+def gpu_torch_reference(device_index, timeout_s=240):
+    """the reference's own composition of torch.nn layers timed on THIS GPU (no kernel of ours),
+    reported next to the bench line.  Runs in a child process after the timed regions, so that neither a crash nor a
+    hang of that foreign code path can cost the bench line; any failure becomes an "error" string."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "torch-gpu", "--gpus", "1",
+                            "--device-index", str(device_index)], capture_output=True, text=True, timeout=timeout_s)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": f"child exited {r.returncode}: {r.stderr.strip()[-300:]}"}
+        return json.loads(lines[-1])
+    except Exception as e:   # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
 def stage_rooflines(prof, nsteps, n_tok, peaks, c=CFG):
     """prof: {C-ABI entry point: (calls, total ms)} recorded with CUDA events around every call of `nsteps` real
     steps (same stream, same pipeline as the timed region).  Algorithmic work per stage as SURVEY.md §8(d) counts
@@ -244,10 +283,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "torch-gpu"])
+    ap.add_argument("--device-index", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--prec", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-greedy", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip timing torch's own cuDNN/cuBLAS composition of the same step on this GPU")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay of fwd+bwd")
     ap.add_argument("--stages", action="store_true", help="also print per-entry-point GPU time (CUDA events) to stderr")
     args = ap.parse_args()
@@ -258,6 +300,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.impl == "torch-gpu":        # internal: the child of gpu_torch_reference()
+        gpu_torch_reference_child(args.device_index)
         return
     t_start = time.time()
 
@@ -499,6 +544,9 @@ def main():
             cpu = {"value": cps, "unit": "captions/s", "cores": threads, "kind": "port",
                    "sample": f"3 full train steps (head+decoder fwd, CE, bwd, clip, Adam) of B=1024 ({dt:.2f} s/step) after 1 warm-up, torch "
                              f"{torch.__version__} CPU (oracle/torch_port.py, pinned to the reference's goldens)"}
+        gpu_ref = None
+        if world == 1 and not args.no_gpu_reference:
+            gpu_ref = gpu_torch_reference(local)
         if not args.no_greedy:
             feats = torch.randn(GREEDY_B, c["E"], device=dev)
             dec.eval()
@@ -530,6 +578,7 @@ def main():
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
             "clocks": clocks, "roofline": roof, "stages": stages, "cpu_baseline": cpu,
+            "gpu_torch_reference": gpu_ref,
             "step_tflops_per_gpu": step_tf, "step_frac_of_sustained_peak": step_tf / peaks["tf_sust"],
             "algorithmic_flops_per_step": flops_step, "loss": loss_val, **extra,
         }
