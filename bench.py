@@ -17,6 +17,10 @@ e2e    : the same step through the public module API with HOST (pinned) inputs: 
 roofline: the dominant kernel (the tcgen05 vocab-projection contraction) timed alone with CUDA events.
 cpu_baseline / --impl reference: the reference's CPU composition (oracle/torch_port.py, pinned to the
          reference's golden vectors) timed on this box's host cores.
+greedy_tokens_per_s_*: greedy decode (configs[2]) of 4096 image features per GPU x 20 tokens, every rank decoding its
+         own batch (no communication), device-timed, max over ranks, tokens of all ranks counted.
+f_rows : timings of the rows widened after the hot path: snt_caption_trim against the HBM roofline,
+         and Trainer.train() over distinct ragged host batches through PrefetchLoader (eager launches, wall clock).
 gpu_torch_reference: the same torch.nn composition on THIS GPU (cuDNN LSTM, cuBLAS, ATen; fp32, TF32 and bf16 autocast),
          SURVEY.md §8(d)(ii) — timed in a child process after the timed regions; a reported baseline only.
 """
@@ -244,6 +248,77 @@ def gpu_torch_reference(device_index, timeout_s=240):
         return {"error": repr(e)[:300]}
 
 
+def measure_f_rows(snt, dev, c, peaks):
+    """Timings of the rows widened after the hot path, one GPU, after the timed regions; each guarded:
+    a failure here becomes an "error" string and never costs the bench line.
+      caption_trim : snt_caption_trim on a batch larger than L2 (4 M captions x 20 ids: 640 MB read + 640 MB written),
+                     CUDA events, HBM roofline; and at the decode batch of configs[2] (latency-bound at that size).
+      trainer_loop : show_and_tell_b200.Trainer over 24 DISTINCT ragged host batches of 1024 captions fed by
+                     PrefetchLoader (pinned staging + side-stream H2D): eager launches, nothing repeats, wall clock
+                     around the whole loop including a final synchronize - what train.py's loop sees."""
+    out = {}
+    try:
+        res = {}
+        for name, B in (("large", 4 << 20), ("configs2", GREEDY_B)):
+            ids = torch.randint(3, c["V"], (B, 20), device=dev)
+            ids[torch.rand(B, 20, device=dev) < 0.05] = 2
+            o, l = snt.ops.trim_captions(ids)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                snt.ops.trim_captions(ids)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / reps
+            nbytes = B * 20 * 16 + B * 4
+            res[name] = {"captions": B, "us": us, "achieved": nbytes / (us * 1e-6) / 1e9, "unit": "GB/s",
+                         "peak": peaks["hbm"], "frac": nbytes / (us * 1e-6) / 1e9 / peaks["hbm"],
+                         "algorithmic_bytes": nbytes,
+                         "note": "includes the two torch.empty output allocations of ops.trim_captions"}
+            del ids, o, l
+        out["caption_trim"] = res
+    except Exception as e:   # noqa: BLE001
+        out["caption_trim"] = {"error": repr(e)[:300]}
+    try:
+        import argparse as _ap
+        from show_and_tell_b200.feed import PrefetchLoader
+        nb = 24
+        batches = []
+        for k in range(nb):
+            b = snt.synthetic.make_batch(c["B"], c["V"], seed=100 + k, pooled_dim=c["POOLED"])
+            batches.append((torch.from_numpy(b["pooled"]), torch.from_numpy(b["captions"]), b["lengths"],
+                            list(range(k * c["B"], (k + 1) * c["B"]))))
+        torch.manual_seed(0)
+        model = snt.CaptionModel(c["E"], c["H"], c["V"], c["L"], backbone=False, precision="bf16").to(dev)
+
+        class _V:                                   # len() is all Trainer needs without a validation loader
+            def __len__(self):
+                return c["V"]
+        opt = _ap.Namespace(num_gpu=1, embed_size=c["E"], hidden_size=c["H"], num_layers=c["L"], learning_rate=1e-3,
+                            max_epochs=1, learning_rate_decay_start=1, learning_rate_decay_every=3,
+                            learning_rate_decay_rate=0.8, grad_clip=0.1, log_step=10 ** 9, language_eval=0,
+                            save_checkpoint_every=10 ** 9, expr_dir=tempfile.gettempdir(), start_from=None,
+                            load_best_score=True, load_pretrained=False, load_model_path=None, vocab_path=None)
+        tr = snt.Trainer(opt, PrefetchLoader(batches, dev), None, vocab=_V(), model=model)
+        tr.train()                                  # warm-up epoch (allocator, workspaces)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tr.train()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["trainer_loop"] = {"value": nb * c["B"] / dt, "unit": "captions/s", "ms_per_step": dt / nb * 1e3,
+                               "batches": nb, "loss": float(tr.last_loss),
+                               "what": "Trainer.train() over distinct ragged host batches through PrefetchLoader, eager "
+                                       "launches, wall clock incl. H2D"}
+        del tr, model, batches
+        torch.cuda.empty_cache()
+    except Exception as e:   # noqa: BLE001
+        out["trainer_loop"] = {"error": repr(e)[:300]}
+    return out
+
+
 def stage_rooflines(prof, nsteps, n_tok, peaks, c=CFG):
     """prof: {C-ABI entry point: (calls, total ms)} recorded with CUDA events around every call of `nsteps` real
     steps (same stream, same pipeline as the timed region).  Algorithmic work per stage as SURVEY.md §8(d) counts
@@ -288,6 +363,7 @@ def main():
     ap.add_argument("--prec", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-greedy", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the timings of the widened rows (trim kernel, Trainer loop)")
     ap.add_argument("--no-gpu-reference", action="store_true",
                     help="skip timing torch's own cuDNN/cuBLAS composition of the same step on this GPU")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay of fwd+bwd")
@@ -512,6 +588,21 @@ def main():
     flops_step = train_flops(c["B"], n_tok)
     step_tf = flops_step * args.steps / t_res / 1e12      # per GPU (max-over-ranks time)
 
+    # greedy decode (BASELINE configs[2]): batch 4096 per GPU, 20 tokens each, no communication (the batch shards);
+    # every rank decodes its own batch, device-timed, max over ranks, tokens of all ranks counted
+    greedy = {}
+    stepper.close()   # no training step follows: release the captured graphs (they hold NCCL work) before more barriers
+    if not args.no_greedy:
+        feats = torch.randn(GREEDY_B, c["E"], device=dev)
+        dec.eval()
+        for prec in ("fp32", "bf16"):
+            dec.sample(feats, precision=prec)
+            reps = 3
+            t_g = timed(lambda: dec.sample(feats, precision=prec), reps)
+            greedy[f"greedy_tokens_per_s_{prec}"] = GREEDY_B * world * 20 * reps / t_g
+        dec.train()
+        del feats
+
     extra = {}
     if rank == 0:
         top = stages[0]
@@ -547,19 +638,9 @@ def main():
         gpu_ref = None
         if world == 1 and not args.no_gpu_reference:
             gpu_ref = gpu_torch_reference(local)
-        if not args.no_greedy:
-            feats = torch.randn(GREEDY_B, c["E"], device=dev)
-            dec.eval()
-            for prec in ("fp32", "bf16"):
-                dec.sample(feats, precision=prec)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                reps = 3
-                for _ in range(reps):
-                    dec.sample(feats, precision=prec)
-                torch.cuda.synchronize()
-                extra[f"greedy_tokens_per_s_{prec}"] = GREEDY_B * 20 * reps / (time.perf_counter() - t0)
-            dec.train()
+        if world == 1 and not args.no_extras:
+            extra["f_rows"] = measure_f_rows(snt, dev, c, peaks)
+        extra.update(greedy)
         line = {
             "metric": "train_captions_per_s", "value": value, "unit": "captions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3,
