@@ -12,6 +12,7 @@ All tensors must live on a CUDA device; nothing here computes on the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -20,6 +21,22 @@ from . import _lib
 from ._lib import PREC, call, host_i32, ptr, require_cuda, stream_ptr, workspace
 
 SAMPLE_STEPS = 20  # models.py:60
+
+# Experimental, off by default (plan item 4; written without a GPU run, enable with SNT_TAIL_OVERLAP=1):
+# `dfeatures` is dx[:B] - the t = 0 rows of the first layer's input gradient - so the head's backward does not depend
+# on the embedding-gradient kernels that follow snt_lstm_bwd on the stream.  With the switch on, _hidden_bwd hands
+# autograd that view plus an event, and _Head.backward runs on a side stream behind the event, joined back into
+# the main stream when its launches are enqueued.
+TAIL_OVERLAP = os.environ.get("SNT_TAIL_OVERLAP", "0") == "1"
+_tail = None          # (data_ptr of the dfeatures view, event recorded once dx is complete)
+_side_streams = {}
+
+
+def _side_stream(dev):
+    st = _side_streams.get(dev.index)
+    if st is None:
+        st = _side_streams[dev.index] = torch.cuda.Stream(dev)
+    return st
 
 
 def _act_dtype(prec):
@@ -100,6 +117,21 @@ class _Head(torch.autograd.Function):
         d_be = torch.empty(E, device=dev)
         p = PREC[prec]
         nb = _lib.lib().snt_head_workspace_bytes(p, B, K, E)
+        global _tail
+        tail, _tail = _tail, None
+        if tail is not None and tail[0] == dfeat.data_ptr():
+            # two-stream tail (see TAIL_OVERLAP): outputs were allocated on the main stream above; the launches go to the
+            # side stream behind "dx complete" and the main stream waits for them before anything else touches the results
+            main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+            side.wait_event(tail[1])
+            with torch.cuda.stream(side):
+                ws = workspace(nb, dev)
+                call("snt_head_bwd", p, ptr(dfeat), ptr(pooled), ptr(yhat), ptr(rstd), ptr(gamma), 1 if training else 0,
+                     B, K, E, ptr(d_w), ptr(d_b), ptr(d_g), ptr(d_be), ptr(ws), ws.numel(), stream_ptr())
+                join = torch.cuda.Event()
+                join.record(side)
+            main.wait_event(join)
+            return None, d_w, d_b, d_g, d_be, None, None, None, None, None, None
         ws = workspace(nb, dev)
         call("snt_head_bwd", p, ptr(dfeat), ptr(pooled), ptr(yhat), ptr(rstd), ptr(gamma), 1 if training else 0,
              B, K, E, ptr(d_w), ptr(d_b), ptr(d_g), ptr(d_be), ptr(ws), ws.numel(), stream_ptr())
@@ -182,7 +214,15 @@ def _hidden_bwd(s, d_hs, w_emb, lstm_w, need_dfeat, grad_ready=None):
             grad_ready([f"lstm.weight_ih_l{k}", f"lstm.weight_hh_l{k}", f"lstm.bias_ih_l{k}", f"lstm.bias_hh_l{k}"],
                        list(grads[k]))
         d_hs = dx
-    dfeat = torch.empty(s.B, s.E, device=dev) if need_dfeat else None
+    global _tail
+    if need_dfeat and TAIL_OVERLAP:
+        ev = torch.cuda.Event()
+        ev.record()                                  # dx of the first layer is complete here
+        dfeat_out = d_hs[:s.B]                       # rows of t = 0: exactly what dfeatures_kernel would copy
+        _tail = (dfeat_out.data_ptr(), ev)
+        dfeat = None                                 # the C call skips its own copy
+    else:
+        dfeat_out = dfeat = torch.empty(s.B, s.E, device=dev) if need_dfeat else None
     d_w_emb = torch.empty_like(w_emb)
     nb = _lib.lib().snt_embed_bwd_workspace_bytes(s.N, s.V)
     ws = workspace(nb, dev)
@@ -191,7 +231,7 @@ def _hidden_bwd(s, d_hs, w_emb, lstm_w, need_dfeat, grad_ready=None):
          ptr(dfeat), ptr(d_w_emb), ptr(ws), ws.numel(), stream_ptr())
     if grad_ready is not None:
         grad_ready(["embed.weight"], [d_w_emb])
-    return dfeat, d_w_emb, grads
+    return dfeat_out, d_w_emb, grads
 
 
 def _flatten_lstm(lstm_w):
