@@ -212,22 +212,69 @@ def run_reference(args, rank):
 
 
 def gpu_torch_reference_child(device_index):
-    """Child process of `gpu_torch_reference`: prints one JSON object."""
-    import show_and_tell_b200 as snt
-    from oracle import torch_port as TP   # a reported baseline (the reference's composition), never the product
+    """Child process of `gpu_torch_reference`: prints one JSON object.  Self-contained on purpose: the composition of
+    torch.nn layers the reference runs (models.py:9-67, train.py:137-146) is written out here, so this leg neither
+    imports the test oracle nor touches the product's kernels."""
+    import torch.nn as nn
+    from torch.nn.utils.rnn import pack_padded_sequence
+    import show_and_tell_b200 as snt          # synthetic batch generator only (numpy, host side)
     c = CFG
     dev = torch.device("cuda", device_index)
     torch.cuda.set_device(dev)
     b = snt.synthetic.make_batch(c["B"], c["V"], embed=c["E"], seed=1, pooled_dim=c["POOLED"])
-    b["targets"] = snt.synthetic.pack_host(b["captions"], b["lengths"])
+    lengths = b["lengths"]
+    pooled = torch.from_numpy(b["pooled"]).to(dev)
+    caps = torch.from_numpy(b["captions"]).to(dev)
+    targets = torch.from_numpy(snt.synthetic.pack_host(b["captions"], lengths)).to(dev)
+
+    class Pair(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = nn.Linear(c["POOLED"], c["E"])                              # models.py:16
+            self.bn = nn.BatchNorm1d(c["E"], momentum=0.01)                       # models.py:17
+            self.embed = nn.Embedding(c["V"], c["E"])                             # models.py:35
+            self.lstm = nn.LSTM(c["E"], c["H"], c["L"], batch_first=True)         # models.py:36
+            self.linear = nn.Linear(c["H"], c["V"])                               # models.py:37
+
+        def forward(self, pooled, captions, lengths):
+            feats = self.bn(self.fc(pooled))                                      # models.py:27-28
+            steps = torch.cat((feats.unsqueeze(1), self.embed(captions)), 1)      # models.py:49-50
+            hiddens, _ = self.lstm(pack_padded_sequence(steps, lengths, batch_first=True))   # models.py:51-52
+            return self.linear(hiddens[0])                                        # models.py:53
+
     out = {"unit": "captions/s",
            "what": "torch.nn composition of the same train step (head, decoder, CE, backward, clip, Adam) on this GPU, "
                    f"torch {torch.__version__}: cuDNN LSTM, cuBLAS, ATen kernels; CUDA events, 10 steps after 3 warm-up"}
     for name, tf32, amp in (("fp32", False, False), ("tf32", True, False), ("bf16_autocast", True, True)):
         try:
-            cps, dt, loss = TP.time_full_train_on(dev, c["B"], c["E"], c["H"], c["V"], c["L"], b, steps=10, warmup=3,
-                                                  tf32=tf32, autocast_bf16=amp)
-            out[name] = {"value": cps, "ms_per_step": dt * 1e3, "loss": loss}
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
+            torch.manual_seed(0)
+            model = Pair().to(dev)
+            opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+            crit = nn.CrossEntropyLoss()
+
+            def one():
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                    loss = crit(model(pooled, caps, lengths), targets)            # train.py:139-143
+                loss.backward()                                                   # train.py:144
+                for p in model.parameters():
+                    p.grad.clamp_(-0.1, 0.1)                                      # train.py:88-91,145
+                opt.step()                                                        # train.py:146
+                return loss
+
+            for _ in range(3):
+                one()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                loss = one()
+            e1.record()
+            torch.cuda.synchronize()
+            dt = e0.elapsed_time(e1) * 1e-3 / 10
+            out[name] = {"value": c["B"] / dt, "ms_per_step": dt * 1e3, "loss": float(loss.detach())}
+            del model, opt
         except Exception as e:   # noqa: BLE001
             out[name] = {"error": repr(e)[:300]}
     print(json.dumps(out), flush=True)

@@ -105,48 +105,6 @@ def time_full_train(B, E, H, V, L, batch, steps=3, warmup=1, threads=None):
     return B / dt, dt, float(loss.detach())
 
 
-def time_full_train_on(device, B, E, H, V, L, batch, steps=10, warmup=3, tf32=False, autocast_bf16=False):
-    """The same full_step with torch's own GPU kernels (cuDNN LSTM, cuBLAS, ATen) on `device`: SURVEY.md §8(d)(ii),
-    "the same module .cuda() on the same B200", in fp32 (tf32=False), TF32 or bf16-autocast arithmetic.
-    -> (captions/s, seconds per step, loss); timed with CUDA events when the device is a GPU."""
-    device = torch.device(device)
-    cuda = device.type == "cuda"
-    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
-    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = bool(tf32)
-    try:
-        torch.manual_seed(0)
-        head = EncoderHeadCPU(E, batch["pooled"].shape[1]).to(device)
-        dec = CaptionDecoderCPU(E, H, V, L).to(device)
-        opt = torch.optim.Adam(list(head.parameters()) + list(dec.parameters()), lr=1e-3)
-        p = torch.from_numpy(batch["pooled"]).to(device)
-        c = torch.from_numpy(batch["captions"]).to(device)
-        t = torch.from_numpy(batch["targets"]).to(device)
-
-        def one():
-            with torch.autocast(device.type, dtype=torch.bfloat16, enabled=bool(autocast_bf16)):
-                return full_step(head, dec, opt, p, c, batch["lengths"], t)
-
-        loss = None
-        for _ in range(warmup):
-            loss = one()
-        if cuda:
-            torch.cuda.synchronize(device)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            loss = one()
-        if cuda:
-            e1.record()
-            torch.cuda.synchronize(device)
-            dt = e0.elapsed_time(e1) * 1e-3 / steps
-        else:
-            dt = (time.perf_counter() - t0) / steps
-        return B / dt, dt, float(loss.detach())
-    finally:
-        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
-
-
 def time_train(B, E, H, V, L, batch, steps=3, warmup=1, threads=None):
     """-> (captions/s, seconds per step, loss)."""
     if threads:
