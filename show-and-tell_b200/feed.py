@@ -84,6 +84,8 @@ class FeatureStore:
         if out is None:
             out = torch.empty(len(rows), self.meta["dim"], dtype=torch.float32,
                               pin_memory=torch.cuda.is_available())
+        elif tuple(out.shape) != (len(rows), self.meta["dim"]) or out.dtype != torch.float32 or out.is_cuda:
+            raise ValueError("FeatureStore.gather: `out` must be a float32 host tensor of shape [len(image_ids), dim]")
         order = np.argsort(rows, kind="stable")            # read the memory map in file order
         dst = out.numpy()
         dst[order] = self.array[rows[order]]               # float16 rows widen here, on the host

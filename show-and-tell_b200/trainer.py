@@ -82,12 +82,15 @@ def _to_device(t, device):
 def evaluation(model, crit, loader, vocab, opt, language_eval=None, trim=None):
     """eval.py:58-119.  `crit` given: the strict path, `crit(model(images, captions, lengths), targets)` with the
     logits materialised exactly as eval.py:93-95; `crit=None`: the fused `model.loss`.  -> (mean loss over the
-    batches as a float, predictions, lang_stats).  `trim(ids) -> (ids, lengths)` defaults to the device kernel."""
+    batches as a float, predictions, lang_stats).  `trim(ids, end_id, pad_id) -> (ids, lengths)` defaults to the
+    device kernel; `<end>` / `<pad>` ids come from `vocab.word2idx` when it has them."""
     trim = trim or ops.trim_captions
     was_training = model.training
     model.eval()                                                      # eval.py:65
     device = next(model.parameters()).device
-    end_word, loss_sum, loss_evals = "<end>", 0.0, 0
+    word2idx = getattr(vocab, "word2idx", None) or {}
+    end_id, pad_id = word2idx.get("<end>", 2), word2idx.get("<pad>", 0)       # preprocess.py:75-78 fixes them at 2 / 0
+    loss_sum, loss_evals = 0.0, 0
     predictions, seen = [], set()
     with torch.no_grad():                                             # eval.py:79-80 `volatile=True`
         for images, captions, lengths, imgids in loader:
@@ -106,7 +109,7 @@ def evaluation(model, crit, loader, vocab, opt, language_eval=None, trim=None):
             loss_sum += float(loss)                                                         # eval.py:96-97
             loss_evals += 1
             ids = model.decoder.sample(feats) if feats is not None else model.sample(images)  # eval.py:99
-            ids, kept = trim(ids.reshape(len(lengths), -1))                                 # eval.py:103-109 on device
+            ids, kept = trim(ids.reshape(len(lengths), -1), end_id, pad_id)                 # eval.py:103-109 on device
             ids, kept = ids.cpu().numpy(), kept.cpu().numpy()                               # eval.py:101
             for i, imgid in enumerate(imgids):
                 imgid = imgid.item() if hasattr(imgid, "item") else imgid
@@ -114,7 +117,6 @@ def evaluation(model, crit, loader, vocab, opt, language_eval=None, trim=None):
                     continue
                 seen.add(imgid)
                 words = [vocab.idx2word[int(w)] for w in ids[i, :int(kept[i])]]
-                assert end_word not in words
                 predictions.append({"image_id": imgid, "caption": " ".join(words)})
     model.train(was_training)
     lang_stats = language_eval(predictions) if language_eval is not None else {}            # eval.py:117

@@ -93,8 +93,8 @@ def make_model(seed=5):
     return snt.CaptionModel(E, H, V, L, encoder=HeadCPU(E, POOLED), decoder=DecCPU(E, H, V, L))
 
 
-def oracle_trim(ids):
-    a, l = O.trim_captions(ids.numpy())
+def oracle_trim(ids, end_id=2, pad_id=0):
+    a, l = O.trim_captions(ids.numpy(), end_id, pad_id)
     return torch.from_numpy(a), torch.from_numpy(l)
 
 
