@@ -177,7 +177,11 @@ ce_finish_kernel(const float2* __restrict__ part, int slabs, int64_t N, const fl
 }
 
 // ---- backward epilogue: dlogits = (2^(y - lse2) - onehot) * scale -> bf16 chunk ------------------------------------
-template <int W>
+// LAZY (experimental, SNT_CEBWD_LAZY=1; written without a GPU run): the one-hot subtraction is not applied
+// to all 32 elements of a chunk (32 compares + 32 predicated subtracts per thread, a quarter of the chunk's instructions)
+// but patched into the staged bf16 row by the one lane whose target column lies in this chunk (one chunk in V/32 per
+// row).  Same arithmetic for that element (same ex2 argument, minus one, one rounding): bit-identical output.
+template <int W, bool LAZY = false>
 struct CeBwdEpiT {
   static constexpr int kWarps = W;
   static constexpr int kStages = W == 16 ? 3 : 0;  // 16 staging buffers (40 KB) fit next to 3 ring stages
@@ -212,16 +216,27 @@ struct CeBwdEpiT {
         float p1 = ex2((__uint_as_float(r[j + 1]) + b.y) * LOG2E - l2);
         float p2 = ex2((__uint_as_float(r[j + 2]) + b.z) * LOG2E - l2);
         float p3 = ex2((__uint_as_float(r[j + 3]) + b.w) * LOG2E - l2);
-        if (trel == j) p0 -= 1.f;
-        if (trel == j + 1) p1 -= 1.f;
-        if (trel == j + 2) p2 -= 1.f;
-        if (trel == j + 3) p3 -= 1.f;
+        if (!LAZY) {
+          if (trel == j) p0 -= 1.f;
+          if (trel == j + 1) p1 -= 1.f;
+          if (trel == j + 2) p2 -= 1.f;
+          if (trel == j + 3) p3 -= 1.f;
+        }
         __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
         pk[j / 2] = *reinterpret_cast<uint32_t*>(&lo);
         pk[j / 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) tc::sts128(wsa + lane * 80 + q * 16, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      if (LAZY && (unsigned)trel < 32u) {  // this row's target column is one of these 32: patch its staged element
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (trel == j) acc = __uint_as_float(r[j]);
+        const float pt = ex2((acc + __ldg(bias + col0 + trel)) * LOG2E - l2) - 1.f;
+        const unsigned short hb = __bfloat16_as_ushort(__float2bfloat16_rn(pt));
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(wsa + (uint32_t)(lane * 80 + trel * 2)), "h"(hb) : "memory");
+      }
       __syncwarp();
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
@@ -488,6 +503,8 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
     dw_bn = c128 < c256 ? 128 : 256;
   }
 
+  const char* lazy_env = getenv("SNT_CEBWD_LAZY");
+  const bool lazy_onehot = lazy_env && lazy_env[0] == '1';
   SideStream* side = side_stream();
   for (int64_t r0 = 0; r0 < N; r0 += w.R) {
     const int64_t r = N - r0 < w.R ? N - r0 : w.R;
@@ -499,7 +516,12 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
     make_sched(r, V, H, &ts);
     // 16 epilogue warps (2 chunks each) hide the TMEM-load / staging / store latencies better than 8 warps with register
     // double-buffering: 58 -> 51 us per chunk pass (measured); SNT_CEBWD_W8 selects the 8-warp variant.
-    if (!getenv("SNT_CEBWD_W8")) {
+    if (lazy_onehot) {
+      CeBwdEpiT<16, true> e;
+      e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;
+      e.out = w.dl; e.ldo = w.Vp;
+      SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeBwdEpiT<16, true>>(ta, tb, ts, e, st)));
+    } else if (!getenv("SNT_CEBWD_W8")) {
       CeBwdEpiT<16> e;
       e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;
       e.out = w.dl; e.ldo = w.Vp;

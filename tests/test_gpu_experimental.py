@@ -38,3 +38,27 @@ def test_two_stream_tail_is_bit_identical(graph):
     assert l0 == l1
     for k in g0:
         assert np.array_equal(g0[k], g1[k]), k
+
+
+@pytest.mark.parametrize("B,E,H,V", [(200, 64, 128, 1000), (1024, 256, 512, 10000)])
+def test_lazy_onehot_epilogue_is_bit_identical(B, E, H, V):
+    """SNT_CEBWD_LAZY=1: the softmax-gradient epilogue patches the one-hot element instead of testing all 32."""
+    import show_and_tell_b200 as snt
+    torch.manual_seed(0)
+    dec = snt.DecoderRNN(E, H, V, 1, precision="bf16").cuda()
+    b = snt.synthetic.make_batch(B, V, embed=E, seed=2)
+    feats, caps = torch.from_numpy(b["features"]).cuda(), torch.from_numpy(b["captions"]).cuda()
+    tg = torch.from_numpy(snt.synthetic.pack_host(b["captions"], b["lengths"])).cuda()
+    out = []
+    for lazy in ("0", "1"):
+        os.environ["SNT_CEBWD_LAZY"] = lazy
+        try:
+            dec.zero_grad(set_to_none=True)
+            loss = dec.loss(feats, caps, b["lengths"], tg)
+            loss.backward()
+            torch.cuda.synchronize()
+            out.append({k: p.grad.detach().cpu().numpy().copy() for k, p in dec.named_parameters()})
+        finally:
+            os.environ.pop("SNT_CEBWD_LAZY", None)
+    for k in out[0]:
+        assert np.array_equal(out[0][k], out[1][k]), k
