@@ -93,6 +93,16 @@ int snt_embed_pack_bwd(const float* dx, const int64_t* captions, int64_t cap_str
                        const int32_t* batch_sizes /*[host] T*/, int T, int64_t B, int64_t E, int64_t V,
                        float* dfeatures, float* d_w_emb, void* ws, int64_t ws_bytes, void* stream);
 
+/* The same backward as two calls (experimental): snt_embed_bwd_plan does the token-dependent half (histogram and scan
+ * of the token ids: needs the captions, not dx) and may be enqueued early, on another stream, while dx is still being
+ * computed; snt_embed_pack_bwd_planned finishes the job on a workspace that went through the plan call with the same
+ * captions / batch_sizes / V.  Together they issue exactly the launches of snt_embed_pack_bwd. */
+int snt_embed_bwd_plan(const int64_t* captions, int64_t cap_stride, const int32_t* batch_sizes /*[host] T*/, int T,
+                       int64_t V, void* ws, int64_t ws_bytes, void* stream);
+int snt_embed_pack_bwd_planned(const float* dx, const int64_t* captions, int64_t cap_stride,
+                               const int32_t* batch_sizes /*[host] T*/, int T, int64_t B, int64_t E, int64_t V,
+                               float* dfeatures, float* d_w_emb, void* ws, int64_t ws_bytes, void* stream);
+
 /* ---- a7  one LSTM layer over the packed sequence  (models.py:52, nn.LSTM, gate rows i|f|g|o) ---------
  * h0 = c0 = 0.  x (act) [N,In].  Saves for backward: gates[N,4H] fp32 (post-activation i,f,g,o),
  * cs[N,H] fp32 (c_t), hs (act) [N,H] (h_t = the layer output), hprev (act) [N,H] (h_{t-1} per row). */

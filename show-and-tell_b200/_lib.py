@@ -40,6 +40,8 @@ SIGNATURES = {
     "snt_embed_pack_fwd": (_int, [_vp, _vp, _vp, _i64, _vp, _int, _i64, _i64, _vp, _vp, _vp]),
     "snt_embed_bwd_workspace_bytes": (_i64, [_i64, _i64]),
     "snt_embed_pack_bwd": (_int, [_vp, _vp, _i64, _vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "snt_embed_bwd_plan": (_int, [_vp, _i64, _vp, _int, _i64, _vp, _i64, _vp]),
+    "snt_embed_pack_bwd_planned": (_int, [_vp, _vp, _i64, _vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
     "snt_lstm_workspace_bytes": (_i64, [_int, _i64, _i64, _i64, _i64]),
     "snt_lstm_fwd": (_int, [_int, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp,
                             _vp, _i64, _vp]),

@@ -862,16 +862,19 @@ int64_t embed_bwd_ws_bytes(int64_t N, int64_t V) {
   return ws_bytes_for(N, 4) * 3 + ws_bytes_for(V + 1, 4) * 6 + ws_bytes_for(emb_chunk_slots(N), 4) * 2 +
          ws_bytes_for(emb_chunk_slots(N) * 1024, 4) + ws_bytes_for(4, 4);
 }
+// phase 0: everything.  phase 1: only the token-dependent half (histogram + scan: needs captions, not dx) - it may run
+// early, on another stream.  phase 2: the rest, for a workspace that already went through phase 1 with the same
+// captions / geometry.  Phase 0 issues exactly the launches of phase 1 + phase 2 in the original order.
 int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions, int64_t cap_stride,
                    int64_t B, int64_t E, int64_t V, float* dfeatures, float* d_w_emb, void* ws,
-                   int64_t ws_bytes, cudaStream_t st) {
+                   int64_t ws_bytes, cudaStream_t st, int phase) {
   const int N = pk.off[pk.T];
   const int n1 = N - pk.off[1];
-  if (dfeatures) {
+  if (phase != 1 && dfeatures) {
     dfeatures_kernel<<<nblocks(B * E, 256), 256, 0, st>>>(dx, pk.off[1], B, E, dfeatures);
     SNT_LAUNCH_CHECK("dfeatures_kernel");
   }
-  if (!d_w_emb) return SNT_OK;
+  if (phase != 1 && !d_w_emb) return SNT_OK;
   Workspace w(ws, ws_bytes);
   int* tok = w.take<int>(N);
   int* perm0 = w.take<int>(N);
@@ -888,17 +891,20 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
   float* partial = w.take<float>(emb_chunk_slots(N) * 1024);
   cl.counter = w.take<int>(4);
   if (!w.ok()) { set_error("embed_pack_bwd: workspace too small"); return SNT_EWORKSPACE; }
-  SNT_REQUIRE(E % 4 == 0 && E <= 1024, "embed_pack_bwd: E must be a multiple of 4 and <= 1024");
+  SNT_REQUIRE(phase == 1 || (E % 4 == 0 && E <= 1024), "embed_pack_bwd: E must be a multiple of 4 and <= 1024");
   SNT_REQUIRE(V < (1LL << 31), "embed_pack_bwd: V too large");
-  SNT_CUDA(cudaMemsetAsync(d_w_emb, 0, sizeof(float) * (size_t)V * E, st));
+  if (phase != 1) SNT_CUDA(cudaMemsetAsync(d_w_emb, 0, sizeof(float) * (size_t)V * E, st));
   if (n1 <= 0) return SNT_OK;
-  SNT_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(V + 1), st));
-  SNT_CUDA(cudaMemsetAsync(cl.counter, 0, sizeof(int) * 4, st));
+  if (phase != 2) SNT_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(V + 1), st));
+  if (phase != 1) SNT_CUDA(cudaMemsetAsync(cl.counter, 0, sizeof(int) * 4, st));
+  if (phase != 2) {
+    emb_tok_kernel<<<nblocks(n1, 256), 256, 0, st>>>(pk, captions, cap_stride, V, tok, count, device_flags());
+    SNT_LAUNCH_CHECK("emb_tok_kernel");
+    emb_scan_kernel<<<1, 1024, 0, st>>>(count, (int)V, start, cursor, multi, small, device_flags());
+    SNT_LAUNCH_CHECK("emb_scan_kernel");
+  }
+  if (phase == 1) return SNT_OK;
   const float* dx1 = dx + (int64_t)pk.off[1] * E;
-  emb_tok_kernel<<<nblocks(n1, 256), 256, 0, st>>>(pk, captions, cap_stride, V, tok, count, device_flags());
-  SNT_LAUNCH_CHECK("emb_tok_kernel");
-  emb_scan_kernel<<<1, 1024, 0, st>>>(count, (int)V, start, cursor, multi, small, device_flags());
-  SNT_LAUNCH_CHECK("emb_scan_kernel");
   emb_place_kernel<<<nblocks(n1, 8), 256, 0, st>>>(tok, n1, count, cursor, perm0, dx1, (int)E, d_w_emb);
   SNT_LAUNCH_CHECK("emb_place_kernel");
   const int slabs = (int)((E + 127) / 128);

@@ -46,7 +46,7 @@ int bn_bwd(const float* dout, const float* yhat, const float* rstd, const float*
 int64_t embed_bwd_ws_bytes(int64_t N, int64_t V);
 int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions, int64_t cap_stride,
                    int64_t B, int64_t E, int64_t V, float* dfeatures, float* d_w_emb, void* ws,
-                   int64_t ws_bytes, cudaStream_t st);
+                   int64_t ws_bytes, cudaStream_t st, int phase = 0);
 
 int clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                double eps, float grad_clip, float grad_scale, int64_t step, cudaStream_t st);

@@ -28,6 +28,10 @@ SAMPLE_STEPS = 20  # models.py:60
 # autograd that view plus an event, and _Head.backward runs on a side stream behind the event, joined back into
 # the main stream when its launches are enqueued.
 TAIL_OVERLAP = os.environ.get("SNT_TAIL_OVERLAP", "0") == "1"
+# Same status (experimental, SNT_EMB_PLAN_EARLY=1): the token-dependent half of the embedding gradient (histogram + scan
+# of the token ids, ~20 us of small launches) needs only the captions, so it is enqueued on the side stream at the START
+# of the loss backward and has long finished when dx arrives (snt_embed_bwd_plan / snt_embed_pack_bwd_planned).
+EMB_PLAN_EARLY = os.environ.get("SNT_EMB_PLAN_EARLY", "0") == "1"
 _tail = None          # (data_ptr of the dfeatures view, event recorded once dx is complete)
 _side_streams = {}
 
@@ -150,7 +154,22 @@ def head(pooled, w_fc, b_fc, gamma, beta, running_mean, running_var, training, m
 # ---------------------------------------------------------------------------------------------------------
 class _Hidden:
     """Tensors saved between forward and backward of the recurrent part."""
-    __slots__ = ("prec", "bs", "bs_ptr", "T", "N", "B", "E", "H", "V", "L", "captions", "layers", "x")
+    __slots__ = ("prec", "bs", "bs_ptr", "T", "N", "B", "E", "H", "V", "L", "captions", "layers", "x", "plan")
+
+
+def _plan_embed_bwd(s, dev):
+    """EMB_PLAN_EARLY: enqueue the token-dependent half of the embedding gradient on the side stream now."""
+    main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+    side.wait_stream(main)                            # the captions (and everything before backward) are complete
+    cap = s.captions
+    with torch.cuda.stream(side):
+        nb = _lib.lib().snt_embed_bwd_workspace_bytes(s.N, s.V)
+        ws = torch.empty(max(int(nb), 1), dtype=torch.uint8, device=dev)      # owned by this backward, not the shared scratch
+        call("snt_embed_bwd_plan", ptr(cap), cap.stride(0) if cap.numel() else 0, s.bs_ptr, s.T, s.V, ptr(ws),
+             ws.numel(), stream_ptr())
+        ev = torch.cuda.Event()
+        ev.record(side)
+    s.plan = (ws, ev)
 
 
 def _hidden_fwd(prec, features, captions, bs, w_emb, lstm_w):
@@ -171,7 +190,7 @@ def _hidden_fwd(prec, features, captions, bs, w_emb, lstm_w):
          bs_ptr, T, E, V, ptr(x) if prec == "fp32" else None, ptr(x) if prec == "bf16" else None, stream_ptr())
     s = _Hidden()
     s.prec, s.bs, s.bs_ptr, s.T, s.N, s.B, s.E, s.V, s.L = prec, bs_arr, bs_ptr, T, N, B, E, V, len(lstm_w)
-    s.captions, s.x, s.layers = captions, x, []
+    s.captions, s.x, s.layers, s.plan = captions, x, [], None
     inp, in_dim = x, E
     H = lstm_w[0][1].shape[1]
     s.H = H
@@ -224,11 +243,21 @@ def _hidden_bwd(s, d_hs, w_emb, lstm_w, need_dfeat, grad_ready=None):
     else:
         dfeat_out = dfeat = torch.empty(s.B, s.E, device=dev) if need_dfeat else None
     d_w_emb = torch.empty_like(w_emb)
-    nb = _lib.lib().snt_embed_bwd_workspace_bytes(s.N, s.V)
-    ws = workspace(nb, dev)
     cap = s.captions
-    call("snt_embed_pack_bwd", ptr(d_hs), ptr(cap), cap.stride(0) if cap.numel() else 0, s.bs_ptr, s.T, s.B, s.E, s.V,
-         ptr(dfeat), ptr(d_w_emb), ptr(ws), ws.numel(), stream_ptr())
+    plan = getattr(s, "plan", None)
+    if plan is not None:
+        ws, ev = plan
+        main = torch.cuda.current_stream(dev)
+        main.wait_event(ev)
+        ws.record_stream(main)                        # allocated on the side stream, consumed here
+        call("snt_embed_pack_bwd_planned", ptr(d_hs), ptr(cap), cap.stride(0) if cap.numel() else 0, s.bs_ptr, s.T,
+             s.B, s.E, s.V, ptr(dfeat), ptr(d_w_emb), ptr(ws), ws.numel(), stream_ptr())
+        s.plan = None
+    else:
+        nb = _lib.lib().snt_embed_bwd_workspace_bytes(s.N, s.V)
+        ws = workspace(nb, dev)
+        call("snt_embed_pack_bwd", ptr(d_hs), ptr(cap), cap.stride(0) if cap.numel() else 0, s.bs_ptr, s.T, s.B, s.E,
+             s.V, ptr(dfeat), ptr(d_w_emb), ptr(ws), ws.numel(), stream_ptr())
     if grad_ready is not None:
         grad_ready(["embed.weight"], [d_w_emb])
     return dfeat_out, d_w_emb, grads
@@ -336,6 +365,8 @@ class _DecoderLoss(torch.autograd.Function):
         dev = dloss.device
         N, H, V = s.N, s.H, w_out.shape[0]
         hs = s.layers[-1][4]
+        if EMB_PLAN_EARLY:
+            _plan_embed_bwd(s, dev)
         dloss = dloss.contiguous().float()
         d_hs = torch.empty(N, H, device=dev)
         d_w_out = torch.empty_like(w_out)

@@ -11,9 +11,10 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("SNT_TEST_EXPERIMENTAL") != "1", reason="experimental switches")]
 
 
-def _step(snt, overlap, graph):
+def _step(snt, overlap, graph, plan_early=False):
     from show_and_tell_b200 import parallel
     snt.ops.TAIL_OVERLAP = overlap
+    snt.ops.EMB_PLAN_EARLY = plan_early
     torch.manual_seed(0)
     enc = snt.EncoderCNN(64, backbone=False).cuda().train()
     dec = snt.DecoderRNN(64, 128, 1000, 1).cuda().train()
@@ -27,6 +28,7 @@ def _step(snt, overlap, graph):
     out = {n: p.grad.detach().cpu().numpy().copy() for m in (enc, dec) for n, p in m.named_parameters()}
     st.close()
     snt.ops.TAIL_OVERLAP = False
+    snt.ops.EMB_PLAN_EARLY = False
     return float(loss), out
 
 
@@ -35,6 +37,18 @@ def test_two_stream_tail_is_bit_identical(graph):
     import show_and_tell_b200 as snt
     l0, g0 = _step(snt, False, graph)
     l1, g1 = _step(snt, True, graph)
+    assert l0 == l1
+    for k in g0:
+        assert np.array_equal(g0[k], g1[k]), k
+
+
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("overlap", [False, True])
+def test_early_embedding_plan_is_bit_identical(graph, overlap):
+    """SNT_EMB_PLAN_EARLY=1 alone and together with the two-stream tail."""
+    import show_and_tell_b200 as snt
+    l0, g0 = _step(snt, False, graph)
+    l1, g1 = _step(snt, overlap, graph, plan_early=True)
     assert l0 == l1
     for k in g0:
         assert np.array_equal(g0[k], g1[k]), k
