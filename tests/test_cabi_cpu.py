@@ -49,6 +49,13 @@ def test_abi_version_and_error_string(snt):
     assert l.snt_lstm_workspace_bytes(5, 100, 10, 8, 16) == -1
     assert l.snt_caption_trim(None, 4, 20, 2, 0, None, None, None) == -1 and b"NULL" in l.snt_last_error()
     assert l.snt_caption_trim(None, 0, 20, 2, 0, None, None, None) == 0      # empty batch: nothing to launch
+    bad = (ctypes.c_int32 * 2)(1, 2)
+    rc = l.snt_embed_bwd_plan(None, 4, ctypes.cast(bad, ctypes.c_void_p), 2, 10, None, 0, None)
+    assert rc == -1 and b"non-increasing" in l.snt_last_error()
+    ok = (ctypes.c_int32 * 2)(2, 1)
+    rc = l.snt_embed_pack_bwd_planned(None, None, 4, ctypes.cast(ok, ctypes.c_void_p), 2, 2, 8, 10, None, None, None, 0,
+                                      None)
+    assert rc == -1 and b"bad arguments" in l.snt_last_error()          # dx is NULL
     bs = (ctypes.c_int32 * 3)(2, 3, 1)   # not non-increasing
     rc = l.snt_embed_pack_fwd(None, None, None, 4, ctypes.cast(bs, ctypes.c_void_p), 3, 8, 10, None, None, None)
     assert rc == -1 and b"non-increasing" in l.snt_last_error()
@@ -172,3 +179,58 @@ def test_host_call_sequence_with_stub_binding(snt, monkeypatch):
     st.step(pooled, caps, b["lengths"], tg)
     assert calls[0] == "snt_head_fwd" and calls[-2:] == ["snt_head_bwd", "snt_clamp_adam_multi"] and st.t == 1
     assert len(st.m) == len(params) and all(m.shape == p.shape for m, p in zip(st.m, params))
+
+
+def test_experimental_switches_host_logic_with_stub_streams(snt, monkeypatch):
+    """SNT_TAIL_OVERLAP / SNT_EMB_PLAN_EARLY (off by default, first GPU run pending): their Python control flow through
+    fake streams and a recording binding - the plan call precedes the loss backward, the planned variant replaces the
+    one-call embedding backward, the head backward is fenced by two events."""
+    import contextlib
+    from show_and_tell_b200 import ops
+    calls, log = [], []
+
+    class Sizes:
+        def __getattr__(self, name):
+            if name.endswith("workspace_bytes"):
+                return lambda *a: 4096
+            raise AttributeError(name)
+
+    class FakeEvent:
+        def record(self, stream=None):
+            log.append("record")
+
+    class FakeStream:
+        def __init__(self, *a, **k):
+            pass
+
+        def wait_event(self, ev):
+            log.append("wait_event")
+
+        def wait_stream(self, st):
+            log.append("wait_stream")
+
+    monkeypatch.setattr(ops._lib, "lib", lambda: Sizes())
+    monkeypatch.setattr(ops, "call", lambda name, *a: calls.append(name))
+    monkeypatch.setattr(ops, "require_cuda", lambda *t: None)
+    monkeypatch.setattr(ops, "workspace", lambda nb, dev: torch.empty(max(int(nb), 1), dtype=torch.uint8))
+    monkeypatch.setattr(ops, "stream_ptr", lambda: None)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: FakeStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None)
+    monkeypatch.setattr(ops, "TAIL_OVERLAP", True)
+    monkeypatch.setattr(ops, "EMB_PLAN_EARLY", True)
+    monkeypatch.setattr(ops, "_side_streams", {})
+    torch.manual_seed(0)
+    enc, dec = snt.EncoderCNN(16, backbone=False), snt.DecoderRNN(16, 24, 50, 1)
+    b = snt.synthetic.make_batch(6, 50, seed=1, pooled_dim=2048)
+    pooled, caps = torch.from_numpy(b["pooled"]), torch.from_numpy(b["captions"])
+    tg = torch.from_numpy(snt.synthetic.pack_host(b["captions"], b["lengths"]))
+    dec.loss(enc.forward_pooled(pooled), caps, b["lengths"], tg).backward()
+    assert calls == ["snt_head_fwd", "snt_embed_pack_fwd", "snt_lstm_fwd", "snt_vocab_ce_fwd", "snt_embed_bwd_plan",
+                     "snt_vocab_ce_bwd", "snt_lstm_bwd", "snt_embed_pack_bwd_planned", "snt_head_bwd"]
+    # plan: wait_stream + record; dx complete: record; planned call: wait_event; head: wait_event, record, wait_event
+    assert log == ["wait_stream", "record", "record", "wait_event", "wait_event", "record", "wait_event"]
+    assert all(p.grad is not None for m in (enc, dec) for p in m.parameters() if p.requires_grad)
+    assert ops._tail is None
