@@ -8,6 +8,7 @@
 //           buffer, which two more tcgen05 contractions consume (dHs = dlogits.W_out, dW_out += dlogits^T.Hs).
 #include "bf16.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc_mc.cuh"
 #include "kernels.cuh"
 
 #include <stdlib.h>
@@ -473,7 +474,13 @@ int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const i
   make_sched(N, V, H, &ts);
   CeFwdEpi e;
   e.M = (int)N; e.V = (int)V; e.bias = b_out; e.part = w.part; e.targets = targets; e.tl = w.tl;
-  SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeFwdEpi>(ta, tb, ts, e, st)));
+  if (tc::mc_enabled()) {  // experimental: pairs of row tiles share the W_out tile through TMA multicast
+    CUtensorMap tbh;
+    SNT_CHECK(tc::make_operand_tmap(&tbh, w.wb, false, V, H, H, CE_BN / 2));
+    SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeFwdEpi>(ta, tbh, ts, e, st)));
+  } else {
+    SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeFwdEpi>(ta, tb, ts, e, st)));
+  }
   int* ticket = ce_ticket();
   if (!ticket) { set_error("vocab_ce_fwd: could not allocate the reduction ticket"); return SNT_EINVAL; }
   // w.nll doubles as the per-block partial sums (ceil(N/64) <= N floats)
@@ -505,6 +512,9 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
 
   const char* lazy_env = getenv("SNT_CEBWD_LAZY");
   const bool lazy_onehot = lazy_env && lazy_env[0] == '1';
+  const bool mc = tc::mc_enabled();  // experimental: W_out tiles shared by pairs of row tiles through TMA multicast
+  CUtensorMap tbh;
+  if (mc) SNT_CHECK(tc::make_operand_tmap(&tbh, w.wb, false, V, H, H, CE_BN / 2));
   SideStream* side = side_stream();
   for (int64_t r0 = 0; r0 < N; r0 += w.R) {
     const int64_t r = N - r0 < w.R ? N - r0 : w.R;
@@ -520,7 +530,13 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
       CeBwdEpiT<16, true> e;
       e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;
       e.out = w.dl; e.ldo = w.Vp;
-      SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeBwdEpiT<16, true>>(ta, tb, ts, e, st)));
+      if (mc) SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeBwdEpiT<16, true>>(ta, tbh, ts, e, st)));
+      else SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeBwdEpiT<16, true>>(ta, tb, ts, e, st)));
+    } else if (mc) {
+      CeBwdEpiT<16> e;
+      e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;
+      e.out = w.dl; e.ldo = w.Vp;
+      SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeBwdEpiT<16>>(ta, tbh, ts, e, st)));
     } else if (!getenv("SNT_CEBWD_W8")) {
       CeBwdEpiT<16> e;
       e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;

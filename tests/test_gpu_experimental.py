@@ -76,3 +76,32 @@ def test_lazy_onehot_epilogue_is_bit_identical(B, E, H, V):
             os.environ.pop("SNT_CEBWD_LAZY", None)
     for k in out[0]:
         assert np.array_equal(out[0][k], out[1][k]), k
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("B,E,H,V", [(10, 64, 128, 1000), (200, 64, 128, 1000), (203, 64, 256, 2500),
+                                     (1024, 256, 512, 10000)])
+def test_multicast_contraction_is_bit_identical(B, E, H, V):
+    """SNT_GEMM_MC=1: pairs of row tiles in a (2,1,1) cluster share the W_out tile through TMA multicast (fused CE forward
+    and the softmax-gradient recompute).  Same MMAs in the same order on the same operands: loss and gradients must
+    not change by a bit.  Row-tile counts here are 1, odd and even (the odd ones exercise the zero-filled partner)."""
+    import show_and_tell_b200 as snt
+    torch.manual_seed(0)
+    dec = snt.DecoderRNN(E, H, V, 1, precision="bf16").cuda()
+    b = snt.synthetic.make_batch(B, V, embed=E, seed=3)
+    feats, caps = torch.from_numpy(b["features"]).cuda(), torch.from_numpy(b["captions"]).cuda()
+    tg = torch.from_numpy(snt.synthetic.pack_host(b["captions"], b["lengths"])).cuda()
+    out = []
+    for mc in ("0", "1"):
+        os.environ["SNT_GEMM_MC"] = mc
+        try:
+            dec.zero_grad(set_to_none=True)
+            loss = dec.loss(feats, caps, b["lengths"], tg)
+            loss.backward()
+            torch.cuda.synchronize()
+            out.append((float(loss), {k: p.grad.detach().cpu().numpy().copy() for k, p in dec.named_parameters()}))
+        finally:
+            os.environ.pop("SNT_GEMM_MC", None)
+    assert out[0][0] == out[1][0]
+    for k in out[0][1]:
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k

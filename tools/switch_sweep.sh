@@ -5,7 +5,7 @@
 set -u
 mkdir -p gpurun_out
 B="python bench.py --steps 30 --warmup 5 --stages --no-cpu-baseline --no-gpu-reference --no-extras --no-greedy"
-SNT_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_experimental.py -q -x > gpurun_out/sweep_tests.log 2>&1
+SNT_TEST_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_gpu_experimental.py -q > gpurun_out/sweep_tests.log 2>&1
 echo "experimental tests rc=$? ($(tail -1 gpurun_out/sweep_tests.log))"
 run() {  # name, then VAR=1 ...
   local name=$1; shift
@@ -16,7 +16,7 @@ name = sys.argv[1]
 try:
     d = json.loads(open(f"gpurun_out/sweep_{name}.json").read().strip().splitlines()[-1])
     st = {e["stage"]: e["us_per_step"] for e in d["stages"]}
-    print(f"{name:18s} {d['ms_per_step']*1e3:8.1f} us/step  ce_bwd {st.get('snt_vocab_ce_bwd', 0):6.1f}  "
+    print(f"{name:18s} {d['ms_per_step']*1e3:8.1f} us/step  ce_fwd {st.get('snt_vocab_ce_fwd', 0):6.1f}  ce_bwd {st.get('snt_vocab_ce_bwd', 0):6.1f}  "
           f"embed_bwd {st.get('snt_embed_pack_bwd', st.get('snt_embed_pack_bwd_planned', 0)):6.1f}  "
           f"head_bwd {st.get('snt_head_bwd', 0):6.1f}  loss {d['loss']:.6f}")
 except Exception as e:
@@ -27,4 +27,5 @@ run baseline SNT_NOOP=1
 run lazy_onehot SNT_CEBWD_LAZY=1
 run tail_overlap SNT_TAIL_OVERLAP=1
 run plan_early SNT_EMB_PLAN_EARLY=1
-run all_three SNT_CEBWD_LAZY=1 SNT_TAIL_OVERLAP=1 SNT_EMB_PLAN_EARLY=1
+run multicast SNT_GEMM_MC=1
+run all_four SNT_CEBWD_LAZY=1 SNT_TAIL_OVERLAP=1 SNT_EMB_PLAN_EARLY=1 SNT_GEMM_MC=1
