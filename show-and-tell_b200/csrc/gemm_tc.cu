@@ -2,6 +2,7 @@
 // the library has no link-time dependency on libcuda and still loads on a machine without a GPU), tile-shape
 // and split-K selection, the deterministic split-K reduction and the exported snt_gemm_bf16.
 #include "gemm_tc.cuh"
+#include "gemm_tc_mc.cuh"
 
 #include <atomic>
 #include <stdlib.h>
@@ -119,7 +120,8 @@ int choose_splits(int64_t M, int64_t N, int64_t K, int bn) {
 template <int BN, bool A_MN, bool B_MN>
 static int run_plain(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, int64_t M, int64_t N,
                      float alpha, float beta, float* C, __nv_bfloat16* Cb, int64_t ldc, const float* bias,
-                     int64_t split_stride, cudaStream_t st, int perm, const float* adev) {
+                     int64_t split_stride, cudaStream_t st, int perm, const float* adev,
+                     const CUtensorMap* tb_mc) {
   if (BN == 256 && ts.kblocks_per_split <= 8 && !getenv("SNT_NO_WIDE_EPI")) {  // short K: epilogue-bound
     PlainEpi<256, true> e;
     e.M = (int)M; e.N = (int)N; e.alpha = alpha; e.beta = beta; e.C = C; e.Cb = Cb; e.ldc = ldc; e.bias = bias;
@@ -129,17 +131,22 @@ static int run_plain(const CUtensorMap& ta, const CUtensorMap& tb, const TileSch
   PlainEpi<BN> e;
   e.M = (int)M; e.N = (int)N; e.alpha = alpha; e.beta = beta; e.C = C; e.Cb = Cb; e.ldc = ldc; e.bias = bias;
   e.split_stride = split_stride; e.row_perm_h = perm; e.alpha_dev = adev;
+  if constexpr (BN >= 128) {
+    // experimental (SNT_GEMM_MC=1): pairs of row tiles share the B tile through TMA multicast (gemm_tc_mc.cuh)
+    if (tb_mc != nullptr) return launch_gemm_tc_mc<BN, A_MN, B_MN, PlainEpi<BN>>(ta, *tb_mc, ts, e, st);
+  }
   return launch_gemm_tc<BN, A_MN, B_MN, PlainEpi<BN>>(ta, tb, ts, e, st);
 }
 
 template <int BN>
 static int run_plain_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts,
                            int64_t M, int64_t N, float alpha, float beta, float* C, __nv_bfloat16* Cb, int64_t ldc,
-                           const float* bias, int64_t split_stride, cudaStream_t st, int perm, const float* adev) {
-  if (!a_mn && !b_mn) return run_plain<BN, false, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev);
-  if (!a_mn && b_mn) return run_plain<BN, false, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev);
-  if (a_mn && !b_mn) return run_plain<BN, true, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev);
-  return run_plain<BN, true, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev);
+                           const float* bias, int64_t split_stride, cudaStream_t st, int perm, const float* adev,
+                           const CUtensorMap* tb_mc) {
+  if (!a_mn && !b_mn) return run_plain<BN, false, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev, tb_mc);
+  if (!a_mn && b_mn) return run_plain<BN, false, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev, tb_mc);
+  if (a_mn && !b_mn) return run_plain<BN, true, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev, tb_mc);
+  return run_plain<BN, true, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev, tb_mc);
 }
 
 int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A,
@@ -178,10 +185,22 @@ int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, 
     out = split_ws; outb = nullptr; e_beta = 0.f; e_bias = nullptr;
     split_stride = M * ldc;
   }
+  // experimental (SNT_GEMM_MC=1): cluster-multicast variant for contractions with at least two row tiles.  A K-major B is
+  // fetched in two half-tile boxes (its own tensor map); an MN-major B already comes in 64-row boxes.
+  CUtensorMap tb_half;
+  const CUtensorMap* tb_mc = nullptr;
+  if (bn >= 128 && ts.num_m >= 2 && mc_enabled()) {
+    if (!b_mn) {
+      SNT_CHECK(make_operand_tmap(&tb_half, B, false, N, K, ldb, bn / 2));
+      tb_mc = &tb_half;
+    } else {
+      tb_mc = &tb;
+    }
+  }
   int rc;
-  if (bn == 256) rc = run_plain_major<256>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev);
-  else if (bn == 128) rc = run_plain_major<128>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev);
-  else rc = run_plain_major<64>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev);
+  if (bn == 256) rc = run_plain_major<256>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev, tb_mc);
+  else if (bn == 128) rc = run_plain_major<128>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev, tb_mc);
+  else rc = run_plain_major<64>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev, nullptr);
   SNT_CHECK(rc);
   if (splits > 1 && !keep_partials) {
     const int64_t total = M * N;

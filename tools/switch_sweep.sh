@@ -1,12 +1,15 @@
 #!/usr/bin/env bash
 # One gpurun call that answers "do the experimental switches work, and what do they buy?" (DESIGN.md §8).
-#   /usr/local/graft/bin/gpurun --timeout 420 -- 'bash tools/switch_sweep.sh'
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/switch_sweep.sh'
 # Results land in gpurun_out/sweep_*.{json,err}; the last lines printed are a summary table.
 set -u
 mkdir -p gpurun_out
 B="python bench.py --steps 30 --warmup 5 --stages --no-cpu-baseline --no-gpu-reference --no-extras --no-greedy"
 SNT_TEST_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_gpu_experimental.py -q > gpurun_out/sweep_tests.log 2>&1
 echo "experimental tests rc=$? ($(tail -1 gpurun_out/sweep_tests.log))"
+# the whole GEMM / parity suites once more with the multicast contraction switched on everywhere it applies
+SNT_GEMM_MC=1 timeout 300 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_parity.py -q -m gpu > gpurun_out/sweep_mc_suite.log 2>&1
+echo "suite under SNT_GEMM_MC=1 rc=$? ($(tail -1 gpurun_out/sweep_mc_suite.log))"
 run() {  # name, then VAR=1 ...
   local name=$1; shift
   env "$@" timeout 120 $B > gpurun_out/sweep_$name.json 2> gpurun_out/sweep_$name.err
