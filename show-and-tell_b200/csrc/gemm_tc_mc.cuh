@@ -1,9 +1,10 @@
 // EXPERIMENTAL (written at the end of round 1 without a GPU run; opt-in through SNT_GEMM_MC=1).
 //
-// Cluster-multicast variant of the contraction core in gemm_tc.cuh: two CTAs of a (2,1,1) cluster work on two row
-// tiles (m, m+1) of the SAME column tile n, so they need the same B tile.  Each CTA fetches its own A tile and HALF of
-// the B tile; the B halves are TMA-multicast into both CTAs' shared memory.  Per k-block a CTA then pulls
-// 16 KB (A) + BN/2 x 128 B from L2 instead of 16 KB + BN x 128 B: 32 KB instead of 48 KB at BN = 256.
+// Cluster-multicast variant of the contraction core in gemm_tc.cuh: the CL (2 or 4) CTAs of a (CL,1,1) cluster work on CL
+// row tiles of the SAME column tile n, so they need the same B tile.  Each CTA fetches its own A tile and 1/CL of the
+// B tile; the B parts are TMA-multicast into every CTA's shared memory.  Per k-block a CTA then pulls
+// 16 KB (A) + BN/CL x 128 B from L2 instead of 16 KB + BN x 128 B: 32 KB (CL = 2) or 24 KB (CL = 4) instead of 48 KB at
+// BN = 256.
 //
 // Why: at 128 x 256 x 64 tiles a CTA moves 48 KB per 4.2 MFLOP; 148 SMs at the ~1000 TFLOP/s these kernels reach pull
 // ~11.4 TB/s out of L2, which is where every large contraction of the step saturates (fused CE forward 71 % of the
@@ -25,13 +26,14 @@
 namespace snt {
 namespace tc {
 
-template <int BN, bool A_MN, bool B_MN, class Epi>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CL = 2>
 __global__ void __launch_bounds__(128 + 32 * Epi::kWarps, 1)
 gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const TileSched ts, const Epi epi) {
-  static_assert(BN >= 128, "the B tile is split in two halves of whole 64-row boxes");
+  static_assert(CL == 2 || CL == 4, "clusters of 2 or 4 row tiles");
+  static_assert(BN / CL >= 64, "the B tile is split into CL parts of whole 64-row boxes");
   using C = Cfg<BN, Epi::kStages>;
-  constexpr uint16_t CMASK = 0x3;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -51,7 +53,7 @@ gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 2);  // released by the MMA issuer of each CTA of the pair
+      mbar_init(&empty[i], CL);  // released by the MMA issuer of every CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -69,10 +71,10 @@ gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   cluster_sync_all();  // the peer's barriers are initialised before any multicast traffic or remote arrive
   const uint32_t tmem_base = *tmem_slot;
   const int crank = (int)cluster_ctarank();
-  const int cluster_id = (int)(blockIdx.x >> 1), n_clusters = (int)(gridDim.x >> 1);
+  const int cluster_id = (int)(blockIdx.x / CL), n_clusters = (int)(gridDim.x / CL);
 
-  TileSched tp = ts;  // the same enumeration over PAIRS of row tiles
-  tp.num_m = (ts.num_m + 1) / 2;
+  TileSched tp = ts;  // the same enumeration over GROUPS of CL row tiles ("pairs" below, for CL = 2)
+  tp.num_m = (ts.num_m + CL - 1) / CL;
   const int total_pairs = tp.num_m * tp.num_n * tp.splits;
 
   if (warp == 0) {
@@ -84,14 +86,14 @@ gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
         int mp, n_blk, split;
         decode_tile(tp, pair, mp, n_blk, split);
-        const int m_blk = 2 * mp + crank;  // may be == ts.num_m (odd row-tile count): TMA zero-fills that A box
+        const int m_blk = CL * mp + crank;  // may be >= ts.num_m (ragged last group): TMA zero-fills that A box
         const int kb0 = split * ts.kblocks_per_split;
         const int kb1 = min(kb0 + ts.kblocks_per_split, ts.kblocks);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);  // both CTAs have finished reading this stage
           uint8_t* sA = smem + stage * C::STAGE_BYTES;
           uint8_t* sB = sA + C::A_BYTES;
-          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);  // own A + own B half + the peer's B half
+          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);  // own A + own B part + the peers' B parts
           if (!A_MN) {
             tma_load_2d(sA, &tmA, &full[stage], kb * BK, ts.a_row0 + m_blk * BM);
           } else {
@@ -100,13 +102,13 @@ gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_load_2d(sA + h * (BK * 128), &tmA, &full[stage], ts.a_row0 + m_blk * BM + h * 64, kb * BK);
           }
           if (!B_MN) {
-            // tmB's box is {BK, BN/2}: rows [crank*BN/2, +BN/2) of the B tile, 128 swizzled bytes per row
-            tma_load_2d_mc(sB + crank * (BN / 2) * 128, &tmB, &full[stage], kb * BK,
-                           ts.b_row0 + n_blk * BN + crank * (BN / 2), CMASK);
+            // tmB's box is {BK, BN/CL}: rows [crank*BN/CL, +BN/CL) of the B tile, 128 swizzled bytes per row
+            tma_load_2d_mc(sB + crank * (BN / CL) * 128, &tmB, &full[stage], kb * BK,
+                           ts.b_row0 + n_blk * BN + crank * (BN / CL), CMASK);
           } else {
 #pragma unroll
-            for (int q = 0; q < BN / 128; ++q) {
-              const int h = crank * (BN / 128) + q;
+            for (int q = 0; q < BN / (64 * CL); ++q) {
+              const int h = crank * (BN / (64 * CL)) + q;
               tma_load_2d_mc(sB + h * (BK * 128), &tmB, &full[stage], ts.b_row0 + n_blk * BN + h * 64, kb * BK, CMASK);
             }
           }
@@ -142,7 +144,7 @@ gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                      : make_smem_desc(b_addr + k * 32, 16, 1024);
             umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit_mc(&empty[stage], CMASK);  // one arrival on this stage's empty barrier in BOTH CTAs
+          umma_commit_mc(&empty[stage], CMASK);  // one arrival on this stage's empty barrier in EVERY CTA of the cluster
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);
@@ -158,7 +160,7 @@ gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
       int mp, n_blk, split;
       decode_tile(tp, pair, mp, n_blk, split);
-      const int m_blk = 2 * mp + crank;
+      const int m_blk = CL * mp + crank;
       const bool valid = m_blk < ts.num_m;  // warp-uniform
       typename Epi::Pre pre;
       if (valid) epi.prefetch(pre, m_blk, n_blk, ew, lane);
@@ -182,29 +184,29 @@ gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-// tmB must have been made with box rows BN/2 when B is K-major (make_operand_tmap(..., BN / 2)); MN-major B uses the
+// tmB must have been made with box rows BN/CL when B is K-major (make_operand_tmap(..., BN / CL)); MN-major B uses the
 // ordinary map (its boxes are 64 rows already).
-template <int BN, bool A_MN, bool B_MN, class Epi>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CL = 2>
 int launch_gemm_tc_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TileSched& ts, const Epi& epi,
                       cudaStream_t st) {
   using C = Cfg<BN, Epi::kStages>;
-  auto kern = gemm_tc_mc_kernel<BN, A_MN, B_MN, Epi>;
+  auto kern = gemm_tc_mc_kernel<BN, A_MN, B_MN, Epi, CL>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     SNT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::SMEM_BYTES + Epi::kWarps * Epi::kSmemPerWarp));
     configured = true;
   }
-  const int pairs = ((ts.num_m + 1) / 2) * ts.num_n * ts.splits;
+  const int pairs = ((ts.num_m + CL - 1) / CL) * ts.num_n * ts.splits;
   if (pairs <= 0) return SNT_OK;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2);
+  cfg.gridDim = dim3(CL);
   cfg.blockDim = dim3(128 + 32 * Epi::kWarps);
   cfg.dynamicSmemBytes = C::SMEM_BYTES + Epi::kWarps * Epi::kSmemPerWarp;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -216,22 +218,27 @@ int launch_gemm_tc_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tile
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
       (void)cudaGetLastError();
-      n = sm_count() / 2;
+      n = sm_count() / CL;
     }
     resident = n;
   }
-  int clusters = min(pairs, min(resident, grid_sms() / 2));
-  if (clusters <= 0) { set_error("launch_gemm_tc_mc: no SM pair available"); return SNT_EINVAL; }
-  cfg.gridDim = dim3((unsigned)(2 * clusters));
+  int clusters = min(pairs, min(resident, grid_sms() / CL));
+  if (clusters <= 0) { set_error("launch_gemm_tc_mc: no SM group available"); return SNT_EINVAL; }
+  cfg.gridDim = dim3((unsigned)(CL * clusters));
   count_launch();
   SNT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, ts, epi));
   return SNT_OK;
 }
 
-inline bool mc_enabled() {
+// SNT_GEMM_MC: unset / 0 = off, 1 or 2 = clusters of 2, 4 = clusters of 4 (only where a 4-way instantiation exists)
+inline int mc_cluster() {
   const char* e = getenv("SNT_GEMM_MC");
-  return e && e[0] == '1';
+  if (!e) return 0;
+  if (e[0] == '1' || e[0] == '2') return 2;
+  if (e[0] == '4') return 4;
+  return 0;
 }
+inline bool mc_enabled() { return mc_cluster() != 0; }
 
 }  // namespace tc
 }  // namespace snt

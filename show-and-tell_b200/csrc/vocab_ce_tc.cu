@@ -474,10 +474,11 @@ int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const i
   make_sched(N, V, H, &ts);
   CeFwdEpi e;
   e.M = (int)N; e.V = (int)V; e.bias = b_out; e.part = w.part; e.targets = targets; e.tl = w.tl;
-  if (tc::mc_enabled()) {  // experimental: pairs of row tiles share the W_out tile through TMA multicast
+  if (const int cl = tc::mc_cluster()) {  // experimental: 2 or 4 row tiles share the W_out tile through TMA multicast
     CUtensorMap tbh;
-    SNT_CHECK(tc::make_operand_tmap(&tbh, w.wb, false, V, H, H, CE_BN / 2));
-    SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeFwdEpi>(ta, tbh, ts, e, st)));
+    SNT_CHECK(tc::make_operand_tmap(&tbh, w.wb, false, V, H, H, CE_BN / cl));
+    if (cl == 4) SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeFwdEpi, 4>(ta, tbh, ts, e, st)));
+    else SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeFwdEpi, 2>(ta, tbh, ts, e, st)));
   } else {
     SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeFwdEpi>(ta, tb, ts, e, st)));
   }
@@ -512,9 +513,10 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
 
   const char* lazy_env = getenv("SNT_CEBWD_LAZY");
   const bool lazy_onehot = lazy_env && lazy_env[0] == '1';
-  const bool mc = tc::mc_enabled();  // experimental: W_out tiles shared by pairs of row tiles through TMA multicast
+  const int mc_cl = tc::mc_cluster();  // experimental: W_out tiles shared by 2 or 4 row tiles through TMA multicast
+  const bool mc = mc_cl != 0;
   CUtensorMap tbh;
-  if (mc) SNT_CHECK(tc::make_operand_tmap(&tbh, w.wb, false, V, H, H, CE_BN / 2));
+  if (mc) SNT_CHECK(tc::make_operand_tmap(&tbh, w.wb, false, V, H, H, CE_BN / (lazy_onehot ? 2 : mc_cl)));
   SideStream* side = side_stream();
   for (int64_t r0 = 0; r0 < N; r0 += w.R) {
     const int64_t r = N - r0 < w.R ? N - r0 : w.R;
@@ -536,7 +538,8 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
       CeBwdEpiT<16> e;
       e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;
       e.out = w.dl; e.ldo = w.Vp;
-      SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeBwdEpiT<16>>(ta, tbh, ts, e, st)));
+      if (mc_cl == 4) SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeBwdEpiT<16>, 4>(ta, tbh, ts, e, st)));
+      else SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeBwdEpiT<16>, 2>(ta, tbh, ts, e, st)));
     } else if (!getenv("SNT_CEBWD_W8")) {
       CeBwdEpiT<16> e;
       e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;

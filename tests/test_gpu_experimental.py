@@ -79,11 +79,12 @@ def test_lazy_onehot_epilogue_is_bit_identical(B, E, H, V):
 
 
 @pytest.mark.timeout(180)
+@pytest.mark.parametrize("cl", ["2", "4"])
 @pytest.mark.parametrize("B,E,H,V", [(10, 64, 128, 1000), (200, 64, 128, 1000), (203, 64, 256, 2500),
                                      (1024, 256, 512, 10000)])
-def test_multicast_contraction_is_bit_identical(B, E, H, V):
-    """SNT_GEMM_MC=1: pairs of row tiles in a (2,1,1) cluster share the W_out tile through TMA multicast (fused CE forward
-    and the softmax-gradient recompute).  Same MMAs in the same order on the same operands: loss and gradients must
+def test_multicast_contraction_is_bit_identical(B, E, H, V, cl):
+    """SNT_GEMM_MC=2|4: 2 or 4 row tiles in a (CL,1,1) cluster share the W_out tile through TMA multicast (fused CE
+    forward and the softmax-gradient recompute; every other contraction with wide tiles uses pairs).  Same MMAs in the same order on the same operands: loss and gradients must
     not change by a bit.  Row-tile counts here are 1, odd and even (the odd ones exercise the zero-filled partner)."""
     import show_and_tell_b200 as snt
     torch.manual_seed(0)
@@ -92,7 +93,7 @@ def test_multicast_contraction_is_bit_identical(B, E, H, V):
     feats, caps = torch.from_numpy(b["features"]).cuda(), torch.from_numpy(b["captions"]).cuda()
     tg = torch.from_numpy(snt.synthetic.pack_host(b["captions"], b["lengths"])).cuda()
     out = []
-    for mc in ("0", "1"):
+    for mc in ("0", cl):
         os.environ["SNT_GEMM_MC"] = mc
         try:
             dec.zero_grad(set_to_none=True)

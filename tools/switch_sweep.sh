@@ -8,8 +8,8 @@ B="python bench.py --steps 30 --warmup 5 --stages --no-cpu-baseline --no-gpu-ref
 SNT_TEST_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_gpu_experimental.py -q > gpurun_out/sweep_tests.log 2>&1
 echo "experimental tests rc=$? ($(tail -1 gpurun_out/sweep_tests.log))"
 # the whole GEMM / parity suites once more with the multicast contraction switched on everywhere it applies
-SNT_GEMM_MC=1 timeout 300 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_parity.py -q -m gpu > gpurun_out/sweep_mc_suite.log 2>&1
-echo "suite under SNT_GEMM_MC=1 rc=$? ($(tail -1 gpurun_out/sweep_mc_suite.log))"
+SNT_GEMM_MC=2 timeout 300 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_parity.py -q -m gpu > gpurun_out/sweep_mc_suite.log 2>&1
+echo "suite under SNT_GEMM_MC=2 rc=$? ($(tail -1 gpurun_out/sweep_mc_suite.log))"
 run() {  # name, then VAR=1 ...
   local name=$1; shift
   env "$@" timeout 120 $B > gpurun_out/sweep_$name.json 2> gpurun_out/sweep_$name.err
@@ -30,5 +30,6 @@ run baseline SNT_NOOP=1
 run lazy_onehot SNT_CEBWD_LAZY=1
 run tail_overlap SNT_TAIL_OVERLAP=1
 run plan_early SNT_EMB_PLAN_EARLY=1
-run multicast SNT_GEMM_MC=1
-run all_four SNT_CEBWD_LAZY=1 SNT_TAIL_OVERLAP=1 SNT_EMB_PLAN_EARLY=1 SNT_GEMM_MC=1
+run multicast2 SNT_GEMM_MC=2
+run multicast4 SNT_GEMM_MC=4
+run all_four SNT_CEBWD_LAZY=1 SNT_TAIL_OVERLAP=1 SNT_EMB_PLAN_EARLY=1 SNT_GEMM_MC=2
