@@ -106,3 +106,22 @@ def test_multicast_contraction_is_bit_identical(B, E, H, V, cl):
     assert out[0][0] == out[1][0]
     for k in out[0][1]:
         assert np.array_equal(out[0][1][k], out[1][1][k]), k
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("cl", ["2", "4"])
+@pytest.mark.parametrize("B", [1, 130, 4096])
+def test_multicast_greedy_tokens_identical(B, cl):
+    """The vocabulary contraction of the greedy decode (argmax epilogue) with the multicast core: same tokens."""
+    import show_and_tell_b200 as snt
+    torch.manual_seed(1)
+    dec = snt.DecoderRNN(256, 512, 10000, 1).cuda().eval()
+    feats = torch.randn(B, 256, device="cuda")
+    ref = dec.sample(feats, precision="bf16").reshape(B, 20)
+    os.environ["SNT_GEMM_MC"] = cl
+    try:
+        got = dec.sample(feats, precision="bf16").reshape(B, 20)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("SNT_GEMM_MC", None)
+    assert torch.equal(ref, got)

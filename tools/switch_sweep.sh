@@ -33,3 +33,19 @@ run plan_early SNT_EMB_PLAN_EARLY=1
 run multicast2 SNT_GEMM_MC=2
 run multicast4 SNT_GEMM_MC=4
 run all_four SNT_CEBWD_LAZY=1 SNT_TAIL_OVERLAP=1 SNT_EMB_PLAN_EARLY=1 SNT_GEMM_MC=2
+# greedy decode (configs[2]) with and without the multicast vocabulary contraction
+for mc in 0 2 4; do
+  SNT_GEMM_MC=$mc timeout 120 python - <<'PY'
+import os, time, torch
+import show_and_tell_b200 as snt
+torch.manual_seed(0)
+dec = snt.DecoderRNN(256, 512, 10000, 1).cuda().eval()
+f = torch.randn(4096, 256, device="cuda")
+dec.sample(f, precision="bf16"); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5): dec.sample(f, precision="bf16")
+e1.record(); torch.cuda.synchronize()
+print(f"greedy bf16 SNT_GEMM_MC={os.environ.get('SNT_GEMM_MC')}: {4096 * 20 * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e6:.1f} M tokens/s")
+PY
+done
