@@ -49,3 +49,4 @@ e1.record(); torch.cuda.synchronize()
 print(f"greedy bf16 SNT_GEMM_MC={os.environ.get('SNT_GEMM_MC')}: {4096 * 20 * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e6:.1f} M tokens/s")
 PY
 done
+timeout 240 python tools/gemm_step_shapes.py 2>&1 | tee gpurun_out/sweep_gemm_shapes.txt
