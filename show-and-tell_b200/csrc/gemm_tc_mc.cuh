@@ -20,6 +20,11 @@
 //     before exit (no CTA may leave while its peer can still write into it);
 //   * tiles are handed out to clusters in pairs of row tiles; an odd last row tile is paired with an out-of-range one,
 //     whose A box is zero-filled by TMA and whose epilogue is skipped.
+//
+// Desk checks done without a GPU: tools/mc_pipeline_sim.py replays this barrier protocol (producer / MMA issuer / epilogue
+// of CL CTAs, random latencies) and asserts deadlock freedom, that no stage is overwritten while a consumer may still
+// read it, and that every consumer sees exactly its round's bytes; the tile enumeration was checked to cover every
+// (m, n, split) exactly once; tools/sass_diff.py shows the validated kernels' SASS untouched.
 #pragma once
 #include "gemm_tc.cuh"
 
