@@ -6,9 +6,10 @@
 // 16 KB (A) + BN/CL x 128 B from L2 instead of 16 KB + BN x 128 B: 32 KB (CL = 2) or 24 KB (CL = 4) instead of 48 KB at
 // BN = 256.
 //
-// Why: at 128 x 256 x 64 tiles a CTA moves 48 KB per 4.2 MFLOP; 148 SMs at the ~1000 TFLOP/s these kernels reach pull
-// ~11.4 TB/s out of L2, which is where every large contraction of the step saturates (fused CE forward 71 % of the
-// sustained cuBLAS rate, the CE-backward contractions 57-74 %).  cuBLAS reaches 1400 with 2-SM tiles for the same reason.
+// Why (a hypothesis to measure, tools/gemm_step_shapes.py): at 128 x 256 x 64 tiles a CTA requests 48 KB per 4.2 MFLOP; 148
+// SMs at ~1000 TFLOP/s ask L2 for ~11.4 TB/s, about what its slices deliver chip-wide, and cuBLAS uses 2-SM tiles for
+// that reason.  Against it: the same core reaches 1337 TFLOP/s on 8192^3, where L2 de-duplicates the tiles many CTAs of a
+// wave request together - the short-K vocabulary contractions may be epilogue-bound instead.
 //
 // Everything else - tile shape, swizzle, descriptors, the epilogue functors, the double-buffered accumulator - is the
 // validated code of gemm_tc.cuh, used unchanged.  The pipeline differences, all mirrored from the cluster mode of the
