@@ -142,6 +142,26 @@ int snt_vocab_ce_bwd(int prec, const void* hs, const float* w_out, const float* 
                      int64_t N, int64_t H, int64_t V, float* d_hs, float* d_w_out, float* d_b_out,
                      void* ws, int64_t ws_bytes, void* stream);
 
+/* ---- a8+a9+a10, training variant: the logits contraction runs ONCE per step (SNT_PREC_BF16 only) -----------
+ * Same mathematics as snt_vocab_ce_fwd + snt_vocab_ce_bwd (models.py:53 + train.py:53,143-144), for callers that
+ * know at forward time that a backward follows.  The forward stores the softmax numerators
+ * u[n,v] = exp(logit[n,v] - c[n]) as bf16 (c[n]: a per-row shift taken from the first 256 vocabulary columns, so no
+ * second sweep over the logits is needed), patches the one-hot into the stored row and saves 1/sum_v u;  the backward
+ * is then two contractions over `u`, without recomputing the logits.  Caller-owned, carried from fwd to bwd:
+ *   u [N, ldu] bf16 with ldu = (V+7)/8*8,  inv_s [N] fp32,  hs_scaled [N,H] bf16,  w_bf16 [V,H] bf16.
+ * A row whose largest logit exceeds the largest of its first 256 logits by more than ~88 would overflow: device flag
+ * bit 2 (snt_read_flags) is raised and the loss is non-finite; use the two-call path above for such models.
+ * Returns SNT_EUNSUPPORTED for SNT_PREC_FP32. */
+int64_t snt_vocab_ce_train_workspace_bytes(int prec, int64_t N, int64_t H, int64_t V);
+int snt_vocab_ce_train_fwd(int prec, const void* hs, const float* w_out, const float* b_out,
+                           const int64_t* targets, int64_t N, int64_t H, int64_t V, float* lse, float* loss,
+                           void* u, float* inv_s, void* hs_scaled, void* w_bf16,
+                           void* ws, int64_t ws_bytes, void* stream);
+int snt_vocab_ce_train_bwd(int prec, const void* u, const float* inv_s, const void* hs_scaled,
+                           const void* w_bf16, const float* dloss, float grad_scale,
+                           int64_t N, int64_t H, int64_t V, float* d_hs, float* d_w_out, float* d_b_out,
+                           void* ws, int64_t ws_bytes, void* stream);
+
 /* ---- a12  greedy decode  (models.py:56-67: fixed `steps` iterations, first-index argmax) ---------------
  * Per-layer weight pointer arrays are [host] arrays of device pointers.  h0/c0 [L,B,H] may be NULL
  * (zeros).  ids[B,steps] int64. */

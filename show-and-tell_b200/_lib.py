@@ -54,6 +54,11 @@ SIGNATURES = {
     "snt_vocab_ce_fwd": (_int, [_int, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
     "snt_vocab_ce_bwd": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i64, _i64, _vp, _vp, _vp,
                                 _vp, _i64, _vp]),
+    "snt_vocab_ce_train_workspace_bytes": (_i64, [_int, _i64, _i64, _i64]),
+    "snt_vocab_ce_train_fwd": (_int, [_int, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _i64, _vp]),
+    "snt_vocab_ce_train_bwd": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i64, _i64, _vp, _vp, _vp,
+                                      _vp, _i64, _vp]),
     "snt_greedy_workspace_bytes": (_i64, [_int, _i64, _i64, _i64, _i64, _int]),
     "snt_greedy_decode": (_int, [_int, _vp, _vp, _int, _pp, _pp, _pp, _pp, _vp, _vp, _vp, _vp,
                                  _i64, _i64, _i64, _i64, _int, _vp, _vp, _i64, _vp]),

@@ -346,6 +346,41 @@ extern "C" int snt_vocab_ce_bwd(int prec, const void* hs, const float* w_out, co
   return SNT_OK;
 }
 
+// training variant with stored softmax numerators: one logits contraction per step (bf16 mode only)
+extern "C" int64_t snt_vocab_ce_train_workspace_bytes(int prec, int64_t N, int64_t H, int64_t V) {
+  if (prec != SNT_PREC_BF16 || N < 1 || H < 1 || V < 1) return -1;
+  return bf16::vocab_ce_train_ws_bytes(N, H, V);
+}
+
+extern "C" int snt_vocab_ce_train_fwd(int prec, const void* hs, const float* w_out, const float* b_out,
+                                      const int64_t* targets, int64_t N, int64_t H, int64_t V, float* lse,
+                                      float* loss, void* u, float* inv_s, void* hs_scaled, void* w_bf16, void* ws,
+                                      int64_t ws_bytes, void* stream) {
+  if (prec != SNT_PREC_BF16) {
+    set_error("snt_vocab_ce_train_fwd: SNT_PREC_BF16 only (use snt_vocab_ce_fwd/bwd in fp32 mode)");
+    return SNT_EUNSUPPORTED;
+  }
+  SNT_REQUIRE(N >= 1 && H >= 1 && V >= 1 && hs && w_out && b_out && targets && lse && loss && u && inv_s &&
+                  hs_scaled && w_bf16,
+              "snt_vocab_ce_train_fwd: bad arguments");
+  return bf16::vocab_ce_train_fwd(hs, w_out, b_out, targets, N, H, V, lse, loss, u, inv_s, hs_scaled, w_bf16, ws,
+                                  ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int snt_vocab_ce_train_bwd(int prec, const void* u, const float* inv_s, const void* hs_scaled,
+                                      const void* w_bf16, const float* dloss, float grad_scale, int64_t N,
+                                      int64_t H, int64_t V, float* d_hs, float* d_w_out, float* d_b_out, void* ws,
+                                      int64_t ws_bytes, void* stream) {
+  if (prec != SNT_PREC_BF16) {
+    set_error("snt_vocab_ce_train_bwd: SNT_PREC_BF16 only");
+    return SNT_EUNSUPPORTED;
+  }
+  SNT_REQUIRE(N >= 1 && H >= 1 && V >= 1 && u && inv_s && hs_scaled && w_bf16 && d_hs && d_w_out && d_b_out,
+              "snt_vocab_ce_train_bwd: bad arguments");
+  return bf16::vocab_ce_train_bwd(u, inv_s, hs_scaled, w_bf16, dloss, grad_scale, N, H, V, d_hs, d_w_out, d_b_out,
+                                  ws, ws_bytes, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // a12: greedy decode
 // ------------------------------------------------------------------------------------------------------------

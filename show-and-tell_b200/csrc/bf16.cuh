@@ -35,9 +35,20 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
                  const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
                  float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st);
 
-// out[c] = beta*out[c] + sum_r in[r*ld + c] for a bf16 matrix; partial needs ((R+255)/256)*C floats
+// Training path with stored softmax numerators (vocab_ce_tc.cu): the logits contraction runs once per step.
+// u [N, pad8(V)] bf16, inv_s [N], hs_scaled [N,H] bf16 and w_bf16 [V,H] bf16 are caller-owned and carried from fwd to bwd.
+int64_t vocab_ce_train_ws_bytes(int64_t N, int64_t H, int64_t V);
+int vocab_ce_train_fwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, int64_t N,
+                       int64_t H, int64_t V, float* lse, float* loss, void* u, float* inv_s, void* hs_scaled,
+                       void* w_bf16, void* ws, int64_t ws_bytes, cudaStream_t st);
+int vocab_ce_train_bwd(const void* u, const float* inv_s, const void* hs_scaled, const void* w_bf16,
+                       const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
+                       float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st);
+
+// out[c] = beta*out[c] + sum_r roww[r] * in[r*ld + c] for a bf16 matrix (roww = NULL: unweighted); partial needs
+// ((R+255)/256)*C floats
 int colsum_bf16(const __nv_bfloat16* in, int64_t R, int64_t C, int64_t ld, float beta, float* out, float* partial,
-                cudaStream_t st);
+                cudaStream_t st, const float* roww = nullptr);
 
 int64_t greedy_ws_bytes(int64_t B, int64_t E, int64_t H, int64_t V, int L);
 int greedy_decode(const float* features, const float* w_emb, int L, const float* const* w_ih,

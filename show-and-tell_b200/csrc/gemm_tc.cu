@@ -2,7 +2,6 @@
 // the library has no link-time dependency on libcuda and still loads on a machine without a GPU), tile-shape
 // and split-K selection, the deterministic split-K reduction and the exported snt_gemm_bf16.
 #include "gemm_tc.cuh"
-#include "gemm_tc_mc.cuh"
 
 #include <atomic>
 #include <stdlib.h>
@@ -94,6 +93,30 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t M, int64_
   }
   if (Cb) Cb[o] = __float2bfloat16_rn(s);
 }
+// same, four columns per thread (N, ldc, split_stride multiples of 4, 16-byte aligned bases, fp32 output only); the
+// partial slices are read once and never again: streaming loads
+__global__ void __launch_bounds__(256)
+splitk_reduce4_kernel(const float* __restrict__ ws, int splits, int64_t M, int64_t N4, int64_t ldc,
+                      int64_t split_stride, float beta, const float* __restrict__ bias, float* __restrict__ C) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= M * N4) return;
+  const int64_t m = i / N4, n = (i - m * N4) * 4;
+  const int64_t o = m * ldc + n;
+  float4 s = __ldcs(reinterpret_cast<const float4*>(ws + o));
+  for (int k = 1; k < splits; ++k) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(ws + (int64_t)k * split_stride + o));
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  if (bias) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
+    s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+  }
+  if (beta != 0.f) {
+    const float4 c = *reinterpret_cast<const float4*>(C + o);
+    s.x += beta * c.x; s.y += beta * c.y; s.z += beta * c.z; s.w += beta * c.w;
+  }
+  *reinterpret_cast<float4*>(C + o) = s;
+}
 
 int64_t gemm_tc_split_ws_elems(int64_t M, int64_t ldc, int splits) { return splits > 1 ? splits * M * ldc : 0; }
 
@@ -120,39 +143,33 @@ int choose_splits(int64_t M, int64_t N, int64_t K, int bn) {
 template <int BN, bool A_MN, bool B_MN>
 static int run_plain(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, int64_t M, int64_t N,
                      float alpha, float beta, float* C, __nv_bfloat16* Cb, int64_t ldc, const float* bias,
-                     int64_t split_stride, cudaStream_t st, int perm, const float* adev,
-                     const CUtensorMap* tb_mc) {
+                     int64_t split_stride, cudaStream_t st, int perm, const float* adev, const float* rs) {
   if (BN == 256 && ts.kblocks_per_split <= 8 && !getenv("SNT_NO_WIDE_EPI")) {  // short K: epilogue-bound
     PlainEpi<256, true> e;
     e.M = (int)M; e.N = (int)N; e.alpha = alpha; e.beta = beta; e.C = C; e.Cb = Cb; e.ldc = ldc; e.bias = bias;
-    e.split_stride = split_stride; e.row_perm_h = perm; e.alpha_dev = adev;
+    e.split_stride = split_stride; e.row_perm_h = perm; e.alpha_dev = adev; e.row_scale = rs;
     return launch_gemm_tc<256, A_MN, B_MN, PlainEpi<256, true>>(ta, tb, ts, e, st);
   }
   PlainEpi<BN> e;
   e.M = (int)M; e.N = (int)N; e.alpha = alpha; e.beta = beta; e.C = C; e.Cb = Cb; e.ldc = ldc; e.bias = bias;
-  e.split_stride = split_stride; e.row_perm_h = perm; e.alpha_dev = adev;
-  if constexpr (BN >= 128) {
-    // experimental (SNT_GEMM_MC=1): pairs of row tiles share the B tile through TMA multicast (gemm_tc_mc.cuh)
-    if (tb_mc != nullptr) return launch_gemm_tc_mc<BN, A_MN, B_MN, PlainEpi<BN>>(ta, *tb_mc, ts, e, st);
-  }
+  e.split_stride = split_stride; e.row_perm_h = perm; e.alpha_dev = adev; e.row_scale = rs;
   return launch_gemm_tc<BN, A_MN, B_MN, PlainEpi<BN>>(ta, tb, ts, e, st);
 }
 
 template <int BN>
 static int run_plain_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts,
                            int64_t M, int64_t N, float alpha, float beta, float* C, __nv_bfloat16* Cb, int64_t ldc,
-                           const float* bias, int64_t split_stride, cudaStream_t st, int perm, const float* adev,
-                           const CUtensorMap* tb_mc) {
-  if (!a_mn && !b_mn) return run_plain<BN, false, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev, tb_mc);
-  if (!a_mn && b_mn) return run_plain<BN, false, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev, tb_mc);
-  if (a_mn && !b_mn) return run_plain<BN, true, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev, tb_mc);
-  return run_plain<BN, true, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev, tb_mc);
+                           const float* bias, int64_t split_stride, cudaStream_t st, int perm, const float* adev, const float* rs) {
+  if (!a_mn && !b_mn) return run_plain<BN, false, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev, rs);
+  if (!a_mn && b_mn) return run_plain<BN, false, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev, rs);
+  if (a_mn && !b_mn) return run_plain<BN, true, false>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev, rs);
+  return run_plain<BN, true, true>(ta, tb, ts, M, N, alpha, beta, C, Cb, ldc, bias, split_stride, st, perm, adev, rs);
 }
 
 int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A,
             int64_t lda, const __nv_bfloat16* B, int64_t ldb, float beta, float* C, __nv_bfloat16* Cb,
             int64_t ldc, const float* bias, int splits, float* split_ws, cudaStream_t st, int row_perm_h,
-            const float* alpha_dev, bool keep_partials, int* splits_used, int force_bn, int n_fastest) {
+            const float* alpha_dev, bool keep_partials, int* splits_used, int force_bn, int n_fastest, const float* row_scale) {
   if (M <= 0 || N <= 0) return SNT_OK;
   SNT_REQUIRE(row_perm_h == 0 || M == 4 * (int64_t)row_perm_h, "gemm_tc: row permutation needs M == 4H");
   SNT_REQUIRE(K >= 1 && A && B && (C || Cb), "gemm_tc: bad arguments");
@@ -185,30 +202,65 @@ int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, 
     out = split_ws; outb = nullptr; e_beta = 0.f; e_bias = nullptr;
     split_stride = M * ldc;
   }
-  // experimental (SNT_GEMM_MC=1): cluster-multicast variant for contractions with at least two row tiles.  A K-major B is
-  // fetched in two half-tile boxes (its own tensor map); an MN-major B already comes in 64-row boxes.
-  CUtensorMap tb_half;
-  const CUtensorMap* tb_mc = nullptr;
-  if (bn >= 128 && ts.num_m >= 2 && mc_enabled()) {
-    if (!b_mn) {
-      SNT_CHECK(make_operand_tmap(&tb_half, B, false, N, K, ldb, bn / 2));
-      tb_mc = &tb_half;
-    } else {
-      tb_mc = &tb;
-    }
-  }
   int rc;
-  if (bn == 256) rc = run_plain_major<256>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev, tb_mc);
-  else if (bn == 128) rc = run_plain_major<128>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev, tb_mc);
-  else rc = run_plain_major<64>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev, nullptr);
+  if (bn == 256) rc = run_plain_major<256>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev, row_scale);
+  else if (bn == 128) rc = run_plain_major<128>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev, row_scale);
+  else rc = run_plain_major<64>(a_mn, b_mn, ta, tb, ts, M, N, e_alpha, e_beta, out, outb, ldc, e_bias, split_stride, st, row_perm_h, alpha_dev, row_scale);
   SNT_CHECK(rc);
   if (splits > 1 && !keep_partials) {
     const int64_t total = M * N;
-    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(split_ws, splits, M, N, ldc, split_stride,
-                                                                           beta, bias, C, Cb);
-    SNT_LAUNCH_CHECK("splitk_reduce_kernel");
+    const bool vec = C && !Cb && N % 4 == 0 && ldc % 4 == 0 && split_stride % 4 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(split_ws) |
+                       reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+    if (vec) {
+      splitk_reduce4_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>(split_ws, splits, M, N / 4, ldc,
+                                                                                 split_stride, beta, bias, C);
+      SNT_LAUNCH_CHECK("splitk_reduce4_kernel");
+    } else {
+      splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(split_ws, splits, M, N, ldc, split_stride,
+                                                                             beta, bias, C, Cb);
+      SNT_LAUNCH_CHECK("splitk_reduce_kernel");
+    }
   }
   return SNT_OK;
+}
+
+// Wave-balanced variant for long contractions whose tile count is not a multiple of the SM count.  The row tiles are
+// cut in two groups: the first fills whole waves of unsplit tiles (written straight to C); the remaining row tiles - less
+// than one wave - are split along K just enough to occupy every SM once more, and reduced by the (small) split-K
+// reduction.  Instead of 2 rounds of full-length tiles (158 tiles on 148 SMs) the job takes 1 round + 1/14 round.
+// `split_ws` must hold 16 * tail_rows * ldc floats with tail_rows < ceil(sms / num_n) * 128 + 128.
+int gemm_tc_balanced(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A,
+                     int64_t lda, const __nv_bfloat16* B, int64_t ldb, float* C, int64_t ldc, float* split_ws,
+                     int64_t split_ws_elems, cudaStream_t st, const float* alpha_dev, int bn, const float* row_scale) {
+  SNT_REQUIRE(bn == 128 || bn == 256, "gemm_tc_balanced: bn must be 128 or 256");
+  const int64_t num_m = (M + BM - 1) / BM, num_n = (N + bn - 1) / bn, kb = (K + BK - 1) / BK;
+  const int64_t sms = grid_sms();
+  const int64_t tiles = num_m * num_n;
+  const int64_t rounds = tiles / sms;
+  int64_t m_a = rounds > 0 ? (rounds * sms) / num_n : 0;  // row tiles of the unsplit part
+  if (m_a > num_m) m_a = num_m;
+  const int64_t tail_m = num_m - m_a;
+  if (tail_m == 0 || tiles % sms == 0 || split_ws == nullptr)
+    return gemm_tc(a_mn, b_mn, M, N, K, alpha, A, lda, B, ldb, 0.f, C, nullptr, ldc, nullptr, 1, nullptr, st, 0, alpha_dev,
+                   false, nullptr, bn, 1, row_scale);
+  const int64_t tail_rows = M - m_a * BM, tail_tiles = tail_m * num_n;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= 16 && s <= kb; ++s) {
+    if ((int64_t)s * tail_rows * ldc > split_ws_elems) break;
+    const int64_t per = (kb + s - 1) / s;
+    const int64_t units = tail_tiles * ((kb + per - 1) / per);
+    const double cost = (double)((units + sms - 1) / sms) * (double)per + (s > 1 ? 2.0 + 0.5 * s : 0.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  if (m_a > 0)
+    SNT_CHECK(gemm_tc(a_mn, b_mn, m_a * BM, N, K, alpha, A, lda, B, ldb, 0.f, C, nullptr, ldc, nullptr, 1, nullptr, st, 0,
+                      alpha_dev, false, nullptr, bn, 1, row_scale));
+  const int64_t r0 = m_a * BM;
+  const __nv_bfloat16* A2 = a_mn ? A + r0 : A + r0 * lda;
+  return gemm_tc(a_mn, b_mn, tail_rows, N, K, alpha, A2, lda, B, ldb, 0.f, C + r0 * ldc, nullptr, ldc, nullptr, best,
+                 split_ws, st, 0, alpha_dev, false, nullptr, bn, 1, row_scale ? row_scale + r0 : nullptr);
 }
 
 }  // namespace tc

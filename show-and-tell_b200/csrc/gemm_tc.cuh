@@ -274,6 +274,7 @@ struct PlainEpi {
   const float* bias;       // may be NULL, length N
   int64_t split_stride;    // elements between split-K partial slices of C
   int row_perm_h;          // != 0: accumulator row 4*j+g is stored to row g*row_perm_h + j (LSTM gate un-interleave)
+  const float* row_scale;  // optional [M]: row m of alpha*acc is multiplied by row_scale[m] (before bias / beta)
 
   using Pre = NoPre;
   __device__ __forceinline__ void prefetch(Pre&, int, int, int, int) const {}
@@ -398,6 +399,7 @@ struct PlainEpi {
     x.row0 = m_blk * BM + (ew & 3) * 32;
     x.n_blk = n_blk; x.split = split; x.lane = lane;
     x.a = alpha_dev ? alpha * alpha_dev[0] : alpha;
+    if (row_scale) x.a *= (x.row0 + lane < M) ? __ldg(row_scale + x.row0 + lane) : 0.f;  // one accumulator row per lane
     const bool bias_al = !bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
     x.vec_ok = C && !Cb && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && bias_al &&
                ((split_stride & 3) == 0);
@@ -441,7 +443,14 @@ int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, 
             int64_t lda, const __nv_bfloat16* B, int64_t ldb, float beta, float* C, __nv_bfloat16* Cb,
             int64_t ldc, const float* bias, int splits, float* split_ws, cudaStream_t st, int row_perm_h = 0,
             const float* alpha_dev = nullptr, bool keep_partials = false, int* splits_used = nullptr,
-            int force_bn = 0, int n_fastest = 0);
+            int force_bn = 0, int n_fastest = 0, const float* row_scale = nullptr);
+
+// C[M,N] (fp32) = alpha * diag(row_scale) . op(A).op(B), wave-balanced: whole waves of unsplit tiles plus a K-split tail
+// (see gemm_tc.cu).  split_ws_elems floats of scratch for the tail's partial sums.
+int gemm_tc_balanced(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A,
+                     int64_t lda, const __nv_bfloat16* B, int64_t ldb, float* C, int64_t ldc, float* split_ws,
+                     int64_t split_ws_elems, cudaStream_t st, const float* alpha_dev, int bn,
+                     const float* row_scale = nullptr);
 
 }  // namespace tc
 }  // namespace snt

@@ -14,7 +14,6 @@
 // At H <= 512 both directions run as ONE persistent cooperative kernel each (further down).
 #include "bf16.cuh"
 #include "gemm_tc.cuh"
-#include "gemm_tc_mc.cuh"
 #include "kernels.cuh"
 
 #include <stdlib.h>
@@ -1322,10 +1321,6 @@ int greedy_decode(const float* features, const float* w_emb, int L, const float*
       SNT_CHECK(tc::make_operand_tmap(&tout_a[q], cat[L - 1][q] + kin[L - 1], false, B, H, ld, tc::BM));
   }
   SNT_CHECK(tc::make_operand_tmap(&tout_b, wout, false, V, H, H, 256));
-  // experimental (SNT_GEMM_MC=2|4, gemm_tc_mc.cuh): 2 or 4 row tiles of the vocabulary contraction share the W_out tile
-  const int mc_cl = tc::mc_cluster();
-  CUtensorMap tout_b_mc;
-  if (mc_cl) SNT_CHECK(tc::make_operand_tmap(&tout_b_mc, wout, false, V, H, H, 256 / mc_cl));
   for (int s = 0; s < steps; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;  // cat[k][cur] = [input_s | h_{s-1}]; h_s goes to cat[k][nxt]
     for (int k = 0; k < L; ++k) {
@@ -1359,9 +1354,7 @@ int greedy_decode(const float* features, const float* w_emb, int L, const float*
     ts.b_row0 = 0;
     ArgmaxEpi e;
     e.M = (int)B; e.V = (int)V; e.bias = b_out; e.part = part;
-    if (mc_cl == 4) SNT_CHECK((tc::launch_gemm_tc_mc<256, false, false, ArgmaxEpi, 4>(tout_a[nxt], tout_b_mc, ts, e, st)));
-    else if (mc_cl == 2) SNT_CHECK((tc::launch_gemm_tc_mc<256, false, false, ArgmaxEpi, 2>(tout_a[nxt], tout_b_mc, ts, e, st)));
-    else SNT_CHECK((tc::launch_gemm_tc<256, false, false, ArgmaxEpi>(tout_a[nxt], tout_b, ts, e, st, true)));
+    SNT_CHECK((tc::launch_gemm_tc<256, false, false, ArgmaxEpi>(tout_a[nxt], tout_b, ts, e, st, true)));
     argmax_finish_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(part, slabs, B, w_emb, (int)E, ids + s, steps,
                                                                    cat[0][nxt], E + H);
     SNT_LAUNCH_CHECK("argmax_finish_kernel");

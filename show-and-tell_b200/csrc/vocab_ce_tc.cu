@@ -8,7 +8,6 @@
 //           buffer, which two more tcgen05 contractions consume (dHs = dlogits.W_out, dW_out += dlogits^T.Hs).
 #include "bf16.cuh"
 #include "gemm_tc.cuh"
-#include "gemm_tc_mc.cuh"
 #include "kernels.cuh"
 
 #include <stdlib.h>
@@ -178,11 +177,7 @@ ce_finish_kernel(const float2* __restrict__ part, int slabs, int64_t N, const fl
 }
 
 // ---- backward epilogue: dlogits = (2^(y - lse2) - onehot) * scale -> bf16 chunk ------------------------------------
-// LAZY (experimental, SNT_CEBWD_LAZY=1; written without a GPU run): the one-hot subtraction is not applied
-// to all 32 elements of a chunk (32 compares + 32 predicated subtracts per thread, a quarter of the chunk's instructions)
-// but patched into the staged bf16 row by the one lane whose target column lies in this chunk (one chunk in V/32 per
-// row).  Same arithmetic for that element (same ex2 argument, minus one, one rounding): bit-identical output.
-template <int W, bool LAZY = false>
+template <int W>
 struct CeBwdEpiT {
   static constexpr int kWarps = W;
   static constexpr int kStages = W == 16 ? 3 : 0;  // 16 staging buffers (40 KB) fit next to 3 ring stages
@@ -217,27 +212,16 @@ struct CeBwdEpiT {
         float p1 = ex2((__uint_as_float(r[j + 1]) + b.y) * LOG2E - l2);
         float p2 = ex2((__uint_as_float(r[j + 2]) + b.z) * LOG2E - l2);
         float p3 = ex2((__uint_as_float(r[j + 3]) + b.w) * LOG2E - l2);
-        if (!LAZY) {
-          if (trel == j) p0 -= 1.f;
-          if (trel == j + 1) p1 -= 1.f;
-          if (trel == j + 2) p2 -= 1.f;
-          if (trel == j + 3) p3 -= 1.f;
-        }
+        if (trel == j) p0 -= 1.f;
+        if (trel == j + 1) p1 -= 1.f;
+        if (trel == j + 2) p2 -= 1.f;
+        if (trel == j + 3) p3 -= 1.f;
         __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
         pk[j / 2] = *reinterpret_cast<uint32_t*>(&lo);
         pk[j / 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) tc::sts128(wsa + lane * 80 + q * 16, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-      if (LAZY && (unsigned)trel < 32u) {  // this row's target column is one of these 32: patch its staged element
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (trel == j) acc = __uint_as_float(r[j]);
-        const float pt = ex2((acc + __ldg(bias + col0 + trel)) * LOG2E - l2) - 1.f;
-        const unsigned short hb = __bfloat16_as_ushort(__float2bfloat16_rn(pt));
-        asm volatile("st.shared.b16 [%0], %1;" ::"r"(wsa + (uint32_t)(lane * 80 + trel * 2)), "h"(hb) : "memory");
-      }
       __syncwarp();
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
@@ -323,7 +307,8 @@ typedef CeBwdEpiT<8> CeBwdEpi;
 constexpr int CSB_ROWS = 256;
 // block = 32 column groups (8 bf16 = one 16-byte load each -> 256 columns) x 8 row lanes; 4 rows in flight per thread
 __global__ void __launch_bounds__(256)
-colsum_bf16_partial_kernel(const bf* __restrict__ in, int64_t R, int64_t C, int64_t ld, float* __restrict__ partial) {
+colsum_bf16_partial_kernel(const bf* __restrict__ in, int64_t R, int64_t C, int64_t ld, float* __restrict__ partial,
+                           const float* __restrict__ roww) {
   __shared__ float red[8][256 + 8];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c = ((int64_t)blockIdx.x * 32 + tx) * 8;
@@ -331,15 +316,16 @@ colsum_bf16_partial_kernel(const bf* __restrict__ in, int64_t R, int64_t C, int6
   float s[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s[k] = 0.f;
-  auto add8 = [&](const uint4& v) {
+  auto add8 = [&](const uint4& v, float w) {
     const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 f = __bfloat1622float2(p[k]);
-      s[2 * k] += f.x;
-      s[2 * k + 1] += f.y;
+      s[2 * k] = fmaf(f.x, w, s[2 * k]);
+      s[2 * k + 1] = fmaf(f.y, w, s[2 * k + 1]);
     }
   };
+  auto wt = [&](int64_t r) { return roww ? __ldg(roww + r) : 1.f; };  // optional per-row weight
   if (c + 8 <= C) {  // ld % 8 == 0 and c % 8 == 0: aligned 16-byte loads
     int64_t r = r0 + ty;
     for (; r + 24 < r1; r += 32) {
@@ -347,12 +333,12 @@ colsum_bf16_partial_kernel(const bf* __restrict__ in, int64_t R, int64_t C, int6
       const uint4 b = __ldcg(reinterpret_cast<const uint4*>(in + (r + 8) * ld + c));
       const uint4 d = __ldcg(reinterpret_cast<const uint4*>(in + (r + 16) * ld + c));
       const uint4 e = __ldcg(reinterpret_cast<const uint4*>(in + (r + 24) * ld + c));
-      add8(a); add8(b); add8(d); add8(e);
+      add8(a, wt(r)); add8(b, wt(r + 8)); add8(d, wt(r + 16)); add8(e, wt(r + 24));
     }
-    for (; r < r1; r += 8) add8(__ldcg(reinterpret_cast<const uint4*>(in + r * ld + c)));
+    for (; r < r1; r += 8) add8(__ldcg(reinterpret_cast<const uint4*>(in + r * ld + c)), wt(r));
   } else if (c < C) {
     for (int64_t r = r0 + ty; r < r1; r += 8)
-      for (int k = 0; k < 8 && c + k < C; ++k) s[k] += __bfloat162float(in[r * ld + c + k]);
+      for (int k = 0; k < 8 && c + k < C; ++k) s[k] = fmaf(__bfloat162float(in[r * ld + c + k]), wt(r), s[k]);
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) red[ty][tx * 8 + k] = s[k];
@@ -375,10 +361,10 @@ __global__ void colsum_bf16_final_kernel(const float* __restrict__ partial, int6
 }
 static int64_t colsum_bf16_partials(int64_t R, int64_t C) { return ((R + CSB_ROWS - 1) / CSB_ROWS) * C; }
 int colsum_bf16(const bf* in, int64_t R, int64_t C, int64_t ld, float beta, float* out, float* partial,
-                       cudaStream_t st) {
+                cudaStream_t st, const float* roww) {
   const int64_t chunks = (R + CSB_ROWS - 1) / CSB_ROWS;
   dim3 grid((unsigned)((C + 255) / 256), (unsigned)chunks);
-  colsum_bf16_partial_kernel<<<grid, 256, 0, st>>>(in, R, C, ld, partial);
+  colsum_bf16_partial_kernel<<<grid, 256, 0, st>>>(in, R, C, ld, partial, roww);
   SNT_LAUNCH_CHECK("colsum_bf16_partial_kernel");
   colsum_bf16_final_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(partial, chunks, C, beta, out);
   SNT_LAUNCH_CHECK("colsum_bf16_final_kernel");
@@ -474,14 +460,7 @@ int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const i
   make_sched(N, V, H, &ts);
   CeFwdEpi e;
   e.M = (int)N; e.V = (int)V; e.bias = b_out; e.part = w.part; e.targets = targets; e.tl = w.tl;
-  if (const int cl = tc::mc_cluster()) {  // experimental: 2 or 4 row tiles share the W_out tile through TMA multicast
-    CUtensorMap tbh;
-    SNT_CHECK(tc::make_operand_tmap(&tbh, w.wb, false, V, H, H, CE_BN / cl));
-    if (cl == 4) SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeFwdEpi, 4>(ta, tbh, ts, e, st)));
-    else SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeFwdEpi, 2>(ta, tbh, ts, e, st)));
-  } else {
-    SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeFwdEpi>(ta, tb, ts, e, st)));
-  }
+  SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeFwdEpi>(ta, tb, ts, e, st)));
   int* ticket = ce_ticket();
   if (!ticket) { set_error("vocab_ce_fwd: could not allocate the reduction ticket"); return SNT_EINVAL; }
   // w.nll doubles as the per-block partial sums (ceil(N/64) <= N floats)
@@ -511,12 +490,6 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
     dw_bn = c128 < c256 ? 128 : 256;
   }
 
-  const char* lazy_env = getenv("SNT_CEBWD_LAZY");
-  const bool lazy_onehot = lazy_env && lazy_env[0] == '1';
-  const int mc_cl = tc::mc_cluster();  // experimental: W_out tiles shared by 2 or 4 row tiles through TMA multicast
-  const bool mc = mc_cl != 0;
-  CUtensorMap tbh;
-  if (mc) SNT_CHECK(tc::make_operand_tmap(&tbh, w.wb, false, V, H, H, CE_BN / (lazy_onehot ? 2 : mc_cl)));
   SideStream* side = side_stream();
   for (int64_t r0 = 0; r0 < N; r0 += w.R) {
     const int64_t r = N - r0 < w.R ? N - r0 : w.R;
@@ -528,19 +501,7 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
     make_sched(r, V, H, &ts);
     // 16 epilogue warps (2 chunks each) hide the TMEM-load / staging / store latencies better than 8 warps with register
     // double-buffering: 58 -> 51 us per chunk pass (measured); SNT_CEBWD_W8 selects the 8-warp variant.
-    if (lazy_onehot) {
-      CeBwdEpiT<16, true> e;
-      e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;
-      e.out = w.dl; e.ldo = w.Vp;
-      if (mc) SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeBwdEpiT<16, true>>(ta, tbh, ts, e, st)));
-      else SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeBwdEpiT<16, true>>(ta, tb, ts, e, st)));
-    } else if (mc) {
-      CeBwdEpiT<16> e;
-      e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;
-      e.out = w.dl; e.ldo = w.Vp;
-      if (mc_cl == 4) SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeBwdEpiT<16>, 4>(ta, tbh, ts, e, st)));
-      else SNT_CHECK((tc::launch_gemm_tc_mc<CE_BN, false, false, CeBwdEpiT<16>, 2>(ta, tbh, ts, e, st)));
-    } else if (!getenv("SNT_CEBWD_W8")) {
+    if (!getenv("SNT_CEBWD_W8")) {
       CeBwdEpiT<16> e;
       e.M = (int)r; e.V = (int)V; e.bias = b_out; e.lse = lse + r0; e.targets = targets + r0;
       e.out = w.dl; e.ldo = w.Vp;
@@ -582,6 +543,356 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
   if (side) SNT_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   scale_vec_kernel<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(w.db, V, scale, dloss, d_b_out);
   SNT_LAUNCH_CHECK("scale_vec_kernel");
+  return SNT_OK;
+}
+
+
+// =====================================================================================================================
+// Training path with STORED softmax numerators: the logits contraction runs ONCE per step.
+//
+// The recompute path above pays 2*N*H*V FLOP twice (forward statistics, then the same contraction again in backward
+// because softmax needs the finished row statistics).  Here the forward pass stores U = exp(logit - c_row) as bf16 for a
+// per-row shift c_row that is known BEFORE the pass, so no second sweep is needed:
+//     softmax = U / S,  S = sum_v U  (fp32, accumulated in the same epilogue),   lse = c + log S.
+// The 1/S factor is a per-ROW scalar, so it folds into the consumers exactly:
+//     dHs[n,:]  = (1/S_n) * sum_v U'[n,v] W[v,:]          -> row scale in the epilogue of the contraction
+//     dW[v,:]   = sum_n U'[n,v] * (Hs[n,:]/S_n)            -> the other operand is pre-scaled (hs_scaled, bf16)
+//     db[v]     = sum_n U'[n,v] / S_n                      -> row-weighted column sums
+// with U'[n,t_n] = U[n,t_n] - S_n (the one-hot, patched into the stored row by the finishing kernel; the patched element
+// is (p-1)*S rounded to bf16 once - the same rounding the recompute path applies to p-1).
+// The shift only has to be within ~70 nats of the row maximum (bf16 has fp32's exponent range): c_row = max over the
+// first 256 vocabulary columns ("pilot" tile, one tiny contraction) + 20.  c <= rowmax + 20 always holds, so S >= e^-20;
+// a row whose maximum exceeded the pilot maximum by more than ~88 nats would overflow: the epilogue then raises device
+// flag bit 2 and the loss comes out non-finite (loud), and SNT_CE_RECOMPUTE=1 selects the recompute path.
+// =====================================================================================================================
+constexpr float CE_SHIFT2 = 20.f * LOG2E;  // pilot shift in the log2 domain
+
+struct RowMaxEpi {  // pilot: per row the maximum of y = logit*log2(e) over each 128-column half of column tile 0
+  static constexpr int kWarps = 8;
+  static constexpr int kStages = 0;
+  static constexpr int kSmemPerWarp = 0;
+  int M, V;
+  const float* bias;
+  float* pm;  // [2][M]
+  using Pre = tc::NoPre;
+  __device__ __forceinline__ void prefetch(Pre&, int, int, int, int) const {}
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int, int, int ew, int lane, const Pre&,
+                                       uint8_t*) const {
+    const int half = ew >> 2;
+    const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
+    float best = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int col0 = half * 128 + c * 32;
+      if (col0 >= V) break;  // warp-uniform
+      uint32_t r[32];
+      tc::tmem_ld32(tmem_rows + (uint32_t)col0, r);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < V) best = fmaxf(best, (__uint_as_float(r[j]) + __ldg(bias + col0 + j)) * LOG2E);
+    }
+    if (row < M) pm[(int64_t)half * M + row] = best;
+  }
+};
+
+// forward epilogue of the stored-numerator path: U = 2^(y - c2) -> bf16 [M, ldo], row sums of the (unrounded) U per
+// 64-column quarter of the tile, and the target logit picked out of the accumulator.  16 warps x 2 chunks of 32 columns.
+struct CeStoreEpi {
+  static constexpr int kWarps = 16;
+  static constexpr int kStages = 3;
+  static constexpr int kSmemPerWarp = 32 * 80;  // transpose stage for whole-row-segment stores (as CeBwdEpiT)
+  int M, V;
+  const float* bias;        // [V]
+  const float* pm;          // [2][M] pilot maxima (log2 domain)
+  const int64_t* targets;   // [M]
+  float* tl;                // [M] target logit
+  float* part;              // [4 * num_n][M] partial row sums
+  bf* out;                  // [M, ldo]
+  int64_t ldo;
+  int* flags;
+
+  struct Pre { float c2; int tgt; };
+  __device__ __forceinline__ void prefetch(Pre& p, int m_blk, int, int ew, int lane) const {
+    const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
+    const bool ok = row < M;
+    p.c2 = ok ? fmaxf(__ldg(pm + row), __ldg(pm + M + row)) + CE_SHIFT2 : 0.f;
+    const int64_t t = ok ? targets[row] : -1;
+    p.tgt = (t >= 0 && t < V) ? (int)t : -1;
+  }
+  __device__ __forceinline__ void load_bias(float4 (&bv)[8], int col0) const {
+    if (col0 + 32 <= V) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) bv[q] = __ldg(reinterpret_cast<const float4*>(bias + col0) + q);
+    }
+  }
+  __device__ __forceinline__ float chunk(const uint32_t (&r)[32], const float4 (&bv)[8], int col0, int row0, int lane,
+                                         float c2, int tgt, uint32_t wsa) const {
+    float s = 0.f;
+    const int trel = tgt - col0;
+    const bool hit = tgt >= 0 && (unsigned)trel < 32u;
+    if (__any_sync(0xffffffffu, hit)) {  // some row of the warp has its target among these 32 columns
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v = (trel == j) ? __uint_as_float(r[j]) : v;
+      if (hit) tl[row0 + lane] = v + __ldg(bias + tgt);
+    }
+    if (col0 + 32 <= V) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = bv[j >> 2];
+        const float p0 = ex2(fmaf(__uint_as_float(r[j]) + b.x, LOG2E, -c2));
+        const float p1 = ex2(fmaf(__uint_as_float(r[j + 1]) + b.y, LOG2E, -c2));
+        const float p2 = ex2(fmaf(__uint_as_float(r[j + 2]) + b.z, LOG2E, -c2));
+        const float p3 = ex2(fmaf(__uint_as_float(r[j + 3]) + b.w, LOG2E, -c2));
+        s += (p0 + p1) + (p2 + p3);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
+        pk[j / 2] = *reinterpret_cast<uint32_t*>(&lo);
+        pk[j / 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tc::sts128(wsa + lane * 80 + q * 16, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + (lane >> 2), cq = lane & 3;
+        const uint4 v = tc::lds128(wsa + rr * 80 + cq * 16);
+        if (row0 + rr < M) *reinterpret_cast<uint4*>(out + (int64_t)(row0 + rr) * ldo + col0 + cq * 8) = v;
+      }
+      __syncwarp();
+    } else if (row0 + lane < M) {
+      bf* orow = out + (int64_t)(row0 + lane) * ldo;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = col0 + j;
+        if (col < V) {
+          const float p = ex2(fmaf(__uint_as_float(r[j]) + bias[col], LOG2E, -c2));
+          s += p;
+          orow[col] = __float2bfloat16_rn(p);
+        }
+      }
+    }
+    return s;
+  }
+  __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane, const Pre& pre,
+                                       uint8_t* wsm) const {
+    const int q4 = ew >> 2;  // 64-column quarter of the tile
+    const int row0 = m_blk * tc::BM + (ew & 3) * 32;
+    const uint32_t wsa = tc::smem_u32(wsm);
+    float s = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int col0 = n_blk * CE_BN + q4 * 64 + c * 32;
+      if (col0 >= V) break;  // warp-uniform
+      uint32_t r[32];
+      float4 b8[8];
+      tc::tmem_ld32(tmem_rows + (uint32_t)(q4 * 64 + c * 32), r);
+      load_bias(b8, col0);
+      tc::tmem_ld_wait();
+      s += chunk(r, b8, col0, row0, lane, pre.c2, pre.tgt, wsa);
+    }
+    if (row0 + lane < M) {
+      part[(int64_t)(n_blk * 4 + q4) * M + row0 + lane] = s;
+      if (!(s < 1e35f)) atomicOr(flags, 4);  // inf / NaN / about to overflow: the pilot shift was too far off
+    }
+  }
+};
+
+// Finishes the stored-numerator forward.  Block = 64 rows x 8 slab groups (512 threads), as ce_finish_kernel:
+//   S = sum of the row's partial sums (fixed order), lse = (c2 + log2 S) ln 2, nll = lse - target logit, mean -> loss;
+//   the one-hot is patched into the stored row (U[n,t] -= S), inv_s[n] = the row scale (1/S up to 2^-9), and the block's 64 rows of Hs are written
+//   scaled by 1/S (the pre-scaled operand of the dW_out contraction).
+__global__ void __launch_bounds__(512)
+ce_finish_u_kernel(const float* __restrict__ part, int slabs, int64_t N, const float* __restrict__ pm,
+                   const float* __restrict__ tl, const int64_t* __restrict__ targets, int64_t V, bf* __restrict__ u,
+                   int64_t ldu, const bf* __restrict__ hs, int H, float* __restrict__ lse, float* __restrict__ inv_s,
+                   bf* __restrict__ hs_scaled, float* __restrict__ block_sum, int* __restrict__ ticket, float inv_n,
+                   float* __restrict__ loss, int* flags) {
+  __shared__ float red[8][64];
+  __shared__ float s_inv[64];
+  __shared__ float wred[16];
+  __shared__ int s_last;
+  const int tx = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int64_t row = (int64_t)blockIdx.x * 64 + tx;
+  float S = 0.f;
+  if (row < N)
+    for (int k = g; k < slabs; k += 8) S += part[(int64_t)k * N + row];
+  red[g][tx] = S;
+  __syncthreads();
+  float nll = 0.f;
+  if (g == 0) {
+    float inv = 0.f;
+    if (row < N) {
+      float St = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) St += red[i][tx];
+      const float c2 = fmaxf(pm[row], pm[N + row]) + CE_SHIFT2;
+      const float l = (c2 + log2f(St)) * LN2;
+      lse[row] = l;
+      inv = 1.f / St;
+      const int64_t t = targets[row];
+      const bool valid = t >= 0 && t < V;
+      if (!valid) atomicOr(flags, 2);
+      nll = l - (valid ? tl[row] : 0.f);
+      if (valid) {
+        // one-hot: U[n,t] <- U[n,t] - S, rounded to bf16 once.  That element carries the dominant term of every gradient
+        // (-W[t,:], -Hs[n,:], -1), so the ROW SCALE is chosen to make it exact: r = (p_t - 1) / stored value, which
+        // differs from 1/S by at most 2^-9 and moves the rounding error onto the small softmax terms of the row.
+        bf* e = u + row * ldu + t;
+        const float ut = __bfloat162float(*e);
+        const bf patched = __float2bfloat16_rn(ut - St);
+        *e = patched;
+        const float pv = __bfloat162float(patched);
+        if (pv != 0.f) inv = (ut * inv - 1.f) / pv;
+      }
+      inv_s[row] = inv;
+    }
+    s_inv[tx] = inv;
+    const float w = warp_sum(nll);
+    if ((tx & 31) == 0) wred[tx >> 5] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    block_sum[blockIdx.x] = wred[0] + wred[1];
+    __threadfence();
+    s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+  }
+  // Hs rows of this block, scaled by 1/S (H % 8 == 0: 16-byte pieces)
+  const int h8 = H >> 3;
+  for (int i = threadIdx.x; i < 64 * h8; i += 512) {
+    const int r = i / h8, c = i - r * h8;
+    const int64_t grow = (int64_t)blockIdx.x * 64 + r;
+    if (grow >= N) break;
+    const float w = s_inv[r];
+    uint4 v = *reinterpret_cast<const uint4*>(hs + grow * H + c * 8);
+    __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(p2[k]);
+      p2[k] = __floats2bfloat162_rn(f.x * w, f.y * w);
+    }
+    *reinterpret_cast<uint4*>(hs_scaled + grow * H + c * 8) = v;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 512) t += __ldcg(block_sum + i);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) tot += wred[i];
+      loss[0] = tot * inv_n;
+      *ticket = 0;  // self-resetting
+    }
+  }
+}
+
+struct CeTrainWs {
+  float* pm; float* part; float* tl; float* bsum; float* cpart; float* sws; float* db; int slabs; int64_t Vp; bool ok;
+};
+// scratch for the K-split tails of the two backward contractions: 16 splits x (less than one wave of row tiles) x H
+static int64_t train_sws_elems(int64_t N, int64_t H, int64_t V) {
+  const int64_t num_n = (H + 255) / 256 > 0 ? (H + 255) / 256 : 1;
+  const int64_t tail_rows = ((int64_t)tc::sm_count() / num_n + 2) * 128;
+  const int64_t cap = N > V ? N : V;
+  return 16 * (tail_rows < cap ? tail_rows : cap) * H;
+}
+static CeTrainWs carve_train(void* ws, int64_t ws_bytes, int64_t N, int64_t H, int64_t V) {
+  Workspace w(ws, ws_bytes);
+  CeTrainWs r;
+  r.slabs = (int)((V + CE_BN - 1) / CE_BN) * 4;
+  r.Vp = pad8(V);
+  r.pm = w.take<float>(2 * N);
+  r.part = w.take<float>((int64_t)r.slabs * N);
+  r.tl = w.take<float>(N);
+  r.bsum = w.take<float>(N);
+  r.cpart = w.take<float>(colsum_bf16_partials(N, V));
+  r.sws = w.take<float>(train_sws_elems(N, H, V));
+  r.db = w.take<float>(V);
+  r.ok = w.ok();
+  return r;
+}
+int64_t vocab_ce_train_ws_bytes(int64_t N, int64_t H, int64_t V) {
+  const int64_t slabs = ((V + CE_BN - 1) / CE_BN) * 4;
+  return ws_bytes_for(2 * N, 4) + ws_bytes_for(slabs * N, 4) + 2 * ws_bytes_for(N, 4) +
+         ws_bytes_for(colsum_bf16_partials(N, V), 4) + ws_bytes_for(train_sws_elems(N, H, V), 4) + ws_bytes_for(V, 4);
+}
+
+int vocab_ce_train_fwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, int64_t N,
+                       int64_t H, int64_t V, float* lse, float* loss, void* u, float* inv_s, void* hs_scaled,
+                       void* w_bf16, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  if (H % 8 != 0) { set_error("bf16 mode: H=%lld must be a multiple of 8", (long long)H); return SNT_EUNSUPPORTED; }
+  SNT_REQUIRE(V < (1LL << 31) && N < (1LL << 31), "vocab_ce_train_fwd: extent too large");
+  CeTrainWs w = carve_train(ws, ws_bytes, N, H, V);
+  if (!w.ok) { set_error("bf16 vocab_ce_train_fwd: workspace too small"); return SNT_EWORKSPACE; }
+  const bf* hs_b = (const bf*)hs;
+  bf* wb = (bf*)w_bf16;
+  SNT_CHECK(cast_bf16(w_out, wb, V * H, st));
+  CUtensorMap ta, tb;
+  SNT_CHECK(tc::make_operand_tmap(&ta, hs_b, false, N, H, H, tc::BM));
+  SNT_CHECK(tc::make_operand_tmap(&tb, wb, false, V, H, H, CE_BN));
+  tc::TileSched ts;
+  make_sched(N, V, H, &ts);
+  {  // pilot: column tile 0 only
+    tc::TileSched tp = ts;
+    tp.num_n = 1;
+    RowMaxEpi e;
+    e.M = (int)N; e.V = (int)V; e.bias = b_out; e.pm = w.pm;
+    SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, RowMaxEpi>(ta, tb, tp, e, st)));
+  }
+  CeStoreEpi e;
+  e.M = (int)N; e.V = (int)V; e.bias = b_out; e.pm = w.pm; e.targets = targets; e.tl = w.tl; e.part = w.part;
+  e.out = (bf*)u; e.ldo = w.Vp; e.flags = device_flags();
+  SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeStoreEpi>(ta, tb, ts, e, st)));
+  int* ticket = ce_ticket();
+  if (!ticket) { set_error("vocab_ce_train_fwd: could not allocate the reduction ticket"); return SNT_EINVAL; }
+  ce_finish_u_kernel<<<(unsigned)((N + 63) / 64), 512, 0, st>>>(w.part, w.slabs, N, w.pm, w.tl, targets, V, (bf*)u, w.Vp,
+                                                               hs_b, (int)H, lse, inv_s, (bf*)hs_scaled, w.bsum, ticket,
+                                                               1.0f / (float)N, loss, device_flags());
+  SNT_LAUNCH_CHECK("ce_finish_u_kernel");
+  return SNT_OK;
+}
+
+int vocab_ce_train_bwd(const void* u, const float* inv_s, const void* hs_scaled, const void* w_bf16,
+                       const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
+                       float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  if (H % 8 != 0) { set_error("bf16 mode: H=%lld must be a multiple of 8", (long long)H); return SNT_EUNSUPPORTED; }
+  CeTrainWs w = carve_train(ws, ws_bytes, N, H, V);
+  if (!w.ok) { set_error("bf16 vocab_ce_train_bwd: workspace too small"); return SNT_EWORKSPACE; }
+  const bf* ub = (const bf*)u;
+  const bf* wb = (const bf*)w_bf16;
+  const float scale = grad_scale / (float)N;
+  // d_b_out = scale * sum_n U'[n,:] / S_n: bandwidth-bound, on the side stream next to the two contractions
+  SideStream* side = side_stream();
+  if (side) {
+    SNT_CUDA(cudaEventRecord(side->fork, st));
+    SNT_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+    SNT_CHECK(colsum_bf16(ub, N, V, w.Vp, 0.f, w.db, w.cpart, side->s, inv_s));
+    scale_vec_kernel<<<(unsigned)((V + 255) / 256), 256, 0, side->s>>>(w.db, V, scale, dloss, d_b_out);
+    SNT_LAUNCH_CHECK("scale_vec_kernel");
+    SNT_CUDA(cudaEventRecord(side->join, side->s));
+  }
+  const int bn = H >= 256 ? 256 : 128;
+  const int64_t sws_elems = train_sws_elems(N, H, V);
+  // dHs[N,H] = diag(scale * r) . U'[N,V] . W_out[V,H]      (B operand MN-major); the column tiles of one 128-row panel
+  // run next to each other so that the panel of U is fetched from HBM once
+  SNT_CHECK(tc::gemm_tc_balanced(false, true, N, H, V, scale, ub, w.Vp, wb, H, d_hs, H, w.sws, sws_elems, st, dloss, bn,
+                                 inv_s));
+  // dW_out[V,H] = scale * U'^T[V,N] . (r * Hs)[N,H]          (both operands MN-major)
+  SNT_CHECK(tc::gemm_tc_balanced(true, true, V, H, N, scale, ub, w.Vp, (const bf*)hs_scaled, H, d_w_out, H, w.sws,
+                                 sws_elems, st, dloss, bn));
+  if (side) {
+    SNT_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+  } else {
+    SNT_CHECK(colsum_bf16(ub, N, V, w.Vp, 0.f, w.db, w.cpart, st, inv_s));
+    scale_vec_kernel<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(w.db, V, scale, dloss, d_b_out);
+    SNT_LAUNCH_CHECK("scale_vec_kernel");
+  }
   return SNT_OK;
 }
 

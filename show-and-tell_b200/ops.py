@@ -32,6 +32,9 @@ TAIL_OVERLAP = os.environ.get("SNT_TAIL_OVERLAP", "0") == "1"
 # of the token ids, ~20 us of small launches) needs only the captions, so it is enqueued on the side stream at the START
 # of the loss backward and has long finished when dx arrives (snt_embed_bwd_plan / snt_embed_pack_bwd_planned).
 EMB_PLAN_EARLY = os.environ.get("SNT_EMB_PLAN_EARLY", "0") == "1"
+# SNT_CE_RECOMPUTE=1: the memory-lean loss backward that recomputes the logits per chunk instead of keeping the bf16 softmax
+# numerators of the whole batch (N x V x 2 bytes) from the forward pass.
+CE_RECOMPUTE = os.environ.get("SNT_CE_RECOMPUTE", "0") == "1"
 _tail = None          # (data_ptr of the dfeatures view, event recorded once dx is complete)
 _side_streams = {}
 
@@ -344,10 +347,24 @@ class _DecoderLoss(torch.autograd.Function):
         lse = torch.empty(N, device=dev)
         loss = torch.empty((), device=dev)
         p = PREC[prec]
-        nb = _lib.lib().snt_vocab_ce_workspace_bytes(p, N, H, V)
-        ws = workspace(nb, dev)
-        call("snt_vocab_ce_fwd", p, ptr(hs), ptr(w_out), ptr(b_out), ptr(targets), N, H, V, ptr(lse), ptr(loss),
-             ptr(ws), ws.numel(), stream_ptr())
+        # A backward will follow: run the logits contraction once and keep the softmax numerators (bf16 mode; see
+        # snt_vocab_ce_train_fwd).  Otherwise (evaluation, fp32 mode, SNT_CE_RECOMPUTE=1): statistics only.
+        ctx.stored = prec == "bf16" and any(ctx.needs_input_grad) and not CE_RECOMPUTE
+        if ctx.stored:
+            u = torch.empty(N, (V + 7) // 8 * 8, device=dev, dtype=torch.bfloat16)
+            inv_s = torch.empty(N, device=dev)
+            hs_scaled = torch.empty(N, H, device=dev, dtype=torch.bfloat16)
+            w_bf16 = torch.empty(V, H, device=dev, dtype=torch.bfloat16)
+            nb = _lib.lib().snt_vocab_ce_train_workspace_bytes(p, N, H, V)
+            ws = workspace(nb, dev)
+            call("snt_vocab_ce_train_fwd", p, ptr(hs), ptr(w_out), ptr(b_out), ptr(targets), N, H, V, ptr(lse),
+                 ptr(loss), ptr(u), ptr(inv_s), ptr(hs_scaled), ptr(w_bf16), ptr(ws), ws.numel(), stream_ptr())
+            ctx.ce_saved = (u, inv_s, hs_scaled, w_bf16)
+        else:
+            nb = _lib.lib().snt_vocab_ce_workspace_bytes(p, N, H, V)
+            ws = workspace(nb, dev)
+            call("snt_vocab_ce_fwd", p, ptr(hs), ptr(w_out), ptr(b_out), ptr(targets), N, H, V, ptr(lse), ptr(loss),
+                 ptr(ws), ws.numel(), stream_ptr())
         ctx.s = s
         ctx.save_for_backward(w_emb, w_out, b_out, targets, lse, *lstm_flat)
         ctx.need_dfeat = features.requires_grad
@@ -372,10 +389,19 @@ class _DecoderLoss(torch.autograd.Function):
         d_w_out = torch.empty_like(w_out)
         d_b_out = torch.empty(V, device=dev)
         p = PREC[s.prec]
-        nb = _lib.lib().snt_vocab_ce_workspace_bytes(p, N, H, V)
-        ws = workspace(nb, dev)
-        call("snt_vocab_ce_bwd", p, ptr(hs), ptr(w_out), ptr(b_out), ptr(targets), ptr(lse), ptr(dloss),
-             float(ctx.grad_scale), N, H, V, ptr(d_hs), ptr(d_w_out), ptr(d_b_out), ptr(ws), ws.numel(), stream_ptr())
+        if ctx.stored:
+            u, inv_s, hs_scaled, w_bf16 = ctx.ce_saved
+            ctx.ce_saved = None
+            nb = _lib.lib().snt_vocab_ce_train_workspace_bytes(p, N, H, V)
+            ws = workspace(nb, dev)
+            call("snt_vocab_ce_train_bwd", p, ptr(u), ptr(inv_s), ptr(hs_scaled), ptr(w_bf16), ptr(dloss),
+                 float(ctx.grad_scale), N, H, V, ptr(d_hs), ptr(d_w_out), ptr(d_b_out), ptr(ws), ws.numel(), stream_ptr())
+            del u, inv_s, hs_scaled, w_bf16
+        else:
+            nb = _lib.lib().snt_vocab_ce_workspace_bytes(p, N, H, V)
+            ws = workspace(nb, dev)
+            call("snt_vocab_ce_bwd", p, ptr(hs), ptr(w_out), ptr(b_out), ptr(targets), ptr(lse), ptr(dloss),
+                 float(ctx.grad_scale), N, H, V, ptr(d_hs), ptr(d_w_out), ptr(d_b_out), ptr(ws), ws.numel(), stream_ptr())
         if ctx.grad_ready is not None:
             ctx.grad_ready(["linear.weight", "linear.bias"], [d_w_out, d_b_out])
         dfeat, d_w_emb, lg = _hidden_bwd(s, d_hs, w_emb, lstm_w, ctx.need_dfeat, ctx.grad_ready)

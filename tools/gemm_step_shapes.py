@@ -1,6 +1,5 @@
 """The contractions of one training step (E256/H512/V10000/B1024: N = 12666 packed rows, CE chunks of 4736 rows) timed
-through snt_gemm_bf16 with the default core and with the multicast core (SNT_GEMM_MC=2, read per call by the library).
-Run under gpurun:  python tools/gemm_step_shapes.py   -> one line per shape: us and TFLOP/s for both cores."""
+through snt_gemm_bf16.  Run under gpurun:  python tools/gemm_step_shapes.py   -> one line per shape: us and TFLOP/s."""
 import ctypes as C
 import os
 import sys
@@ -46,15 +45,6 @@ SHAPES = [  # name, M, N, K, transA, transB, bf16 out
 
 if __name__ == "__main__":
     for name, M, N, K, tA, tB, bf in SHAPES:
-        os.environ.pop("SNT_GEMM_MC", None)
-        us0, c0 = time_gemm(M, N, K, tA, tB, bf)
-        os.environ["SNT_GEMM_MC"] = "2"
-        try:
-            us1, c1 = time_gemm(M, N, K, tA, tB, bf)
-            same = bool(torch.equal(c0, c1))
-        except Exception as e:  # noqa: BLE001
-            us1, same = float("nan"), repr(e)[:80]
-        os.environ.pop("SNT_GEMM_MC", None)
+        us0, _ = time_gemm(M, N, K, tA, tB, bf)
         fl = 2.0 * M * N * K
-        print(f"{name:38s} M={M:6d} N={N:6d} K={K:6d}  default {us0:8.1f} us {fl / us0 / 1e6:7.1f} TF/s   "
-              f"multicast {us1:8.1f} us {fl / us1 / 1e6:7.1f} TF/s   identical={same}", flush=True)
+        print(f"{name:38s} M={M:6d} N={N:6d} K={K:6d}  {us0:8.1f} us {fl / us0 / 1e6:7.1f} TF/s", flush=True)
