@@ -1,28 +1,31 @@
 #!/usr/bin/env python
-"""bench.py — the caption-decoder train step (BASELINE.json configs[1]) on N B200s, one JSON line on rank 0.
+"""bench.py — the caption-decoder hot path (BASELINE.json) on N B200s; rank 0 prints ONE JSON line.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--prec bf16|fp32]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--config default|scaled]
+                  [--scaling weak|strong] [--prec bf16|fp32]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" = one pass of the hot path over one synthetic COCO-shaped batch: encoder head on
 precomputed pooled 2048-d features -> gather/concat/pack -> LSTM -> vocab Linear fused with log-softmax + CE ->
-BPTT -> (N>1: gradient all-reduce overlapped with BPTT) -> clip_gradient + Adam.  Per GPU: B=1024 captions
-(weak scaling; global batch 1024*N sorted by length and sharded by strided rows).
+BPTT -> (N>1: gradient all-reduce overlapped with BPTT) -> clip_gradient + Adam, through the native step executor
+(parallel.DataParallelStep -> snt_step_run), eager launches, no CUDA graph.
 
-value  : captions/s, inputs resident in HBM, CUDA events, max over ranks.  Forward + backward (+ all-reduces) are
-         replayed as one CUDA graph once the fixed benchmark batch has been stepped twice eagerly (--no-graph: eager
-         launches); the optimizer launch stays outside the graph.
-e2e    : the same step through the public module API with HOST (pinned) inputs: H2D copies of that step's
-         pooled features / captions / targets and a D2H read of the loss inside the timed region.
-roofline: the dominant kernel (the tcgen05 vocab-projection contraction) timed alone with CUDA events.
-cpu_baseline / --impl reference: the reference's CPU composition (oracle/torch_port.py, pinned to the
-         reference's golden vectors) timed on this box's host cores.
-greedy_tokens_per_s_*: greedy decode (configs[2]) of 4096 image features per GPU x 20 tokens, every rank decoding its
-         own batch (no communication), device-timed, max over ranks, tokens of all ranks counted.
-f_rows : timings of the rows widened after the hot path: snt_caption_trim against the HBM roofline,
-         and Trainer.train() over distinct ragged host batches through PrefetchLoader (eager launches, wall clock).
-gpu_torch_reference: the same torch.nn composition on THIS GPU (cuDNN LSTM, cuBLAS, ATen; fp32, TF32 and bf16 autocast),
-         SURVEY.md §8(d)(ii) — timed in a child process after the timed regions; a reported baseline only.
+value   : train captions/s with the inputs resident in HBM, CUDA events, max over ranks.  The timed region cycles over
+          NB = 8 DISTINCT ragged batches (different lengths, tokens and features each), so nothing depends on one
+          replayed batch signature; `fixed_batch` repeats batch 0 for comparison.
+e2e     : the same loop with HOST (pinned) inputs: every step pays the H2D copies of its own pooled features and
+          captions (double-buffered on a side stream) and a D2H read of its loss inside the timed region.
+roofline: the stage with the largest share of the step, timed by CUDA events inside snt_step_run (snt_step_profile);
+          `traffic` is read from the ncu capture committed under profiles/ (profiles/r02_traffic.json), never a literal.
+greedy  : the second half of BASELINE's metric - greedy sample() of 4096 image features per GPU x 20 tokens
+          (configs[2]) - as an object with its own roofline, cpu_baseline, e2e (features from the host, ids back) and
+          the torch/cuDNN arm on the same GPU.
+configs3: the scaled decoder (E512/H1024/L2/V32000, batch 2048) timed the same way (N=1), also as `--config scaled`.
+strong_8192 (N>1): BASELINE configs[4] as written - global batch 8192 sharded over the N ranks.
+cpu_baseline / --impl reference: the reference's CPU composition (oracle/torch_port.py, pinned to the reference's
+          golden vectors) timed on this box's host cores.
+gpu_torch_reference: the same torch.nn composition on THIS GPU (cuDNN LSTM, cuBLAS; fp32, TF32, bf16 autocast), timed
+          in a child process after the timed regions - the bar to beat.
 """
 from __future__ import annotations
 
@@ -41,9 +44,15 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
-CFG = dict(B=1024, E=256, H=512, V=10000, L=1, POOLED=2048)          # BASELINE.json configs[1]
+CONFIGS = {
+    "default": dict(B=1024, E=256, H=512, V=10000, L=1, POOLED=2048, name="BASELINE configs[1]"),
+    "scaled": dict(B=2048, E=512, H=1024, V=32000, L=2, POOLED=2048, name="BASELINE configs[3]"),
+}
+CFG = CONFIGS["default"]
 GREEDY_B = 4096                                                       # BASELINE.json configs[2]
-EXTRA_WARMUP_MULTI_GPU = 120                                          # untimed steps added to --warmup when N > 1
+STRONG_GLOBAL_B = 8192                                                # BASELINE.json configs[4]
+NB = 8                                                                # distinct ragged batches in the timed region
+EXTRA_WARMUP_MULTI_GPU = 60                                           # untimed steps added to --warmup when N > 1
 
 
 def load_peaks():
@@ -54,10 +63,18 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+def m_tok(c):
+    """MAC per token: sum_k 4H(in_k + H) + H V."""
+    return sum(4 * c["H"] * ((c["E"] if k == 0 else c["H"]) + c["H"]) for k in range(c["L"])) + c["H"] * c["V"]
+
+
 def train_flops(B, N, c=CFG):
     """Algorithmic FLOPs of one train step: 3 * 2 * (N*M_tok + B*M_head)."""
-    m_tok = 4 * c["H"] * (c["E"] + c["H"]) + c["H"] * c["V"]
-    return 6.0 * (N * m_tok + B * c["POOLED"] * c["E"])
+    return 6.0 * (N * m_tok(c) + B * c["POOLED"] * c["E"])
+
+
+def greedy_flops_per_token(c=CFG):
+    return 2.0 * m_tok(c)
 
 
 class ClockSampler:
@@ -178,37 +195,61 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": float(max(pw)), "source": self.source}
 
 
-def make_global_batch(world, c=CFG, seed=1):
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arms
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_train_baseline(c, steps, warmup, threads):
+    """oracle/torch_port.py (head + decoder fwd, CE, bwd, clip, Adam) on the host cores: (captions/s, s/step, loss)."""
     import show_and_tell_b200 as snt
-    return snt.synthetic.make_batch(c["B"] * world, c["V"], embed=c["E"], seed=seed, pooled_dim=c["POOLED"])
+    from oracle import torch_port as TP   # the checker timed as the CPU baseline, never shipped
+    b = snt.synthetic.make_batch(c["B"], c["V"], embed=c["E"], seed=1, pooled_dim=c["POOLED"])
+    b["targets"] = snt.synthetic.pack_host(b["captions"], b["lengths"])
+    cps, dt, loss = TP.time_full_train(c["B"], c["E"], c["H"], c["V"], c["L"], b, steps=steps, warmup=warmup,
+                                       threads=threads)
+    return cps, dt, loss, int(sum(b["lengths"]))
+
+
+def cpu_greedy_baseline(c, batch, threads):
+    """oracle/torch_port.py greedy loop on a bounded sample of the decode batch: (tokens/s, s per sample)."""
+    from oracle import torch_port as TP
+    feats = np.random.default_rng(1).standard_normal((batch, c["E"])).astype(np.float32)
+    tps, dt = TP.time_greedy(batch, c["E"], c["H"], c["V"], c["L"], feats, steps=2, warmup=1, threads=threads)
+    return tps, dt
 
 
 def run_reference(args, rank):
     """The reference's own CPU composition, all host threads, same config/metric.  Rank 0 only."""
     if rank != 0:
         return
-    import show_and_tell_b200 as snt
-    from oracle import torch_port as TP
-    c = CFG
+    c = CONFIGS[args.config]
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    b = snt.synthetic.make_batch(c["B"], c["V"], embed=c["E"], seed=1, pooled_dim=c["POOLED"])
-    b["targets"] = snt.synthetic.pack_host(b["captions"], b["lengths"])
-    steps, warm = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
-    cps, dt, loss = TP.time_full_train(c["B"], c["E"], c["H"], c["V"], c["L"], b, steps=steps, warmup=warm,
-                                       threads=threads)
+    steps, warm = max(1, args.steps), max(1, args.warmup)
+    cps, dt, loss, n_tok = cpu_train_baseline(c, steps, warm, threads)
+    g_tps, g_dt = cpu_greedy_baseline(c, 512, threads)
+    what = (f"torch {torch.__version__} CPU, oracle/torch_port.py pinned to the reference's goldens "
+            f"(/root/reference is absent on the GPU box)")
     line = {"impl": "reference", "metric": "train_captions_per_s", "value": cps, "unit": "captions/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "decoder train step on precomputed 2048-d features: head(Linear+BN) + DecoderRNN fwd + CE + "
-                                   "bwd + clip/Adam; E256/H512/V10000/L1, batch 1024 (BASELINE configs[1])",
-                       "device": "cpu", "threads": threads},
+            "config": workload_config(c, c["B"], 1, "fp32", n_tok, 20, device="cpu", threads=threads),
             "cpu_baseline": {"value": cps, "unit": "captions/s", "cores": threads, "kind": "port",
-                             "sample": f"{steps} full steps of B=1024 (N={int(sum(b['lengths']))} tokens), torch "
-                                       f"{torch.__version__} CPU, oracle/torch_port.py pinned to the reference's goldens"},
+                             "sample": f"{steps} full steps of B={c['B']} (N={n_tok} tokens), {what}"},
             "e2e": {"value": cps, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "greedy": {"metric": "greedy_decode_tokens_per_s", "value": g_tps, "unit": "tokens/s",
+                       "sample": f"2 x sample() of 512 image features x 20 tokens ({g_dt:.2f} s each), {what}"},
             "loss": loss}
     print(json.dumps(line), flush=True)
+
+
+def workload_config(c, b_local, world, prec, n_tok, max_len, **extra):
+    d = {"workload": f"decoder train step on precomputed {c['POOLED']}-d features: head(Linear+BN) + embed/pack + "
+                     f"{c['L']}-layer LSTM + fused vocab-CE + BPTT + clip/Adam; E{c['E']}/H{c['H']}/V{c['V']}/L{c['L']}, "
+                     f"batch {b_local} per GPU ({c['name']})",
+         "global_batch": b_local * world, "tokens_per_rank": n_tok, "max_len": max_len, "parallelism": f"dp{world}",
+         "precision_mode": prec}
+    d.update(extra)
+    return d
 
 
 def gpu_torch_reference_child(device_index):
@@ -242,9 +283,21 @@ def gpu_torch_reference_child(device_index):
             hiddens, _ = self.lstm(pack_padded_sequence(steps, lengths, batch_first=True))   # models.py:51-52
             return self.linear(hiddens[0])                                        # models.py:53
 
+        @torch.no_grad()
+        def sample(self, features):                                               # models.py:56-67
+            x, states, out = features.unsqueeze(1), None, []
+            for _ in range(20):
+                h, states = self.lstm(x, states)
+                tok = self.linear(h.squeeze(1)).max(1, keepdim=True)[1]
+                out.append(tok)
+                x = self.embed(tok)
+            return torch.cat(out, 1)
+
     out = {"unit": "captions/s",
            "what": "torch.nn composition of the same train step (head, decoder, CE, backward, clip, Adam) on this GPU, "
-                   f"torch {torch.__version__}: cuDNN LSTM, cuBLAS, ATen kernels; CUDA events, 10 steps after 3 warm-up"}
+                   f"torch {torch.__version__}: cuDNN LSTM, cuBLAS, ATen kernels; CUDA events, 10 steps after 3 warm-up; "
+                   "greedy: the reference's 20-step sample() loop on 4096 features"}
+    gfeat = torch.randn(GREEDY_B, c["E"], device=dev)
     for name, tf32, amp in (("fp32", False, False), ("tf32", True, False), ("bf16_autocast", True, True)):
         try:
             torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
@@ -274,13 +327,23 @@ def gpu_torch_reference_child(device_index):
             torch.cuda.synchronize()
             dt = e0.elapsed_time(e1) * 1e-3 / 10
             out[name] = {"value": c["B"] / dt, "ms_per_step": dt * 1e3, "loss": float(loss.detach())}
+            model.eval()
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                model.sample(gfeat)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(3):
+                    model.sample(gfeat)
+                e1.record()
+            torch.cuda.synchronize()
+            out[name]["greedy_tokens_per_s"] = GREEDY_B * 20 * 3 / (e0.elapsed_time(e1) * 1e-3)
             del model, opt
         except Exception as e:   # noqa: BLE001
             out[name] = {"error": repr(e)[:300]}
     print(json.dumps(out), flush=True)
 
 
-def gpu_torch_reference(device_index, timeout_s=240):
+def gpu_torch_reference(device_index, timeout_s=300):
     """the reference's own composition of torch.nn layers timed on THIS GPU (no kernel of ours),
     reported next to the bench line.  Runs in a child process after the timed regions, so that neither a crash nor a
     hang of that foreign code path can cost the bench line; any failure becomes an "error" string."""
@@ -295,36 +358,244 @@ def gpu_torch_reference(device_index, timeout_s=240):
         return {"error": repr(e)[:300]}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# per-stage rooflines
+# ---------------------------------------------------------------------------------------------------------------------
+def stage_rooflines(prof_us, n_tok, peaks, c=CFG, b_local=None):
+    """prof_us: {stage: microseconds per step} (snt_step_profile events, mean over real steps).  Algorithmic work per
+    stage as SURVEY.md §8(d) counts it: no credit for recomputation, dgrad + wgrad = 2x the forward contraction."""
+    B = b_local or c["B"]
+    E, H, V, K, L = c["E"], c["H"], c["V"], c["POOLED"], c["L"]
+    N = n_tok
+    lstm_mac = sum(4 * H * ((E if k == 0 else H) + H) for k in range(L))
+    n_par = V * E + sum(4 * H * ((E if k == 0 else H) + H) + 8 * H for k in range(L)) + V * H + V + E * K + 3 * E
+    work = {   # stage -> (bound, algorithmic FLOPs or bytes per step)
+        "vocab_ce_fwd": ("tensor", 2.0 * N * V * H),
+        "vocab_ce_bwd": ("tensor", 4.0 * N * V * H),
+        "lstm_fwd": ("tensor", 2.0 * N * lstm_mac),
+        "lstm_bwd": ("tensor", 4.0 * N * lstm_mac),
+        "head_fwd": ("tensor", 2.0 * B * K * E),
+        "head_bwd": ("tensor", 2.0 * B * K * E),
+        "embed_pack_fwd": ("hbm", 4.0 * N * E + 2.0 * N * E),                # read fp32 rows, write bf16 rows
+        "embed_pack_bwd": ("hbm", 4.0 * N * E + 4.0 * V * E),                # read dx, write dense d_w_emb
+        "clamp_adam": ("hbm", 28.0 * n_par),                                 # read p,g,m,v; write p,m,v
+    }
+    out = []
+    for name, us in sorted(prof_us.items(), key=lambda kv: -kv[1]):
+        ent = {"stage": name, "us_per_step": us}
+        if name in work and us > 0:
+            bound, w = work[name]
+            if bound == "tensor":
+                ach, peak, unit = w / (us * 1e-6) / 1e12, peaks["tf_sust"], "TFLOP/s"
+            else:
+                ach, peak, unit = w / (us * 1e-6) / 1e9, peaks["hbm"], "GB/s"
+            ent.update({"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                        "algorithmic_work": w})
+        out.append(ent)
+    return out
+
+
+def load_traffic():
+    """profiles/r02_traffic.json: DRAM bytes per stage of one training step from the committed `ncu --set full` capture of
+    this tree (written by profiles/ncu_traffic.py from the capture's raw page)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except ValueError:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------------
+class Workload:
+    """Model pair + stepper + NB distinct ragged batches (host pinned and device resident) for one configuration."""
+
+    def __init__(self, snt, c, b_local, world, rank, dev, prec, nb=NB):
+        from show_and_tell_b200 import parallel
+        self.c, self.b_local, self.world, self.dev = c, b_local, world, dev
+        torch.manual_seed(0)
+        self.enc = snt.EncoderCNN(c["E"], backbone=False, precision=prec).to(dev).train()
+        self.dec = snt.DecoderRNN(c["E"], c["H"], c["V"], c["L"], precision=prec).to(dev).train()
+        self.stepper = parallel.DataParallelStep(self.enc, self.dec)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        self.batches = []
+        for k in range(nb):
+            gb = snt.synthetic.make_batch(b_local * world, c["V"], embed=c["E"], seed=1 + k, pooled_dim=c["POOLED"])
+            sh = parallel.shard_batch(gb, world, rank)
+            hp, hc = pin(sh["pooled"]), pin(sh["captions"])
+            self.batches.append(dict(lengths=np.asarray(sh["lengths"], dtype=np.int64), n_tok=int(sum(sh["lengths"])),
+                                     n_glob=sh["n_tokens_global"], hp=hp, hc=hc, dp=hp.to(dev), dc=hc.to(dev)))
+        self.i = 0
+
+    def step_resident(self, fixed=False):
+        b = self.batches[0 if fixed else self.i % len(self.batches)]
+        self.i += 1
+        return self.stepper.step(b["dp"], b["dc"], b["lengths"], None, b["n_glob"] if self.world > 1 else None)
+
+    def mean_tokens(self):
+        return float(np.mean([b["n_tok"] for b in self.batches]))
+
+
+class E2E:
+    """Host-input loop: step i's H2D copies are issued on a side stream while step i-1 computes (double buffered), and
+    the loss of step i-1 is read back (pinned D2H + event) while step i runs; every step still pays its own copies and
+    its own loss read inside the timed region."""
+
+    def __init__(self, wl):
+        self.wl = wl
+        dev = wl.dev
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        tc = max(b["hc"].shape[1] for b in wl.batches)
+        self.bufs = [dict(p=torch.empty_like(wl.batches[0]["dp"]),
+                          c=torch.empty(wl.b_local, tc, dtype=torch.int64, device=dev),
+                          ev=torch.cuda.Event(), done=torch.cuda.Event()) for _ in range(2)]
+        self.loss_host = torch.zeros(1).pin_memory()
+        self.loss_ev = torch.cuda.Event()
+        self.i, self.pending, self.last = 0, False, float("nan")
+        self.h2d = int(np.mean([b["hp"].numel() * 4 + b["hc"].numel() * 8 for b in wl.batches]))
+
+    def _issue(self, k):
+        b, src = self.bufs[k & 1], self.wl.batches[k % len(self.wl.batches)]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(b["done"])          # the step that last used this slot has finished
+            b["p"].copy_(src["hp"], non_blocking=True)
+            b["c"][:, :src["hc"].shape[1]].copy_(src["hc"], non_blocking=True)
+            b["ev"].record(self.copy_stream)
+
+    def step(self):
+        wl, i = self.wl, self.i
+        b, src = self.bufs[i & 1], wl.batches[i % len(wl.batches)]
+        if i == 0:
+            self._issue(0)
+        self._issue(i + 1)                                  # prefetch the next step's inputs
+        cur = torch.cuda.current_stream()
+        cur.wait_event(b["ev"])
+        loss = wl.stepper.step(b["p"], b["c"][:, :src["hc"].shape[1]], src["lengths"], None,
+                               src["n_glob"] if wl.world > 1 else None)
+        b["done"].record(cur)
+        if self.pending:
+            self.loss_ev.synchronize()                      # previous step's loss has landed on the host
+            self.last = float(self.loss_host[0])
+        self.loss_host.copy_(loss.reshape(1), non_blocking=True)
+        self.loss_ev.record(cur)
+        self.pending = True
+        self.i = i + 1
+        return self.last
+
+    def final_loss(self):
+        self.loss_ev.synchronize()
+        return float(self.loss_host[0])
+
+
+def profile_stages(wl, nsteps=10):
+    """Mean device time per stage over `nsteps` real steps (CUDA events inside snt_step_run) + the optimizer launch."""
+    eng = wl.stepper.engine
+    acc = {}
+    eng.profile(True)
+    for _ in range(nsteps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        opt = wl.stepper.optimizer
+        wl.stepper.optimizer = False
+        wl.step_resident()
+        wl.stepper.optimizer = opt
+        prof = eng.profile_read()
+        e0.record()
+        lo, hi = 0, wl.stepper.flat.numel
+        wl.stepper.t += 1
+        eng.adam(lo, hi, wl.stepper.t, wl.stepper.lr, wl.stepper.betas, wl.stepper.eps, wl.stepper.grad_clip)
+        e1.record()
+        torch.cuda.synchronize()
+        prof["clamp_adam"] = e0.elapsed_time(e1)
+        for k, v in prof.items():
+            acc[k] = acc.get(k, 0.0) + v * 1e3 / nsteps
+    eng.profile(False)
+    return acc
+
+
+def measure_greedy(snt, dec, c, dev, world, timed, peaks, rank, with_cpu):
+    """BASELINE configs[2]: greedy sample() of 4096 image features per GPU x 20 tokens, every rank its own batch (the
+    batch shards with no communication), device-timed, max over ranks, tokens of all ranks counted."""
+    out = {"metric": "greedy_decode_tokens_per_s", "unit": "tokens/s", "higher_is_better": True,
+           "config": {"workload": f"DecoderRNN.sample(): 20 greedy steps (LSTM step -> vocab Linear -> first-index argmax "
+                                  f"-> embed), E{c['E']}/H{c['H']}/V{c['V']}/L{c['L']}, batch {GREEDY_B} image features per "
+                                  "GPU (BASELINE configs[2])", "batch_per_gpu": GREEDY_B, "steps": 20}}
+    feats_h = torch.randn(GREEDY_B, c["E"]).pin_memory()
+    feats = feats_h.to(dev)
+    dec.eval()
+    reps = 5
+    for prec in ("bf16", "fp32"):
+        dec.sample(feats, precision=prec)
+        t = timed(lambda: dec.sample(feats, precision=prec), reps)
+        tps = GREEDY_B * world * 20 * reps / t
+        if prec == "bf16":
+            out["value"], out["dtype"], out["ms_per_decode"] = tps, "bf16", t / reps * 1e3
+            tf = tps / world * greedy_flops_per_token(c) / 1e12
+            out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                               "frac": tf / peaks["tf_sust"], "traffic": None,
+                               "algorithmic_work_per_token": greedy_flops_per_token(c),
+                               "kernel": "per step: gemm_tc<128,LstmFwdEpi> ([x|h] concatenated operand) + "
+                                         "gemm_tc<256,ArgmaxEpi> (logits stay in TMEM) + argmax_finish",
+                               "timing": f"CUDA events around {reps} whole sample() calls (20 steps each)"}
+        else:
+            out["fp32_faithful"] = {"value": tps, "ms_per_decode": t / reps * 1e3,
+                                    "note": "token-exact mode (fp32 operands, FFMA accumulation)"}
+    # e2e: features from pinned host memory, ids back to the host, inside the timed region
+    ids_h = torch.empty(GREEDY_B, 20, dtype=torch.int64).pin_memory()
+
+    def one_e2e():
+        f = feats_h.to(dev, non_blocking=True)
+        ids_h.copy_(dec.sample(f, precision="bf16"), non_blocking=True)
+    one_e2e()
+    t = timed(one_e2e, reps)
+    out["e2e"] = {"value": GREEDY_B * world * 20 * reps / t, "unit": "tokens/s",
+                  "h2d_bytes_per_step": GREEDY_B * c["E"] * 4, "d2h_bytes_per_step": GREEDY_B * 20 * 8}
+    dec.train()
+    if with_cpu and rank == 0:
+        threads = os.cpu_count() or 1
+        tps, dt = cpu_greedy_baseline(c, 512, threads)
+        out["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
+                               "sample": f"2 x sample() of 512 image features x 20 tokens ({dt:.2f} s each) after 1 warm-up, "
+                                         f"torch {torch.__version__} CPU (oracle/torch_port.py)"}
+    return out
+
+
 def measure_f_rows(snt, dev, c, peaks):
     """Timings of the rows widened after the hot path, one GPU, after the timed regions; each guarded:
     a failure here becomes an "error" string and never costs the bench line.
-      caption_trim : snt_caption_trim on a batch larger than L2 (4 M captions x 20 ids: 640 MB read + 640 MB written),
-                     CUDA events, HBM roofline; and at the decode batch of configs[2] (latency-bound at that size).
+      caption_trim : snt_caption_trim on a batch larger than L2 (4 M captions x 20 ids), CUDA events, HBM roofline.
       trainer_loop : show_and_tell_b200.Trainer over 24 DISTINCT ragged host batches of 1024 captions fed by
-                     PrefetchLoader (pinned staging + side-stream H2D): eager launches, nothing repeats, wall clock
-                     around the whole loop including a final synchronize - what train.py's loop sees."""
+                     PrefetchLoader (pinned staging + side-stream H2D): wall clock around the whole loop including a
+                     final synchronize - what train.py's loop sees.
+      trunk_feed   : the frozen ResNet-152 trunk (cuDNN, channels-last bf16, side stream) feeding the decoder step:
+                     trunk alone, decoder alone, and both overlapped (feed.TrunkFeed), images/s."""
     out = {}
     try:
         res = {}
         for name, B in (("large", 4 << 20), ("configs2", GREEDY_B)):
             ids = torch.randint(3, c["V"], (B, 20), device=dev)
             ids[torch.rand(B, 20, device=dev) < 0.05] = 2
-            o, l = snt.ops.trim_captions(ids)
+            lengths = torch.empty(B, dtype=torch.int32, device=dev)
+            o = torch.empty_like(ids)
+            L = snt._lib
+            f = lambda: L.call("snt_caption_trim", L.ptr(ids), B, 20, 2, 0, L.ptr(lengths), L.ptr(o), L.stream_ptr())
+            f()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 10
             torch.cuda.synchronize()
             e0.record()
             for _ in range(reps):
-                snt.ops.trim_captions(ids)
+                f()
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / reps
             nbytes = B * 20 * 16 + B * 4
             res[name] = {"captions": B, "us": us, "achieved": nbytes / (us * 1e-6) / 1e9, "unit": "GB/s",
                          "peak": peaks["hbm"], "frac": nbytes / (us * 1e-6) / 1e9 / peaks["hbm"],
-                         "algorithmic_bytes": nbytes,
-                         "note": "includes the two torch.empty output allocations of ops.trim_captions"}
-            del ids, o, l
+                         "algorithmic_bytes": nbytes}
+            del ids, o, lengths
         out["caption_trim"] = res
     except Exception as e:   # noqa: BLE001
         out["caption_trim"] = {"error": repr(e)[:300]}
@@ -357,47 +628,59 @@ def measure_f_rows(snt, dev, c, peaks):
         dt = time.perf_counter() - t0
         out["trainer_loop"] = {"value": nb * c["B"] / dt, "unit": "captions/s", "ms_per_step": dt / nb * 1e3,
                                "batches": nb, "loss": float(tr.last_loss),
-                               "what": "Trainer.train() over distinct ragged host batches through PrefetchLoader, eager "
-                                       "launches, wall clock incl. H2D"}
+                               "what": "Trainer.train() over distinct ragged host batches through PrefetchLoader, "
+                                       "wall clock incl. H2D"}
         del tr, model, batches
         torch.cuda.empty_cache()
     except Exception as e:   # noqa: BLE001
         out["trainer_loop"] = {"error": repr(e)[:300]}
+    try:
+        out["trunk_feed"] = measure_trunk_feed(snt, dev, c)
+    except Exception as e:   # noqa: BLE001
+        out["trunk_feed"] = {"error": repr(e)[:300]}
     return out
 
 
-def stage_rooflines(prof, nsteps, n_tok, peaks, c=CFG):
-    """prof: {C-ABI entry point: (calls, total ms)} recorded with CUDA events around every call of `nsteps` real
-    steps (same stream, same pipeline as the timed region).  Algorithmic work per stage as SURVEY.md §8(d) counts
-    it (no credit for the backward's recompute of the logits)."""
-    B, E, H, V, K = c["B"], c["E"], c["H"], c["V"], c["POOLED"]
-    N = n_tok
-    n_par = V * E + 4 * H * (E + H) + 8 * H + V * H + V + E * K + 3 * E
-    work = {   # stage -> (bound, algorithmic FLOPs or bytes per step)
-        "snt_vocab_ce_fwd": ("tensor", 2.0 * N * V * H),
-        "snt_vocab_ce_bwd": ("tensor", 4.0 * N * V * H),
-        "snt_lstm_fwd": ("tensor", 2.0 * N * 4 * H * (E + H)),
-        "snt_lstm_bwd": ("tensor", 4.0 * N * 4 * H * (E + H)),
-        "snt_head_fwd": ("tensor", 2.0 * B * K * E),
-        "snt_head_bwd": ("tensor", 2.0 * B * K * E),
-        "snt_embed_pack_fwd": ("hbm", 4.0 * N * E + 2.0 * N * E),            # read fp32 rows, write bf16 rows
-        "snt_embed_pack_bwd": ("hbm", 4.0 * N * E + 4.0 * V * E),            # read dx, write dense d_w_emb
-        "snt_clamp_adam_multi": ("hbm", 28.0 * n_par),                       # read p,g,m,v; write p,m,v
-    }
-    out = []
-    for name, (calls, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-        us = ms / nsteps * 1e3
-        ent = {"stage": name, "launches_per_step": calls / nsteps, "us_per_step": us}
-        if name in work:
-            bound, w = work[name]
-            if bound == "tensor":
-                ach, peak, unit = w / (us * 1e-6) / 1e12, peaks["tf_sust"], "TFLOP/s"
-            else:
-                ach, peak, unit = w / (us * 1e-6) / 1e9, peaks["hbm"], "GB/s"
-            ent.update({"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                        "algorithmic_work": w})
-        out.append(ent)
-    return out
+def measure_trunk_feed(snt, dev, c, batch=128, iters=6):
+    """f3: the frozen ResNet-152 trunk as the producer of the hot path's input (batch 128 images of 3x224x224, the
+    reference's default batch, config.py:17): images/s of (a) the trunk alone, (b) the decoder step alone on its pooled
+    features, (c) TrunkFeed on a side stream overlapped with the decoder step of the previous batch."""
+    from show_and_tell_b200 import parallel
+    from show_and_tell_b200.feed import TrunkFeed
+    torch.manual_seed(0)
+    enc = snt.EncoderCNN(c["E"], backbone=True, precision="bf16").to(dev).train()
+    dec = snt.DecoderRNN(c["E"], c["H"], c["V"], c["L"], precision="bf16").to(dev).train()
+    st = parallel.DataParallelStep(enc, dec)
+    feed = TrunkFeed(enc, bn_mode="eval")
+    b = snt.synthetic.make_batch(batch, c["V"], seed=7)
+    caps = torch.from_numpy(b["captions"]).to(dev)
+    imgs = [torch.randn(batch, 3, 224, 224, device=dev) for _ in range(2)]
+
+    def clock(fn, n):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn(n)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n
+
+    pooled = feed.pooled(imgs[0])
+    st.step(pooled, caps, b["lengths"])
+    t_trunk = clock(lambda n: [feed.pooled(imgs[i & 1]) for i in range(n)], iters)
+    t_dec = clock(lambda n: [st.step(pooled, caps, b["lengths"]) for _ in range(n)], iters)
+
+    def overlapped(n):
+        ticket = feed.submit(imgs[0])
+        for i in range(n):
+            p = feed.result(ticket)
+            ticket = feed.submit(imgs[(i + 1) & 1])   # trunk of batch i+1 on the side stream ...
+            st.step(p, caps, b["lengths"])            # ... while the decoder trains on batch i
+        feed.result(ticket)
+    overlapped(2)
+    t_ov = clock(overlapped, iters)
+    return {"batch": batch, "trunk_images_per_s": batch / t_trunk, "decoder_captions_per_s": batch / t_dec,
+            "overlapped_images_per_s": batch / t_ov, "serial_images_per_s": batch / (t_trunk + t_dec),
+            "what": "ResNet-152 trunk (cuDNN, channels-last bf16, eval-mode BN, side stream) + decoder train step on its "
+                    "pooled features; wall clock over 6 iterations"}
 
 
 def main():
@@ -406,15 +689,17 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference", "torch-gpu"])
+    ap.add_argument("--config", default="default", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: BASELINE configs[4] as written, global batch 8192 sharded over the ranks")
     ap.add_argument("--device-index", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--prec", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-greedy", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the timings of the widened rows (trim kernel, Trainer loop)")
+    ap.add_argument("--no-extras", action="store_true", help="skip f_rows / configs3 / strong_8192")
     ap.add_argument("--no-gpu-reference", action="store_true",
                     help="skip timing torch's own cuDNN/cuBLAS composition of the same step on this GPU")
-    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay of fwd+bwd")
-    ap.add_argument("--stages", action="store_true", help="also print per-entry-point GPU time (CUDA events) to stderr")
+    ap.add_argument("--stages", action="store_true", help="also print per-stage GPU time (CUDA events) to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -435,7 +720,6 @@ def main():
 
     import torch.distributed as dist
     import show_and_tell_b200 as snt
-    from show_and_tell_b200 import parallel
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
     torch.cuda.set_device(local)
@@ -443,27 +727,10 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # all-reduce CTAs are placed first when SMs free up
-
         dist.init_process_group("nccl", device_id=dev)
-    c = CFG
+    c = CONFIGS[args.config]
     peaks = load_peaks()
-
-    torch.manual_seed(0)
-    enc = snt.EncoderCNN(c["E"], backbone=False, precision=args.prec).to(dev).train()
-    dec = snt.DecoderRNN(c["E"], c["H"], c["V"], c["L"], precision=args.prec).to(dev).train()
-    # forward + backward (+ all-reduce) are replayed as one CUDA graph once the same batch has been stepped twice eagerly
-    # (the benchmark batch is fixed); the optimizer launch stays outside the graph
-    stepper = parallel.DataParallelStep(enc, dec, cuda_graph=not args.no_graph, graph_after=2)
-
-    gb = make_global_batch(world)
-    sh = parallel.shard_batch(gb, world, rank)
-    lengths = sh["lengths"]
-    targets_h = snt.synthetic.pack_host(sh["captions"], lengths)
-    n_tok = int(sum(lengths))
-    n_tok_global = sh["n_tokens_global"]
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    pooled_h, caps_h, tg_h = pin(sh["pooled"]), pin(sh["captions"]), pin(targets_h)
-    pooled_d, caps_d, tg_d = pooled_h.to(dev), caps_h.to(dev), tg_h.to(dev)
+    b_local = c["B"] if args.scaling == "weak" else max(1, STRONG_GLOBAL_B // world)
 
     def barrier():
         if world > 1:
@@ -477,46 +744,6 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    step_resident = lambda: stepper.step(pooled_d, caps_d, lengths, tg_d, n_tok_global)
-
-    # e2e: HOST inputs.  Step i's H2D copies are issued on a side stream while step i-1 computes (double
-    # buffered), and the loss of step i-1 is read back (pinned D2H + event) while step i runs; every step still
-    # pays its own copies and its own loss read inside the timed region.
-    copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [dict(p=torch.empty_like(pooled_d), c=torch.empty_like(caps_d), t=torch.empty_like(tg_d),
-                 ev=torch.cuda.Event(), done=torch.cuda.Event()) for _ in range(2)]
-    loss_host = torch.zeros(1).pin_memory()
-    loss_ev = torch.cuda.Event()
-    e2e_state = {"i": 0, "pending": False, "last": float("nan")}
-
-    def issue_copy(slot):
-        b = bufs[slot]
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(b["done"])          # the step that last used this slot has finished
-            b["p"].copy_(pooled_h, non_blocking=True)
-            b["c"].copy_(caps_h, non_blocking=True)
-            b["t"].copy_(tg_h, non_blocking=True)
-            b["ev"].record(copy_stream)
-
-    def step_e2e():
-        i = e2e_state["i"]
-        b = bufs[i & 1]
-        if i == 0:
-            issue_copy(0)
-        issue_copy((i + 1) & 1)                        # prefetch the next step's inputs
-        cur = torch.cuda.current_stream()
-        cur.wait_event(b["ev"])
-        loss = stepper.step(b["p"], b["c"], lengths, b["t"], n_tok_global)
-        b["done"].record(cur)
-        if e2e_state["pending"]:
-            loss_ev.synchronize()                      # previous step's loss has landed on the host
-            e2e_state["last"] = float(loss_host[0])
-        loss_host.copy_(loss.reshape(1), non_blocking=True)
-        loss_ev.record(cur)
-        e2e_state["pending"] = True
-        e2e_state["i"] = i + 1
-        return e2e_state["last"]
-
     def timed(fn, k):
         barrier()
         st = torch.cuda.current_stream()
@@ -528,191 +755,178 @@ def main():
         barrier()
         return max_over_ranks(e0.elapsed_time(e1) * 1e-3)
 
+    wl = Workload(snt, c, b_local, world, rank, dev, args.prec)
     phase("warm-up")
-    for _ in range(args.warmup):
-        step_resident()
+    for _ in range(args.warmup + (EXTRA_WARMUP_MULTI_GPU if world > 1 else 0)):
+        wl.step_resident()
     phase("warm-up done")
     if os.environ.get("SNT_BENCH_GC", "freeze") == "freeze":
-        # Everything allocated so far (torch, modules, CUDA graph, NCCL state) is long-lived: move it to the permanent
-        # generation so that the cyclic collector's full passes stay short.  A full collection over the whole heap in
-        # the middle of a multi-GPU run pauses one rank's host thread for tens of ms and, through the next all-reduce,
-        # every GPU of the job.
+        # Everything allocated so far is long-lived: move it to the permanent generation so that the cyclic collector's
+        # full passes stay short (a full collection in the middle of a multi-GPU run pauses one rank's host thread for
+        # tens of ms and, through the next all-reduce, every GPU of the job).
         import gc
         gc.collect()
         gc.freeze()
-    elif os.environ.get("SNT_BENCH_GC") == "off":
-        import gc
-        gc.collect()
-        gc.disable()
     sampler = ClockSampler(local)
     L = snt._lib.lib()
     if world == 1:
-        # one GPU: NVML is polled from a background thread for the whole timed region (no measurable effect on the step)
-        sampler.start()
-        L.snt_launch_count(1)
-        r0 = stepper.replayed_kernels
-        t_res = timed(step_resident, args.steps)
-        launches = int(L.snt_launch_count(0)) + stepper.replayed_kernels - r0
-        # keep the same step running so that the 100 ms poll sees the loaded clocks
+        sampler.start()          # NVML polled from a background thread for the whole timed region
+    else:
+        sampler.open_manual()    # polling while ranks exchange gradients stretches the step: sample right after instead
+    L.snt_launch_count(1)
+    t_res = timed(wl.step_resident, args.steps)
+    launches = int(L.snt_launch_count(0))
+    if world == 1:
         n_extra = int(np.ceil(max(0.0, 1.5 - t_res) / max(t_res / args.steps, 1e-6)))
         for _ in range(n_extra):
-            step_resident()
+            wl.step_resident()
         torch.cuda.synchronize()
         clocks = sampler.stop()
-        clocks["sampled_over"] = "timed region + continuation of the same step to >= 1.5 s"
+        clocks["sampled_over"] = "timed region + continuation of the same loop to >= 1.5 s"
     else:
-        # N > 1: any NVML / nvidia-smi polling while the ranks exchange gradients stretches the step 3-6x (measured:
-        # 1.56 ms -> 4.5-9.8 ms at N=2), so the clocks are sampled on demand while the GPU is busy with the SAME step
-        # immediately after the timed region, never inside it.  Step counts are identical on
-        # every rank (a wall-clock loop would issue different numbers of all-reduces per rank and hang).
-        # Multi-GPU steps need a much longer warm-up than W: measured at N=2, successive blocks of 30 steps take 5.7,
-        # 3.6, 2.7 and then a steady 1.56 ms per step (the caching allocator keeps growing its pool while gradient
-        # blocks are still held by NCCL's stream, NCCL sets up its channels lazily).  EXTRA_WARMUP more untimed steps
-        # (identical on every rank) put the timed region in the steady state a training run lives in.
-        for _ in range(EXTRA_WARMUP_MULTI_GPU):
-            step_resident()
-        sampler.open_manual()
-        L.snt_launch_count(1)
-        r0 = stepper.replayed_kernels
-        t_res = timed(step_resident, args.steps)
-        launches = int(L.snt_launch_count(0)) + stepper.replayed_kernels - r0
         for _ in range(4):
             for _ in range(5):
-                step_resident()
+                wl.step_resident()
             sampler.sample_once()
         torch.cuda.synchronize()
         clocks = sampler.stop()
         clocks["sampled_over"] = "20 more steps of the same load right after the timed region (polling inside it perturbs multi-GPU steps)"
-    if os.environ.get("SNT_BENCH_DEBUG"):
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-        barrier()
-        evs[0].record()
-        for i in range(args.steps):
-            step_resident()
-            evs[i + 1].record()
-        barrier()
-        if rank == 0:
-            per = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-            print("[dbg] per-step ms: " + " ".join(f"{x:.2f}" for x in per), file=sys.stderr)
-        t2 = timed(step_resident, args.steps)
-        if rank == 0:
-            print(f"[dbg] resident again, no clock sampler: {t2 / args.steps * 1e3:.3f} ms/step "
-                  f"(with sampler {t_res / args.steps * 1e3:.3f})", file=sys.stderr)
+    t_fixed = timed(lambda: wl.step_resident(fixed=True), args.steps)
+    phase("timed regions done; stage profile")
 
-    phase("timed region done; stage profile")
-    # per-stage GPU time: CUDA events around every C-ABI call of 10 more real steps (rank 0's stream)
     stages = None
-    graph_mode, stepper.cuda_graph = stepper.cuda_graph, False   # the per-call events need eager C-ABI calls
     if rank == 0:
-        snt._lib.profile_begin()
-    for _ in range(10):
-        step_resident()
-    if rank == 0:
-        prof = snt._lib.profile_end()
-        stages = stage_rooflines(prof, 10, n_tok, peaks)
+        prof = profile_stages(wl, 10)
+        stages = stage_rooflines(prof, wl.mean_tokens(), peaks, c, b_local)
         if args.stages:
             tot = sum(e["us_per_step"] for e in stages)
             for e in stages:
-                print(f"[stages] {e['stage']:24s} {e['us_per_step']:9.1f} us/step {100 * e['us_per_step'] / tot:5.1f}%  "
+                print(f"[stages] {e['stage']:16s} {e['us_per_step']:9.1f} us/step {100 * e['us_per_step'] / tot:5.1f}%  "
                       f"{e.get('achieved', 0):8.1f} {e.get('unit', '')} ({100 * e.get('frac', 0):4.1f}% of peak)",
                       file=sys.stderr)
             print(f"[stages] sum {tot:.1f} us/step", file=sys.stderr)
-    stepper.cuda_graph = graph_mode
-    phase("stage profile done; e2e pre-steps")
+    else:
+        for _ in range(10):      # keep every rank's step count (and its collectives) aligned with rank 0's profile steps
+            opt = wl.stepper.optimizer
+            wl.stepper.optimizer = False
+            wl.step_resident()
+            wl.stepper.optimizer = opt
+            wl.stepper.t += 1
+            wl.stepper.engine.adam(0, wl.stepper.flat.numel, wl.stepper.t, wl.stepper.lr, wl.stepper.betas,
+                                   wl.stepper.eps, wl.stepper.grad_clip)
+    phase("stage profile done; e2e")
+    e2e = E2E(wl)
+    for _ in range(4):
+        e2e.step()
+    t_e2e = timed(e2e.step, args.steps)
+    e2e.step()
+    loss_val = e2e.final_loss()
+    phase("e2e done")
 
-    for _ in range(8):            # both host-buffer slots get captured (graph mode) before the timed region
-        step_e2e()
-    phase("e2e pre-steps done; e2e timed")
-    t_e2e = timed(step_e2e, args.steps)
-    phase("e2e timed done")
-    loss_val = step_e2e()
-    loss_ev.synchronize()
-    loss_val = float(loss_host[0])
-
-    total_caps = c["B"] * world
+    total_caps = b_local * world
     value = total_caps * args.steps / t_res
-    e2e_value = total_caps * args.steps / t_e2e
-    flops_step = train_flops(c["B"], n_tok)
+    n_tok = wl.mean_tokens()
+    flops_step = train_flops(b_local, n_tok, c)
     step_tf = flops_step * args.steps / t_res / 1e12      # per GPU (max-over-ranks time)
 
-    # greedy decode (BASELINE configs[2]): batch 4096 per GPU, 20 tokens each, no communication (the batch shards);
-    # every rank decodes its own batch, device-timed, max over ranks, tokens of all ranks counted
-    greedy = {}
-    stepper.close()   # no training step follows: release the captured graphs (they hold NCCL work) before more barriers
+    strong = None
+    if world > 1 and args.scaling == "weak" and args.config == "default" and not args.no_extras:
+        # BASELINE configs[4] as written: global batch 8192 over the N ranks (4096 / 2048 / 1024 captions per GPU)
+        phase("strong-scaling leg")
+        ws = Workload(snt, c, STRONG_GLOBAL_B // world, world, rank, dev, args.prec, nb=4)
+        for _ in range(20):
+            ws.step_resident()
+        ks = max(10, args.steps // 2)
+        t_s = timed(ws.step_resident, ks)
+        strong = {"global_batch": STRONG_GLOBAL_B, "batch_per_gpu": STRONG_GLOBAL_B // world, "n_gpus": world,
+                  "value": STRONG_GLOBAL_B * ks / t_s, "unit": "captions/s", "ms_per_step": t_s / ks * 1e3,
+                  "steps": ks, "scaling": "strong",
+                  "what": "BASELINE configs[4]: data-parallel train step, global batch 8192 sharded by strided rows"}
+        ws.stepper.close()
+        del ws
+        torch.cuda.empty_cache()
+
+    greedy = None
     if not args.no_greedy:
-        feats = torch.randn(GREEDY_B, c["E"], device=dev)
-        dec.eval()
-        for prec in ("fp32", "bf16"):
-            dec.sample(feats, precision=prec)
-            reps = 3
-            t_g = timed(lambda: dec.sample(feats, precision=prec), reps)
-            greedy[f"greedy_tokens_per_s_{prec}"] = GREEDY_B * world * 20 * reps / t_g
-        dec.train()
-        del feats
+        phase("greedy")
+        greedy = measure_greedy(snt, wl.dec, CFG if args.config == "default" else c, dev, world, timed, peaks, rank,
+                                with_cpu=(world == 1 and not args.no_cpu_baseline)) if c["L"] >= 1 else None
 
     extra = {}
     if rank == 0:
         top = stages[0]
+        traffic = load_traffic()
+        tr_stage = (traffic or {}).get("stages", {}).get(top["stage"]) if args.config == "default" else None
         roof = {"bound": top.get("bound"), "achieved": top.get("achieved"), "peak": top.get("peak"),
                 "unit": top.get("unit"), "frac": top.get("frac"),
-                # dram__bytes_read.sum + dram__bytes_write.sum of the stage's nine tensor-core launches, one ncu --set
-                # full capture (profiles/r01_ncu_hot_kernels.txt); null for any other stage
-                "traffic": 7.6840e+08 if top["stage"] == "snt_vocab_ce_bwd" else None,
-                "traffic_unit": "bytes per step (ncu, profiles/r01_ncu_hot_kernels.txt)",
-                "kernel": top["stage"] + " (largest share of the step; tcgen05 GEMMs gemm_tc_kernel<256,CeBwdEpiT<16>> + "
-                          "dHs/dW_out gemm_tc_kernel<128,PlainEpi> per 37-row-tile chunk)" if top["stage"] == "snt_vocab_ce_bwd"
-                          else top["stage"],
+                "traffic": tr_stage["dram_bytes"] if tr_stage else None,
+                "traffic_source": (traffic or {}).get("source") if tr_stage else None,
+                "kernel": top["stage"] + (" (" + tr_stage["kernels"] + ")" if tr_stage and "kernels" in tr_stage else ""),
                 "us_per_step": top["us_per_step"],
-                # share of the summed per-stage GPU time of the same (eager) profiling steps - comparable with the
-                # kernel shares of the ncu launch list in profiles/
                 "share_of_step": top["us_per_step"] / max(sum(e["us_per_step"] for e in stages), 1e-9),
                 "algorithmic_work_per_step": top.get("algorithmic_work"),
                 "peak_source": f"{peaks['src']} (MEASURED_PEAKS.json: sustained bf16 for a stage inside a long step)",
-                "timing": "CUDA events around the C-ABI call on the launching stream, mean of 10 eagerly launched steps "
-                          "(the timed region itself replays forward+backward as one CUDA graph on one GPU)"}
+                "timing": "CUDA events inside snt_step_run around the stage on its launching stream, mean of 10 real steps"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import torch_port as TP   # bench's cpu_baseline leg: the checker timed, never shipped
             threads = os.cpu_count() or 1
-            b1 = {"pooled": np.ascontiguousarray(gb["pooled"][: c["B"]]), "captions": gb["captions"][: c["B"]],
-                  "lengths": gb["lengths"][: c["B"]]}
-            b1["targets"] = snt.synthetic.pack_host(b1["captions"], b1["lengths"])
-            cps, dt, _ = TP.time_full_train(c["B"], c["E"], c["H"], c["V"], c["L"], b1, steps=3, warmup=1,
-                                            threads=threads)
+            cps, dt, _, ntk = cpu_train_baseline(c, 3, 1, threads)
             cpu = {"value": cps, "unit": "captions/s", "cores": threads, "kind": "port",
-                   "sample": f"3 full train steps (head+decoder fwd, CE, bwd, clip, Adam) of B=1024 ({dt:.2f} s/step) after 1 warm-up, torch "
-                             f"{torch.__version__} CPU (oracle/torch_port.py, pinned to the reference's goldens)"}
+                   "sample": f"3 full train steps (head+decoder fwd, CE, bwd, clip, Adam) of B={c['B']} ({dt:.2f} s/step) "
+                             f"after 1 warm-up, torch {torch.__version__} CPU (oracle/torch_port.py, pinned to the "
+                             "reference's goldens)"}
         gpu_ref = None
-        if world == 1 and not args.no_gpu_reference:
+        if world == 1 and not args.no_gpu_reference and args.config == "default":
             gpu_ref = gpu_torch_reference(local)
+            if greedy is not None and isinstance(gpu_ref, dict):
+                greedy["gpu_torch_reference"] = {k: v.get("greedy_tokens_per_s") for k, v in gpu_ref.items()
+                                                 if isinstance(v, dict) and "greedy_tokens_per_s" in v}
         if world == 1 and not args.no_extras:
+            if args.config == "default":
+                try:      # BASELINE configs[3] in the same record
+                    c3 = CONFIGS["scaled"]
+                    w3 = Workload(snt, c3, c3["B"], 1, 0, dev, args.prec, nb=4)
+                    for _ in range(4):
+                        w3.step_resident()
+                    k3 = 12
+                    t3 = timed(w3.step_resident, k3)
+                    f3 = train_flops(c3["B"], w3.mean_tokens(), c3)
+                    st3 = stage_rooflines(profile_stages(w3, 4), w3.mean_tokens(), peaks, c3, c3["B"])
+                    extra["configs3"] = {"value": c3["B"] * k3 / t3, "unit": "captions/s", "ms_per_step": t3 / k3 * 1e3,
+                                         "steps": k3, "config": workload_config(c3, c3["B"], 1, args.prec,
+                                                                                int(w3.mean_tokens()), 20),
+                                         "step_tflops": f3 * k3 / t3 / 1e12,
+                                         "step_frac_of_sustained_peak": f3 * k3 / t3 / 1e12 / peaks["tf_sust"],
+                                         "stages": st3}
+                    w3.stepper.close()
+                    del w3
+                    torch.cuda.empty_cache()
+                except Exception as e:   # noqa: BLE001
+                    extra["configs3"] = {"error": repr(e)[:300]}
             extra["f_rows"] = measure_f_rows(snt, dev, c, peaks)
-        extra.update(greedy)
         line = {
             "metric": "train_captions_per_s", "value": value, "unit": "captions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16" if args.prec == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "decoder train step on precomputed 2048-d features: head(Linear+BN) + embed/pack + "
-                                   "LSTM + fused vocab-CE fwd + BPTT bwd + clip/Adam; E256/H512/V10000/L1, "
-                                   "batch 1024 per GPU (BASELINE configs[1]; N>1 = configs[4] weak-scaled)",
-                       "global_batch": total_caps, "tokens_per_rank": n_tok, "max_len": int(max(lengths)),
-                       "parallelism": f"dp{world}", "precision_mode": args.prec,
-                       "extra_warmup_steps": EXTRA_WARMUP_MULTI_GPU if world > 1 else 0,
-                       "launch_mode": "fwd+bwd replayed as one CUDA graph, optimizer eager" if stepper.cuda_graph else "eager",
-                       "l2": "no explicit flush: each step streams ~0.6 GB of activations/weights (> 126 MB L2)"},
-            "e2e": {"value": e2e_value, "unit": "captions/s", "ms_per_step": t_e2e / args.steps * 1e3,
-                    "h2d_bytes_per_step": int(pooled_h.numel() * 4 + caps_h.numel() * 8 + tg_h.numel() * 8),
-                    "d2h_bytes_per_step": 4},
+            "config": workload_config(c, b_local, world, args.prec, int(n_tok), int(max(b["lengths"][0] for b in wl.batches)),
+                                      batches=f"{NB} distinct ragged batches cycled in the timed region (resident in HBM)",
+                                      extra_warmup_steps=EXTRA_WARMUP_MULTI_GPU if world > 1 else 0,
+                                      launch_mode="eager launches through the native step executor (no CUDA graph)",
+                                      l2="no explicit flush: each step streams ~0.9 GB of activations/weights (> 126 MB L2)"),
+            "fixed_batch": {"value": total_caps * args.steps / t_fixed, "ms_per_step": t_fixed / args.steps * 1e3,
+                            "what": "the same loop repeating batch 0"},
+            "e2e": {"value": total_caps * args.steps / t_e2e, "unit": "captions/s", "ms_per_step": t_e2e / args.steps * 1e3,
+                    "h2d_bytes_per_step": e2e.h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
             "clocks": clocks, "roofline": roof, "stages": stages, "cpu_baseline": cpu,
-            "gpu_torch_reference": gpu_ref,
+            "gpu_torch_reference": gpu_ref, "greedy": greedy, "strong_8192": strong,
             "step_tflops_per_gpu": step_tf, "step_frac_of_sustained_peak": step_tf / peaks["tf_sust"],
             "algorithmic_flops_per_step": flops_step, "loss": loss_val, **extra,
         }
         print(json.dumps(line), flush=True)
     phase("line printed; teardown")
-    stepper.close()   # graphs holding NCCL collectives must be released before barrier()/destroy_process_group()
+    wl.stepper.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

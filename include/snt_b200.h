@@ -93,16 +93,6 @@ int snt_embed_pack_bwd(const float* dx, const int64_t* captions, int64_t cap_str
                        const int32_t* batch_sizes /*[host] T*/, int T, int64_t B, int64_t E, int64_t V,
                        float* dfeatures, float* d_w_emb, void* ws, int64_t ws_bytes, void* stream);
 
-/* The same backward as two calls (experimental): snt_embed_bwd_plan does the token-dependent half (histogram and scan
- * of the token ids: needs the captions, not dx) and may be enqueued early, on another stream, while dx is still being
- * computed; snt_embed_pack_bwd_planned finishes the job on a workspace that went through the plan call with the same
- * captions / batch_sizes / V.  Together they issue exactly the launches of snt_embed_pack_bwd. */
-int snt_embed_bwd_plan(const int64_t* captions, int64_t cap_stride, const int32_t* batch_sizes /*[host] T*/, int T,
-                       int64_t V, void* ws, int64_t ws_bytes, void* stream);
-int snt_embed_pack_bwd_planned(const float* dx, const int64_t* captions, int64_t cap_stride,
-                               const int32_t* batch_sizes /*[host] T*/, int T, int64_t B, int64_t E, int64_t V,
-                               float* dfeatures, float* d_w_emb, void* ws, int64_t ws_bytes, void* stream);
-
 /* ---- a7  one LSTM layer over the packed sequence  (models.py:52, nn.LSTM, gate rows i|f|g|o) ---------
  * h0 = c0 = 0.  x (act) [N,In].  Saves for backward: gates[N,4H] fp32 (post-activation i,f,g,o),
  * cs[N,H] fp32 (c_t), hs (act) [N,H] (h_t = the layer output), hprev (act) [N,H] (h_{t-1} per row). */
@@ -191,6 +181,63 @@ int snt_clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, doub
 int snt_clamp_adam_multi(int count, float* const* p, const float* const* g, float* const* m, float* const* v,
                          const int64_t* n, double lr, double beta1, double beta2, double eps, float grad_clip,
                          float grad_scale, int64_t step, void* stream);
+
+/* ---- the whole teacher-forced step as ONE native call sequence  (train.py:137-146 for the models.py pair) --------
+ * forward (encoder head -> gather/concat/pack -> L LSTM layers -> fused vocab-CE), backward (CE -> BPTT -> embedding
+ * gradient and head backward on two streams) in the order of the stage functions above, with every activation carved
+ * out of one caller-owned workspace.  No autograd graph, no per-stage host round trip: a step costs the host a few
+ * function calls, so ragged batches (a different batch_sizes[] every step) run at the speed of the GPU without any
+ * graph capture.  The packed geometry comes from the [host] batch_sizes of THIS call.
+ *
+ * Phases (bit mask for snt_step_run), to be issued in this order with the same descriptor and workspace; a
+ * data-parallel caller starts its gradient all-reduce between them (one process per GPU; the reference's
+ * nn.DataParallel, train.py:43-44):
+ *   SNT_STEP_FWD       loss
+ *   SNT_STEP_BWD_CE    d_w_out, d_b_out                       (ready first: overlaps all of BPTT)
+ *   SNT_STEP_BWD_LSTM  d_w_ih / d_w_hh / d_b_ih / d_b_hh of every layer
+ *   SNT_STEP_BWD_TAIL  d_w_emb and the head gradients (d_w_fc, d_b_fc, d_bn_w, d_bn_b), optional d_features
+ * Gradients are WRITTEN (not accumulated) with the factor grad_scale folded in; `loss` = grad_scale * mean CE.
+ * K = 0: no encoder head, `input` holds features[B,E] (then the head pointers may be NULL).
+ * targets = NULL: targets are gathered on the device from `captions` (eval.py:91: pack(captions, lengths)). */
+enum { SNT_STEP_FWD = 1, SNT_STEP_BWD_CE = 2, SNT_STEP_BWD_LSTM = 4, SNT_STEP_BWD_TAIL = 8, SNT_STEP_ALL = 15 };
+
+typedef struct snt_step {
+  int32_t struct_bytes;          /* = sizeof(snt_step): guards against a stale binding */
+  int32_t prec;                  /* SNT_PREC_* */
+  int32_t L, T;                  /* LSTM layers; timesteps of this batch */
+  int32_t training;              /* head BatchNorm: batch statistics + running-stat update (models.py:28 in train()) */
+  int32_t reserved;
+  int64_t B, E, H, V, K;         /* captions, embed, hidden, vocab, pooled width (0: no head) */
+  int64_t cap_stride;            /* row pitch of captions in elements */
+  const int32_t* batch_sizes;    /* [host] T */
+  const float* input;            /* pooled[B,K] (K > 0) or features[B,E] */
+  const int64_t* captions;       /* [B, cap_stride] */
+  const int64_t* targets;        /* [N] or NULL */
+  const float *w_fc, *b_fc, *bn_w, *bn_b;
+  float *bn_rm, *bn_rv;
+  float bn_momentum, bn_eps;
+  const float *w_emb, *w_out, *b_out;
+  const float *w_ih[SNT_MAX_LAYERS], *w_hh[SNT_MAX_LAYERS], *b_ih[SNT_MAX_LAYERS], *b_hh[SNT_MAX_LAYERS];
+  float *d_w_fc, *d_b_fc, *d_bn_w, *d_bn_b, *d_w_emb, *d_w_out, *d_b_out;
+  float *d_w_ih[SNT_MAX_LAYERS], *d_w_hh[SNT_MAX_LAYERS], *d_b_ih[SNT_MAX_LAYERS], *d_b_hh[SNT_MAX_LAYERS];
+  float* d_features;             /* optional [B,E]: gradient w.r.t. `input` when K = 0 */
+  float grad_scale;
+  float pad_;
+  float* loss;                   /* device scalar */
+  void* ws;
+  int64_t ws_bytes;              /* >= snt_step_workspace_bytes(prec, L, B, N, E, H, V, K) with N >= sum(batch_sizes) */
+} snt_step;
+
+int64_t snt_step_workspace_bytes(int prec, int L, int64_t B, int64_t N, int64_t E, int64_t H, int64_t V, int64_t K);
+int snt_step_run(const snt_step* step, int phases, void* stream);
+
+/* Per-stage device time of snt_step_run (diagnostics).  snt_step_profile(1) makes every later run record a CUDA-event
+ * pair around each stage on the stream it is enqueued on; snt_step_profile_read synchronises the device and returns the
+ * milliseconds of the last run per slot: 0 head fwd, 1 gather/pack (+ targets), 2+k LSTM fwd of layer k, 10 vocab-CE fwd,
+ * 11 vocab-CE bwd, 12+k LSTM bwd of layer k, 20 embedding gradient, 21 head bwd (runs beside 20 on a second stream). */
+#define SNT_STEP_PROFILE_SLOTS 22
+int snt_step_profile(int enable);
+int snt_step_profile_read(float* ms, int slots);
 
 #ifdef __cplusplus
 }

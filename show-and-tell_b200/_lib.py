@@ -40,8 +40,6 @@ SIGNATURES = {
     "snt_embed_pack_fwd": (_int, [_vp, _vp, _vp, _i64, _vp, _int, _i64, _i64, _vp, _vp, _vp]),
     "snt_embed_bwd_workspace_bytes": (_i64, [_i64, _i64]),
     "snt_embed_pack_bwd": (_int, [_vp, _vp, _i64, _vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
-    "snt_embed_bwd_plan": (_int, [_vp, _i64, _vp, _int, _i64, _vp, _i64, _vp]),
-    "snt_embed_pack_bwd_planned": (_int, [_vp, _vp, _i64, _vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
     "snt_lstm_workspace_bytes": (_i64, [_int, _i64, _i64, _i64, _i64]),
     "snt_lstm_fwd": (_int, [_int, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp,
                             _vp, _i64, _vp]),
@@ -59,6 +57,10 @@ SIGNATURES = {
                                       _vp, _i64, _vp]),
     "snt_vocab_ce_train_bwd": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i64, _i64, _vp, _vp, _vp,
                                       _vp, _i64, _vp]),
+    "snt_step_workspace_bytes": (_i64, [_int, _int, _i64, _i64, _i64, _i64, _i64, _i64]),
+    "snt_step_run": (_int, [_vp, _int, _vp]),
+    "snt_step_profile": (_int, [_int]),
+    "snt_step_profile_read": (_int, [C.POINTER(_f32), _int]),
     "snt_greedy_workspace_bytes": (_i64, [_int, _i64, _i64, _i64, _i64, _int]),
     "snt_greedy_decode": (_int, [_int, _vp, _vp, _int, _pp, _pp, _pp, _pp, _vp, _vp, _vp, _vp,
                                  _i64, _i64, _i64, _i64, _int, _vp, _vp, _i64, _vp]),

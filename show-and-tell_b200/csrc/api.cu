@@ -134,30 +134,6 @@ extern "C" int snt_embed_pack_bwd(const float* dx, const int64_t* captions, int6
                         (cudaStream_t)stream);
 }
 
-// The same backward in two calls (experimental): the token-dependent half needs only the captions
-// and may be enqueued early, on another stream, while dx is still being computed.
-extern "C" int snt_embed_bwd_plan(const int64_t* captions, int64_t cap_stride, const int32_t* batch_sizes, int T,
-                                  int64_t V, void* ws, int64_t ws_bytes, void* stream) {
-  PackInfo pk;
-  SNT_CHECK(make_pack(batch_sizes, T, &pk));
-  SNT_REQUIRE(V >= 1, "snt_embed_bwd_plan: bad arguments");
-  SNT_REQUIRE(T == 1 || (captions && cap_stride >= T - 1), "snt_embed_bwd_plan: captions narrower than T-1");
-  return embed_pack_bwd(pk, nullptr, captions, cap_stride, batch_sizes[0], 0, V, nullptr, nullptr, ws, ws_bytes,
-                        (cudaStream_t)stream, 1);
-}
-
-extern "C" int snt_embed_pack_bwd_planned(const float* dx, const int64_t* captions, int64_t cap_stride,
-                                          const int32_t* batch_sizes, int T, int64_t B, int64_t E, int64_t V,
-                                          float* dfeatures, float* d_w_emb, void* ws, int64_t ws_bytes,
-                                          void* stream) {
-  PackInfo pk;
-  SNT_CHECK(make_pack(batch_sizes, T, &pk));
-  SNT_REQUIRE(dx && E >= 1 && V >= 1 && B >= batch_sizes[0], "snt_embed_pack_bwd_planned: bad arguments");
-  SNT_REQUIRE(T == 1 || (captions && cap_stride >= T - 1), "snt_embed_pack_bwd_planned: captions narrower than T-1");
-  return embed_pack_bwd(pk, dx, captions, cap_stride, B, E, V, dfeatures, d_w_emb, ws, ws_bytes,
-                        (cudaStream_t)stream, 2);
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // a7: one LSTM layer over the packed sequence
 // ------------------------------------------------------------------------------------------------------------

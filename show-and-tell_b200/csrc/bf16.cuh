@@ -30,7 +30,8 @@ int linear_bwd(const float* dlogits, const void* hs, const float* w_out, int64_t
 
 int64_t vocab_ce_ws_bytes(int64_t N, int64_t H, int64_t V);
 int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, int64_t N,
-                 int64_t H, int64_t V, float* lse, float* loss, void* ws, int64_t ws_bytes, cudaStream_t st);
+                 int64_t H, int64_t V, float* lse, float* loss, void* ws, int64_t ws_bytes, cudaStream_t st,
+                 float loss_scale = 1.f);
 int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, const float* lse,
                  const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
                  float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st);
@@ -40,7 +41,7 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
 int64_t vocab_ce_train_ws_bytes(int64_t N, int64_t H, int64_t V);
 int vocab_ce_train_fwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, int64_t N,
                        int64_t H, int64_t V, float* lse, float* loss, void* u, float* inv_s, void* hs_scaled,
-                       void* w_bf16, void* ws, int64_t ws_bytes, cudaStream_t st);
+                       void* w_bf16, void* ws, int64_t ws_bytes, cudaStream_t st, float loss_scale = 1.f);
 int vocab_ce_train_bwd(const void* u, const float* inv_s, const void* hs_scaled, const void* w_bf16,
                        const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
                        float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st);

@@ -29,7 +29,9 @@ struct SideStream {
   cudaStream_t s = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
-SideStream* side_stream();  // NULL if the stream could not be created
+// which = 0: the stream the stage functions use for their column sums; which = 1: the step executor's stream for whole
+// stages that run next to the main stream (head backward, embedding-gradient plan).  NULL if it could not be created.
+SideStream* side_stream(int which = 0);
 void count_launch();   // bumps the process-wide kernel-launch counter (snt_launch_count)
 
 #define SNT_CHECK(expr)                                  \

@@ -57,11 +57,11 @@ int* device_flags() {
   return flags[dev];
 }
 
-SideStream* side_stream() {
-  static SideStream tab[64];
+SideStream* side_stream(int which) {
+  static SideStream tab[2][64];
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  SideStream& x = tab[dev];
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || which < 0 || which > 1) return nullptr;
+  SideStream& x = tab[which][dev];
   if (!x.s) {
     if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming);

@@ -1021,11 +1021,12 @@ int clamp_adam_multi(int count, float* const* p, const float* const* g, float* c
   SNT_REQUIRE(step >= 1, "clamp_adam_multi: step must be >= 1");
   const double bc1 = 1.0 - pow(beta1, (double)step);
   const double bc2 = 1.0 - pow(beta2, (double)step);
-  for (int base = 0; base < count; base += ADAM_MAX_TENSORS) {
+  int k = 0;  // next tensor to place: carried across launches (empty tensors are skipped without using a table slot)
+  while (k < count) {
     AdamTable tb;
     tb.count = 0;
     int blocks = 0;
-    for (int k = base; k < count && tb.count < ADAM_MAX_TENSORS; ++k) {
+    for (; k < count && tb.count < ADAM_MAX_TENSORS; ++k) {
       if (n[k] <= 0) continue;
       SNT_REQUIRE(p[k] && g[k] && m[k] && v[k], "clamp_adam_multi: NULL tensor %d", k);
       const int c = tb.count++;

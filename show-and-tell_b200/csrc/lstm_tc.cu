@@ -174,6 +174,7 @@ constexpr int PF_FLAGS_PER_STEP = 8;  // k-blocks of 64 hidden units (H <= 512)
 
 struct PersistFwdParams {
   int H, T, num_n;
+  int m_base;  // first 128-row block of this launch (batches wider than one co-resident group take several launches)
   const bf* gx; float* cs; bf* hs; bf* hprev; bf* act;
   int* flags;  // [num_m0][T][PF_FLAGS_PER_STEP] arrival counters, zeroed before the launch
 #ifdef SNT_LSTM_DBG
@@ -219,7 +220,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int n_blk = blockIdx.x % p.num_n, m_blk = blockIdx.x / p.num_n;
+  const int n_blk = blockIdx.x % p.num_n, m_blk = p.m_base + blockIdx.x / p.num_n;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -438,6 +439,7 @@ constexpr int PB_PART_FLOATS = 128 * 128;
 
 struct PersistBwdParams {
   int H, T, ns;
+  int m_base;  // first 128-row block of this launch
   const float* d_hs; const bf* act; const float* cs; bf* dg;
   float* part;   // [num_m0][ns*ns][2][128*128] partial dL/dh tiles: [finalizer slice][8-unit group][row][8]
   int* dgflag;   // [num_m0][T][PB_FLAGS_PER_STEP]
@@ -467,7 +469,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int rank = blockIdx.x % (NS * NS), m_blk = blockIdx.x / (NS * NS);
+  const int rank = blockIdx.x % (NS * NS), m_blk = p.m_base + blockIdx.x / (NS * NS);
   const int nq = rank / NS, ks = rank % NS;
 
   if (warp == 0 && elect_one()) {
@@ -999,19 +1001,26 @@ int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const flo
     const size_t smem = (size_t)(KB + PF_STAGES) * 16384 + 1024 + 256;
     int coop = 0, max_smem = 0;
     persist_caps(&coop, &max_smem);
-    if (coop == 1 && !getenv("SNT_NO_PERSISTENT") && (int64_t)num_m0 * num_n <= tc::sm_count() &&
+    // Sequences are independent, so a batch wider than one co-resident group of row blocks (floor(SMs / num_n): 9 at
+    // H = 512, i.e. 1152 sequences) simply takes several launches, each over its own group of 128-row blocks.
+    const int group = num_n > 0 ? tc::sm_count() / num_n : 0;
+    if (coop == 1 && !getenv("SNT_NO_PERSISTENT") && group >= 1 &&
         smem <= (size_t)max_smem && KB <= PF_FLAGS_PER_STEP && w.flags != nullptr) {
       PersistFwdParams pp;
       pp.H = (int)H; pp.T = T; pp.num_n = num_n; pp.gx = w.gx; pp.cs = cs; pp.hs = hs_b; pp.hprev = hp_b; pp.act = act;
-      pp.flags = w.flags;
+      pp.flags = w.flags; pp.m_base = 0;
 #ifdef SNT_LSTM_DBG
       static long long* dbg_dev = nullptr;
       if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * SNT_MAX_T * 12);
       cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * SNT_MAX_T * 12, st);
       pp.dbg = dbg_dev;
 #endif
-      SNT_CHECK(launch_persistent<PersistFwdParams>(lstm_fwd_persistent_kernel<1>, lstm_fwd_persistent_kernel<4>,
-                                                    num_m0 * num_n, num_n, smem, ta, tb, pk, pp, st));
+      for (int m0 = 0; m0 < num_m0; m0 += group) {
+        pp.m_base = m0;
+        const int nb = num_m0 - m0 < group ? num_m0 - m0 : group;
+        SNT_CHECK(launch_persistent<PersistFwdParams>(lstm_fwd_persistent_kernel<1>, lstm_fwd_persistent_kernel<4>,
+                                                      nb * num_n, num_n, smem, ta, tb, pk, pp, st));
+      }
 #ifdef SNT_LSTM_DBG
       {
         static int printed = 0;
@@ -1078,9 +1087,9 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
     const size_t nflags = (size_t)num_m0 * T * PB_FLAGS_PER_STEP;
     int coop = 0, max_smem = 0;
     persist_caps(&coop, &max_smem);
-    const bool can_persist = coop == 1 && !getenv("SNT_NO_PERSISTENT") && (H == 256 || H == 512) &&
-                             (int64_t)num_m0 * ns * ns <= tc::sm_count() && smem <= (size_t)max_smem && w.flags &&
-                             w.w_hh_t && w.part;
+    const int group = ns > 0 ? tc::sm_count() / (ns * ns) : 0;  // row blocks that are co-resident in one launch
+    const bool can_persist = coop == 1 && !getenv("SNT_NO_PERSISTENT") && (H == 256 || H == 512) && group >= 1 &&
+                             smem <= (size_t)max_smem && w.flags && w.w_hh_t && w.part;
     // one launch: W_ih' (for dX), and either W_hh'^T + cleared counters (persistent) or W_hh' (per-step path)
     SNT_CHECK(prep_launch(w_ih, w_hh, nullptr, nullptr, In, H, w.w_ih, can_persist ? nullptr : w.w_hh, nullptr,
                           can_persist ? w.w_hh_t : nullptr, can_persist ? w.flags : nullptr,
@@ -1098,12 +1107,16 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
       cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * SNT_MAX_T * 12, st);
       pp.dbg = dbg_dev;
 #endif
-      if (ns == 4)
-        SNT_CHECK(launch_persistent<PersistBwdParams>(lstm_bwd_persistent_kernel<4>, nullptr, num_m0 * ns * ns, 1, smem,
-                                                      ta, tb, pk, pp, st));
-      else
-        SNT_CHECK(launch_persistent<PersistBwdParams>(lstm_bwd_persistent_kernel<2>, nullptr, num_m0 * ns * ns, 1, smem,
-                                                      ta, tb, pk, pp, st));
+      for (int m0 = 0; m0 < num_m0; m0 += group) {
+        pp.m_base = m0;
+        const int nb = num_m0 - m0 < group ? num_m0 - m0 : group;
+        if (ns == 4)
+          SNT_CHECK(launch_persistent<PersistBwdParams>(lstm_bwd_persistent_kernel<4>, nullptr, nb * ns * ns, 1, smem,
+                                                        ta, tb, pk, pp, st));
+        else
+          SNT_CHECK(launch_persistent<PersistBwdParams>(lstm_bwd_persistent_kernel<2>, nullptr, nb * ns * ns, 1, smem,
+                                                        ta, tb, pk, pp, st));
+      }
 #ifdef SNT_LSTM_DBG
       {
         static int printed = 0;

@@ -181,7 +181,7 @@ template <int W>
 struct CeBwdEpiT {
   static constexpr int kWarps = W;
   static constexpr int kStages = W == 16 ? 3 : 0;  // 16 staging buffers (40 KB) fit next to 3 ring stages
-  static constexpr int kSmemPerWarp = 32 * 80;  // 32 rows x (64 B of bf16 + 16 B pad): transpose stage for coalesced stores
+  static constexpr int kSmemPerWarp = 32 * 64;  // swizzled 32 x 64-byte transpose stage for coalesced stores (tc::stage_addr)
   int M;                    // rows in this chunk
   int V;
   const float* bias;        // [V]
@@ -221,13 +221,16 @@ struct CeBwdEpiT {
         pk[j / 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) tc::sts128(wsa + lane * 80 + q * 16, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      for (int q = 0; q < 4; ++q)
+        tc::sts128(tc::stage_addr(wsa, lane, q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       __syncwarp();
+      uint4 v[4];  // all four loads first, then the stores: no load waits behind a store
+#pragma unroll
+      for (int it = 0; it < 4; ++it) v[it] = tc::lds128(tc::stage_addr(wsa, it * 8 + (lane >> 2), lane & 3));
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const int rr = it * 8 + (lane >> 2), cq = lane & 3;
-        const uint4 v = tc::lds128(wsa + rr * 80 + cq * 16);
-        if (row0 + rr < M) *reinterpret_cast<uint4*>(out + (int64_t)(row0 + rr) * ldo + col0 + cq * 8) = v;
+        if (row0 + rr < M) *reinterpret_cast<uint4*>(out + (int64_t)(row0 + rr) * ldo + col0 + cq * 8) = v[it];
       }
       __syncwarp();
     } else if (row0 + lane < M) {
@@ -446,7 +449,8 @@ static int* ce_ticket() {
 }
 
 int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, int64_t N,
-                 int64_t H, int64_t V, float* lse, float* loss, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                 int64_t H, int64_t V, float* lse, float* loss, void* ws, int64_t ws_bytes, cudaStream_t st,
+                 float loss_scale) {
   if (H % 8 != 0) { set_error("bf16 mode: H=%lld must be a multiple of 8", (long long)H); return SNT_EUNSUPPORTED; }
   SNT_REQUIRE(V < (1LL << 31) && N < (1LL << 31), "vocab_ce_fwd: extent too large");
   CeWs w = carve(ws, ws_bytes, N, H, V);
@@ -465,7 +469,7 @@ int vocab_ce_fwd(const void* hs, const float* w_out, const float* b_out, const i
   if (!ticket) { set_error("vocab_ce_fwd: could not allocate the reduction ticket"); return SNT_EINVAL; }
   // w.nll doubles as the per-block partial sums (ceil(N/64) <= N floats)
   ce_finish_kernel<<<(unsigned)((N + 63) / 64), 512, 0, st>>>(w.part, w.slabs, N, w.tl, targets, V, lse, w.nll, ticket,
-                                                             1.0f / (float)N, loss, device_flags());
+                                                             loss_scale / (float)N, loss, device_flags());
   SNT_LAUNCH_CHECK("ce_finish_kernel");
   return SNT_OK;
 }
@@ -601,7 +605,7 @@ struct RowMaxEpi {  // pilot: per row the maximum of y = logit*log2(e) over each
 struct CeStoreEpi {
   static constexpr int kWarps = 16;
   static constexpr int kStages = 3;
-  static constexpr int kSmemPerWarp = 32 * 80;  // transpose stage for whole-row-segment stores (as CeBwdEpiT)
+  static constexpr int kSmemPerWarp = 32 * 64 + 256;  // swizzled transpose stage (as CeBwdEpiT) + this warp's 64 bias values
   int M, V;
   const float* bias;        // [V]
   const float* pm;          // [2][M] pilot maxima (log2 domain)
@@ -612,18 +616,24 @@ struct CeStoreEpi {
   int64_t ldo;
   int* flags;
 
-  struct Pre { float c2; int tgt; };
-  __device__ __forceinline__ void prefetch(Pre& p, int m_blk, int, int ew, int lane) const {
+  // everything the tile needs from global memory, fetched one tile ahead (gemm_tc_kernel): the row's shift and target,
+  // and two of the 64 bias values of this warp's column quarter (lane and lane + 32), shared through shared memory
+  struct Pre { float c2; int tgt; float b0, b1; };
+  __device__ __forceinline__ void prefetch(Pre& p, int m_blk, int n_blk, int ew, int lane) const {
     const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
     const bool ok = row < M;
     p.c2 = ok ? fmaxf(__ldg(pm + row), __ldg(pm + M + row)) + CE_SHIFT2 : 0.f;
     const int64_t t = ok ? targets[row] : -1;
     p.tgt = (t >= 0 && t < V) ? (int)t : -1;
+    const int c0 = n_blk * CE_BN + (ew >> 2) * 64 + lane;
+    p.b0 = c0 < V ? __ldg(bias + c0) : 0.f;
+    p.b1 = c0 + 32 < V ? __ldg(bias + c0 + 32) : 0.f;
   }
-  __device__ __forceinline__ void load_bias(float4 (&bv)[8], int col0) const {
-    if (col0 + 32 <= V) {
+  __device__ __forceinline__ void load_bias(float4 (&bv)[8], uint32_t bsa) const {  // 32 floats, broadcast reads
 #pragma unroll
-      for (int q = 0; q < 8; ++q) bv[q] = __ldg(reinterpret_cast<const float4*>(bias + col0) + q);
+    for (int q = 0; q < 8; ++q) {
+      const uint4 u = tc::lds128(bsa + q * 16);
+      bv[q] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
     }
   }
   __device__ __forceinline__ float chunk(const uint32_t (&r)[32], const float4 (&bv)[8], int col0, int row0, int lane,
@@ -652,13 +662,16 @@ struct CeStoreEpi {
         pk[j / 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) tc::sts128(wsa + lane * 80 + q * 16, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      for (int q = 0; q < 4; ++q)
+        tc::sts128(tc::stage_addr(wsa, lane, q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       __syncwarp();
+      uint4 v[4];  // all four loads first, then the stores: no load waits behind a store
+#pragma unroll
+      for (int it = 0; it < 4; ++it) v[it] = tc::lds128(tc::stage_addr(wsa, it * 8 + (lane >> 2), lane & 3));
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const int rr = it * 8 + (lane >> 2), cq = lane & 3;
-        const uint4 v = tc::lds128(wsa + rr * 80 + cq * 16);
-        if (row0 + rr < M) *reinterpret_cast<uint4*>(out + (int64_t)(row0 + rr) * ldo + col0 + cq * 8) = v;
+        if (row0 + rr < M) *reinterpret_cast<uint4*>(out + (int64_t)(row0 + rr) * ldo + col0 + cq * 8) = v[it];
       }
       __syncwarp();
     } else if (row0 + lane < M) {
@@ -679,7 +692,10 @@ struct CeStoreEpi {
                                        uint8_t* wsm) const {
     const int q4 = ew >> 2;  // 64-column quarter of the tile
     const int row0 = m_blk * tc::BM + (ew & 3) * 32;
-    const uint32_t wsa = tc::smem_u32(wsm);
+    const uint32_t wsa = tc::smem_u32(wsm), bsa = wsa + 32 * 64;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bsa + lane * 4), "f"(pre.b0) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bsa + 128 + lane * 4), "f"(pre.b1) : "memory");
+    __syncwarp();
     float s = 0.f;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
@@ -688,7 +704,7 @@ struct CeStoreEpi {
       uint32_t r[32];
       float4 b8[8];
       tc::tmem_ld32(tmem_rows + (uint32_t)(q4 * 64 + c * 32), r);
-      load_bias(b8, col0);
+      load_bias(b8, bsa + c * 128);
       tc::tmem_ld_wait();
       s += chunk(r, b8, col0, row0, lane, pre.c2, pre.tgt, wsa);
     }
@@ -825,7 +841,7 @@ int64_t vocab_ce_train_ws_bytes(int64_t N, int64_t H, int64_t V) {
 
 int vocab_ce_train_fwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, int64_t N,
                        int64_t H, int64_t V, float* lse, float* loss, void* u, float* inv_s, void* hs_scaled,
-                       void* w_bf16, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                       void* w_bf16, void* ws, int64_t ws_bytes, cudaStream_t st, float loss_scale) {
   if (H % 8 != 0) { set_error("bf16 mode: H=%lld must be a multiple of 8", (long long)H); return SNT_EUNSUPPORTED; }
   SNT_REQUIRE(V < (1LL << 31) && N < (1LL << 31), "vocab_ce_train_fwd: extent too large");
   CeTrainWs w = carve_train(ws, ws_bytes, N, H, V);
@@ -853,7 +869,7 @@ int vocab_ce_train_fwd(const void* hs, const float* w_out, const float* b_out, c
   if (!ticket) { set_error("vocab_ce_train_fwd: could not allocate the reduction ticket"); return SNT_EINVAL; }
   ce_finish_u_kernel<<<(unsigned)((N + 63) / 64), 512, 0, st>>>(w.part, w.slabs, N, w.pm, w.tl, targets, V, (bf*)u, w.Vp,
                                                                hs_b, (int)H, lse, inv_s, (bf*)hs_scaled, w.bsum, ticket,
-                                                               1.0f / (float)N, loss, device_flags());
+                                                               loss_scale / (float)N, loss, device_flags());
   SNT_LAUNCH_CHECK("ce_finish_u_kernel");
   return SNT_OK;
 }

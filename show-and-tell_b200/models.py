@@ -57,16 +57,20 @@ class EncoderCNN(nn.Module):
         return ops.head(pooled, self.resnet.fc.weight, self.resnet.fc.bias, bn.weight, bn.bias, bn.running_mean,
                         bn.running_var, self.training, bn.momentum, bn.eps, self.precision)
 
-    def forward(self, images):
-        """models.py:25-29."""
+    def pooled(self, images):
+        """images[B,3,224,224] -> the frozen trunk's pooled activations [B,2048] (models.py:27 without the fc),
+        under no_grad (models.py:14-15)."""
         if not self.has_backbone:
             raise RuntimeError("EncoderCNN(backbone=False) has no CNN: call forward_pooled(pooled[B,2048])")
         r = self.resnet
-        with torch.no_grad():                                   # frozen trunk (models.py:14-15)
+        with torch.no_grad():
             x = r.maxpool(r.relu(r.bn1(r.conv1(images))))
             x = r.layer4(r.layer3(r.layer2(r.layer1(x))))
-            pooled = torch.flatten(r.avgpool(x), 1)
-        return self.forward_pooled(pooled)
+            return torch.flatten(r.avgpool(x), 1)
+
+    def forward(self, images):
+        """models.py:25-29."""
+        return self.forward_pooled(self.pooled(images))
 
 
 class DecoderRNN(nn.Module):
@@ -81,7 +85,6 @@ class DecoderRNN(nn.Module):
         self.num_layers = num_layers
         self.precision = precision                # teacher-forced path: "bf16" (tcgen05) or "fp32" (faithful)
         self.sample_precision = sample_precision  # greedy decode defaults to the token-exact fp32 mode
-        self.grad_ready = None                    # set by parallel.DataParallelStep
         self.init_weights()
 
     def init_weights(self):
@@ -104,7 +107,7 @@ class DecoderRNN(nn.Module):
         """criterion(self(features, captions, lengths), targets) of train.py:139-143 as one fused op: the vocab
         projection is fused with log-softmax + cross-entropy and the logits never reach HBM as a whole."""
         return ops.decoder_loss(features, captions, lengths, targets, self.embed.weight, self._lstm_weights(),
-                                self.linear.weight, self.linear.bias, self.precision, self.grad_ready, grad_scale)
+                                self.linear.weight, self.linear.bias, self.precision, grad_scale)
 
     def sample(self, features, states=None, precision=None):
         """Samples captions for given image features (Greedy search), models.py:56-67: always 20 steps,

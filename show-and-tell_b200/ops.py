@@ -22,29 +22,9 @@ from ._lib import PREC, call, host_i32, ptr, require_cuda, stream_ptr, workspace
 
 SAMPLE_STEPS = 20  # models.py:60
 
-# Experimental, off by default (plan item 4; written without a GPU run, enable with SNT_TAIL_OVERLAP=1):
-# `dfeatures` is dx[:B] - the t = 0 rows of the first layer's input gradient - so the head's backward does not depend
-# on the embedding-gradient kernels that follow snt_lstm_bwd on the stream.  With the switch on, _hidden_bwd hands
-# autograd that view plus an event, and _Head.backward runs on a side stream behind the event, joined back into
-# the main stream when its launches are enqueued.
-TAIL_OVERLAP = os.environ.get("SNT_TAIL_OVERLAP", "0") == "1"
-# Same status (experimental, SNT_EMB_PLAN_EARLY=1): the token-dependent half of the embedding gradient (histogram + scan
-# of the token ids, ~20 us of small launches) needs only the captions, so it is enqueued on the side stream at the START
-# of the loss backward and has long finished when dx arrives (snt_embed_bwd_plan / snt_embed_pack_bwd_planned).
-EMB_PLAN_EARLY = os.environ.get("SNT_EMB_PLAN_EARLY", "0") == "1"
 # SNT_CE_RECOMPUTE=1: the memory-lean loss backward that recomputes the logits per chunk instead of keeping the bf16 softmax
 # numerators of the whole batch (N x V x 2 bytes) from the forward pass.
 CE_RECOMPUTE = os.environ.get("SNT_CE_RECOMPUTE", "0") == "1"
-_tail = None          # (data_ptr of the dfeatures view, event recorded once dx is complete)
-_side_streams = {}
-
-
-def _side_stream(dev):
-    st = _side_streams.get(dev.index)
-    if st is None:
-        st = _side_streams[dev.index] = torch.cuda.Stream(dev)
-    return st
-
 
 def _act_dtype(prec):
     return torch.float32 if prec == "fp32" else torch.bfloat16
@@ -124,21 +104,6 @@ class _Head(torch.autograd.Function):
         d_be = torch.empty(E, device=dev)
         p = PREC[prec]
         nb = _lib.lib().snt_head_workspace_bytes(p, B, K, E)
-        global _tail
-        tail, _tail = _tail, None
-        if tail is not None and tail[0] == dfeat.data_ptr():
-            # two-stream tail (see TAIL_OVERLAP): outputs were allocated on the main stream above; the launches go to the
-            # side stream behind "dx complete" and the main stream waits for them before anything else touches the results
-            main, side = torch.cuda.current_stream(dev), _side_stream(dev)
-            side.wait_event(tail[1])
-            with torch.cuda.stream(side):
-                ws = workspace(nb, dev)
-                call("snt_head_bwd", p, ptr(dfeat), ptr(pooled), ptr(yhat), ptr(rstd), ptr(gamma), 1 if training else 0,
-                     B, K, E, ptr(d_w), ptr(d_b), ptr(d_g), ptr(d_be), ptr(ws), ws.numel(), stream_ptr())
-                join = torch.cuda.Event()
-                join.record(side)
-            main.wait_event(join)
-            return None, d_w, d_b, d_g, d_be, None, None, None, None, None, None
         ws = workspace(nb, dev)
         call("snt_head_bwd", p, ptr(dfeat), ptr(pooled), ptr(yhat), ptr(rstd), ptr(gamma), 1 if training else 0,
              B, K, E, ptr(d_w), ptr(d_b), ptr(d_g), ptr(d_be), ptr(ws), ws.numel(), stream_ptr())
@@ -157,22 +122,7 @@ def head(pooled, w_fc, b_fc, gamma, beta, running_mean, running_var, training, m
 # ---------------------------------------------------------------------------------------------------------
 class _Hidden:
     """Tensors saved between forward and backward of the recurrent part."""
-    __slots__ = ("prec", "bs", "bs_ptr", "T", "N", "B", "E", "H", "V", "L", "captions", "layers", "x", "plan")
-
-
-def _plan_embed_bwd(s, dev):
-    """EMB_PLAN_EARLY: enqueue the token-dependent half of the embedding gradient on the side stream now."""
-    main, side = torch.cuda.current_stream(dev), _side_stream(dev)
-    side.wait_stream(main)                            # the captions (and everything before backward) are complete
-    cap = s.captions
-    with torch.cuda.stream(side):
-        nb = _lib.lib().snt_embed_bwd_workspace_bytes(s.N, s.V)
-        ws = torch.empty(max(int(nb), 1), dtype=torch.uint8, device=dev)      # owned by this backward, not the shared scratch
-        call("snt_embed_bwd_plan", ptr(cap), cap.stride(0) if cap.numel() else 0, s.bs_ptr, s.T, s.V, ptr(ws),
-             ws.numel(), stream_ptr())
-        ev = torch.cuda.Event()
-        ev.record(side)
-    s.plan = (ws, ev)
+    __slots__ = ("prec", "bs", "bs_ptr", "T", "N", "B", "E", "H", "V", "L", "captions", "layers", "x")
 
 
 def _hidden_fwd(prec, features, captions, bs, w_emb, lstm_w):
@@ -193,7 +143,7 @@ def _hidden_fwd(prec, features, captions, bs, w_emb, lstm_w):
          bs_ptr, T, E, V, ptr(x) if prec == "fp32" else None, ptr(x) if prec == "bf16" else None, stream_ptr())
     s = _Hidden()
     s.prec, s.bs, s.bs_ptr, s.T, s.N, s.B, s.E, s.V, s.L = prec, bs_arr, bs_ptr, T, N, B, E, V, len(lstm_w)
-    s.captions, s.x, s.layers, s.plan = captions, x, [], None
+    s.captions, s.x, s.layers = captions, x, []
     inp, in_dim = x, E
     H = lstm_w[0][1].shape[1]
     s.H = H
@@ -211,11 +161,9 @@ def _hidden_fwd(prec, features, captions, bs, w_emb, lstm_w):
     return inp, s
 
 
-def _hidden_bwd(s, d_hs, w_emb, lstm_w, need_dfeat, grad_ready=None):
+def _hidden_bwd(s, d_hs, w_emb, lstm_w, need_dfeat):
     """BPTT through the layers (top to bottom), then the gather's backward.  `gates` buffers are consumed.
-    -> (dfeatures | None, d_w_emb, [(d_w_ih, d_w_hh, d_b_ih, d_b_hh)] per layer).
-    grad_ready(names, tensors), when given, is called as soon as each group of gradients has been enqueued
-    (the data-parallel wrapper starts its allreduce there, overlapping the rest of BPTT)."""
+    -> (dfeatures | None, d_w_emb, [(d_w_ih, d_w_hh, d_b_ih, d_b_hh)] per layer)."""
     dev = d_hs.device
     p = PREC[s.prec]
     H = s.H
@@ -232,38 +180,15 @@ def _hidden_bwd(s, d_hs, w_emb, lstm_w, need_dfeat, grad_ready=None):
         call("snt_lstm_bwd", p, ptr(d_hs), ptr(gates), ptr(cs), ptr(hprev), ptr(inp), in_dim, H, ptr(w_ih), ptr(w_hh),
              s.bs_ptr, s.T, ptr(d_w_ih), ptr(d_w_hh), ptr(d_b), ptr(dx), ptr(ws), ws.numel(), stream_ptr())
         grads[k] = (d_w_ih, d_w_hh, d_b, d_b.clone())  # b_ih and b_hh receive the same gradient
-        if grad_ready is not None:
-            grad_ready([f"lstm.weight_ih_l{k}", f"lstm.weight_hh_l{k}", f"lstm.bias_ih_l{k}", f"lstm.bias_hh_l{k}"],
-                       list(grads[k]))
         d_hs = dx
-    global _tail
-    if need_dfeat and TAIL_OVERLAP:
-        ev = torch.cuda.Event()
-        ev.record()                                  # dx of the first layer is complete here
-        dfeat_out = d_hs[:s.B]                       # rows of t = 0: exactly what dfeatures_kernel would copy
-        _tail = (dfeat_out.data_ptr(), ev)
-        dfeat = None                                 # the C call skips its own copy
-    else:
-        dfeat_out = dfeat = torch.empty(s.B, s.E, device=dev) if need_dfeat else None
+    dfeat = torch.empty(s.B, s.E, device=dev) if need_dfeat else None
     d_w_emb = torch.empty_like(w_emb)
     cap = s.captions
-    plan = getattr(s, "plan", None)
-    if plan is not None:
-        ws, ev = plan
-        main = torch.cuda.current_stream(dev)
-        main.wait_event(ev)
-        ws.record_stream(main)                        # allocated on the side stream, consumed here
-        call("snt_embed_pack_bwd_planned", ptr(d_hs), ptr(cap), cap.stride(0) if cap.numel() else 0, s.bs_ptr, s.T,
-             s.B, s.E, s.V, ptr(dfeat), ptr(d_w_emb), ptr(ws), ws.numel(), stream_ptr())
-        s.plan = None
-    else:
-        nb = _lib.lib().snt_embed_bwd_workspace_bytes(s.N, s.V)
-        ws = workspace(nb, dev)
-        call("snt_embed_pack_bwd", ptr(d_hs), ptr(cap), cap.stride(0) if cap.numel() else 0, s.bs_ptr, s.T, s.B, s.E,
-             s.V, ptr(dfeat), ptr(d_w_emb), ptr(ws), ws.numel(), stream_ptr())
-    if grad_ready is not None:
-        grad_ready(["embed.weight"], [d_w_emb])
-    return dfeat_out, d_w_emb, grads
+    nb = _lib.lib().snt_embed_bwd_workspace_bytes(s.N, s.V)
+    ws = workspace(nb, dev)
+    call("snt_embed_pack_bwd", ptr(d_hs), ptr(cap), cap.stride(0) if cap.numel() else 0, s.bs_ptr, s.T, s.B, s.E,
+         s.V, ptr(dfeat), ptr(d_w_emb), ptr(ws), ws.numel(), stream_ptr())
+    return dfeat, d_w_emb, grads
 
 
 def _flatten_lstm(lstm_w):
@@ -334,7 +259,7 @@ class _DecoderLoss(torch.autograd.Function):
     log-softmax / cross-entropy: the [N,V] logits are never materialised as a whole."""
 
     @staticmethod
-    def forward(ctx, features, captions, targets, bs, prec, grad_ready, grad_scale, w_emb, w_out, b_out, *lstm_flat):
+    def forward(ctx, features, captions, targets, bs, prec, grad_scale, want_grad, w_emb, w_out, b_out, *lstm_flat):
         lstm_w = _unflatten_lstm(lstm_flat)
         hs, s = _hidden_fwd(prec, features, captions, bs, w_emb, lstm_w)
         N, H, V = s.N, s.H, w_out.shape[0]
@@ -349,7 +274,7 @@ class _DecoderLoss(torch.autograd.Function):
         p = PREC[prec]
         # A backward will follow: run the logits contraction once and keep the softmax numerators (bf16 mode; see
         # snt_vocab_ce_train_fwd).  Otherwise (evaluation, fp32 mode, SNT_CE_RECOMPUTE=1): statistics only.
-        ctx.stored = prec == "bf16" and any(ctx.needs_input_grad) and not CE_RECOMPUTE
+        ctx.stored = prec == "bf16" and want_grad and any(ctx.needs_input_grad) and not CE_RECOMPUTE
         if ctx.stored:
             u = torch.empty(N, (V + 7) // 8 * 8, device=dev, dtype=torch.bfloat16)
             inv_s = torch.empty(N, device=dev)
@@ -368,7 +293,6 @@ class _DecoderLoss(torch.autograd.Function):
         ctx.s = s
         ctx.save_for_backward(w_emb, w_out, b_out, targets, lse, *lstm_flat)
         ctx.need_dfeat = features.requires_grad
-        ctx.grad_ready = grad_ready
         ctx.grad_scale = grad_scale
         if grad_scale != 1.0:  # data-parallel: this rank's share of the global-mean loss
             loss = loss * grad_scale
@@ -382,8 +306,6 @@ class _DecoderLoss(torch.autograd.Function):
         dev = dloss.device
         N, H, V = s.N, s.H, w_out.shape[0]
         hs = s.layers[-1][4]
-        if EMB_PLAN_EARLY:
-            _plan_embed_bwd(s, dev)
         dloss = dloss.contiguous().float()
         d_hs = torch.empty(N, H, device=dev)
         d_w_out = torch.empty_like(w_out)
@@ -402,11 +324,7 @@ class _DecoderLoss(torch.autograd.Function):
             ws = workspace(nb, dev)
             call("snt_vocab_ce_bwd", p, ptr(hs), ptr(w_out), ptr(b_out), ptr(targets), ptr(lse), ptr(dloss),
                  float(ctx.grad_scale), N, H, V, ptr(d_hs), ptr(d_w_out), ptr(d_b_out), ptr(ws), ws.numel(), stream_ptr())
-        if ctx.grad_ready is not None:
-            ctx.grad_ready(["linear.weight", "linear.bias"], [d_w_out, d_b_out])
-        dfeat, d_w_emb, lg = _hidden_bwd(s, d_hs, w_emb, lstm_w, ctx.need_dfeat, ctx.grad_ready)
-        if ctx.grad_ready is not None:
-            ctx.grad_ready(None, None)  # end of backward: the wrapper waits for its collectives here
+        dfeat, d_w_emb, lg = _hidden_bwd(s, d_hs, w_emb, lstm_w, ctx.need_dfeat)
         ctx.s = None
         return (dfeat, None, None, None, None, None, None, d_w_emb, d_w_out, d_b_out, *_flatten_lstm(lg))
 
@@ -417,13 +335,12 @@ def decoder_logits(features, captions, lengths, w_emb, lstm_w, w_out, b_out, pre
     return _DecoderLogits.apply(features, captions, bs, prec, w_emb, w_out, b_out, *_flatten_lstm(lstm_w))
 
 
-def decoder_loss(features, captions, lengths, targets, w_emb, lstm_w, w_out, b_out, prec="bf16", grad_ready=None,
-                 grad_scale=1.0):
+def decoder_loss(features, captions, lengths, targets, w_emb, lstm_w, w_out, b_out, prec="bf16", grad_scale=1.0):
     """mean_n CE(logits_n, targets_n) over the N packed rows (train.py:53,143)."""
     features, captions = _prep_inputs(features, captions)
     bs = batch_sizes_from_lengths(lengths, captions.shape[1] + 1)
-    return _DecoderLoss.apply(features, captions, targets, bs, prec, grad_ready, float(grad_scale), w_emb, w_out,
-                              b_out, *_flatten_lstm(lstm_w))
+    return _DecoderLoss.apply(features, captions, targets, bs, prec, float(grad_scale), torch.is_grad_enabled(), w_emb,
+                              w_out, b_out, *_flatten_lstm(lstm_w))
 
 
 # ---------------------------------------------------------------------------------------------------------

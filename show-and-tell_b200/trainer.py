@@ -17,8 +17,8 @@ What necessarily differs (SURVEY.md Appendix B lists the reference's defects; no
     whose timestep 0 is the image feature (models.py:50);
   * torch-0.1.12 idioms (`Variable`, `volatile=True`, `loss.data[0]`) are gone; evaluation runs under `no_grad`, and the
     module's train/eval mode is restored afterwards (the reference leaves the model in eval mode for good);
-  * forward + loss are the fused `DecoderRNN.loss` and clip_gradient + Adam one fused launch
-    (`parallel.DataParallelStep`); with `world_size > 1` (one process per GPU under torchrun, instead of train.py:43-44's
+  * forward + loss + backward are one native call sequence (`parallel.DataParallelStep` -> `snt_step_run`) and
+    clip_gradient + Adam one fused launch over flat parameter buffers; with `world_size > 1` (one process per GPU under torchrun, instead of train.py:43-44's
     `nn.DataParallel`) gradients are all-reduced over NCCL in readiness order;
   * sampled ids are cut at `<end>` on the device (`snt_caption_trim`) and copied to the host once per batch, instead
     of a Python loop over every word id (eval.py:101-109);
@@ -175,15 +175,14 @@ class Trainer(object):
         self.stepper.lr = lr
 
     def train_step(self, images, captions, lengths):
-        """train.py:123-146 for one loader batch -> the (device) loss of this rank."""
+        """train.py:123-146 for one loader batch -> the (device) loss of this rank.  The targets are
+        pack(captions, lengths) (eval.py:91), gathered on the device by the step executor."""
         device = next(self.model.parameters()).device
         images, captions = _to_device(images, device), _to_device(captions, device)
-        lengths = [int(l) for l in lengths]
-        targets = pack_padded_sequence(captions, lengths, batch_first=True)[0]
         world = getattr(self.stepper, "world", 1)
         # several ranks: the SUM all-reduce of gradients scaled by 1/world = the average of the ranks' mean losses
-        n_global = sum(lengths) * world if world > 1 else None
-        return self.stepper.step(images, captions, lengths, targets, n_global)
+        n_global = int(sum(int(l) for l in lengths)) * world if world > 1 else None
+        return self.stepper.step(images, captions, lengths, None, n_global)
 
     def validate(self):
         crit = None if self.fused_eval else self.criterion

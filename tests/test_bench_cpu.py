@@ -27,9 +27,9 @@ def test_stage_rooflines_table():
     import bench
     peaks = dict(hbm=6549.8, tf_burst=1590.0, tf_sust=1400.1, src="test")
     n_tok = 12666
-    prof = {"snt_vocab_ce_bwd": (10, 4.85), "snt_clamp_adam_multi": (10, 0.46), "snt_unknown": (10, 0.01)}
-    st = bench.stage_rooflines(prof, 10, n_tok, peaks)
-    assert [e["stage"] for e in st] == ["snt_vocab_ce_bwd", "snt_clamp_adam_multi", "snt_unknown"]   # by time
+    prof = {"vocab_ce_bwd": 485.0, "clamp_adam": 46.0, "unknown_stage": 1.0}
+    st = bench.stage_rooflines(prof, n_tok, peaks)
+    assert [e["stage"] for e in st] == ["vocab_ce_bwd", "clamp_adam", "unknown_stage"]   # by time
     ce = st[0]
     assert ce["bound"] == "tensor" and ce["us_per_step"] == pytest.approx(485.0)
     assert ce["algorithmic_work"] == 4.0 * n_tok * 10000 * 512                 # recompute not credited
@@ -39,6 +39,14 @@ def test_stage_rooflines_table():
     n_par = 10000 * 256 + 4 * 512 * 768 + 8 * 512 + 10000 * 512 + 10000 + 256 * 2048 + 3 * 256
     assert adam["bound"] == "hbm" and adam["algorithmic_work"] == 28.0 * n_par and adam["unit"] == "GB/s"
     assert "bound" not in st[2]
+
+
+def test_scaled_config_figures_match_survey():
+    import bench
+    c3 = bench.CONFIGS["scaled"]
+    assert bench.m_tok(c3) == 47_448_064                     # M_tok of cfg4 (E512/H1024/L2/V32000)
+    assert abs(bench.train_flops(2048, 25702, c3) / 1e12 - 7.330) < 0.01       # "7.330 TFLOP/step"
+    assert abs(bench.greedy_flops_per_token(bench.CFG) / 1e6 - 13.39) < 0.01   # "13.39 MFLOP/token"
 
 
 def test_gpu_reference_child_failure_is_soft():

@@ -49,13 +49,18 @@ def test_abi_version_and_error_string(snt):
     assert l.snt_lstm_workspace_bytes(5, 100, 10, 8, 16) == -1
     assert l.snt_caption_trim(None, 4, 20, 2, 0, None, None, None) == -1 and b"NULL" in l.snt_last_error()
     assert l.snt_caption_trim(None, 0, 20, 2, 0, None, None, None) == 0      # empty batch: nothing to launch
-    bad = (ctypes.c_int32 * 2)(1, 2)
-    rc = l.snt_embed_bwd_plan(None, 4, ctypes.cast(bad, ctypes.c_void_p), 2, 10, None, 0, None)
-    assert rc == -1 and b"non-increasing" in l.snt_last_error()
-    ok = (ctypes.c_int32 * 2)(2, 1)
-    rc = l.snt_embed_pack_bwd_planned(None, None, 4, ctypes.cast(ok, ctypes.c_void_p), 2, 2, 8, 10, None, None, None, 0,
-                                      None)
-    assert rc == -1 and b"bad arguments" in l.snt_last_error()          # dx is NULL
+    # the step executor validates its descriptor before touching the device
+    from show_and_tell_b200 import engine
+    d = engine.SntStep()
+    assert l.snt_step_run(ctypes.c_void_p(ctypes.addressof(d)), 15, None) == -1 and b"descriptor size" in l.snt_last_error()
+    d.struct_bytes = ctypes.sizeof(engine.SntStep)
+    d.prec, d.L = 1, 0
+    assert l.snt_step_run(ctypes.c_void_p(ctypes.addressof(d)), 15, None) == -1 and b"L=0" in l.snt_last_error()
+    d.L = 1
+    assert l.snt_step_run(ctypes.c_void_p(ctypes.addressof(d)), 16, None) == -1 and b"phase" in l.snt_last_error()
+    assert l.snt_step_workspace_bytes(1, 1, 64, 700, 64, 128, 1000, 2048) > 0
+    assert l.snt_step_workspace_bytes(1, 1, 64, 10, 64, 128, 1000, 2048) == -1      # N < B
+    assert l.snt_vocab_ce_train_workspace_bytes(0, 100, 64, 1000) == -1              # bf16 mode only
     bs = (ctypes.c_int32 * 3)(2, 3, 1)   # not non-increasing
     rc = l.snt_embed_pack_fwd(None, None, None, 4, ctypes.cast(bs, ctypes.c_void_p), 3, 8, 10, None, None, None)
     assert rc == -1 and b"non-increasing" in l.snt_last_error()
@@ -160,8 +165,22 @@ def test_host_call_sequence_with_stub_binding(snt, monkeypatch):
     pooled, caps = torch.from_numpy(b["pooled"]), torch.from_numpy(b["captions"])
     tg = torch.from_numpy(snt.synthetic.pack_host(b["captions"], b["lengths"]))
     dec.loss(enc.forward_pooled(pooled), caps, b["lengths"], tg).backward()
-    assert calls == ["snt_head_fwd", "snt_embed_pack_fwd", "snt_lstm_fwd", "snt_lstm_fwd", "snt_vocab_ce_fwd",
-                     "snt_vocab_ce_bwd", "snt_lstm_bwd", "snt_lstm_bwd", "snt_embed_pack_bwd", "snt_head_bwd"]
+    # bf16 mode with a backward to follow: the stored-numerator loss (one logits contraction per step)
+    assert calls == ["snt_head_fwd", "snt_embed_pack_fwd", "snt_lstm_fwd", "snt_lstm_fwd", "snt_vocab_ce_train_fwd",
+                     "snt_vocab_ce_train_bwd", "snt_lstm_bwd", "snt_lstm_bwd", "snt_embed_pack_bwd", "snt_head_bwd"]
+    calls.clear()
+    dec.precision = "fp32"                                                        # fp32 mode: statistics + recompute
+    dec.loss(enc.forward_pooled(pooled), caps, b["lengths"], tg).backward()
+    assert calls[4:6] == ["snt_vocab_ce_fwd", "snt_vocab_ce_bwd"]
+    dec.precision = "bf16"
+    calls.clear()
+    with torch.no_grad():                                                         # no backward: statistics only
+        dec.loss(enc.forward_pooled(pooled), caps, b["lengths"], tg)
+    assert calls[-1] == "snt_vocab_ce_fwd"
+    for p in list(enc.parameters()) + list(dec.parameters()):
+        p.grad = None
+    calls.clear()
+    dec.loss(enc.forward_pooled(pooled), caps, b["lengths"], tg).backward()
     params = [p for m in (enc, dec) for p in m.parameters() if p.requires_grad]
     assert all(p.grad is not None and p.grad.shape == p.shape for p in params)
     calls.clear()
@@ -172,65 +191,61 @@ def test_host_call_sequence_with_stub_binding(snt, monkeypatch):
     ids = torch.zeros(3, 20, dtype=torch.int64)
     ops.trim_captions(ids)
     assert calls == ["snt_greedy_decode", "snt_caption_trim"]
-    # the data-parallel step object (world size 1) on top: forward, backward, then ONE fused clip + Adam launch
-    from show_and_tell_b200 import parallel
-    calls.clear()
-    st = parallel.DataParallelStep(enc.train(), dec.train())
-    st.step(pooled, caps, b["lengths"], tg)
-    assert calls[0] == "snt_head_fwd" and calls[-2:] == ["snt_head_bwd", "snt_clamp_adam_multi"] and st.t == 1
-    assert len(st.m) == len(params) and all(m.shape == p.shape for m, p in zip(st.m, params))
 
 
-def test_experimental_switches_host_logic_with_stub_streams(snt, monkeypatch):
-    """SNT_TAIL_OVERLAP / SNT_EMB_PLAN_EARLY (off by default, first GPU run pending): their Python control flow through
-    fake streams and a recording binding - the plan call precedes the loss backward, the planned variant replaces the
-    one-call embedding backward, the head backward is fenced by two events."""
-    import contextlib
-    from show_and_tell_b200 import ops
-    calls, log = [], []
+def test_step_descriptor_matches_header(snt, tmp_path):
+    """engine.SntStep (ctypes) against struct snt_step of include/snt_b200.h, compiled here with gcc: same size and the
+    same offsets for a field of every group."""
+    import ctypes as C
+    import subprocess
+    from show_and_tell_b200 import engine
+    src = tmp_path / "sz.c"
+    fields = ["prec", "B", "batch_sizes", "bn_momentum", "w_emb", "w_ih", "b_hh", "d_w_fc", "d_w_ih", "d_features",
+              "grad_scale", "loss", "ws_bytes"]
+    src.write_text('#include "snt_b200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(void){\n'
+                   'printf("%zu", sizeof(snt_step));\n' +
+                   "".join(f'printf(" %zu", offsetof(snt_step, {f}));\n' for f in fields) + "return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got[0] == C.sizeof(engine.SntStep)
+    assert got[1:] == [getattr(engine.SntStep, f).offset for f in fields]
 
-    class Sizes:
-        def __getattr__(self, name):
-            if name.endswith("workspace_bytes"):
-                return lambda *a: 4096
-            raise AttributeError(name)
 
-    class FakeEvent:
-        def record(self, stream=None):
-            log.append("record")
-
-    class FakeStream:
-        def __init__(self, *a, **k):
-            pass
-
-        def wait_event(self, ev):
-            log.append("wait_event")
-
-        def wait_stream(self, st):
-            log.append("wait_stream")
-
-    monkeypatch.setattr(ops._lib, "lib", lambda: Sizes())
-    monkeypatch.setattr(ops, "call", lambda name, *a: calls.append(name))
-    monkeypatch.setattr(ops, "require_cuda", lambda *t: None)
-    monkeypatch.setattr(ops, "workspace", lambda nb, dev: torch.empty(max(int(nb), 1), dtype=torch.uint8))
-    monkeypatch.setattr(ops, "stream_ptr", lambda: None)
-    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
-    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: FakeStream())
-    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
-    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None)
-    monkeypatch.setattr(ops, "TAIL_OVERLAP", True)
-    monkeypatch.setattr(ops, "EMB_PLAN_EARLY", True)
-    monkeypatch.setattr(ops, "_side_streams", {})
+def test_engine_batch_sizes_and_flat_params(snt):
+    """Host logic of the native step: batch_sizes (bincount form) == the broadcast form of ops, pack errors as torch
+    raises them; FlatParams lays tensors out in readiness order, keeps module values, and detects a moved module."""
+    from show_and_tell_b200 import engine, ops
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        l = np.sort(rng.integers(1, 21, size=int(rng.integers(1, 300))))[::-1]
+        bs, n = engine.batch_sizes(l.tolist())
+        assert n == int(l.sum()) and np.array_equal(bs, ops.batch_sizes_from_lengths(l.tolist()))
+    with pytest.raises(RuntimeError, match="sorted in decreasing order"):
+        engine.batch_sizes([3, 5])
+    with pytest.raises(RuntimeError, match="greater than 0"):
+        engine.batch_sizes([3, 0])
+    with pytest.raises(RuntimeError, match="exceeds"):
+        engine.batch_sizes([9, 2], max_steps=8)
     torch.manual_seed(0)
-    enc, dec = snt.EncoderCNN(16, backbone=False), snt.DecoderRNN(16, 24, 50, 1)
-    b = snt.synthetic.make_batch(6, 50, seed=1, pooled_dim=2048)
-    pooled, caps = torch.from_numpy(b["pooled"]), torch.from_numpy(b["captions"])
-    tg = torch.from_numpy(snt.synthetic.pack_host(b["captions"], b["lengths"]))
-    dec.loss(enc.forward_pooled(pooled), caps, b["lengths"], tg).backward()
-    assert calls == ["snt_head_fwd", "snt_embed_pack_fwd", "snt_lstm_fwd", "snt_vocab_ce_fwd", "snt_embed_bwd_plan",
-                     "snt_vocab_ce_bwd", "snt_lstm_bwd", "snt_embed_pack_bwd_planned", "snt_head_bwd"]
-    # plan: wait_stream + record; dx complete: record; planned call: wait_event; head: wait_event, record, wait_event
-    assert log == ["wait_stream", "record", "record", "wait_event", "wait_event", "record", "wait_event"]
-    assert all(p.grad is not None for m in (enc, dec) for p in m.parameters() if p.requires_grad)
-    assert ops._tail is None
+    enc, dec = snt.EncoderCNN(16, backbone=False), snt.DecoderRNN(16, 24, 50, 2)
+    before = {k: v.clone() for k, v in dec.state_dict().items()}
+    flat = engine.FlatParams(enc, dec)
+    assert flat.names[:2] == ["linear.weight", "linear.bias"] and flat.names[2].endswith("_l1")
+    assert flat.names[-5] == "embed.weight" and flat.names[-1] == "encoder.bn.bias"
+    lo, hi = flat.bucket_range["early"]
+    assert lo == 0 and hi == flat.bucket_range["mid"][0] and flat.bucket_range["late"][1] == flat.numel
+    assert all(o % 64 == 0 for o in flat.offsets) and flat.intact()
+    for k, v in dec.state_dict().items():
+        assert torch.equal(v, before[k])
+    dec.linear.weight.data.add_(1.0)                                   # the module writes through to the flat buffer
+    assert float(flat.p[0]) == float(before["linear.weight"].reshape(-1)[0] + 1.0)
+    dec.load_state_dict(before)                                        # in-place copy: still on the flat buffer
+    assert flat.intact() and float(flat.p[0]) == float(before["linear.weight"].reshape(-1)[0])
+    flat.attach_grads()
+    flat.g.fill_(2.0)
+    assert float(dec.embed.weight.grad.sum()) == 2.0 * dec.embed.weight.numel()
+    dec.double()                                                       # moved off the buffer
+    assert not flat.intact()
+    with pytest.raises(snt._lib.SntError, match="no CPU fallback"):
+        engine.StepEngine(engine.FlatParams(None, snt.DecoderRNN(16, 24, 50, 1)))

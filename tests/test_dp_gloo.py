@@ -1,18 +1,20 @@
-"""World-size-2 check of the data-parallel host logic on CPU (gloo): strided sharding of the length-sorted
-batch, N_rank/N_global loss weighting, and the readiness-ordered asynchronous gradient all-reduce
-(show_and_tell_b200.parallel) reproduce the single-process step on the GLOBAL batch.  The per-rank compute here
-is the CPU baseline port (test infrastructure) — the CUDA kernels are covered by the -m gpu tests."""
+"""World-size-2 check of the data-parallel host logic on CPU (gloo): strided sharding of the length-sorted batch,
+N_rank/N_global loss weighting, the initial broadcast from rank 0, the three contiguous gradient buckets of the flat
+buffer all-reduced in readiness order and the staged optimizer (show_and_tell_b200.parallel.DataParallelStep) reproduce
+the single-process step - gradients AND updated parameters - on the GLOBAL batch.  The per-rank compute here is the
+CPU baseline port (test infrastructure) behind the engine interface; the CUDA executor behind the same class is covered
+by tests/test_gpu_step.py and tests/multi_gpu_parity.py (NCCL, 2 GPUs)."""
 import os
 import socket
 
 import numpy as np
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-B, E, H, V, L = 22, 16, 24, 97, 1
+B, E, H, V, L = 22, 16, 24, 97, 2
+LR, CLIP = 1e-2, 0.1
 
 
 def _free_port():
@@ -21,63 +23,103 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _global_batch():
+def _global_batch(seed=3):
     import show_and_tell_b200 as snt
-    b = snt.synthetic.make_batch(B, V, embed=E, seed=3)
-    return b
+    return snt.synthetic.make_batch(B, V, embed=E, seed=seed)
 
 
-def _model():
+def _model(seed=11):
     from oracle import torch_port as TP
-    torch.manual_seed(11)
-    return TP.CaptionDecoderCPU(E, H, V, L)
+    torch.manual_seed(seed)
+    dec = TP.CaptionDecoderCPU(E, H, V, L)
+    dec.num_layers = L
+    return dec
+
+
+class PortEngine:
+    """The engine interface of parallel.DataParallelStep on the CPU port: prepare / run(phases) / adam / loss / flat.
+    Gradients are computed with torch autograd in the first phase and copied into the flat buffer bucket by bucket, in
+    the phase the CUDA executor finalises them."""
+
+    def __init__(self, dec):
+        from show_and_tell_b200 import engine
+        self.dec = dec
+        self.flat = engine.FlatParams(None, dec)
+        self.loss = torch.zeros(())
+        self.scale = 1.0
+        self.phases = []
+
+    def prepare(self, inputs, captions, lengths, targets, grad_scale):
+        self.batch = (inputs, captions, [int(l) for l in lengths], targets)
+        self.scale = grad_scale
+        return int(sum(self.batch[2]))
+
+    def set_grad_scale(self, s):
+        self.scale = s
+
+    def run(self, phases):
+        from show_and_tell_b200 import engine as E_
+        self.phases.append(phases)
+        f = self.flat
+        if phases & E_.PH_FWD:
+            inputs, captions, lengths, targets = self.batch
+            if targets is None:
+                targets = torch.nn.utils.rnn.pack_padded_sequence(captions, lengths, batch_first=True)[0]
+            loss = torch.nn.functional.cross_entropy(self.dec(inputs, captions, lengths), targets) * self.scale
+            self.autograd = dict(zip(f.names, torch.autograd.grad(loss, f.params)))
+            self.loss = loss.detach()
+        for bit, bucket in ((E_.PH_BWD_CE, "early"), (E_.PH_BWD_LSTM, "mid"), (E_.PH_BWD_TAIL, "late")):
+            if phases & bit:
+                lo, hi = f.bucket_range[bucket]
+                for n, o, p in zip(f.names, f.offsets, f.params):
+                    if lo <= o < hi:
+                        f.g[o:o + p.numel()].copy_(self.autograd[n].reshape(-1))
+
+    def adam(self, lo, hi, step, lr, betas, eps, grad_clip):
+        f = self.flat
+        g = f.g[lo:hi].clamp(-grad_clip, grad_clip)                       # train.py:88-91
+        f.m[lo:hi].mul_(betas[0]).add_(g, alpha=1 - betas[0])              # torch.optim.Adam
+        f.v[lo:hi].mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+        bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
+        f.p[lo:hi].addcdiv_(f.m[lo:hi], (f.v[lo:hi].sqrt() / bc2 ** 0.5).add_(eps), value=-lr / bc1)
 
 
 def _worker(rank, world, port, q):
     import sys
     sys.path.insert(0, ROOT)
     import show_and_tell_b200 as snt
-    from show_and_tell_b200 import parallel
+    from show_and_tell_b200 import engine, parallel
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
-    gb = _global_batch()
-    sh = parallel.shard_batch(gb, world, rank)
-    assert sh["lengths"] == sorted(sh["lengths"], reverse=True)          # every shard stays sorted
-    targets = snt.synthetic.pack_host(sh["captions"], sh["lengths"])
-    dec = _model()
-    scale = sum(sh["lengths"]) / sh["n_tokens_global"]
-    logits = dec(torch.from_numpy(sh["features"]), torch.from_numpy(sh["captions"]), sh["lengths"])
-    loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(targets)) * scale
-    loss.backward()
-    red = parallel.GradAllReducer()
-    groups = [["linear.weight", "linear.bias"],
-              ["lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0"], ["embed.weight"]]
-    named = dict(dec.named_parameters())
-    for g in groups:                       # the order ops._DecoderLoss.backward reports gradients in
-        red(g, [named[n].grad for n in g])
-    red(None, None)                        # end of backward: wait for the collectives
-    # deferred mode (what DataParallelStep uses with its optimizer): the end-of-backward call does not wait, the owner
-    # waits for the early groups first, updates their parameters, then for the rest
-    t1, t2, t3 = torch.ones(5), torch.ones(7), torch.ones(3)
-    red2 = parallel.GradAllReducer()
-    red2.defer = True
-    red2(["a"], [t1])
-    red2(["b", "c"], [t2, t3])
-    red2(None, None)
-    assert len(red2.groups) == 2 and len(red2.pending) >= 2
-    assert red2.wait_groups(1) == ["a"] and float(t1[0]) == world and len(red2.groups) == 1
-    red2.finish()
-    assert float(t2[0]) == world and float(t3[0]) == world and not red2.pending and not red2.groups
-    tot = loss.detach().clone()
-    dist.all_reduce(tot)
+    dec = _model(seed=11 + 7 * rank)                  # ranks start DIFFERENT: the stepper must broadcast rank 0's
+    eng = PortEngine(dec)
+    st = parallel.DataParallelStep(None, dec, lr=LR, grad_clip=CLIP, engine=eng)
+    ref0 = _model(seed=11)
+    for k, v in ref0.state_dict().items():
+        assert torch.equal(dec.state_dict()[k], v), k                     # broadcast from rank 0 happened
+    losses = []
+    for it in range(2):                               # two steps: the second one runs on the UPDATED parameters
+        gb = _global_batch(seed=3 + it)
+        sh = parallel.shard_batch(gb, world, rank)
+        assert sh["lengths"] == sorted(sh["lengths"], reverse=True)       # every shard stays sorted
+        loss = st.step(torch.from_numpy(sh["features"]), torch.from_numpy(sh["captions"]), sh["lengths"], None,
+                       sh["n_tokens_global"])
+        tot = loss.clone()
+        dist.all_reduce(tot)
+        losses.append(float(tot))
+        if it == 0:
+            grads0 = {n: st.flat.grad(n).clone().numpy() for n in st.flat.names}
+    assert eng.phases[:3] == [engine.PH_FWD | engine.PH_BWD_CE, engine.PH_BWD_LSTM, engine.PH_BWD_TAIL]
+    assert st.reducer.order[:3] == ["early", "mid", "late"] and not st.reducer.pending
     if rank == 0:
-        q.put(({k: p.grad.numpy().copy() for k, p in named.items()}, float(tot), red.order, red.bytes))
+        q.put((grads0, {k: v.numpy().copy() for k, v in dec.state_dict().items()}, losses, st.reducer.bytes, st.t))
     dist.barrier()
+    st.close()
     dist.destroy_process_group()
 
 
-def test_dp2_matches_global_batch():
+def test_dp2_step_matches_global_batch_step():
     import show_and_tell_b200 as snt
     world = 2
     ctx = mp.get_context("spawn")
@@ -86,21 +128,32 @@ def test_dp2_matches_global_batch():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    grads, loss, order, nbytes = q.get(timeout=180)
+    grads0, state, losses, nbytes, t = q.get(timeout=180)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    gb = _global_batch()
-    dec = _model()
-    targets = snt.synthetic.pack_host(gb["captions"], gb["lengths"])
-    ref = torch.nn.functional.cross_entropy(
-        dec(torch.from_numpy(gb["features"]), torch.from_numpy(gb["captions"]), gb["lengths"]), torch.from_numpy(targets))
-    ref.backward()
-    assert abs(loss - float(ref)) < 1e-6 * abs(float(ref))
-    for k, p in dec.named_parameters():
-        np.testing.assert_allclose(grads[k], p.grad.numpy(), rtol=2e-5, atol=2e-7, err_msg=k)
-    assert order[:2] == ["linear.weight", "linear.bias"] and order[-1] == "embed.weight"
-    assert nbytes == sum(p.numel() * 4 for p in dec.parameters())
+    # single process, global batch, torch's own clip + Adam (train.py:137-146)
+    dec = _model(seed=11)
+    opt = torch.optim.Adam(dec.parameters(), lr=LR)
+    for it in range(2):
+        gb = _global_batch(seed=3 + it)
+        targets = torch.from_numpy(snt.synthetic.pack_host(gb["captions"], gb["lengths"]))
+        opt.zero_grad()
+        ref = torch.nn.functional.cross_entropy(
+            dec(torch.from_numpy(gb["features"]), torch.from_numpy(gb["captions"]), gb["lengths"]), targets)
+        ref.backward()
+        assert abs(losses[it] - float(ref)) < 2e-6 * abs(float(ref))
+        if it == 0:
+            for k, p in dec.named_parameters():
+                np.testing.assert_allclose(grads0[k], p.grad.numpy(), rtol=2e-5, atol=2e-7, err_msg=k)
+        for p in dec.parameters():
+            p.grad.clamp_(-CLIP, CLIP)
+        opt.step()
+    for k, v in dec.state_dict().items():
+        np.testing.assert_allclose(state[k], v.numpy(), rtol=1e-4, atol=2e-6, err_msg=k)
+    assert t == 2
+    padded = sum((p.numel() + 63) // 64 * 64 for p in dec.parameters())
+    assert nbytes == 2 * 4 * padded                                     # every parameter all-reduced exactly once per step
 
 
 def test_strided_shard_balances_tokens():

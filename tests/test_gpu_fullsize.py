@@ -1,0 +1,119 @@
+"""BASELINE.json's configurations at FULL size against the pinned CPU port (oracle/torch_port.py: torch.nn on the host,
+checked against the reference's own golden vectors by tests/test_oracle_golden.py) in float64:
+  configs[1]  decoder train step, E256/H512/V10000/L1, batch 1024           loss, every gradient, dfeatures
+  configs[3]  scaled decoder, E512/H1024/V32000/L2, batch 2048               loss, every gradient
+  configs[2]  greedy sample(), batch 4096                                    token ids, gated by the fp64 top-2 margin
+Tolerances are north_star's: fp32 mode loss 1e-5 / gradients 1e-4, bf16 mode loss 1e-3 / gradients 1e-2 (relative,
+Frobenius); greedy tokens exact in fp32 mode wherever the fp64 margin exceeds fp32 rounding noise (1e-4 at these sizes:
+logits are sums of 512 products), bf16 mode gated at 3e-2.  No self-comparison: the CUDA path never checks itself here."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import torch_port as TP
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": dict(loss=1e-5, grad=1e-4), "bf16": dict(loss=1e-3, grad=1e-2)}
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _port64_step(dec_state, E, H, V, L, feats, caps, lengths, targets):
+    """train.py:137-144 on the CPU port in float64 -> loss, gradients by state_dict name, dfeatures."""
+    torch.set_num_threads(torch.get_num_threads())
+    ref = TP.CaptionDecoderCPU(E, H, V, L).double()
+    ref.load_state_dict({k: v.double() for k, v in dec_state.items()})
+    f = torch.from_numpy(feats).double().requires_grad_(True)
+    loss = torch.nn.functional.cross_entropy(ref(f, torch.from_numpy(caps), lengths), torch.from_numpy(targets))
+    loss.backward()
+    return float(loss), {k: p.grad.numpy() for k, p in ref.named_parameters()}, f.grad.numpy()
+
+
+def _cuda_step(dec, feats, caps, lengths, targets):
+    dec.zero_grad(set_to_none=True)
+    f = _t(feats).requires_grad_(True)
+    loss = dec.loss(f, _t(caps), lengths, _t(targets))
+    loss.backward()
+    return float(loss), {k: p.grad.detach().cpu().numpy() for k, p in dec.named_parameters()}, f.grad.cpu().numpy()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("cfg", ["configs1", "configs3"])
+def test_train_step_vs_port_fp64(cfg):
+    import show_and_tell_b200 as snt
+    B, E, H, V, L = (1024, 256, 512, 10000, 1) if cfg == "configs1" else (2048, 512, 1024, 32000, 2)
+    torch.manual_seed(0)
+    dec = snt.DecoderRNN(E, H, V, L, precision="fp32")
+    state = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    b = snt.synthetic.make_batch(B, V, embed=E, seed=1)
+    targets = snt.synthetic.pack_host(b["captions"], b["lengths"])
+    loss64, g64, df64 = _port64_step(state, E, H, V, L, b["features"], b["captions"], b["lengths"], targets)
+    dec = dec.cuda()
+    report = {}
+    for prec in ("fp32", "bf16"):
+        dec.precision = prec
+        loss, g, df = _cuda_step(dec, b["features"], b["captions"], b["lengths"], targets)
+        tol = TOL[prec]
+        errs = {k: rel_err(g[k], g64[k]) for k in g64}
+        errs["dfeatures"] = rel_err(df, df64)
+        report[prec] = (abs(loss - loss64) / loss64, max(errs.values()))
+        assert abs(loss - loss64) / loss64 < tol["loss"], (prec, loss, loss64)
+        for k, e in errs.items():
+            assert e < tol["grad"], (prec, k, e)
+    print(f"{cfg}: (loss rel err, worst gradient rel err) per mode = {report}")
+    # the native step executor on the same batch (bf16): identical to the autograd path it replaces
+    from show_and_tell_b200 import parallel
+    st = parallel.DataParallelStep(None, dec, optimizer=False)
+    loss_n = float(st.step(_t(b["features"]), _t(b["captions"]), b["lengths"]))
+    assert loss_n == loss
+    for k in g:
+        assert np.array_equal(st.flat.grad(k).cpu().numpy(), g[k]), k
+
+
+def _port64_greedy(state, E, H, V, L, feats, steps=20):
+    """models.py:56-67 on the CPU port in float64, with the top-2 logit margin of every step."""
+    ref = TP.CaptionDecoderCPU(E, H, V, L).double().eval()
+    ref.load_state_dict({k: v.double() for k, v in state.items()})
+    ids, margins = [], []
+    with torch.no_grad():
+        x, states = torch.from_numpy(feats).double()[:, None, :], None
+        for _ in range(steps):
+            h, states = ref.lstm(x, states)
+            top = ref.linear(h[:, 0, :]).topk(2, dim=1)
+            tok = top.indices[:, :1]
+            ids.append(tok)
+            margins.append(top.values[:, 0] - top.values[:, 1])
+            x = ref.embed(tok)
+    return torch.cat(ids, 1).numpy(), torch.stack(margins, 1).numpy()
+
+
+@pytest.mark.timeout(600)
+def test_greedy_configs2_vs_port_fp64():
+    import show_and_tell_b200 as snt
+    B, E, H, V, L = 4096, 256, 512, 10000, 1
+    torch.manual_seed(0)
+    dec = snt.DecoderRNN(E, H, V, L)
+    state = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    feats = snt.synthetic.make_batch(B, V, embed=E, seed=1)["features"]
+    ref, marg = _port64_greedy(state, E, H, V, L, feats)
+    dec = dec.cuda().eval()
+    counts = {}
+    for prec, gate in (("fp32", 1e-4), ("bf16", 3e-2)):
+        ids = dec.sample(_t(feats), precision=prec).cpu().numpy()
+        assert ids.shape == (B, 20) and ids.dtype == np.int64
+        exact = gated = failed = 0
+        for r in range(B):
+            d = np.nonzero(ids[r] != ref[r])[0]
+            if d.size == 0:
+                exact += 1
+            elif marg[r, d[0]] < gate:
+                gated += 1            # first divergence at a near-tie of the fp64 reference: admissible
+            else:
+                failed += 1
+        counts[prec] = (exact, gated, failed)
+        assert failed == 0, (prec, counts)
+    print(f"configs[2] greedy rows (exact, gated by margin, failed): {counts}")
+    assert counts["fp32"][0] > 0.9 * B

@@ -56,6 +56,8 @@ class StepperCPU:
             g["lr"] = self.lr
         self.lrs.append(self.lr)
         self.calls += 1
+        if targets is None:                                         # the Trainer leaves the pack to the stepper (eval.py:91)
+            targets = torch.nn.utils.rnn.pack_padded_sequence(captions, [int(l) for l in lengths], batch_first=True)[0]
         self.model.zero_grad()
         loss = self.model.loss(images, captions, lengths, targets)
         loss.backward()
