@@ -193,8 +193,9 @@ int snt_clamp_adam_multi(int count, float* const* p, const float* const* g, floa
  * data-parallel caller starts its gradient all-reduce between them (one process per GPU; the reference's
  * nn.DataParallel, train.py:43-44):
  *   SNT_STEP_FWD       loss
- *   SNT_STEP_BWD_CE    d_w_out, d_b_out                       (ready first: overlaps all of BPTT)
- *   SNT_STEP_BWD_LSTM  d_w_ih / d_w_hh / d_b_ih / d_b_hh of every layer
+ *   SNT_STEP_BWD_CE    d_w_out                                (ready first: overlaps all of BPTT)
+ *   SNT_STEP_BWD_LSTM  d_b_out; d_w_ih / d_w_hh / d_b_ih / d_b_hh of every layer   (d_b_out = column sums of the stored
+ *                      softmax numerators: one HBM-bound pass that runs beside the latency-bound BPTT recurrence)
  *   SNT_STEP_BWD_TAIL  d_w_emb and the head gradients (d_w_fc, d_b_fc, d_bn_w, d_bn_b), optional d_features
  * Gradients are WRITTEN (not accumulated) with the factor grad_scale folded in; `loss` = grad_scale * mean CE.
  * K = 0: no encoder head, `input` holds features[B,E] (then the head pointers may be NULL).

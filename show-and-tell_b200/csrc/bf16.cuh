@@ -22,6 +22,11 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
              const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh, float* d_w_ih,
              float* d_w_hh, float* d_bias, float* dx, void* ws, int64_t ws_bytes, cudaStream_t st);
 
+// step executor hooks (lstm_tc.cu): event recorded right before the next lstm_bwd() launches its recurrence; whether the
+// recurrence of this hidden size runs as the persistent cooperative kernel (128 of 148 SMs, latency-bound)
+void lstm_bwd_gate_event(cudaEvent_t e);
+bool lstm_bwd_is_persistent(int64_t H);
+
 int64_t linear_ws_bytes(int64_t N, int64_t H, int64_t V);
 int linear_fwd(const void* hs, const float* w_out, const float* b_out, int64_t N, int64_t H, int64_t V,
                float* logits, void* ws, int64_t ws_bytes, cudaStream_t st);
@@ -44,12 +49,17 @@ int vocab_ce_train_fwd(const void* hs, const float* w_out, const float* b_out, c
                        void* w_bf16, void* ws, int64_t ws_bytes, cudaStream_t st, float loss_scale = 1.f);
 int vocab_ce_train_bwd(const void* u, const float* inv_s, const void* hs_scaled, const void* w_bf16,
                        const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
-                       float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st);
+                       float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st,
+                       bool defer_bias = false);
+// the d_b_out half of vocab_ce_train_bwd(defer_bias = true), on any stream, with caller-owned scratch
+int64_t vocab_ce_train_bias_part_elems(int64_t N, int64_t V);
+int vocab_ce_train_bias(const void* u, const float* inv_s, const float* dloss, float grad_scale, int64_t N, int64_t V,
+                        float* d_b_out, float* part, float* db, cudaStream_t st, int max_blocks);
 
 // out[c] = beta*out[c] + sum_r roww[r] * in[r*ld + c] for a bf16 matrix (roww = NULL: unweighted); partial needs
 // ((R+255)/256)*C floats
 int colsum_bf16(const __nv_bfloat16* in, int64_t R, int64_t C, int64_t ld, float beta, float* out, float* partial,
-                cudaStream_t st, const float* roww = nullptr);
+                cudaStream_t st, const float* roww = nullptr, int max_blocks = 0);
 
 int64_t greedy_ws_bytes(int64_t B, int64_t E, int64_t H, int64_t V, int L);
 int greedy_decode(const float* features, const float* w_emb, int L, const float* const* w_ih,

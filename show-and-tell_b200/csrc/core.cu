@@ -66,6 +66,7 @@ SideStream* side_stream(int which) {
     if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&x.aux, cudaEventDisableTiming);
   }
   return &x;
 }

@@ -50,7 +50,10 @@ __global__ void unperm_vec_kernel(const float* __restrict__ in, int H, float* __
 
 // ---- forward step epilogue ---------------------------------------------------------------------------------------------
 struct LstmFwdEpi {
-  static constexpr int kWarps = 4;
+  // 16 epilogue warps: warp -> (TMEM lane quadrant ew & 3, 32-column chunk ew >> 2), i.e. 8 hidden units of 32 rows each.
+  // (With 4 warps - one per quadrant, four chunks each, 243 registers - the gate math ran one warp per scheduler with
+  // nothing to hide its MUFU / load latencies behind: ncu showed the tensor pipe 28 % active in the greedy step.)
+  static constexpr int kWarps = 16;
   static constexpr int kStages = 0;
   static constexpr int kSmemPerWarp = 0;
   int bs, bs_next, H;
@@ -64,90 +67,82 @@ struct LstmFwdEpi {
   bf* act;              // [bs, 4H]   sigma(i), sigma(f), tanh(g), sigma(o), interleaved, kept for BPTT (NULL: skip)
   int ldh, ldn;         // row pitches of hs / hprev_next in elements
 
-  // everything the epilogue reads from global memory for its 128 columns (4 chunks x 8 hidden units)
+  // everything the epilogue reads from global memory for its 32 columns (8 hidden units), fetched one tile ahead
   struct Pre {
-    uint4 gx[4][4];   // bf16 input projection, 32 values per chunk
-    float4 cp[4][2];  // c_{t-1}, 8 values per chunk
+    uint4 gx[4];   // bf16 input projection (or the bias packed the same way), 32 values
+    float4 cp[2];  // c_{t-1}, 8 values
   };
   __device__ __forceinline__ void prefetch(Pre& p, int m_blk, int n_blk, int ew, int lane) const {
-    const int row = m_blk * tc::BM + ew * 32 + lane;
-    if (row >= bs) return;
+    const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
     const int H4 = 4 * H;
+    const int col0 = n_blk * 128 + (ew >> 2) * 32;
+    if (row >= bs || col0 >= H4) return;
+    if (gx) {
+      const uint4* g4 = reinterpret_cast<const uint4*>(gx + (int64_t)row * H4 + col0);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int col0 = n_blk * 128 + c * 32;
-      if (col0 < H4) {
-        if (gx) {
-          const uint4* g4 = reinterpret_cast<const uint4*>(gx + (int64_t)row * H4 + col0);
+      for (int q = 0; q < 4; ++q) p.gx[q] = __ldg(g4 + q);
+    } else {  // bias only, packed to the same bf16 layout as a Gx' row would have
 #pragma unroll
-          for (int q = 0; q < 4; ++q) p.gx[c][q] = __ldg(g4 + q);
-        } else {  // bias only, packed to the same bf16 layout as a Gx' row would have
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * q));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * q + 4));
-            p.gx[c][q] = make_uint4(pack_bf2(b0.x, b0.y), pack_bf2(b0.z, b0.w), pack_bf2(b1.x, b1.y), pack_bf2(b1.z, b1.w));
-          }
-        }
-        if (c_prev) {
-          const float4* c4 = reinterpret_cast<const float4*>(c_prev + (int64_t)row * H + (col0 >> 2));
-          p.cp[c][0] = c4[0];
-          p.cp[c][1] = c4[1];
-        } else {
-          p.cp[c][0] = p.cp[c][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+      for (int q = 0; q < 4; ++q) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * q));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * q + 4));
+        p.gx[q] = make_uint4(pack_bf2(b0.x, b0.y), pack_bf2(b0.z, b0.w), pack_bf2(b1.x, b1.y), pack_bf2(b1.z, b1.w));
       }
+    }
+    if (c_prev) {
+      const float4* c4 = reinterpret_cast<const float4*>(c_prev + (int64_t)row * H + (col0 >> 2));
+      p.cp[0] = c4[0];
+      p.cp[1] = c4[1];
+    } else {
+      p.cp[0] = p.cp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane,
                                        const Pre& p, uint8_t*) const {
-    const int row = m_blk * tc::BM + ew * 32 + lane;
+    const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
     const bool ok = row < bs;
     const int H4 = 4 * H;
+    const int c = ew >> 2;
+    const int col0 = n_blk * 128 + c * 32;
+    if (col0 >= H4) return;  // warp-uniform
+    uint32_t r[32];
+    tc::tmem_ld32(tmem_rows + (uint32_t)(c * 32), r);
+    tc::tmem_ld_wait();
+    if (!ok) return;
+    const int j0 = col0 >> 2;
+    float4 g[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int col0 = n_blk * 128 + c * 32;
-      if (col0 >= H4) break;  // warp-uniform
-      uint32_t r[32];
-      tc::tmem_ld32(tmem_rows + (uint32_t)(c * 32), r);
-      tc::tmem_ld_wait();
-      if (!ok) continue;
-      const int j0 = col0 >> 2;
-      float4 g[8];
+    for (int q = 0; q < 4; ++q) {  // 8 bf16 = 2 hidden units per 16-byte load
+      const uint4 v = p.gx[q];
+      const float2 a = unpack_bf2(v.x), b = unpack_bf2(v.y), c2 = unpack_bf2(v.z), d = unpack_bf2(v.w);
+      g[2 * q] = make_float4(a.x, a.y, b.x, b.y);
+      g[2 * q + 1] = make_float4(c2.x, c2.y, d.x, d.y);
+    }
+    const float cp[8] = {p.cp[0].x, p.cp[0].y, p.cp[0].z, p.cp[0].w, p.cp[1].x, p.cp[1].y, p.cp[1].z, p.cp[1].w};
+    float cn[8], hn[8];
+    uint32_t ap[16];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {  // 8 bf16 = 2 hidden units per 16-byte load
-        const uint4 v = p.gx[c][q];
-        const float2 a = unpack_bf2(v.x), b = unpack_bf2(v.y), c2 = unpack_bf2(v.z), d = unpack_bf2(v.w);
-        g[2 * q] = make_float4(a.x, a.y, b.x, b.y);
-        g[2 * q + 1] = make_float4(c2.x, c2.y, d.x, d.y);
-      }
-      const float cp[8] = {p.cp[c][0].x, p.cp[c][0].y, p.cp[c][0].z, p.cp[c][0].w,
-                           p.cp[c][1].x, p.cp[c][1].y, p.cp[c][1].z, p.cp[c][1].w};
-      float cn[8], hn[8];
-      uint32_t ap[16];
+    for (int u = 0; u < 8; ++u) {
+      const float i_ = sigm(__uint_as_float(r[4 * u]) + g[u].x);
+      const float f_ = sigm(__uint_as_float(r[4 * u + 1]) + g[u].y);
+      const float g_ = tanh_(__uint_as_float(r[4 * u + 2]) + g[u].z);
+      const float o_ = sigm(__uint_as_float(r[4 * u + 3]) + g[u].w);
+      cn[u] = f_ * cp[u] + i_ * g_;
+      hn[u] = o_ * tanh_(cn[u]);
+      ap[2 * u] = pack_bf2(i_, f_);
+      ap[2 * u + 1] = pack_bf2(g_, o_);
+    }
+    float4* cd = reinterpret_cast<float4*>(cs + (int64_t)row * H + j0);
+    cd[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+    cd[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+    const uint4 hv = make_uint4(pack_bf2(hn[0], hn[1]), pack_bf2(hn[2], hn[3]), pack_bf2(hn[4], hn[5]),
+                                pack_bf2(hn[6], hn[7]));
+    *reinterpret_cast<uint4*>(hs + (int64_t)row * ldh + j0) = hv;
+    if (row < bs_next) *reinterpret_cast<uint4*>(hprev_next + (int64_t)row * ldn + j0) = hv;
+    if (act) {  // training only
+      uint4* ad = reinterpret_cast<uint4*>(act + (int64_t)row * H4 + col0);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float i_ = sigm(__uint_as_float(r[4 * u]) + g[u].x);
-        const float f_ = sigm(__uint_as_float(r[4 * u + 1]) + g[u].y);
-        const float g_ = tanh_(__uint_as_float(r[4 * u + 2]) + g[u].z);
-        const float o_ = sigm(__uint_as_float(r[4 * u + 3]) + g[u].w);
-        cn[u] = f_ * cp[u] + i_ * g_;
-        hn[u] = o_ * tanh_(cn[u]);
-        ap[2 * u] = pack_bf2(i_, f_);
-        ap[2 * u + 1] = pack_bf2(g_, o_);
-      }
-      float4* cd = reinterpret_cast<float4*>(cs + (int64_t)row * H + j0);
-      cd[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
-      cd[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
-      const uint4 hv = make_uint4(pack_bf2(hn[0], hn[1]), pack_bf2(hn[2], hn[3]), pack_bf2(hn[4], hn[5]),
-                                  pack_bf2(hn[6], hn[7]));
-      *reinterpret_cast<uint4*>(hs + (int64_t)row * ldh + j0) = hv;
-      if (row < bs_next) *reinterpret_cast<uint4*>(hprev_next + (int64_t)row * ldn + j0) = hv;
-      if (act) {  // training only
-        uint4* ad = reinterpret_cast<uint4*>(act + (int64_t)row * H4 + col0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) ad[q] = make_uint4(ap[4 * q], ap[4 * q + 1], ap[4 * q + 2], ap[4 * q + 3]);
-      }
+      for (int q = 0; q < 4; ++q) ad[q] = make_uint4(ap[4 * q], ap[4 * q + 1], ap[4 * q + 2], ap[4 * q + 3]);
     }
   }
 };
@@ -1068,6 +1063,13 @@ int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const flo
   return SNT_OK;
 }
 
+// One-shot hook for the step executor: the next lstm_bwd() on this thread records `e` on its stream right BEFORE it
+// launches the recurrence (after the weight preparation).  Background work of a lower-priority stream that waits for `e`
+// is then released at the same moment as the cooperative BPTT kernel, whose CTAs the block scheduler places first.
+static thread_local cudaEvent_t g_bptt_gate = nullptr;
+void lstm_bwd_gate_event(cudaEvent_t e) { g_bptt_gate = e; }
+bool lstm_bwd_is_persistent(int64_t H) { return (H == 256 || H == 512) && !getenv("SNT_NO_PERSISTENT"); }
+
 int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* cs, const void* hprev,
              const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh, float* d_w_ih,
              float* d_w_hh, float* d_bias, float* dx, void* ws, int64_t ws_bytes, cudaStream_t st) {
@@ -1094,6 +1096,10 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
     SNT_CHECK(prep_launch(w_ih, w_hh, nullptr, nullptr, In, H, w.w_ih, can_persist ? nullptr : w.w_hh, nullptr,
                           can_persist ? w.w_hh_t : nullptr, can_persist ? w.flags : nullptr,
                           (int64_t)sizeof(int) * 2 * nflags, nullptr, 0, st));
+    if (g_bptt_gate) {  // see lstm_bwd_gate_event(): released at the moment the recurrence kernel becomes eligible
+      SNT_CUDA(cudaEventRecord(g_bptt_gate, st));
+      g_bptt_gate = nullptr;
+    }
     if (can_persist) {
       CUtensorMap ta, tb;
       SNT_CHECK(tc::make_operand_tmap(&ta, dg, false, N, 4 * H, 4 * H, tc::BM));
@@ -1158,29 +1164,57 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
         (int64_t)bs_next * H, w.dc_state, dg + (int64_t)pk.off[t] * 4 * H);
     SNT_LAUNCH_CHECK("lstm_bwd_point_kernel");
   }
-  // bias gradient = column sums of dG': bandwidth-bound, runs on the side stream next to the weight-gradient GEMMs
+  // Tail of the stage: dW_ih = dG'^T.X, dW_hh = dG'^T.Hprev (rows come out interleaved: un-permuted on store), the bias
+  // gradient (column sums of dG') and dX = dG'.W_ih'.  Each weight gradient has too few output tiles to fill the GPU and
+  // needs a K split; when both fit next to each other (H <= 512: 16 + 32 tiles of 128 x 256) they run CONCURRENTLY on the
+  // two streams with grids sized to share the SMs in proportion to their work (48 + 96 CTAs at E256/H512, three K
+  // slices each) instead of one after the other at 128 CTAs each.  The column sums follow dW_ih on the side stream, next
+  // to dX.
   SideStream* side = side_stream();
+  const int sms = tc::grid_sms();
+  const int64_t rt = (4 * H + tc::BM - 1) / tc::BM;
+  const int64_t t1 = rt * ((In + 255) / 256), t2 = rt * ((H + 255) / 256);
+  const int64_t kb_n = (N + tc::BK - 1) / tc::BK;
+  int c1 = 0, c2 = 0;  // K slices of the concurrent mode (0: sequential)
+  if (side && In >= 256 && H >= 256 && t1 + t2 <= sms && kb_n >= 16 && !getenv("SNT_NO_WGRAD_OVERLAP")) {
+    const double share1 = (double)In / (double)(In + H);
+    c1 = (int)((double)sms * share1 / (double)t1);
+    c2 = (int)((double)(sms - (c1 < 1 ? 1 : c1) * t1) / (double)t2);
+    if (c1 < 1) c1 = 1;
+    if (c2 < 1) c2 = 1;
+    if (c1 > MAX_SPLITS) c1 = MAX_SPLITS;
+    if (c2 > MAX_SPLITS) c2 = MAX_SPLITS;
+    while (c1 > 1 && kb_n / c1 < 4) --c1;
+    while (c2 > 1 && kb_n / c2 < 4) --c2;
+    if ((int64_t)c1 * 4 * H * In + (int64_t)c2 * 4 * H * H > (int64_t)MAX_SPLITS * 4 * H * (In > H ? In : H)) c1 = c2 = 0;
+  }
   if (side) {
     SNT_CUDA(cudaEventRecord(side->fork, st));
     SNT_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
-    SNT_CHECK(colsum_bf16(dg, N, 4 * H, 4 * H, 0.f, w.tmp, w.cpart, side->s));
-    unperm_vec_kernel<<<(unsigned)((4 * H + 255) / 256), 256, 0, side->s>>>(w.tmp, (int)H, d_bias);
-    SNT_LAUNCH_CHECK("unperm_vec_kernel");
-    SNT_CUDA(cudaEventRecord(side->join, side->s));
   }
-  // weight gradients over the whole packed sequence (rows come out interleaved: un-permute on store)
-  int s1 = tc::choose_splits(4 * H, In, N, 0), s2 = tc::choose_splits(4 * H, H, N, 0);
-  if (s1 > MAX_SPLITS) s1 = MAX_SPLITS;
-  if (s2 > MAX_SPLITS) s2 = MAX_SPLITS;
-  SNT_CHECK(tc::gemm_tc(true, true, 4 * H, In, N, 1.f, dg, 4 * H, (const bf*)x, In, 0.f, d_w_ih, nullptr, In,
-                        nullptr, s1, w.sws, st, (int)H));
-  SNT_CHECK(tc::gemm_tc(true, true, 4 * H, H, N, 1.f, dg, 4 * H, (const bf*)hprev, H, 0.f, d_w_hh, nullptr, H,
-                        nullptr, s2, w.sws, st, (int)H));
-  if (!side) {
-    SNT_CHECK(colsum_bf16(dg, N, 4 * H, 4 * H, 0.f, w.tmp, w.cpart, st));
-    unperm_vec_kernel<<<(unsigned)((4 * H + 255) / 256), 256, 0, st>>>(w.tmp, (int)H, d_bias);
+  if (c1 > 0) {
+    float* sws2 = w.sws + align_up((int64_t)c1 * 4 * H * In, 64);
+    SNT_CHECK(tc::gemm_tc(true, true, 4 * H, In, N, 1.f, dg, 4 * H, (const bf*)x, In, 0.f, d_w_ih, nullptr, In,
+                          nullptr, c1, w.sws, side->s, (int)H, nullptr, false, nullptr, 256));
+    SNT_CHECK(tc::gemm_tc(true, true, 4 * H, H, N, 1.f, dg, 4 * H, (const bf*)hprev, H, 0.f, d_w_hh, nullptr, H,
+                          nullptr, c2, sws2, st, (int)H, nullptr, false, nullptr, 256));
+  } else {
+    int s1 = tc::choose_splits(4 * H, In, N, 0), s2 = tc::choose_splits(4 * H, H, N, 0);
+    if (s1 > MAX_SPLITS) s1 = MAX_SPLITS;
+    if (s2 > MAX_SPLITS) s2 = MAX_SPLITS;
+    SNT_CHECK(tc::gemm_tc(true, true, 4 * H, In, N, 1.f, dg, 4 * H, (const bf*)x, In, 0.f, d_w_ih, nullptr, In,
+                          nullptr, s1, w.sws, st, (int)H));
+    SNT_CHECK(tc::gemm_tc(true, true, 4 * H, H, N, 1.f, dg, 4 * H, (const bf*)hprev, H, 0.f, d_w_hh, nullptr, H,
+                          nullptr, s2, w.sws, st, (int)H));
+  }
+  // bias gradient = column sums of dG': bandwidth-bound, on the side stream
+  {
+    cudaStream_t cs = side ? side->s : st;
+    SNT_CHECK(colsum_bf16(dg, N, 4 * H, 4 * H, 0.f, w.tmp, w.cpart, cs));
+    unperm_vec_kernel<<<(unsigned)((4 * H + 255) / 256), 256, 0, cs>>>(w.tmp, (int)H, d_bias);
     SNT_LAUNCH_CHECK("unperm_vec_kernel");
   }
+  if (side) SNT_CUDA(cudaEventRecord(side->join, side->s));
   if (dx)
     SNT_CHECK(tc::gemm_tc(false, true, N, In, 4 * H, 1.f, dg, 4 * H, w.w_ih, In, 0.f, dx, nullptr, In, nullptr, 1,
                           nullptr, st));
@@ -1197,17 +1231,29 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
 struct ArgmaxEpi {
   static constexpr int kWarps = 8;
   static constexpr int kStages = 0;
-  static constexpr int kSmemPerWarp = 0;
+  static constexpr int kSmemPerWarp = 4 * 32 * 4;  // this warp's 128 bias values (4 chunks of 32 columns)
   int M, V;
   const float* bias;
   float2* part;  // [slabs][M]: (max logit, index as int bits)
 
-  using Pre = tc::NoPre;
-  __device__ __forceinline__ void prefetch(Pre&, int, int, int, int) const {}
+  // The 128 bias values of the warp's half tile: four coalesced loads per lane one tile ahead, handed to every lane
+  // through shared memory (broadcast reads).  Loading bias[col] right where it is added put a dependent global load in
+  // front of every FADD: ncu's source page had 40 % of the kernel's stall samples on those adds (long scoreboard).
+  struct Pre { float b[4]; };
+  __device__ __forceinline__ void prefetch(Pre& p, int, int n_blk, int ew, int lane) const {
+    const int c0 = n_blk * 256 + (ew >> 2) * 128 + lane;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) p.b[c] = c0 + c * 32 < V ? __ldg(bias + c0 + c * 32) : 0.f;
+  }
   __device__ __forceinline__ void tile(uint32_t tmem_rows, int m_blk, int n_blk, int, int ew, int lane,
-                                       const Pre&, uint8_t*) const {
+                                       const Pre& pre, uint8_t* wsm) const {
     const int half = ew >> 2;
     const int row = m_blk * tc::BM + (ew & 3) * 32 + lane;
+    const uint32_t bsa = tc::smem_u32(wsm);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bsa + (uint32_t)(c * 128 + lane * 4)), "f"(pre.b[c]) : "memory");
+    __syncwarp();
     float best = -INFINITY;
     int bi = 0x7fffffff;
 #pragma unroll 1
@@ -1217,16 +1263,24 @@ struct ArgmaxEpi {
       if (col0 >= V) break;  // warp-uniform
       uint32_t r[32];
       tc::tmem_ld32(tmem_rows + (uint32_t)cofs, r);
+      float bv[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 u = tc::lds128(bsa + (uint32_t)(c * 128 + q * 16));
+        bv[4 * q] = __uint_as_float(u.x); bv[4 * q + 1] = __uint_as_float(u.y);
+        bv[4 * q + 2] = __uint_as_float(u.z); bv[4 * q + 3] = __uint_as_float(u.w);
+      }
       tc::tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = col0 + j;
         if (col < V) {
-          const float x = __uint_as_float(r[j]) + __ldg(bias + col);
+          const float x = __uint_as_float(r[j]) + bv[j];
           if (x > best || bi == 0x7fffffff) { best = x; bi = col; }  // strict '>' keeps the first maximum
         }
       }
     }
+    __syncwarp();  // the next tile's bias values overwrite the stage
     if (row < M) part[(int64_t)(n_blk * 2 + half) * M + row] = make_float2(best, __int_as_float(bi));
   }
 };

@@ -10,9 +10,12 @@
 //     executor's side stream during the forward pass - it needs the captions only;
 //   * the head backward (5 small launches) runs on that stream next to the embedding-gradient kernels: dfeatures is
 //     literally dx[:B], the t = 0 rows of the first layer's input gradient.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "bf16.cuh"
 
+namespace snt { namespace tc { int grid_sms(); } }
 using namespace snt;
 
 namespace {
@@ -34,6 +37,14 @@ pack_targets_kernel(const __grid_constant__ PackInfo pk, const int64_t* __restri
 __global__ void scale_scalar_kernel(float* x, float s) { x[0] *= s; }
 
 inline int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
+
+// SMs left over next to the persistent recurrence kernels (8 row blocks x 16 CTAs = 128 at H = 512), minus the SMs
+// reserved for collectives in flight (snt_set_sm_reserve): the width of the narrow column-sum grid that runs beside the
+// BPTT.  At least 8, so that the pass still ends within the recurrence.
+int free_sms_beside_recurrence() {
+  const int f = tc::grid_sms() - 128;
+  return f < 8 ? 8 : f;
+}
 
 // Optional per-stage timing (snt_step_profile): one CUDA-event pair per stage slot, recorded on the stream the stage is
 // enqueued on.  Off by default (no events, no overhead).
@@ -68,6 +79,7 @@ struct StepBufs {
   Layer layer[SNT_MAX_LAYERS];
   float *lse, *inv_s, *d_hs, *dx[2];
   void *u, *hs_scaled, *w_bf16;
+  float *bias_part, *bias_db;  // scratch of the deferred d_b_out column sums (bf16 mode)
   void *scratch, *head_ws, *emb_ws;
   int64_t scratch_bytes, head_bytes, emb_bytes;
   bool ok;
@@ -110,8 +122,11 @@ StepBufs carve(int prec, int L, int64_t B, int64_t N, int64_t E, int64_t H, int6
     b.u = w.take<char>(N * ((V + 7) / 8 * 8) * 2);
     b.hs_scaled = w.take<char>(N * H * 2);
     b.w_bf16 = w.take<char>(V * H * 2);
+    b.bias_part = w.take<float>(bf16::vocab_ce_train_bias_part_elems(N, V));
+    b.bias_db = w.take<float>(V);
   } else {
     b.u = b.hs_scaled = b.w_bf16 = nullptr;
+    b.bias_part = b.bias_db = nullptr;
   }
   b.scratch_bytes = stage_scratch_bytes(prec, L, B, N, E, H, V, K);
   b.scratch = w.take<char>(b.scratch_bytes);
@@ -142,7 +157,10 @@ extern "C" int64_t snt_step_workspace_bytes(int prec, int L, int64_t B, int64_t 
   add(N * 4); add(N * 4); add(N * H * 4);
   add(N * dxw * 4);
   if (L > 1) add(N * dxw * 4);
-  if (prec == SNT_PREC_BF16) { add(N * ((V + 7) / 8 * 8) * 2); add(N * H * 2); add(V * H * 2); }
+  if (prec == SNT_PREC_BF16) {
+    add(N * ((V + 7) / 8 * 8) * 2); add(N * H * 2); add(V * H * 2);
+    add(bf16::vocab_ce_train_bias_part_elems(N, V) * 4); add(V * 4);
+  }
   add(stage_scratch_bytes(prec, L, B, N, E, H, V, K));
   if (K > 0) add(snt_head_workspace_bytes(prec, B, K, E));
   add(snt_embed_bwd_workspace_bytes(N, V));
@@ -181,6 +199,9 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
   const int64_t* targets = d->targets ? d->targets : b.targets;
   const float* feats = K > 0 ? b.feats : d->input;
   const bool bf = prec == SNT_PREC_BF16;
+  // d_b_out beside the BPTT instead of beside the vocabulary contractions: only where the recurrence runs as the
+  // persistent cooperative kernel (latency-bound, HBM idle, 20 SMs free); elsewhere the per-step contractions fill the GPU
+  const bool defer_bias = bf && side != nullptr && bf16::lstm_bwd_is_persistent(H) && !getenv("SNT_NO_BIAS_DEFER");
 
   if (phases & SNT_STEP_FWD) {
     if (side) {  // token-dependent half of the embedding gradient: needs the captions only
@@ -233,9 +254,9 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
     SNT_REQUIRE(d->d_w_out && d->d_b_out, "snt_step_run: NULL output-layer gradient");
     const void* hs_last = b.layer[L - 1].hs;
     StageTimer tm(ST_CE_B, st);
-    if (bf)
+    if (bf)  // with a side stream, d_b_out is deferred to the BPTT phase (below)
       SNT_CHECK(bf16::vocab_ce_train_bwd(b.u, b.inv_s, b.hs_scaled, b.w_bf16, nullptr, d->grad_scale, N, H, V, b.d_hs,
-                                         d->d_w_out, d->d_b_out, b.scratch, b.scratch_bytes, st));
+                                         d->d_w_out, d->d_b_out, b.scratch, b.scratch_bytes, st, defer_bias));
     else
       SNT_CHECK(snt_vocab_ce_bwd(prec, hs_last, d->w_out, d->b_out, targets, b.lse, nullptr, d->grad_scale, N, H, V,
                                  b.d_hs, d->d_w_out, d->d_b_out, b.scratch, b.scratch_bytes, st));
@@ -243,6 +264,28 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
 
   // gradient w.r.t. the input of layer k lands in dx[k & 1]; layer 0's is dx[0]
   if (phases & SNT_STEP_BWD_LSTM) {
+    SNT_REQUIRE(d->d_b_out, "snt_step_run: NULL output-layer gradient");
+    bool bias_pending = false;
+    int bias_blocks = 0;
+    if (defer_bias) {
+      // d_b_out = column sums of the stored softmax numerators (one more pass over the N x V matrix): HBM-bound, it needs
+      // no tensor core and only a few SMs.  Next to the two vocabulary contractions that read the same matrix it costs
+      // them ~55 us of bandwidth; here it runs on the SMs the cooperative BPTT kernel leaves free (128 of 148 busy, HBM
+      // idle).  Two ways to stay out of the recurrence's way.  If the caller's stream has a higher priority than the side stream
+      // (parallel.DataParallelStep runs the step on a high-priority stream), the pass is BACKGROUND work: the usual wide
+      // grid of short blocks, released at the moment the cooperative kernel becomes eligible (gate event), so the block
+      // scheduler places the recurrence first and the column sums soak up whatever is left - two or more blocks per
+      // free SM.  On a default-priority stream: a grid narrow enough never to take an SM the recurrence needs.
+      int prio = 0;
+      const bool background = cudaStreamGetPriority(st, &prio) == cudaSuccess && prio < 0 && !getenv("SNT_NO_BACKGROUND");
+      if (background) {
+        bf16::lstm_bwd_gate_event(side->fork);   // recorded by snt_lstm_bwd of the top layer, after its weight preparation
+      } else {
+        SNT_CUDA(cudaEventRecord(side->fork, st));
+      }
+      bias_pending = true;
+      bias_blocks = background ? 0 : free_sms_beside_recurrence();
+    }
     const float* d_out = b.d_hs;
     for (int k = L - 1; k >= 0; --k) {
       SNT_REQUIRE(d->d_w_ih[k] && d->d_w_hh[k] && d->d_b_ih[k] && d->d_b_hh[k],
@@ -256,8 +299,16 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
                              b.scratch_bytes, st));
       // b_ih and b_hh enter the gates as a sum: they receive the same gradient
       SNT_CUDA(cudaMemcpyAsync(d->d_b_hh[k], d->d_b_ih[k], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
+      if (bias_pending) {  // enqueued after the top layer's launches: its gate event has been recorded by now
+        bias_pending = false;
+        SNT_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+        SNT_CHECK(bf16::vocab_ce_train_bias(b.u, b.inv_s, nullptr, d->grad_scale, N, V, d->d_b_out, b.bias_part,
+                                            b.bias_db, side->s, bias_blocks));
+        SNT_CUDA(cudaEventRecord(side->aux, side->s));
+      }
       d_out = dx;
     }
+    if (defer_bias) SNT_CUDA(cudaStreamWaitEvent(st, side->aux, 0));  // d_b_out is final when this phase ends
   }
 
   if (phases & SNT_STEP_BWD_TAIL) {

@@ -308,52 +308,6 @@ typedef CeBwdEpiT<8> CeBwdEpi;
 
 // ---- column sums of a bf16 matrix (for d_b_out), deterministic two pass -----------------------------------------------
 constexpr int CSB_ROWS = 256;
-// block = 32 column groups (8 bf16 = one 16-byte load each -> 256 columns) x 8 row lanes; 4 rows in flight per thread
-__global__ void __launch_bounds__(256)
-colsum_bf16_partial_kernel(const bf* __restrict__ in, int64_t R, int64_t C, int64_t ld, float* __restrict__ partial,
-                           const float* __restrict__ roww) {
-  __shared__ float red[8][256 + 8];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t c = ((int64_t)blockIdx.x * 32 + tx) * 8;
-  const int64_t r0 = (int64_t)blockIdx.y * CSB_ROWS, r1 = min(R, r0 + CSB_ROWS);
-  float s[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) s[k] = 0.f;
-  auto add8 = [&](const uint4& v, float w) {
-    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = __bfloat1622float2(p[k]);
-      s[2 * k] = fmaf(f.x, w, s[2 * k]);
-      s[2 * k + 1] = fmaf(f.y, w, s[2 * k + 1]);
-    }
-  };
-  auto wt = [&](int64_t r) { return roww ? __ldg(roww + r) : 1.f; };  // optional per-row weight
-  if (c + 8 <= C) {  // ld % 8 == 0 and c % 8 == 0: aligned 16-byte loads
-    int64_t r = r0 + ty;
-    for (; r + 24 < r1; r += 32) {
-      const uint4 a = __ldcg(reinterpret_cast<const uint4*>(in + r * ld + c));
-      const uint4 b = __ldcg(reinterpret_cast<const uint4*>(in + (r + 8) * ld + c));
-      const uint4 d = __ldcg(reinterpret_cast<const uint4*>(in + (r + 16) * ld + c));
-      const uint4 e = __ldcg(reinterpret_cast<const uint4*>(in + (r + 24) * ld + c));
-      add8(a, wt(r)); add8(b, wt(r + 8)); add8(d, wt(r + 16)); add8(e, wt(r + 24));
-    }
-    for (; r < r1; r += 8) add8(__ldcg(reinterpret_cast<const uint4*>(in + r * ld + c)), wt(r));
-  } else if (c < C) {
-    for (int64_t r = r0 + ty; r < r1; r += 8)
-      for (int k = 0; k < 8 && c + k < C; ++k) s[k] = fmaf(__bfloat162float(in[r * ld + c + k]), wt(r), s[k]);
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) red[ty][tx * 8 + k] = s[k];
-  __syncthreads();
-  const int64_t cc = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (cc < C) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    partial[(int64_t)blockIdx.y * C + cc] = t;
-  }
-}
 __global__ void colsum_bf16_final_kernel(const float* __restrict__ partial, int64_t chunks, int64_t C, float beta,
                                          float* __restrict__ out) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -362,12 +316,71 @@ __global__ void colsum_bf16_final_kernel(const float* __restrict__ partial, int6
   for (int64_t k = 0; k < chunks; ++k) s += partial[k * C + c];
   out[c] = (beta != 0.f ? beta * out[c] : 0.f) + s;
 }
+// Partial sums per (256-column slab, 256-row chunk) item.  Block = 32 column groups (8 bf16 = one 16-byte load each) x 32
+// row lanes, 8 independent loads in flight per thread (128 KB per block).  The grid walks the items with a stride, so the
+// same kernel (same summation order, bit-identical results) runs either wide - one block per item - or NARROW: a few
+// blocks on the SMs a cooperative persistent kernel leaves free (the BPTT recurrence occupies 128 of 148 SMs and is
+// latency-bound, HBM idle), instead of next to the contractions that read the same matrix.
+__global__ void __launch_bounds__(1024)
+colsum_bf16_partial_kernel(const bf* __restrict__ in, int64_t R, int64_t C, int64_t ld, float* __restrict__ partial,
+                          const float* __restrict__ roww, int slabs, int chunks) {
+  __shared__ float red[32][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int item = blockIdx.x; item < slabs * chunks; item += gridDim.x) {
+    const int slab = item % slabs, chunk = item / slabs;
+    const int64_t c = ((int64_t)slab * 32 + tx) * 8;
+    const int64_t r0 = (int64_t)chunk * CSB_ROWS, r1 = min(R, r0 + CSB_ROWS);
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
+    if (c + 8 <= C) {
+      uint4 v[8];
+      float w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {  // rows r0 + ty + 32 i: all loads issued before the first use
+        const int64_t r = r0 + ty + 32 * i;
+        const bool ok = r < r1;
+        v[i] = ok ? __ldcs(reinterpret_cast<const uint4*>(in + r * ld + c)) : make_uint4(0u, 0u, 0u, 0u);
+        w[i] = ok ? (roww ? __ldg(roww + r) : 1.f) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(p[k]);
+          s[2 * k] = fmaf(f.x, w[i], s[2 * k]);
+          s[2 * k + 1] = fmaf(f.y, w[i], s[2 * k + 1]);
+        }
+      }
+    } else if (c < C) {
+      for (int64_t r = r0 + ty; r < r1; r += 32)
+        for (int k = 0; k < 8 && c + k < C; ++k)
+          s[k] = fmaf(__bfloat162float(in[r * ld + c + k]), roww ? __ldg(roww + r) : 1.f, s[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[ty][tx * 8 + k] = s[k];
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      const int64_t cc = (int64_t)slab * 256 + threadIdx.x;
+      if (cc < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
+        partial[(int64_t)chunk * C + cc] = t;
+      }
+    }
+    __syncthreads();
+  }
+}
 static int64_t colsum_bf16_partials(int64_t R, int64_t C) { return ((R + CSB_ROWS - 1) / CSB_ROWS) * C; }
 int colsum_bf16(const bf* in, int64_t R, int64_t C, int64_t ld, float beta, float* out, float* partial,
-                cudaStream_t st, const float* roww) {
+                cudaStream_t st, const float* roww, int max_blocks) {
   const int64_t chunks = (R + CSB_ROWS - 1) / CSB_ROWS;
   dim3 grid((unsigned)((C + 255) / 256), (unsigned)chunks);
-  colsum_bf16_partial_kernel<<<grid, 256, 0, st>>>(in, R, C, ld, partial, roww);
+  const int64_t items = (int64_t)grid.x * chunks;
+  const int64_t blocks = (max_blocks > 0 && items > max_blocks) ? max_blocks : items;
+  colsum_bf16_partial_kernel<<<(unsigned)blocks, 1024, 0, st>>>(in, R, C, ld, partial, roww, (int)grid.x, (int)chunks);
   SNT_LAUNCH_CHECK("colsum_bf16_partial_kernel");
   colsum_bf16_final_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(partial, chunks, C, beta, out);
   SNT_LAUNCH_CHECK("colsum_bf16_final_kernel");
@@ -874,9 +887,22 @@ int vocab_ce_train_fwd(const void* hs, const float* w_out, const float* b_out, c
   return SNT_OK;
 }
 
+// d_b_out of the stored-numerator path on its own (see vocab_ce_train_bwd(defer_bias)): column sums of U' weighted by the
+// row scales, from a grid of at most `max_blocks` blocks (0: the wide grid).  part: vocab_ce_train_bias_part_elems(N, V)
+// floats, db: V floats - caller-owned, so the call may overlap later stages that reuse the stage workspace.
+int64_t vocab_ce_train_bias_part_elems(int64_t N, int64_t V) { return colsum_bf16_partials(N, V); }
+int vocab_ce_train_bias(const void* u, const float* inv_s, const float* dloss, float grad_scale, int64_t N, int64_t V,
+                        float* d_b_out, float* part, float* db, cudaStream_t st, int max_blocks) {
+  SNT_REQUIRE(u && inv_s && d_b_out && part && db, "vocab_ce_train_bias: NULL argument");
+  SNT_CHECK(colsum_bf16((const bf*)u, N, V, pad8(V), 0.f, db, part, st, inv_s, max_blocks));
+  scale_vec_kernel<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(db, V, grad_scale / (float)N, dloss, d_b_out);
+  SNT_LAUNCH_CHECK("scale_vec_kernel");
+  return SNT_OK;
+}
+
 int vocab_ce_train_bwd(const void* u, const float* inv_s, const void* hs_scaled, const void* w_bf16,
                        const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
-                       float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                       float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st, bool defer_bias) {
   if (H % 8 != 0) { set_error("bf16 mode: H=%lld must be a multiple of 8", (long long)H); return SNT_EUNSUPPORTED; }
   CeTrainWs w = carve_train(ws, ws_bytes, N, H, V);
   if (!w.ok) { set_error("bf16 vocab_ce_train_bwd: workspace too small"); return SNT_EWORKSPACE; }
@@ -884,7 +910,8 @@ int vocab_ce_train_bwd(const void* u, const float* inv_s, const void* hs_scaled,
   const bf* wb = (const bf*)w_bf16;
   const float scale = grad_scale / (float)N;
   // d_b_out = scale * sum_n U'[n,:] / S_n: bandwidth-bound, on the side stream next to the two contractions
-  SideStream* side = side_stream();
+  // (defer_bias: the caller runs vocab_ce_train_bias later, next to a stage that leaves HBM idle)
+  SideStream* side = defer_bias ? nullptr : side_stream();
   if (side) {
     SNT_CUDA(cudaEventRecord(side->fork, st));
     SNT_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
@@ -904,7 +931,7 @@ int vocab_ce_train_bwd(const void* u, const float* inv_s, const void* hs_scaled,
                                  sws_elems, st, dloss, bn));
   if (side) {
     SNT_CUDA(cudaStreamWaitEvent(st, side->join, 0));
-  } else {
+  } else if (!defer_bias) {
     SNT_CHECK(colsum_bf16(ub, N, V, w.Vp, 0.f, w.db, w.cpart, st, inv_s));
     scale_vec_kernel<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(w.db, V, scale, dloss, d_b_out);
     SNT_LAUNCH_CHECK("scale_vec_kernel");

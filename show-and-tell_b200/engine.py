@@ -68,13 +68,14 @@ def batch_sizes(lengths, max_steps=None):
 class FlatParams:
     """Flat fp32 storage for the trainable parameters of (encoder head, decoder), in gradient-readiness order."""
 
-    BUCKETS = ("early", "mid", "late")   # linear.* | lstm.* | embed.weight + head
+    BUCKETS = ("early", "mid", "late")   # linear.weight | linear.bias, lstm.* | embed.weight + head
 
     def __init__(self, encoder, decoder):
         self.encoder, self.decoder = encoder, decoder
         L = decoder.num_layers
         named = []                                           # (bucket, name, parameter)
-        named += [("early", "linear.weight", decoder.linear.weight), ("early", "linear.bias", decoder.linear.bias)]
+        # linear.bias is final one phase after linear.weight: its column sums run beside the BPTT (csrc/step.cu)
+        named += [("early", "linear.weight", decoder.linear.weight), ("mid", "linear.bias", decoder.linear.bias)]
         for k in reversed(range(L)):
             for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
                 named.append(("mid", f"lstm.{n}_l{k}", getattr(decoder.lstm, f"{n}_l{k}")))

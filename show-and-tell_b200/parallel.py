@@ -103,6 +103,13 @@ class DataParallelStep:
         self.sm_reserve = int(os.environ.get("SNT_SM_RESERVE", "16")) if sm_reserve is None else int(sm_reserve)
         self._inflight = []   # events of the last steps (world > 1): bounds how far the host runs ahead
         self.max_run_ahead = 16
+        # The step runs on its own HIGH-priority stream (ordered after the caller's current stream at entry, and the
+        # caller's stream after it at exit).  The executor's side streams have default (= lowest) priority, so whatever
+        # they carry - the output-bias column sums, the head backward - is background work for the block scheduler: it
+        # fills the SMs the cooperative recurrence kernels leave free and never delays them (csrc/step.cu).
+        self._stream = None
+        if self.flat.p.is_cuda and os.environ.get("SNT_STEP_PRIORITY", "1") != "0":
+            self._stream = torch.cuda.Stream(device=self.flat.p.device, priority=-1)
         if self.world > 1:
             self.sync_from_rank0()
 
@@ -145,6 +152,16 @@ class DataParallelStep:
         """inputs: pooled[B,2048] (or images[B,3,H,W] for an encoder with its backbone) when an encoder head is
         attached, else features[B,E].  targets=None: pack(captions, lengths) (eval.py:91), gathered on the device.
         Returns this rank's share of the global mean loss (sum over ranks = global-batch loss)."""
+        if self._stream is None:
+            return self._step(inputs, captions, lengths, targets, n_tokens_global)
+        cur = torch.cuda.current_stream(self.flat.p.device)
+        self._stream.wait_stream(cur)
+        with torch.cuda.stream(self._stream):
+            loss = self._step(inputs, captions, lengths, targets, n_tokens_global)
+        cur.wait_stream(self._stream)
+        return loss
+
+    def _step(self, inputs, captions, lengths, targets=None, n_tokens_global=None):
         eng, flat = self.engine, self.flat
         cuda = flat.p.is_cuda
         if not flat.intact():
