@@ -727,6 +727,9 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # all-reduce CTAs are placed first when SMs free up
+        # The cooperative recurrence kernels need 128 of the 148 SMs at once: an all-reduce in flight with more than 20
+        # CTAs makes the BPTT launch wait for the whole collective (measured: BPTT stage 294 -> 406 us at 8 GPUs).
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
         dist.init_process_group("nccl", device_id=dev)
     c = CONFIGS[args.config]
     peaks = load_peaks()
@@ -903,6 +906,21 @@ def main():
                     torch.cuda.empty_cache()
                 except Exception as e:   # noqa: BLE001
                     extra["configs3"] = {"error": repr(e)[:300]}
+            try:          # the fp32-faithful mode (fp32 operands, FFMA accumulation) on the same step
+                wf = Workload(snt, c, c["B"], 1, 0, dev, "fp32", nb=2)
+                for _ in range(2):
+                    wf.step_resident()
+                kf = 5
+                tf_ = timed(wf.step_resident, kf)
+                extra["fp32_faithful_train"] = {"value": c["B"] * kf / tf_, "unit": "captions/s",
+                                                "ms_per_step": tf_ / kf * 1e3, "steps": kf,
+                                                "what": "the same train step in the fp32-faithful mode (no operand "
+                                                        "rounding: loss <= 1e-5, gradients <= 1e-4 of the fp64 reference)"}
+                wf.stepper.close()
+                del wf
+                torch.cuda.empty_cache()
+            except Exception as e:   # noqa: BLE001
+                extra["fp32_faithful_train"] = {"error": repr(e)[:300]}
             extra["f_rows"] = measure_f_rows(snt, dev, c, peaks)
         line = {
             "metric": "train_captions_per_s", "value": value, "unit": "captions/s", "n_gpus": world,

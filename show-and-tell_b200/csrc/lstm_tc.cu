@@ -1143,7 +1143,10 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
       persistent = true;
     }
   }
-  // split-K keeps all SMs busy on the small per-step contraction; its partials never leave L2
+  // Per-step path: split-K keeps all SMs busy on the small per-step contraction; its partials never leave L2.  (Tried in
+  // round 2: the cell backward as the EPILOGUE of an unsplit contraction - one launch per step instead of two.  At
+  // configs[3] it was 235 us per training step SLOWER: with one tile per CTA nothing overlaps the epilogue, and its
+  // 36 bytes per hidden unit of row-per-lane traffic run at a single SM's bandwidth instead of the whole GPU's.)
   const int want_splits = 4;
   for (int t = T - 1; t >= 0 && !persistent; --t) {
     const int bs = pk.off[t + 1] - pk.off[t];
@@ -1285,34 +1288,59 @@ struct ArgmaxEpi {
   }
 };
 
-// one warp per row: first global maximum over the slab partials, id out, next input = bf16(W_emb[id])
+// First global maximum over the slab partials, id out, next input = bf16(W_emb[id]).  Block = 32 rows x 8 warps: while
+// scanning, lane = row and warp w takes slabs w, w + 8, ... (consecutive rows of a slab are contiguous: coalesced 256-byte
+// reads, ~10 independent loads per thread, all in flight); the 8 candidates of a row are combined through shared memory
+// (greater value, lower index on ties = the first maximum), then every warp copies 4 of the 32 embedding rows.  Launched
+// with programmatic stream serialization: the prologue of the next step's contraction overlaps this kernel.
 __global__ void __launch_bounds__(256)
 argmax_finish_kernel(const float2* __restrict__ part, int slabs, int64_t B, const float* __restrict__ w_emb, int E,
                      int64_t* __restrict__ ids, int64_t ids_stride, bf* __restrict__ x_next, int64_t ldx) {
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= B) return;
+  __shared__ float sval[8][32];
+  __shared__ int sidx[8][32];
+  __shared__ int sbest[32];
+  tc::pdl_launch_dependents();
+  tc::pdl_wait();  // the slab partials come from the preceding contraction
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * 32;
+  const int64_t row = row0 + lane;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int k = lane; k < slabs; k += 32) {
-    const float2 p = part[(int64_t)k * B + row];
-    const int idx = __float_as_int(p.y);
-    if (idx != 0x7fffffff && (p.x > best || (p.x == best && idx < bi) || bi == 0x7fffffff)) { best = p.x; bi = idx; }
+  if (row < B) {
+#pragma unroll 4
+    for (int k = warp; k < slabs; k += 8) {  // ascending column ranges: strict '>' keeps the first maximum
+      const float2 p = __ldcg(part + (int64_t)k * B + row);
+      const int idx = __float_as_int(p.y);
+      if (idx != 0x7fffffff && (p.x > best || bi == 0x7fffffff)) { best = p.x; bi = idx; }
+    }
   }
+  sval[warp][lane] = best;
+  sidx[warp][lane] = bi;
+  __syncthreads();
+  if (warp == 0) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (oi != 0x7fffffff && (ob > best || (ob == best && oi < bi) || bi == 0x7fffffff)) { best = ob; bi = oi; }
+    for (int w = 1; w < 8; ++w) {
+      const float ob = sval[w][lane];
+      const int oi = sidx[w][lane];
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+    }
+    sbest[lane] = bi;
+    if (row < B) ids[row * ids_stride] = bi;
   }
-  if (lane == 0) ids[row * ids_stride] = bi;
-  const float* src = w_emb + (int64_t)bi * E;
-  for (int e = lane * 4; e < E; e += 128) {  // E % 8 == 0
-    const float4 v = *reinterpret_cast<const float4*>(src + e);
-    uint2 o;
-    o.x = pack_bf2(v.x, v.y);
-    o.y = pack_bf2(v.z, v.w);
-    *reinterpret_cast<uint2*>(x_next + row * ldx + e) = o;
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int r = warp * 4 + q;
+    if (row0 + r >= B) break;
+    const float* src = w_emb + (int64_t)sbest[r] * E;
+    bf* dst = x_next + (row0 + r) * ldx;
+    for (int e = lane * 4; e < E; e += 128) {  // E % 8 == 0
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + e));
+      uint2 o;
+      o.x = pack_bf2(v.x, v.y);
+      o.y = pack_bf2(v.z, v.w);
+      *reinterpret_cast<uint2*>(dst + e) = o;
+    }
   }
 }
 
@@ -1422,9 +1450,20 @@ int greedy_decode(const float* features, const float* w_emb, int L, const float*
     ArgmaxEpi e;
     e.M = (int)B; e.V = (int)V; e.bias = b_out; e.part = part;
     SNT_CHECK((tc::launch_gemm_tc<256, false, false, ArgmaxEpi>(tout_a[nxt], tout_b, ts, e, st, true)));
-    argmax_finish_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(part, slabs, B, w_emb, (int)E, ids + s, steps,
-                                                                   cat[0][nxt], E + H);
-    SNT_LAUNCH_CHECK("argmax_finish_kernel");
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)((B + 31) / 32));
+      cfg.blockDim = dim3(256);
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      SNT_CUDA(cudaLaunchKernelEx(&cfg, argmax_finish_kernel, (const float2*)part, slabs, B, w_emb, (int)E, ids + s,
+                                  (int64_t)steps, cat[0][nxt], E + H));
+      count_launch();
+    }
   }
   return SNT_OK;
 }

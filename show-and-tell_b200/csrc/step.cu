@@ -201,6 +201,11 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
   const bool bf = prec == SNT_PREC_BF16;
   // d_b_out beside the BPTT instead of beside the vocabulary contractions: only where the recurrence runs as the
   // persistent cooperative kernel (latency-bound, HBM idle, 20 SMs free); elsewhere the per-step contractions fill the GPU
+  // (measured at configs[3], H = 1024, per-step launches: moving the pass there - narrow or as background work - cost the
+  // BPTT stage as much as it saved the vocabulary stage)
+  int st_prio = 0;
+  const bool background = side != nullptr && cudaStreamGetPriority((cudaStream_t)stream, &st_prio) == cudaSuccess &&
+                          st_prio < 0 && !getenv("SNT_NO_BACKGROUND");
   const bool defer_bias = bf && side != nullptr && bf16::lstm_bwd_is_persistent(H) && !getenv("SNT_NO_BIAS_DEFER");
 
   if (phases & SNT_STEP_FWD) {
@@ -276,8 +281,6 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
       // grid of short blocks, released at the moment the cooperative kernel becomes eligible (gate event), so the block
       // scheduler places the recurrence first and the column sums soak up whatever is left - two or more blocks per
       // free SM.  On a default-priority stream: a grid narrow enough never to take an SM the recurrence needs.
-      int prio = 0;
-      const bool background = cudaStreamGetPriority(st, &prio) == cudaSuccess && prio < 0 && !getenv("SNT_NO_BACKGROUND");
       if (background) {
         bf16::lstm_bwd_gate_event(side->fork);   // recorded by snt_lstm_bwd of the top layer, after its weight preparation
       } else {

@@ -15,8 +15,9 @@ trip.  The host needs ~0.1 ms to enqueue a step, so ragged batches (new lengths 
 and no CUDA-graph capture is involved.  Parameters, gradients and Adam moments live in flat buffers laid out in
 readiness order (engine.FlatParams): each of the three gradient buckets is one contiguous all-reduce.
 
-Launch the ranks with TORCH_NCCL_HIGH_PRIORITY=1, as bench.py does (the all-reduce CTAs are then placed first when SMs
-free up).
+Launch the ranks with TORCH_NCCL_HIGH_PRIORITY=1 and NCCL_MAX_CTAS=16, as bench.py does: the all-reduce CTAs are then
+placed first when SMs free up, and an all-reduce in flight never holds more than the 20 SMs the cooperative recurrence
+kernels (128 CTAs that must all be resident) leave free - otherwise the BPTT launch waits for the whole collective.
 """
 from __future__ import annotations
 

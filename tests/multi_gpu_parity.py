@@ -44,6 +44,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
+    os.environ.setdefault("NCCL_MAX_CTAS", "16")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     report, ok = {}, True
     for prec, tol in (("fp32", 2e-5), ("bf16", 2e-3)):
