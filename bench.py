@@ -541,7 +541,7 @@ def measure_greedy(snt, dec, c, dev, world, timed, peaks, rank, with_cpu):
                                "timing": f"CUDA events around {reps} whole sample() calls (20 steps each)"}
         else:
             out["fp32_faithful"] = {"value": tps, "ms_per_decode": t / reps * 1e3,
-                                    "note": "token-exact mode (fp32 operands, FFMA accumulation)"}
+                                    "note": "token-exact mode: fp32 operands, each product as six exact bf16 partial products on the tensor cores, fp32 accumulation (csrc/gemm_x3.cu)"}
     # e2e: features from pinned host memory, ids back to the host, inside the timed region
     ids_h = torch.empty(GREEDY_B, 20, dtype=torch.int64).pin_memory()
 
@@ -906,7 +906,7 @@ def main():
                     torch.cuda.empty_cache()
                 except Exception as e:   # noqa: BLE001
                     extra["configs3"] = {"error": repr(e)[:300]}
-            try:          # the fp32-faithful mode (fp32 operands, FFMA accumulation) on the same step
+            try:          # the fp32-faithful mode (fp32 operands split into bf16 triples, fp32 accumulation) on the same step
                 wf = Workload(snt, c, c["B"], 1, 0, dev, "fp32", nb=2)
                 for _ in range(2):
                     wf.step_resident()

@@ -14,8 +14,13 @@
  *  - Packed (time-major) layout, as torch.nn.utils.rnn.pack_padded_sequence produces it
  *    (models.py:51): `batch_sizes[t]` = #sequences longer than t (non-increasing, host int32[T]),
  *    off[t] = sum_{t'<t} batch_sizes[t'], packed row of (t, b) = off[t] + b, N = off[T].
- *  - `prec`: SNT_PREC_FP32 = fp32 operands and fp32 FFMA accumulation (the "fp32-accumulate" faithful
- *    mode); SNT_PREC_BF16 = bf16 operands on tcgen05 tensor cores with fp32 accumulation in TMEM.
+ *  - `prec`: SNT_PREC_FP32 = the "fp32-accumulate" faithful mode: fp32 operands without rounding, fp32
+ *    accumulation.  Large contractions run on the tcgen05 tensor cores with every fp32 value split exactly
+ *    into three bf16 pieces and each product evaluated as its six significant partial products
+ *    (csrc/gemm_x3.cu; contractions longer than 2048 are summed in slices so the accumulator's truncation
+ *    stays below 6e-6); small ones on an FFMA kernel.  The large ones borrow stream-ordered scratch
+ *    (cudaMallocAsync / cudaFreeAsync on the caller's stream) for the expanded operands.
+ *    SNT_PREC_BF16 = bf16 operands on tcgen05 tensor cores with fp32 accumulation in TMEM.
  *    Tensors marked (act) are fp32 in FP32 mode and bf16 in BF16 mode.
  *  - There is no CPU fallback anywhere: without a CUDA device every compute entry point fails.
  */

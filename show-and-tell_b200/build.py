@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libsnt_b200.so")
-SOURCES = ["core.cu", "kernels.cu", "gemm_f32.cu", "gemm_tc.cu", "bf16_path.cu", "vocab_ce_tc.cu", "lstm_tc.cu", "api.cu", "step.cu"]
+SOURCES = ["core.cu", "kernels.cu", "gemm_f32.cu", "gemm_x3.cu", "gemm_tc.cu", "bf16_path.cu", "vocab_ce_tc.cu", "lstm_tc.cu", "api.cu", "step.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("SNT_NVCC_EXTRA", "").split()

@@ -2,6 +2,7 @@
 // SNT_PREC_FP32 ("fp32-faithful") pipelines built from the SIMT fp32 contraction (gemm_f32.cu) and the
 // pointwise / HBM-bound kernels (kernels.cu).  SNT_PREC_BF16 dispatches to the tcgen05 pipelines (bf16.cuh).
 #include "kernels.cuh"
+#include "x3.cuh"
 #include "bf16.cuh"
 
 using namespace snt;
@@ -137,6 +138,34 @@ extern "C" int snt_embed_pack_bwd(const float* dx, const int64_t* captions, int6
 // ------------------------------------------------------------------------------------------------------------
 // a7: one LSTM layer over the packed sequence
 // ------------------------------------------------------------------------------------------------------------
+// Stream-ordered scratch for loops that contract many activation blocks against the SAME fp32 weight on the tensor cores
+// (gemm_x3.cu): the weight is expanded into its bf16 slots once, each step expands only its activations.  Freed (on the
+// stream) when the object goes out of scope.
+namespace {
+struct X3Loop {
+  cudaStream_t st;
+  void* base = nullptr;
+  char* cur = nullptr;
+  char* end = nullptr;
+  explicit X3Loop(cudaStream_t s) : st(s) {}
+  ~X3Loop() { x3::scratch_free(base, st); }
+  int open(int64_t bytes) {
+    SNT_CHECK(x3::scratch_alloc(&base, bytes, st));
+    cur = (char*)base;
+    end = cur + bytes;
+    return SNT_OK;
+  }
+  void* take(int64_t bytes) {
+    bytes = align_up(bytes, 256);
+    if (!cur || cur + bytes > end) return nullptr;
+    void* r = cur;
+    cur += bytes;
+    return r;
+  }
+  static int64_t need(int64_t elems) { return align_up(elems * 2, 256); }
+};
+}  // namespace
+
 extern "C" int64_t snt_lstm_workspace_bytes(int prec, int64_t N, int64_t B, int64_t In, int64_t H) {
   if (!valid_prec(prec) || N < 1 || B < 1 || In < 1 || H < 1) return -1;
   if (prec == SNT_PREC_BF16) return bf16::lstm_ws_bytes(N, B, In, H);
@@ -167,13 +196,31 @@ extern "C" int snt_lstm_fwd(int prec, const void* x, int64_t In, int64_t H, cons
   // input projection for every timestep at once: gates = x . W_ih^T + (b_ih + b_hh)
   SNT_CHECK(gemm_f32(0, 1, N, 4 * H, In, 1.f, (const float*)x, In, w_ih, In, 0.f, gates, 4 * H, bsum, st));
   SNT_CUDA(cudaMemsetAsync(hp_f, 0, sizeof(float) * (size_t)pk.off[1] * H, st));  // h_{-1} = 0
+  // tensor-core path of the recurrence: W_hh expanded once, h_{t-1} per step
+  const int64_t B0 = pk.off[1];
+  X3Loop xl(st);
+  x3::Operand whh, hop;
+  void* hbuf = nullptr;
+  const bool tc_rec = T > 1 && x3::worth_it(B0, 4 * H, H);
+  if (tc_rec) {
+    SNT_CHECK(xl.open(X3Loop::need(x3::operand_elems(4 * H, H, true)) + X3Loop::need(x3::operand_elems(B0, H, true))));
+    void* wbuf = xl.take(x3::operand_elems(4 * H, H, true) * 2);
+    hbuf = xl.take(x3::operand_elems(B0, H, true) * 2);
+    SNT_CHECK(x3::expand(w_hh, 4 * H, H, H, true, true, wbuf, &whh, st));
+  }
   for (int t = 0; t < T; ++t) {
     const int bs = pk.off[t + 1] - pk.off[t];
     const int bs_next = t + 1 < T ? pk.off[t + 2] - pk.off[t + 1] : 0;
     float* g_t = gates + (int64_t)pk.off[t] * 4 * H;
-    if (t > 0)  // gates_t += h_{t-1} . W_hh^T
-      SNT_CHECK(gemm_f32(0, 1, bs, 4 * H, H, 1.f, hp_f + (int64_t)pk.off[t] * H, H, w_hh, H, 1.f, g_t, 4 * H,
-                         nullptr, st));
+    if (t > 0) {  // gates_t += h_{t-1} . W_hh^T
+      if (tc_rec && bs >= 32) {
+        SNT_CHECK(x3::expand(hp_f + (int64_t)pk.off[t] * H, bs, H, H, true, false, hbuf, &hop, st));
+        SNT_CHECK(x3::gemm(hop, whh, bs, 4 * H, 1.f, 1.f, g_t, 4 * H, nullptr, nullptr, 0, st));
+      } else {
+        SNT_CHECK(gemm_f32(0, 1, bs, 4 * H, H, 1.f, hp_f + (int64_t)pk.off[t] * H, H, w_hh, H, 1.f, g_t, 4 * H,
+                           nullptr, st));
+      }
+    }
     const float* c_prev = t > 0 ? cs + (int64_t)pk.off[t - 1] * H : nullptr;
     SNT_CHECK(lstm_point_fwd<float>(g_t, c_prev, cs + (int64_t)pk.off[t] * H, hs_f + (int64_t)pk.off[t] * H,
                                     bs_next > 0 ? hp_f + (int64_t)pk.off[t + 1] * H : nullptr, bs, bs_next, H, st));
@@ -204,6 +251,21 @@ extern "C" int snt_lstm_bwd(int prec, const float* d_hs, float* gates, const flo
   float* dc_state = w.take<float>(B * H);
   float* part = w.take<float>(colsum_partial_count(N, 4 * H));
   if (!w.ok()) { set_error("snt_lstm_bwd: workspace too small"); return SNT_EWORKSPACE; }
+  // tensor-core path of the reverse recurrence: W_hh (as the [4H, H] MN-major operand) expanded once, dG_t per step
+  X3Loop xl(st);
+  x3::Operand whh, gop;
+  void* gbuf = nullptr;
+  float* sws = nullptr;                      // K-split slices: [bs, H] has few output tiles
+  const int64_t sws_elems = 8 * B * H;
+  const bool tc_rec = T > 1 && x3::worth_it(B, H, 4 * H);
+  if (tc_rec) {
+    SNT_CHECK(xl.open(X3Loop::need(x3::operand_elems(4 * H, H, false)) + X3Loop::need(x3::operand_elems(B, 4 * H, true)) +
+                      align_up(sws_elems * 4, 256)));
+    sws = (float*)xl.take(sws_elems * 4);
+    void* wbuf = xl.take(x3::operand_elems(4 * H, H, false) * 2);
+    gbuf = xl.take(x3::operand_elems(B, 4 * H, true) * 2);
+    SNT_CHECK(x3::expand(w_hh, 4 * H, H, H, false, true, wbuf, &whh, st));
+  }
   for (int t = T - 1; t >= 0; --t) {
     const int bs = pk.off[t + 1] - pk.off[t];
     const int bs_next = t + 1 < T ? pk.off[t + 2] - pk.off[t + 1] : 0;
@@ -211,8 +273,14 @@ extern "C" int snt_lstm_bwd(int prec, const float* d_hs, float* gates, const flo
     const float* c_prev = t > 0 ? cs + (int64_t)pk.off[t - 1] * H : nullptr;
     SNT_CHECK(lstm_point_bwd(g_t, cs + (int64_t)pk.off[t] * H, c_prev, d_hs + (int64_t)pk.off[t] * H, dh_rec,
                              dc_state, bs, bs_next, H, st));
-    if (t > 0)  // dh_{t-1} (recurrent part) = dG_t . W_hh
-      SNT_CHECK(gemm_f32(0, 0, bs, H, 4 * H, 1.f, g_t, 4 * H, w_hh, H, 0.f, dh_rec, H, nullptr, st));
+    if (t > 0) {  // dh_{t-1} (recurrent part) = dG_t . W_hh
+      if (tc_rec && bs >= 32) {
+        SNT_CHECK(x3::expand(g_t, bs, 4 * H, 4 * H, true, false, gbuf, &gop, st));
+        SNT_CHECK(x3::gemm(gop, whh, bs, H, 1.f, 0.f, dh_rec, H, nullptr, sws, sws_elems, st));
+      } else {
+        SNT_CHECK(gemm_f32(0, 0, bs, H, 4 * H, 1.f, g_t, 4 * H, w_hh, H, 0.f, dh_rec, H, nullptr, st));
+      }
+    }
   }
   // weight gradients over the whole packed sequence
   SNT_CHECK(gemm_f32(1, 0, 4 * H, In, N, 1.f, gates, 4 * H, (const float*)x, In, 0.f, d_w_ih, In, nullptr, st));
@@ -283,9 +351,25 @@ extern "C" int snt_vocab_ce_fwd(int prec, const void* hs, const float* w_out, co
   float* nll = w.take<float>(N);
   if (!w.ok()) { set_error("snt_vocab_ce_fwd: workspace too small"); return SNT_EWORKSPACE; }
   const float* hs_f = (const float*)hs;
+  // tensor-core path: W_out expanded into its bf16 slots once, the rows of Hs chunk by chunk (gemm_x3.cu)
+  X3Loop xl(st);
+  x3::Operand wx, ax;
+  void* abuf = nullptr;
+  const bool tc = x3::worth_it(R, V, H);
+  if (tc) {
+    SNT_CHECK(xl.open(X3Loop::need(x3::operand_elems(V, H, true)) + X3Loop::need(x3::operand_elems(R, H, true))));
+    void* wbuf = xl.take(x3::operand_elems(V, H, true) * 2);
+    abuf = xl.take(x3::operand_elems(R, H, true) * 2);
+    SNT_CHECK(x3::expand(w_out, V, H, H, true, true, wbuf, &wx, st));
+  }
   for (int64_t r0 = 0; r0 < N; r0 += R) {
     const int64_t r = N - r0 < R ? N - r0 : R;
-    SNT_CHECK(gemm_f32(0, 1, r, V, H, 1.f, hs_f + r0 * H, H, w_out, H, 0.f, chunk, V, b_out, st));
+    if (tc && r >= 32) {
+      SNT_CHECK(x3::expand(hs_f + r0 * H, r, H, H, true, false, abuf, &ax, st));
+      SNT_CHECK(x3::gemm(ax, wx, r, V, 1.f, 0.f, chunk, V, b_out, nullptr, 0, st));
+    } else {
+      SNT_CHECK(gemm_f32(0, 1, r, V, H, 1.f, hs_f + r0 * H, H, w_out, H, 0.f, chunk, V, b_out, st));
+    }
     SNT_CHECK(ce_rows_fwd(chunk, r, V, V, targets + r0, lse + r0, nll + r0, st));
   }
   return reduce_sum(nll, N, 1.0f / (float)N, loss, st);
@@ -310,12 +394,42 @@ extern "C" int snt_vocab_ce_bwd(int prec, const void* hs, const float* w_out, co
   if (!w.ok()) { set_error("snt_vocab_ce_bwd: workspace too small"); return SNT_EWORKSPACE; }
   const float* hs_f = (const float*)hs;
   const float scale = grad_scale / (float)N;
+  // tensor-core path: W_out expanded once per call in both roles (the [V,H] K-major operand of the logits recompute and
+  // the [V,H] MN-major operand of dHs = dlogits . W_out); the chunk-dependent operands are expanded per chunk
+  X3Loop xl(st);
+  x3::Operand wx, wxt, ax, cx;
+  void *abuf = nullptr, *cbuf = nullptr;
+  float* sws = nullptr;                      // K-split slices of dHs (a chunk has few output tiles)
+  const int64_t sws_elems = 8 * R * H;
+  const bool tc = x3::worth_it(R, V, H);
+  if (tc) {
+    SNT_CHECK(xl.open(X3Loop::need(x3::operand_elems(V, H, true)) + X3Loop::need(x3::operand_elems(V, H, false)) +
+                      X3Loop::need(x3::operand_elems(R, H, true)) + X3Loop::need(x3::operand_elems(R, V, true)) +
+                      align_up(sws_elems * 4, 256)));
+    sws = (float*)xl.take(sws_elems * 4);
+    void* w1 = xl.take(x3::operand_elems(V, H, true) * 2);
+    void* w2 = xl.take(x3::operand_elems(V, H, false) * 2);
+    abuf = xl.take(x3::operand_elems(R, H, true) * 2);
+    cbuf = xl.take(x3::operand_elems(R, V, true) * 2);
+    SNT_CHECK(x3::expand(w_out, V, H, H, true, true, w1, &wx, st));
+    SNT_CHECK(x3::expand(w_out, V, H, H, false, true, w2, &wxt, st));
+  }
   for (int64_t r0 = 0; r0 < N; r0 += R) {
     const int64_t r = N - r0 < R ? N - r0 : R;
     const float acc = r0 > 0 ? 1.f : 0.f;
-    SNT_CHECK(gemm_f32(0, 1, r, V, H, 1.f, hs_f + r0 * H, H, w_out, H, 0.f, chunk, V, b_out, st));
+    if (tc && r >= 32) {
+      SNT_CHECK(x3::expand(hs_f + r0 * H, r, H, H, true, false, abuf, &ax, st));
+      SNT_CHECK(x3::gemm(ax, wx, r, V, 1.f, 0.f, chunk, V, b_out, nullptr, 0, st));
+    } else {
+      SNT_CHECK(gemm_f32(0, 1, r, V, H, 1.f, hs_f + r0 * H, H, w_out, H, 0.f, chunk, V, b_out, st));
+    }
     SNT_CHECK(ce_rows_bwd(chunk, r, V, V, targets + r0, lse + r0, dloss, scale, st));
-    SNT_CHECK(gemm_f32(0, 0, r, H, V, 1.f, chunk, V, w_out, H, 0.f, d_hs + r0 * H, H, nullptr, st));
+    if (tc && r >= 32) {
+      SNT_CHECK(x3::expand(chunk, r, V, V, true, false, cbuf, &cx, st));
+      SNT_CHECK(x3::gemm(cx, wxt, r, H, 1.f, 0.f, d_hs + r0 * H, H, nullptr, sws, sws_elems, st));
+    } else {
+      SNT_CHECK(gemm_f32(0, 0, r, H, V, 1.f, chunk, V, w_out, H, 0.f, d_hs + r0 * H, H, nullptr, st));
+    }
     SNT_CHECK(gemm_f32(1, 0, V, H, r, 1.f, chunk, V, hs_f + r0 * H, H, acc, d_w_out, H, nullptr, st));
     SNT_CHECK(colsum(chunk, r, V, V, acc, d_b_out, part, st));
   }
@@ -406,17 +520,53 @@ extern "C" int snt_greedy_decode(int prec, const float* features, const float* w
       SNT_CUDA(cudaMemsetAsync(c[k], 0, sizeof(float) * B * H, st));
     }
   }
+  // Tensor-core path (gemm_x3.cu): every weight is expanded into its bf16 slots ONCE per decode; a step expands only its
+  // activations (x_s and h_{s-1} per layer, h_s for the vocabulary projection).
+  X3Loop xl(st);
+  x3::Operand wih_x[SNT_MAX_LAYERS], whh_x[SNT_MAX_LAYERS], wout_x, a_in, a_h;
+  void *abuf_in = nullptr, *abuf_h = nullptr;
+  const bool tc = x3::worth_it(B, 4 * H, E < H ? E : H) && x3::worth_it(B, V, H);
+  if (tc) {
+    int64_t bytes = X3Loop::need(x3::operand_elems(V, H, true)) + X3Loop::need(x3::operand_elems(B, E > H ? E : H, true)) +
+                    X3Loop::need(x3::operand_elems(B, H, true));
+    for (int k = 0; k < L; ++k)
+      bytes += X3Loop::need(x3::operand_elems(4 * H, k == 0 ? E : H, true)) + X3Loop::need(x3::operand_elems(4 * H, H, true));
+    SNT_CHECK(xl.open(bytes));
+    for (int k = 0; k < L; ++k) {
+      const int64_t in_dim = k == 0 ? E : H;
+      void* b1 = xl.take(x3::operand_elems(4 * H, in_dim, true) * 2);
+      void* b2 = xl.take(x3::operand_elems(4 * H, H, true) * 2);
+      SNT_CHECK(x3::expand(w_ih[k], 4 * H, in_dim, in_dim, true, true, b1, &wih_x[k], st));
+      SNT_CHECK(x3::expand(w_hh[k], 4 * H, H, H, true, true, b2, &whh_x[k], st));
+    }
+    void* b3 = xl.take(x3::operand_elems(V, H, true) * 2);
+    SNT_CHECK(x3::expand(w_out, V, H, H, true, true, b3, &wout_x, st));
+    abuf_in = xl.take(x3::operand_elems(B, E > H ? E : H, true) * 2);
+    abuf_h = xl.take(x3::operand_elems(B, H, true) * 2);
+  }
   for (int s = 0; s < steps; ++s) {
     const float* inp = s == 0 ? features : x;
     int64_t in_dim = E;
     for (int k = 0; k < L; ++k) {
-      SNT_CHECK(gemm_f32(0, 1, B, 4 * H, in_dim, 1.f, inp, in_dim, w_ih[k], in_dim, 0.f, gates, 4 * H, bsum[k], st));
-      SNT_CHECK(gemm_f32(0, 1, B, 4 * H, H, 1.f, h[k], H, w_hh[k], H, 1.f, gates, 4 * H, nullptr, st));
+      if (tc) {
+        SNT_CHECK(x3::expand(inp, B, in_dim, in_dim, true, false, abuf_in, &a_in, st));
+        SNT_CHECK(x3::gemm(a_in, wih_x[k], B, 4 * H, 1.f, 0.f, gates, 4 * H, bsum[k], nullptr, 0, st));
+        SNT_CHECK(x3::expand(h[k], B, H, H, true, false, abuf_h, &a_h, st));
+        SNT_CHECK(x3::gemm(a_h, whh_x[k], B, 4 * H, 1.f, 1.f, gates, 4 * H, nullptr, nullptr, 0, st));
+      } else {
+        SNT_CHECK(gemm_f32(0, 1, B, 4 * H, in_dim, 1.f, inp, in_dim, w_ih[k], in_dim, 0.f, gates, 4 * H, bsum[k], st));
+        SNT_CHECK(gemm_f32(0, 1, B, 4 * H, H, 1.f, h[k], H, w_hh[k], H, 1.f, gates, 4 * H, nullptr, st));
+      }
       SNT_CHECK(lstm_point_fwd<float>(gates, c[k], c[k], h[k], nullptr, (int)B, 0, H, st));
       inp = h[k];
       in_dim = H;
     }
-    SNT_CHECK(gemm_f32(0, 1, B, V, H, 1.f, inp, H, w_out, H, 0.f, logits, V, b_out, st));
+    if (tc) {
+      SNT_CHECK(x3::expand(inp, B, H, H, true, false, abuf_h, &a_h, st));
+      SNT_CHECK(x3::gemm(a_h, wout_x, B, V, 1.f, 0.f, logits, V, b_out, nullptr, 0, st));
+    } else {
+      SNT_CHECK(gemm_f32(0, 1, B, V, H, 1.f, inp, H, w_out, H, 0.f, logits, V, b_out, st));
+    }
     SNT_CHECK(argmax_gather(logits, B, V, V, w_emb, E, ids + s, steps, x, st));
   }
   return SNT_OK;

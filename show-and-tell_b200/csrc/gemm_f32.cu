@@ -3,6 +3,7 @@
 // nn.Linear / nn.LSTM (models.py:16,52,53); only the summation order differs.
 // Tile 128x128x16, 256 threads, 8x8 outputs per thread, register-prefetch double buffering.
 #include "common.cuh"
+#include "x3.cuh"
 
 namespace snt {
 
@@ -115,6 +116,9 @@ int gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, float alph
              const float* bias, cudaStream_t st) {
   if (M <= 0 || N <= 0) return SNT_OK;
   SNT_REQUIRE(K >= 0 && A && B && C, "gemm_f32: bad arguments");
+  // large contractions run on the tensor cores as six bf16 partial products per fp32 product (gemm_x3.cu); small ones,
+  // and everything under SNT_FP32_FFMA=1, on the FFMA kernel below
+  if (x3::worth_it(M, N, K)) return x3::gemm_f32_tc(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, st);
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
   SNT_REQUIRE(grid.y <= 65535, "gemm_f32: M too large");
   const bool a_k = (transA == 0), b_k = (transB != 0);
