@@ -503,9 +503,7 @@ def profile_stages(wl, nsteps=10):
         wl.stepper.optimizer = opt
         prof = eng.profile_read()
         e0.record()
-        lo, hi = 0, wl.stepper.flat.numel
-        wl.stepper.t += 1
-        eng.adam(lo, hi, wl.stepper.t, wl.stepper.lr, wl.stepper.betas, wl.stepper.eps, wl.stepper.grad_clip)
+        wl.stepper.update()      # clip + Adam; several ranks: including the gradient exchange
         e1.record()
         torch.cuda.synchronize()
         prof["clamp_adam"] = e0.elapsed_time(e1)
@@ -814,9 +812,7 @@ def main():
             wl.stepper.optimizer = False
             wl.step_resident()
             wl.stepper.optimizer = opt
-            wl.stepper.t += 1
-            wl.stepper.engine.adam(0, wl.stepper.flat.numel, wl.stepper.t, wl.stepper.lr, wl.stepper.betas,
-                                   wl.stepper.eps, wl.stepper.grad_clip)
+            wl.stepper.update()
     phase("stage profile done; e2e")
     e2e = E2E(wl)
     for _ in range(max(args.warmup, 12)):       # first calls: pinned staging, side-stream copy buffers, allocator growth
@@ -931,6 +927,11 @@ def main():
                                       batches=f"{NB} distinct ragged batches cycled in the timed region (resident in HBM)",
                                       extra_warmup_steps=EXTRA_WARMUP_MULTI_GPU if world > 1 else 0,
                                       launch_mode="eager launches through the native step executor (no CUDA graph)",
+                                      exchange=("none (one GPU)" if world == 1 else
+                                                "gradient all-reduce + clip/Adam + parameter broadcast fused in one kernel over "
+                                                "NVSwitch multicast memory (snt_dp_adam_shard: multimem.ld_reduce / multimem.st, "
+                                                "optimizer sharded over the ranks)" if wl.stepper.grads_are_local else
+                                                "three bucketed NCCL all-reduces overlapped with backward"),
                                       l2="no explicit flush: each step streams ~0.9 GB of activations/weights (> 126 MB L2)"),
             "fixed_batch": {"value": total_caps * args.steps / t_fixed, "ms_per_step": t_fixed / args.steps * 1e3,
                             "what": "the same loop repeating batch 0"},
@@ -943,6 +944,8 @@ def main():
             "algorithmic_flops_per_step": flops_step, "loss": loss_val, **extra,
         }
         print(json.dumps(line), flush=True)
+    if os.environ.get("SNT_DP_DEBUG") and hasattr(wl.stepper, "exchange_report"):
+        print(f"[dp] rank {rank} exchange: {wl.stepper.exchange_report()}", file=sys.stderr, flush=True)
     phase("line printed; teardown")
     wl.stepper.close()
     if world > 1:

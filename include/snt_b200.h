@@ -187,6 +187,20 @@ int snt_clamp_adam_multi(int count, float* const* p, const float* const* g, floa
                          const int64_t* n, double lr, double beta1, double beta2, double eps, float grad_clip,
                          float grad_scale, int64_t step, void* stream);
 
+/* ---- data-parallel gradient exchange fused with clip_gradient + Adam  (replaces nn.DataParallel's gather / re-replicate,
+ * train.py:43-44, and train.py:88-91,145-146, for one process per GPU on an NVLink / NVSwitch node) --------------------
+ * The flat gradient buffer and the flat parameter buffer of every rank are mapped behind one multicast address each
+ * (mc_g, mc_p; e.g. torch.distributed._symmetric_memory).  This rank owns the flat indices [lo, hi) (multiples of 4):
+ * the sum of all ranks' gradients is read through the switch (multimem.ld_reduce), clamp + Adam run on this rank's m, v
+ * and its local copy p of the parameters, and the updated parameters are stored to every rank (multimem.st).
+ * The caller runs a cross-rank barrier before (every rank's gradients are written) and after (every rank's parameters
+ * have arrived) on the same stream.  m and v are meaningful on the owner rank of an index only.
+ * max_blocks > 0: a grid of at most that many (256-thread) blocks, for a bucket that is exchanged as background work
+ * while the cooperative recurrence kernel runs on 128 of the SMs. */
+int snt_dp_adam_shard(const float* mc_g, float* mc_p, const float* p, float* m, float* v, int64_t lo, int64_t hi,
+                      double lr, double beta1, double beta2, double eps, float grad_clip, float grad_scale,
+                      int64_t step, int max_blocks, void* stream);
+
 /* ---- the whole teacher-forced step as ONE native call sequence  (train.py:137-146 for the models.py pair) --------
  * forward (encoder head -> gather/concat/pack -> L LSTM layers -> fused vocab-CE), backward (CE -> BPTT -> embedding
  * gradient and head backward on two streams) in the order of the stage functions above, with every activation carved

@@ -66,6 +66,7 @@ SIGNATURES = {
                                  _i64, _i64, _i64, _i64, _int, _vp, _vp, _i64, _vp]),
     "snt_caption_trim": (_int, [_vp, _i64, _int, _i64, _i64, _vp, _vp, _vp]),
     "snt_clamp_adam": (_int, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f32, _f32, _i64, _vp]),
+    "snt_dp_adam_shard": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64, _f64, _f64, _f64, _f32, _f32, _i64, _int, _vp]),
     "snt_clamp_adam_multi": (_int, [_int, _pp, _pp, _pp, _pp, C.POINTER(_i64), _f64, _f64, _f64, _f64, _f32, _f32,
                                     _i64, _vp]),
 }

@@ -572,6 +572,13 @@ extern "C" int snt_greedy_decode(int prec, const float* features, const float* w
   return SNT_OK;
 }
 
+extern "C" int snt_dp_adam_shard(const float* mc_g, float* mc_p, const float* p, float* m, float* v, int64_t lo,
+                                 int64_t hi, double lr, double beta1, double beta2, double eps, float grad_clip,
+                                 float grad_scale, int64_t step, int max_blocks, void* stream) {
+  return dp_adam_shard(mc_g, mc_p, p, m, v, lo, hi, lr, beta1, beta2, eps, grad_clip, grad_scale, step, max_blocks,
+                       (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // f4: words before the first <end> (eval.py:101-109)
 // ------------------------------------------------------------------------------------------------------------

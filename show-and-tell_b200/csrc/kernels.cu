@@ -1061,6 +1061,93 @@ int clamp_adam(float* p, const float* g, float* m, float* v, int64_t n, double l
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Data-parallel exchange fused with the optimizer, over NVLink / NVSwitch multicast memory (one process per GPU):
+// the flat gradient and parameter buffers of every rank are mapped behind one MULTICAST address each.  Every rank owns
+// one contiguous shard of the flat index range and, for it alone,
+//   g   = multimem.ld_reduce.add  [mc_g + i]       the switch sums the ranks' gradients in flight: the all-reduce
+//   p,m,v <- clamp + Adam                           1/world of the optimizer's work and traffic per GPU
+//   multimem.st [mc_p + i] <- p                     the new parameters land in every rank's buffer: the broadcast
+// so the gradient all-reduce, the optimizer and the parameter broadcast are ONE kernel whose cost shrinks with the
+// number of GPUs, nothing of the exchange runs beside (and competes with) the backward pass, and replicas stay
+// bit-identical by construction (each value is reduced and updated exactly once).  The caller brackets the launch with
+// two cross-rank barriers: all gradients written before, all parameters delivered after.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+constexpr int DP_UNROLL = 4;  // float4s per thread: all their multicast reads are in flight before the first is used
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+dp_adam_shard_kernel(const float* __restrict__ mc_g, float* __restrict__ mc_p, const float* __restrict__ p,
+                     float* __restrict__ m, float* __restrict__ v, int64_t lo, int64_t hi, float step_size, float beta1,
+                     float beta2, float omb1, float omb2, float eps, float rsqrt_bc2, float grad_clip, float grad_scale) {
+  // a block covers THREADS * DP_UNROLL consecutive float4s per round; thread t takes float4s t, t + THREADS, ... of them
+  // (coalesced); the grid walks the shard with a stride (a narrow grid serves a bucket that is exchanged beside the
+  // cooperative recurrence kernel: it may never occupy more SMs than that kernel leaves free)
+  constexpr int64_t PER = (int64_t)THREADS * DP_UNROLL * 4;
+  for (int64_t b0 = lo + (int64_t)blockIdx.x * PER; b0 < hi; b0 += (int64_t)gridDim.x * PER) {
+    const int64_t base = b0 + (int64_t)threadIdx.x * 4;
+    float4 gg[DP_UNROLL], pp[DP_UNROLL], mm[DP_UNROLL], vv[DP_UNROLL];
+#pragma unroll
+    for (int k = 0; k < DP_UNROLL; ++k) {
+      const int64_t i = base + (int64_t)k * THREADS * 4;
+      if (i < hi) gg[k] = multimem_ld_reduce_add(mc_g + i);
+    }
+#pragma unroll
+    for (int k = 0; k < DP_UNROLL; ++k) {
+      const int64_t i = base + (int64_t)k * THREADS * 4;
+      if (i < hi) {
+        pp[k] = *reinterpret_cast<const float4*>(p + i);
+        mm[k] = *reinterpret_cast<const float4*>(m + i);
+        vv[k] = *reinterpret_cast<const float4*>(v + i);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < DP_UNROLL; ++k) {
+      const int64_t i = base + (int64_t)k * THREADS * 4;
+      if (i >= hi) continue;  // lo, hi multiples of 4: whole float4s
+      adam1(pp[k].x, gg[k].x, mm[k].x, vv[k].x, step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip, grad_scale);
+      adam1(pp[k].y, gg[k].y, mm[k].y, vv[k].y, step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip, grad_scale);
+      adam1(pp[k].z, gg[k].z, mm[k].z, vv[k].z, step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip, grad_scale);
+      adam1(pp[k].w, gg[k].w, mm[k].w, vv[k].w, step_size, beta1, beta2, omb1, omb2, eps, rsqrt_bc2, grad_clip, grad_scale);
+      *reinterpret_cast<float4*>(m + i) = mm[k];
+      *reinterpret_cast<float4*>(v + i) = vv[k];
+      multimem_st(mc_p + i, pp[k]);
+    }
+  }
+}
+int dp_adam_shard(const float* mc_g, float* mc_p, const float* p, float* m, float* v, int64_t lo, int64_t hi, double lr,
+                  double beta1, double beta2, double eps, float grad_clip, float grad_scale, int64_t step, int max_blocks,
+                  cudaStream_t st) {
+  if (hi <= lo) return SNT_OK;
+  SNT_REQUIRE(mc_g && mc_p && p && m && v, "dp_adam_shard: NULL pointer");
+  SNT_REQUIRE(step >= 1 && lo >= 0 && (lo & 3) == 0 && (hi & 3) == 0, "dp_adam_shard: shard bounds must be multiples of 4");
+  SNT_REQUIRE(((reinterpret_cast<uintptr_t>(mc_g) | reinterpret_cast<uintptr_t>(mc_p) | reinterpret_cast<uintptr_t>(p) |
+                reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
+              "dp_adam_shard: buffers must be 16-byte aligned");
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const float a0 = (float)(lr / bc1), a1 = (float)beta1, a2 = (float)beta2, a3 = (float)(1.0 - beta1),
+              a4 = (float)(1.0 - beta2), a5 = (float)eps, a6 = (float)(1.0 / sqrt(bc2));
+  // max_blocks > 0: a bounded grid that walks the shard with a stride.  The blocks stay small (256 threads) so that they
+  // fit into whatever thread slots and registers free up on an SM next to other background work - a 1024-thread block
+  // needs a whole empty SM and starved behind the output-bias column sums for the length of the BPTT (measured).
+  unsigned grid = nblocks((hi - lo) / 4, 256 * DP_UNROLL);
+  if (max_blocks > 0 && grid > (unsigned)max_blocks) grid = (unsigned)max_blocks;
+  dp_adam_shard_kernel<256><<<grid, 256, 0, st>>>(mc_g, mc_p, p, m, v, lo, hi, a0, a1, a2, a3, a4, a5, a6, grad_clip,
+                                                  grad_scale);
+  SNT_LAUNCH_CHECK("dp_adam_shard_kernel");
+  return SNT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // f4: the caller-side tail of sample() (eval.py:101-109): a caption is the words before the first <end>.
 // One warp per caption; a row of `steps` ids is scanned 32 at a time, the first hit ends the caption.
 // HBM-bound (8 or 16 bytes per token), latency-trivial: it exists so that eval needs ONE device->host copy of

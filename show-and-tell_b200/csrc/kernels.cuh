@@ -55,6 +55,11 @@ int clamp_adam_multi(int count, float* const* p, const float* const* g, float* c
                      const int64_t* n, double lr, double beta1, double beta2, double eps, float grad_clip,
                      float grad_scale, int64_t step, cudaStream_t st);
 
+// the data-parallel exchange fused with the optimizer over multicast memory (kernels.cu): flat indices [lo, hi) of this rank
+int dp_adam_shard(const float* mc_g, float* mc_p, const float* p, float* m, float* v, int64_t lo, int64_t hi, double lr,
+                  double beta1, double beta2, double eps, float grad_clip, float grad_scale, int64_t step, int max_blocks,
+                  cudaStream_t st);
+
 // lengths[b] = index of the first end_id in ids[b,0..steps) (steps if none); ids_out (optional, may alias ids) = ids with
 // everything from that position on replaced by pad_id
 int caption_trim(const int64_t* ids, int64_t B, int steps, int64_t end_id, int64_t pad_id, int32_t* lengths,

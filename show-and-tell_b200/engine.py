@@ -70,7 +70,9 @@ class FlatParams:
 
     BUCKETS = ("early", "mid", "late")   # linear.weight | linear.bias, lstm.* | embed.weight + head
 
-    def __init__(self, encoder, decoder):
+    def __init__(self, encoder, decoder, alloc=None):
+        """alloc(numel) -> a zeroed fp32 CUDA tensor: used for the parameter and the gradient buffer, so that a
+        data-parallel caller can place them in symmetric (peer-mapped, multicast) memory."""
         self.encoder, self.decoder = encoder, decoder
         L = decoder.num_layers
         named = []                                           # (bucket, name, parameter)
@@ -98,8 +100,10 @@ class FlatParams:
             self.bucket_range[b] = (start, off)
         # offsets were appended bucket by bucket, which is the order of `named` already (early, mid, late)
         self.numel = off
-        self.p = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.g = torch.zeros(off, dtype=torch.float32, device=dev)
+        if alloc is None:
+            alloc = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)   # noqa: E731
+        self.p = alloc(off)
+        self.g = alloc(off)
         self.m = torch.zeros(off, dtype=torch.float32, device=dev)
         self.v = torch.zeros(off, dtype=torch.float32, device=dev)
         self.gviews = []
@@ -249,6 +253,17 @@ class StepEngine:
         v = list(ms)
         return {"head_fwd": v[0], "embed_pack_fwd": v[1], "lstm_fwd": sum(v[2:10]), "vocab_ce_fwd": v[10],
                 "vocab_ce_bwd": v[11], "lstm_bwd": sum(v[12:20]), "embed_pack_bwd": v[20], "head_bwd": v[21]}
+
+    def dp_adam_shard(self, mc_g, mc_p, lo, hi, step, lr, betas, eps, grad_clip, max_blocks=0):
+        """The data-parallel exchange fused with clip_gradient + Adam on this rank's shard flat[lo:hi] (include/snt_b200.h:
+        snt_dp_adam_shard): mc_g / mc_p are the multicast addresses of the flat gradient / parameter buffers."""
+        f = self.flat
+        if hi <= lo:
+            return
+        _lib.call("snt_dp_adam_shard", C.c_void_p(mc_g), C.c_void_p(mc_p), C.c_void_p(f.p.data_ptr()),
+                  C.c_void_p(f.m.data_ptr()), C.c_void_p(f.v.data_ptr()), int(lo), int(hi), float(lr), float(betas[0]),
+                  float(betas[1]), float(eps), float(grad_clip if grad_clip is not None else 0.0), 1.0, int(step),
+                  int(max_blocks), _lib.stream_ptr())
 
     def adam(self, lo, hi, step, lr, betas, eps, grad_clip):
         """clip_gradient + Adam (train.py:88-91,145-146) on flat[lo:hi]."""

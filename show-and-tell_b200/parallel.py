@@ -91,9 +91,13 @@ class DataParallelStep:
         self.group = group
         self.world = dist.get_world_size(group) if (distributed and dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self._symm = None          # (handle of g, handle of p) when the flat buffers live in symmetric multicast memory
         if engine is None:
             head = encoder if (encoder is not None and any(p.requires_grad for p in encoder.parameters())) else None
-            engine = StepEngine(FlatParams(head, decoder))
+            alloc = self._symmetric_alloc(decoder) if (self.world > 1 and optimizer) else None
+            engine = StepEngine(FlatParams(head, decoder, alloc=alloc))
+            if alloc is not None:
+                self._symm_rendezvous(engine.flat)
         self.engine = engine
         self.flat = engine.flat
         self.params = self.flat.params
@@ -110,9 +114,105 @@ class DataParallelStep:
         # fills the SMs the cooperative recurrence kernels leave free and never delays them (csrc/step.cu).
         self._stream = None
         if self.flat.p.is_cuda and os.environ.get("SNT_STEP_PRIORITY", "1") != "0":
-            self._stream = torch.cuda.Stream(device=self.flat.p.device, priority=-1)
+            self._stream = torch.cuda.Stream(device=self.flat.p.device, priority=-2)
         if self.world > 1:
             self.sync_from_rank0()
+
+    # ---- fused exchange: gradients, optimizer and parameter broadcast as one kernel over NVSwitch multicast memory ------
+    def _symmetric_alloc(self, decoder):
+        """-> allocator of symmetric (peer-mapped) fp32 buffers, or None when this job cannot use them (CPU tensors, no
+        multicast support, SNT_DP_FUSED=0): the bucketed NCCL all-reduce below is the fallback, decided identically on
+        every rank."""
+        dev = next(decoder.parameters()).device
+        if dev.type != "cuda" or os.environ.get("SNT_DP_FUSED", "1") == "0":
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            from torch._C._distributed_c10d import _SymmetricMemory
+            ok = bool(_SymmetricMemory.has_multicast_support(torch._C._autograd.DeviceType.CUDA, dev.index or 0))
+        except Exception:   # noqa: BLE001 - API absent in this torch build
+            ok = False
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag) == 0:
+            return None
+
+        def alloc(n):
+            t = symm_mem.empty(n, dtype=torch.float32, device=dev)
+            t.zero_()
+            return t
+        return alloc
+
+    def _symm_rendezvous(self, flat):
+        import torch.distributed._symmetric_memory as symm_mem
+        name = (self.group or dist.group.WORLD).group_name
+        hg = symm_mem.rendezvous(flat.g, name)
+        hp = symm_mem.rendezvous(flat.p, name)
+        if not hg.multicast_ptr or not hp.multicast_ptr:
+            raise RuntimeError("symmetric memory came back without a multicast mapping (set SNT_DP_FUSED=0 to use the "
+                               "NCCL all-reduce path)")
+        self._symm = (hg, hp)
+
+        def shard(lo, hi):   # this rank's contiguous, 256-float aligned share of flat[lo:hi]
+            per = (hi - lo + self.world - 1) // self.world
+            per = (per + 255) // 256 * 256
+            return (min(lo + self.rank * per, hi), min(lo + (self.rank + 1) * per, hi))
+        self._shard = shard(0, flat.numel)
+        self._bucket_shard = {b: shard(*flat.bucket_range[b]) for b in flat.BUCKETS}
+        # the exchange runs on its own default-priority stream: background work beside the high-priority step stream
+        # (priority between the step's stream and the executor's side streams: when thread slots free up on an SM the
+        # exchange blocks are placed before more column-sum blocks, but never before the step's own kernels)
+        self._xstream = torch.cuda.Stream(device=flat.p.device, priority=-1)
+        sms = torch.cuda.get_device_properties(flat.p.device).multi_processor_count
+        self._narrow = 8 * max(8, sms - 128)  # blocks of a bucket exchanged beside the cooperative recurrence kernel
+        self._pipelined = os.environ.get("SNT_DP_PIPELINE", "1") != "0"
+        self._dbg = [] if os.environ.get("SNT_DP_DEBUG") else None     # (bucket, _, events) per exchange: exchange_report()
+
+    def _exchange_bucket(self, bucket, channel, narrow):
+        """Exchange + update of one readiness bucket on the exchange stream, ordered after everything enqueued so far on
+        the step's stream: barrier (this bucket's gradients are final on every rank) -> snt_dp_adam_shard."""
+        hg, hp = self._symm
+        cur = torch.cuda.current_stream(self.flat.p.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        lo, hi = self._bucket_shard[bucket]
+        dbg = self._dbg
+        with torch.cuda.stream(self._xstream):
+            self._xstream.wait_event(ev)
+            if dbg is not None:
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                e[0].record()
+            hg.barrier(channel)
+            if dbg is not None:
+                e[1].record()
+            self.engine.dp_adam_shard(hg.multicast_ptr, hp.multicast_ptr, lo, hi, self.t, self.lr, self.betas, self.eps,
+                                      self.grad_clip, self._narrow if narrow else 0)
+            if dbg is not None:
+                e[2].record()
+                dbg.append((bucket, None, e))
+
+    def exchange_report(self, last=30):
+        """SNT_DP_DEBUG=1: mean microseconds of (wait at the barrier, exchange kernel) per bucket over the last exchanges."""
+        if not self._dbg:
+            return {}
+        torch.cuda.synchronize()
+        acc = {}
+        for bucket, _, e in self._dbg[-3 * last:]:
+            a = acc.setdefault(bucket, [0.0, 0.0, 0])
+            a[0] += e[0].elapsed_time(e[1]) * 1e3
+            a[1] += e[1].elapsed_time(e[2]) * 1e3
+            a[2] += 1
+        return {b: {"barrier_us": a[0] / a[2], "kernel_us": a[1] / a[2]} for b, a in acc.items()}
+
+    def _fused_update(self):
+        """barrier (every rank's gradients are written) -> snt_dp_adam_shard on this rank's shard -> barrier (every
+        rank's parameters have arrived).  Replaces three NCCL all-reduces, the optimizer launch and any broadcast."""
+        hg, hp = self._symm
+        eng = self.engine
+        hg.barrier(0)
+        eng.dp_adam_shard(hg.multicast_ptr, hp.multicast_ptr, self._shard[0], self._shard[1], self.t, self.lr, self.betas,
+                          self.eps, self.grad_clip)
+        hp.barrier(1)
 
     # the reference's DataParallel re-replicates the module from device 0 every step (train.py:43-44); with one process
     # per GPU the replicas are made identical once, here, and stay identical because every rank applies the same
@@ -162,6 +262,46 @@ class DataParallelStep:
         cur.wait_stream(self._stream)
         return loss
 
+    @property
+    def grads_are_local(self):
+        """True when the exchange is fused with the optimizer: flat.g then holds this rank's own gradients (their sum over
+        ranks exists only inside the update), and the Adam moments are kept by the owner rank of each shard."""
+        return self._symm is not None
+
+    def gather_moments(self):
+        """-> (m, v) complete on every rank (collective).  With the fused exchange each rank maintains the moments of its own
+        shard only; this assembles them, e.g. for a checkpoint or a parity check."""
+        m, v = self.flat.m, self.flat.v
+        if self._symm is not None:
+            own = torch.zeros_like(m, dtype=torch.bool)
+            for lo, hi in (self._bucket_shard.values() if self._pipelined else [self._shard]):
+                own[lo:hi] = True
+            m, v = m * own, v * own
+            for t in (m, v):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            return m, v
+        return m.clone(), v.clone()
+
+    def update(self):
+        """clip_gradient + Adam (train.py:145-146) on the gradients of the last step; several ranks: including their
+        exchange.  Called by step() unless `optimizer` is False."""
+        eng, flat = self.engine, self.flat
+        self.t += 1
+        if self.world > 1 and self._symm is not None:
+            self._fused_update()
+            return
+        lo_e, hi_e = flat.bucket_range["early"]
+        lo_m, hi_m = flat.bucket_range["mid"]
+        lo_l, hi_l = flat.bucket_range["late"]
+        if self.world > 1 and self.reducer.pending:
+            # update what has landed while the last bucket is still on the wire
+            self.reducer.wait(2)
+            eng.adam(lo_e, hi_m, self.t, self.lr, self.betas, self.eps, self.grad_clip)
+            self.reducer.wait()
+            eng.adam(lo_l, hi_l, self.t, self.lr, self.betas, self.eps, self.grad_clip)
+        else:
+            eng.adam(lo_e, hi_l, self.t, self.lr, self.betas, self.eps, self.grad_clip)
+
     def _step(self, inputs, captions, lengths, targets=None, n_tokens_global=None):
         eng, flat = self.engine, self.flat
         cuda = flat.p.is_cuda
@@ -176,8 +316,24 @@ class DataParallelStep:
         n_local = eng.prepare(inputs, captions, lengths, targets, 1.0)
         if self.world > 1 and n_tokens_global is not None:
             eng.set_grad_scale(n_local / float(n_tokens_global))
-        if self.world == 1:
-            eng.run(PH_ALL)
+        if self._symm is not None and self.optimizer and self._pipelined:
+            # fused exchange, bucket by bucket as the gradients become final: linear.weight is reduced, updated and
+            # broadcast while the BPTT runs (on the SMs the recurrence leaves free), the LSTM weights during the tail of
+            # backward; only embed.weight + head remain for the end of the step
+            self.t += 1
+            eng.run(PH_FWD | PH_BWD_CE)
+            self._exchange_bucket("early", 0, narrow=True)
+            eng.run(PH_BWD_LSTM)
+            self._exchange_bucket("mid", 1, narrow=True)
+            eng.run(PH_BWD_TAIL)
+            self._exchange_bucket("late", 2, narrow=False)
+            with torch.cuda.stream(self._xstream):
+                self._symm[1].barrier(3)                      # every rank's parameters have arrived
+            torch.cuda.current_stream(flat.p.device).wait_stream(self._xstream)
+            flat.attach_grads()
+            return self._finish_step(cuda)
+        if self.world == 1 or self._symm is not None:
+            eng.run(PH_ALL)      # (fused exchange in one piece: update())
         else:
             red = self.reducer
             reserve = cuda and self.sm_reserve > 0
@@ -191,24 +347,16 @@ class DataParallelStep:
             red.start("late", flat.slice(flat.g, "late"))     # embed.weight + head: final only now
         flat.attach_grads()
         if self.optimizer:
-            self.t += 1
-            lo_e, hi_e = flat.bucket_range["early"]
-            lo_m, hi_m = flat.bucket_range["mid"]
-            lo_l, hi_l = flat.bucket_range["late"]
-            if self.world > 1:
-                # update what has landed while the last bucket is still on the wire
-                self.reducer.wait(2)
-                eng.adam(lo_e, hi_m, self.t, self.lr, self.betas, self.eps, self.grad_clip)
-                self.reducer.wait()
-                eng.adam(lo_l, hi_l, self.t, self.lr, self.betas, self.eps, self.grad_clip)
-            else:
-                eng.adam(lo_e, hi_l, self.t, self.lr, self.betas, self.eps, self.grad_clip)
-        elif self.world > 1:
+            self.update()
+        elif self.reducer is not None and self._symm is None:
             self.reducer.wait()
+        return self._finish_step(cuda)
+
+    def _finish_step(self, cuda):
         if self.world > 1 and cuda:
-            if self.sm_reserve > 0:
+            if self.sm_reserve > 0 and self._symm is None:
                 _lib.lib().snt_set_sm_reserve(0)
             ev = torch.cuda.Event()
             ev.record()
             self._inflight.append(ev)
-        return eng.loss
+        return self.engine.loss
