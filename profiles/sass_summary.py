@@ -1,5 +1,6 @@
 """Per-kernel counts of the SASS mnemonics that prove a Blackwell-native kernel (B200_PROFILING.md): UTC*MMA (tcgen05.mma),
-LDTM/STTM (tcgen05.ld/st), UTMALDG/UTMASTG/UBLKCP (TMA), HMMA (legacy mma.sync: expected 0), plus registers per thread.
+LDTM/STTM (tcgen05.ld/st), UTMALDG/UTMASTG/UBLKCP (TMA), HMMA (legacy mma.sync: expected 0), LDGMC (multimem.ld_reduce over
+NVSwitch multicast memory), plus registers per thread.
 
     python profiles/sass_summary.py show-and-tell_b200/libsnt_b200.so > profiles/r02_sass_summary.txt
 """
@@ -21,7 +22,7 @@ for line in res.splitlines():
     if m and cur:
         regs[cur] = (int(m.group(1)), int(m.group(2)))
 demangle = lambda names: dict(zip(names, subprocess.run(["c++filt"] + names, capture_output=True, text=True).stdout.splitlines()))
-KEYS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "HMMA", "MUFU", "FFMA"]
+KEYS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "HMMA", "MUFU", "FFMA", "LDGMC"]
 counts = collections.OrderedDict()
 cur = None
 for line in sass.splitlines():
@@ -41,7 +42,7 @@ for line in sass.splitlines():
                 counts[cur][k] += 1
 names = demangle(list(counts))
 print(f"# {so}: {len(counts)} kernels; columns = instruction counts in the SASS of each kernel (cuobjdump -sass), regs/thread, static smem")
-print(f"{'UTC*MMA':>8s} {'LDTM':>5s} {'STTM':>5s} {'UTMALDG':>8s} {'UTMASTG':>8s} {'UBLKCP':>7s} {'UTCBAR':>7s} {'HMMA':>5s} {'MUFU':>5s} {'FFMA':>6s} {'insts':>6s} {'regs':>5s}  kernel")
+print(f"{'UTC*MMA':>8s} {'LDTM':>5s} {'STTM':>5s} {'UTMALDG':>8s} {'UTMASTG':>8s} {'UBLKCP':>7s} {'UTCBAR':>7s} {'HMMA':>5s} {'MUFU':>5s} {'FFMA':>6s} {'LDGMC':>6s} {'insts':>6s} {'regs':>5s}  kernel")
 tc = 0
 for k, c in counts.items():
     n = names.get(k, k)
@@ -52,5 +53,6 @@ for k, c in counts.items():
     mma = c["UTCHMMA"] + c["UTCQMMA"]
     tc += mma > 0
     print(f"{mma:8d} {c['LDTM']:5d} {c['STTM']:5d} {c['UTMALDG']:8d} {c['UTMASTG']:8d} {c['UBLKCP']:7d} {c['UTCBAR']:7d} "
-          f"{c['HMMA']:5d} {c['MUFU']:5d} {c['FFMA']:6d} {c['_n']:6d} {str(r):>5s}  {n}")
-print(f"# kernels with tcgen05.mma (UTC*MMA): {tc}; kernels with legacy HMMA: {sum(1 for c in counts.values() if c['HMMA'])}")
+          f"{c['HMMA']:5d} {c['MUFU']:5d} {c['FFMA']:6d} {c['LDGMC']:6d} {c['_n']:6d} {str(r):>5s}  {n}")
+print(f"# kernels with tcgen05.mma (UTC*MMA): {tc}; kernels with legacy HMMA: {sum(1 for c in counts.values() if c['HMMA'])}; "
+      f"kernels with multimem.ld_reduce (LDGMC, NVSwitch in-flight reduction): {sum(1 for c in counts.values() if c['LDGMC'])}")

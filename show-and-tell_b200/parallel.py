@@ -137,20 +137,40 @@ class DataParallelStep:
         if int(flag) == 0:
             return None
 
-        def alloc(n):
-            t = symm_mem.empty(n, dtype=torch.float32, device=dev)
-            t.zero_()
-            return t
+        state = self._symm_state = {"failed": False}
+
+        def alloc(n):   # a failed symmetric allocation degrades to a plain buffer; the ranks agree on the outcome later
+            try:
+                if not state["failed"]:
+                    t = symm_mem.empty(n, dtype=torch.float32, device=dev)
+                    t.zero_()
+                    return t
+            except Exception:   # noqa: BLE001
+                state["failed"] = True
+            return torch.zeros(n, dtype=torch.float32, device=dev)
         return alloc
 
     def _symm_rendezvous(self, flat):
         import torch.distributed._symmetric_memory as symm_mem
-        name = (self.group or dist.group.WORLD).group_name
-        hg = symm_mem.rendezvous(flat.g, name)
-        hp = symm_mem.rendezvous(flat.p, name)
-        if not hg.multicast_ptr or not hp.multicast_ptr:
-            raise RuntimeError("symmetric memory came back without a multicast mapping (set SNT_DP_FUSED=0 to use the "
-                               "NCCL all-reduce path)")
+        # every rank must hold symmetric buffers before anyone enters the (collective) rendezvous; whatever goes wrong on
+        # any rank - here or in the rendezvous - sends ALL ranks to the NCCL all-reduce path (the buffers stay valid
+        # plain CUDA memory)
+        flag = torch.tensor([0 if self._symm_state["failed"] else 1], device=flat.p.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag) == 0:
+            return
+        hg = hp = None
+        try:
+            name = (self.group or dist.group.WORLD).group_name
+            hg = symm_mem.rendezvous(flat.g, name)
+            hp = symm_mem.rendezvous(flat.p, name)
+            ok = bool(hg.multicast_ptr) and bool(hp.multicast_ptr)
+        except Exception:   # noqa: BLE001
+            ok = False
+        flag = torch.tensor([1 if ok else 0], device=flat.p.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag) == 0:
+            return
         self._symm = (hg, hp)
 
         def shard(lo, hi):   # this rank's contiguous, 256-float aligned share of flat[lo:hi]
@@ -205,13 +225,15 @@ class DataParallelStep:
         return {b: {"barrier_us": a[0] / a[2], "kernel_us": a[1] / a[2]} for b, a in acc.items()}
 
     def _fused_update(self):
-        """barrier (every rank's gradients are written) -> snt_dp_adam_shard on this rank's shard -> barrier (every
-        rank's parameters have arrived).  Replaces three NCCL all-reduces, the optimizer launch and any broadcast."""
+        """The whole exchange in one piece (a step that ran with optimizer=False, then update()): barrier (every rank's
+        gradients are written) -> snt_dp_adam_shard on this rank's share of every bucket -> barrier (every rank's
+        parameters have arrived).  Index ownership is the same as in the pipelined step: by bucket."""
         hg, hp = self._symm
-        eng = self.engine
         hg.barrier(0)
-        eng.dp_adam_shard(hg.multicast_ptr, hp.multicast_ptr, self._shard[0], self._shard[1], self.t, self.lr, self.betas,
-                          self.eps, self.grad_clip)
+        for b in self.flat.BUCKETS:
+            lo, hi = self._bucket_shard[b]
+            self.engine.dp_adam_shard(hg.multicast_ptr, hp.multicast_ptr, lo, hi, self.t, self.lr, self.betas, self.eps,
+                                      self.grad_clip)
         hp.barrier(1)
 
     # the reference's DataParallel re-replicates the module from device 0 every step (train.py:43-44); with one process
@@ -274,7 +296,7 @@ class DataParallelStep:
         m, v = self.flat.m, self.flat.v
         if self._symm is not None:
             own = torch.zeros_like(m, dtype=torch.bool)
-            for lo, hi in (self._bucket_shard.values() if self._pipelined else [self._shard]):
+            for lo, hi in self._bucket_shard.values():
                 own[lo:hi] = True
             m, v = m * own, v * own
             for t in (m, v):
