@@ -212,7 +212,7 @@ int snt_dp_adam_shard(const float* mc_g, float* mc_p, const float* p, float* m, 
  * data-parallel caller starts its gradient all-reduce between them (one process per GPU; the reference's
  * nn.DataParallel, train.py:43-44):
  *   SNT_STEP_FWD       loss
- *   SNT_STEP_BWD_CE    d_w_out                                (ready first: overlaps all of BPTT)
+ *   SNT_STEP_BWD_CE    d_w_out                                (ready first: overlaps all of BPTT; but see below)
  *   SNT_STEP_BWD_LSTM  d_b_out; d_w_ih / d_w_hh / d_b_ih / d_b_hh of every layer   (d_b_out = column sums of the stored
  *                      softmax numerators: one HBM-bound pass that runs beside the latency-bound BPTT recurrence)
  *   SNT_STEP_BWD_TAIL  d_w_emb and the head gradients (d_w_fc, d_b_fc, d_bn_w, d_bn_b), optional d_features
@@ -250,6 +250,12 @@ typedef struct snt_step {
 
 int64_t snt_step_workspace_bytes(int prec, int L, int64_t B, int64_t N, int64_t E, int64_t H, int64_t V, int64_t K);
 int snt_step_run(const snt_step* step, int phases, void* stream);
+/* 1 when a snt_step_run call whose mask holds BOTH SNT_STEP_BWD_CE and SNT_STEP_BWD_LSTM runs the d_w_out contraction
+ * beside the BPTT recurrence instead of in front of it (bf16 mode, persistent recurrence kernel occupying at most two
+ * thirds of the SMs: batch <= 1024 at H = 512): d_w_out is then final when BWD_LSTM ends, not when BWD_CE ends, and a
+ * data-parallel caller exchanges it together with the LSTM gradients.  Issuing the two phases in separate calls keeps the
+ * contraction in BWD_CE. */
+int snt_step_overlaps_dw_out(int prec, int64_t B, int64_t H);
 
 /* Per-stage device time of snt_step_run (diagnostics).  snt_step_profile(1) makes every later run record a CUDA-event
  * pair around each stage on the stream it is enqueued on; snt_step_profile_read synchronises the device and returns the

@@ -59,6 +59,7 @@ SIGNATURES = {
                                       _vp, _i64, _vp]),
     "snt_step_workspace_bytes": (_i64, [_int, _int, _i64, _i64, _i64, _i64, _i64, _i64]),
     "snt_step_run": (_int, [_vp, _int, _vp]),
+    "snt_step_overlaps_dw_out": (_int, [_int, _i64, _i64]),
     "snt_step_profile": (_int, [_int]),
     "snt_step_profile_read": (_int, [C.POINTER(_f32), _int]),
     "snt_greedy_workspace_bytes": (_i64, [_int, _i64, _i64, _i64, _i64, _int]),

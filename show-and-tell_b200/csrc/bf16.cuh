@@ -26,6 +26,7 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
 // recurrence of this hidden size runs as the persistent cooperative kernel (128 of 148 SMs, latency-bound)
 void lstm_bwd_gate_event(cudaEvent_t e);
 bool lstm_bwd_is_persistent(int64_t H);
+int lstm_bwd_persistent_ctas(int64_t B, int64_t H);  // SMs its widest launch occupies (0: per-step launches)
 
 int64_t linear_ws_bytes(int64_t N, int64_t H, int64_t V);
 int linear_fwd(const void* hs, const float* w_out, const float* b_out, int64_t N, int64_t H, int64_t V,
@@ -50,7 +51,11 @@ int vocab_ce_train_fwd(const void* hs, const float* w_out, const float* b_out, c
 int vocab_ce_train_bwd(const void* u, const float* inv_s, const void* hs_scaled, const void* w_bf16,
                        const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
                        float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st,
-                       bool defer_bias = false);
+                       bool defer_bias = false, bool defer_dw = false);
+// the dW_out half of vocab_ce_train_bwd(defer_dw = true), on any stream, with caller-owned split-K scratch
+int64_t vocab_ce_train_sws_elems(int64_t N, int64_t H, int64_t V);
+int vocab_ce_train_dw(const void* u, const void* hs_scaled, const float* dloss, float grad_scale, int64_t N, int64_t H,
+                      int64_t V, float* d_w_out, float* sws, int64_t sws_elems, cudaStream_t st, int max_ctas);
 // the d_b_out half of vocab_ce_train_bwd(defer_bias = true), on any stream, with caller-owned scratch
 int64_t vocab_ce_train_bias_part_elems(int64_t N, int64_t V);
 int vocab_ce_train_bias(const void* u, const float* inv_s, const float* dloss, float grad_scale, int64_t N, int64_t V,

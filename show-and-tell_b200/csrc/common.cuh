@@ -30,7 +30,8 @@ struct SideStream {
   cudaEvent_t fork = nullptr, join = nullptr, aux = nullptr;
 };
 // which = 0: the stream the stage functions use for their column sums; which = 1: the step executor's stream for whole
-// stages that run next to the main stream (head backward, embedding-gradient plan).  NULL if it could not be created.
+// stages that run next to the main stream (head backward, embedding-gradient plan); which = 2: the executor's stream for
+// the dW_out contraction beside the BPTT recurrence.  NULL if it could not be created.
 SideStream* side_stream(int which = 0);
 void count_launch();   // bumps the process-wide kernel-launch counter (snt_launch_count)
 

@@ -58,9 +58,9 @@ int* device_flags() {
 }
 
 SideStream* side_stream(int which) {
-  static SideStream tab[2][64];
+  static SideStream tab[3][64];
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || which < 0 || which > 1) return nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || which < 0 || which > 2) return nullptr;
   SideStream& x = tab[which][dev];
   if (!x.s) {
     if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;

@@ -40,9 +40,16 @@ int sm_count() {
 }
 
 static std::atomic<int> g_sm_reserve{0};
+static thread_local int g_grid_cap = 0;  // > 0: upper bound on the grids this thread launches (set_grid_cap)
 int grid_sms() {
-  const int n = sm_count() - g_sm_reserve.load();
+  int n = sm_count() - g_sm_reserve.load();
+  if (g_grid_cap > 0 && n > g_grid_cap) n = g_grid_cap;
   return n < 1 ? 1 : n;
+}
+int set_grid_cap(int n) {
+  const int old = g_grid_cap;
+  g_grid_cap = n < 0 ? 0 : n;
+  return old;
 }
 int set_sm_reserve(int n) { return g_sm_reserve.exchange(n < 0 ? 0 : n); }
 

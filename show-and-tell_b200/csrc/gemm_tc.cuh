@@ -247,6 +247,9 @@ int make_operand_tmap(CUtensorMap* out, const void* base, bool mn_major, int64_t
                       int box_rows);
 int sm_count();
 int grid_sms();  // SMs a persistent grid may occupy: sm_count() minus the reserve set through snt_set_sm_reserve()
+// Caps the persistent grids launched by THIS thread until reset with 0 (returns the previous cap): a contraction that runs
+// beside a cooperative kernel is sized for the SMs that kernel leaves free.
+int set_grid_cap(int n);
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TileSched& ts, const Epi& epi,

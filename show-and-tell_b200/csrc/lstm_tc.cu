@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace snt {
 namespace bf16 {
@@ -431,6 +432,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 constexpr int PB_STAGES = 6;
 constexpr int PB_FLAGS_PER_STEP = 16;  // CTAs per row block (ns * ns, ns <= 4)
 constexpr int PB_PART_FLOATS = 128 * 128;
+constexpr int PS_THREADS = 128 + 32 * (4 + 16);  // phase-split BPTT kernel: control warps, P1 group, P2 group
 
 struct PersistBwdParams {
   int H, T, ns;
@@ -444,7 +446,14 @@ struct PersistBwdParams {
 #endif
 };
 
-template <int NS>
+// RB = row blocks per CTA.  A step of this recurrence is a chain of L2 round trips (two counter exchanges, two fenced
+// publications) during which the CTA's tensor core, TMA ring and epilogue warps mostly wait.  With RB = 2 a CTA owns the
+// same weight slice for TWO consecutive 128-row blocks and every role walks the items (t, row block 0), (t, row block 1),
+// (t-1, row block 0), ... in that one order: while row block 0's step is on the wire, row block 1's is computed.  The
+// recurrence then needs half the CTAs (64 instead of 128 at B = 1024) for about the same wall time, and the step executor
+// runs the dW_out contraction on the SMs that are left (csrc/step.cu).  Item i depends only on items < i of the CTAs of
+// the same group, and every role of every CTA walks the items in the same order: no circular wait.
+template <int NS, int RB>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                            const __grid_constant__ PackInfo pk, const PersistBwdParams p) {
@@ -459,12 +468,12 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   uint64_t* full = reinterpret_cast<uint64_t*>(sA + PB_STAGES * 16384);
   uint64_t* empty = full + PB_STAGES;
   uint64_t* wbar = empty + PB_STAGES;
-  uint64_t* tfull = wbar + 1;                         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
+  uint64_t* tfull = wbar + 1;                         // [RB][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2 * RB);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int rank = blockIdx.x % (NS * NS), m_blk = p.m_base + blockIdx.x / (NS * NS);
+  const int rank = blockIdx.x % (NS * NS);
   const int nq = rank / NS, ks = rank % NS;
 
   if (warp == 0 && elect_one()) {
@@ -474,12 +483,11 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < PB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(wbar, 1);
-    mbar_init(&tfull[0], 1);
-    mbar_init(&tfull[1], 1);
+    for (int i = 0; i < 2 * RB; ++i) mbar_init(&tfull[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 256 * RB);
     tmem_relinquish();
   }
   tcgen05_fence_before();
@@ -487,11 +495,17 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // this row block is alive for steps [0, t_end); going backward it starts at t_end - 1.  Step index s counts from
-  // there: t = t_end - 1 - s.  s = 0 has no recurrent term (no row of the block is alive at t + 1).
-  int t_end = 0;
-  while (t_end < p.T && m_blk * BM < pk.off[t_end + 1] - pk.off[t_end]) ++t_end;
-  float* my_part = p.part + ((int64_t)m_blk * (NS * NS) + rank) * 2 * PB_PART_FLOATS;
+  // Row block r of this CTA is alive for steps [0, t_end[r]); going backward it starts at t_end[r] - 1.  Its step index
+  // s = t_end[r] - 1 - t counts from there; s = 0 has no recurrent term (no row of the block is alive at t + 1).
+  // batch_sizes is non-increasing, so t_end[0] >= t_end[1]; a row block past the end of the batch has t_end = 0.
+  int m_blk[RB], t_end[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    m_blk[r] = p.m_base + (int)(blockIdx.x / (NS * NS)) * RB + r;
+    int te = 0;
+    while (te < p.T && m_blk[r] * BM < pk.off[te + 1] - pk.off[te]) ++te;
+    t_end[r] = te;
+  }
 
   if (warp == 0) {
     // ============ TMA producer (lane 0 issues; lanes 0..NS-1 poll the CTAs that publish this K range) ============
@@ -501,35 +515,39 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       mbar_arrive_expect_tx(wbar, (uint32_t)(KB * 16384));
       for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * 16384, &tmB, wbar, 512 * ks + kb * BK, 128 * nq);
     }
-    for (int s = 1; s < t_end; ++s) {
-      const int t = t_end - 1 - s;
-      // gate columns 512ks + 64kb.. are units 128ks + 16kb..: finalised by CTA (nq' = ks, ks' = kb * NS / 8)
-      const int* f = p.dgflag + ((int64_t)m_blk * p.T + (t + 1)) * PB_FLAGS_PER_STEP + ks * NS;
-      int kb = 0;
-      const long long t0 = clock64();
-      while (kb < KB) {
-        const int v = lane < NS ? ld_acquire_gpu(f + lane) : 0;
-        const unsigned waiting = __ballot_sync(0xffffffffu, lane < NS && v < 1);
-        const int ready = waiting ? (KB / NS) * (__ffs((int)waiting) - 1) : KB;
-        if (ready <= kb) {
-          if (clock64() - t0 > SNT_MBAR_TIMEOUT_CYCLES) {
-            if (lane == 0) printf("snt: lstm bwd persistent flag timeout block %d step %d\n", (int)blockIdx.x, t);
-            __trap();
+    for (int t = t_end[0] - 2; t >= 0; --t) {
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        if (t + 1 >= t_end[r]) continue;  // s = 0 (or row block not alive): nothing to contract
+        const int s = t_end[r] - 1 - t;
+        // gate columns 512ks + 64kb.. are units 128ks + 16kb..: finalised by CTA (nq' = ks, ks' = kb * NS / 8)
+        const int* f = p.dgflag + ((int64_t)m_blk[r] * p.T + (t + 1)) * PB_FLAGS_PER_STEP + ks * NS;
+        int kb = 0;
+        const long long t0 = clock64();
+        while (kb < KB) {
+          const int v = lane < NS ? ld_acquire_gpu(f + lane) : 0;
+          const unsigned waiting = __ballot_sync(0xffffffffu, lane < NS && v < 1);
+          const int ready = waiting ? (KB / NS) * (__ffs((int)waiting) - 1) : KB;
+          if (ready <= kb) {
+            if (clock64() - t0 > SNT_MBAR_TIMEOUT_CYCLES) {
+              if (lane == 0) printf("snt: lstm bwd persistent flag timeout block %d step %d\n", (int)blockIdx.x, t);
+              __trap();
+            }
+            continue;
           }
-          continue;
-        }
-        if (lane == 0) {
-          if (kb == 0) DBG_STAMP(s, 0);
-          for (int k = kb; k < ready; ++k) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], 16384);
-            tma_load_2d(sA + stage * 16384, &tmA, &full[stage], 512 * ks + k * BK, pk.off[t + 1] + m_blk * BM);
-            if (++stage == PB_STAGES) { stage = 0; phase ^= 1; }
+          if (lane == 0) {
+            if (kb == 0 && r == 0) DBG_STAMP(s, 0);
+            for (int k = kb; k < ready; ++k) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full[stage], 16384);
+              tma_load_2d(sA + stage * 16384, &tmA, &full[stage], 512 * ks + k * BK, pk.off[t + 1] + m_blk[r] * BM);
+              if (++stage == PB_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (ready == KB && r == 0) DBG_STAMP(s, 1);
           }
-          if (ready == KB) DBG_STAMP(s, 1);
+          kb = ready;
+          __syncwarp();
         }
-        kb = ready;
-        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -539,23 +557,29 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       mbar_wait(wbar, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int s = 1; s < t_end; ++s) {
-        const uint32_t tmem_d = tmem_base + (uint32_t)((s & 1) * 128);
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&full[stage], phase);
-          if (kb == 0) DBG_STAMP(s, 2);
-          tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * 16384);
-          const uint32_t b_addr = smem_u32(sW + kb * 16384);
+      for (int t = t_end[0] - 2; t >= 0; --t) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem_d, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
-                      idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty[stage]);
-          if (++stage == PB_STAGES) { stage = 0; phase ^= 1; }
+        for (int r = 0; r < RB; ++r) {
+          if (t + 1 >= t_end[r]) continue;
+          const int s = t_end[r] - 1 - t;
+          // accumulator (r, s & 1) is free: its previous reader (step s-2's phase 1) finished before dG'_{t+1} could exist
+          const uint32_t tmem_d = tmem_base + (uint32_t)(r * 256 + (s & 1) * 128);
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&full[stage], phase);
+            if (kb == 0 && r == 0) DBG_STAMP(s, 2);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(sA + stage * 16384);
+            const uint32_t b_addr = smem_u32(sW + kb * 16384);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_d, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
+                        idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty[stage]);
+            if (++stage == PB_STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (r == 0) DBG_STAMP(s, 3);
+          umma_commit(&tfull[r * 2 + (s & 1)]);
         }
-        DBG_STAMP(s, 3);
-        umma_commit(&tfull[s & 1]);
       }
     }
   } else if (warp >= 4) {
@@ -568,21 +592,23 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     const int row_l1 = q * 32 + lane;
     const int wi = warp - 4, j = lane & 3;
     const int row_l = wi * 8 + (lane >> 2);
-    const int row = m_blk * BM + row_l;
     const int H = p.H, H4 = 4 * p.H;
     const int u0 = 128 * nq + WS * ks;  // first unit this CTA finalises
     constexpr int KP = WS / 8;          // 8-unit groups in this CTA's slice
     const bool stamp = threadIdx.x == 128;
-    float dcreg[UG][8];
+    float dcreg[RB][UG][8];
 #pragma unroll
-    for (int g = 0; g < UG; ++g)
+    for (int r = 0; r < RB; ++r)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) dcreg[g][u] = 0.f;
-    // inputs of one step for this thread's row and the 4 unit pairs k = 4g..4g+3
+      for (int g = 0; g < UG; ++g)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dcreg[r][g][u] = 0.f;
+    // inputs of one item (step t of row block mb) for this thread's row and the 4 unit pairs k = 4g..4g+3
     float2 dh2[4], c2[4], p2[4];
     uint4 a4[4];
-    auto load_inputs = [&](int t, int g) {
+    auto load_inputs = [&](int t, int mb, int g) {
       const int bs = pk.off[t + 1] - pk.off[t];
+      const int row = mb * BM + row_l;
       if (row < bs) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
@@ -596,109 +622,122 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         }
       }
     };
-    if (t_end > 0) load_inputs(t_end - 1, 0);
-    for (int s = 0; s < t_end; ++s) {
-      const int t = t_end - 1 - s;
+    if (t_end[0] > 0) load_inputs(t_end[0] - 1, m_blk[0], 0);
+    for (int t = t_end[0] - 1; t >= 0; --t) {
       const int bs = pk.off[t + 1] - pk.off[t];
       const int bs_next = t + 1 < p.T ? pk.off[t + 2] - pk.off[t + 1] : 0;
-      const bool ok = row < bs;
-      const bool has_next = row < bs_next;  // rows still alive at step t+1 carry recurrent gradient
-      const int par = s & 1;
-      const int* pf = p.pflag + ((int64_t)m_blk * p.T + t) * PB_FLAGS_PER_STEP;
-      if (s > 0) {
-        // ---- phase 1: this K-split's partial tile, chunk c (32 units of the 128-unit tile) -> scratch ----
-        mbar_wait(&tfull[par], (uint32_t)(((s >> 1) & 1) ^ (par ^ 1)));
-        if (stamp) DBG_STAMP(s, 4);
-        tcgen05_fence_after();
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (uint32_t)(par * 128 + c * 32) + ((uint32_t)(q * 32) << 16), r);
-        tmem_ld_wait();
-        tcgen05_fence_before();
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        if (t >= t_end[r]) continue;
+        const int s = t_end[r] - 1 - t;
+        const int row = m_blk[r] * BM + row_l;
+        const bool ok = row < bs;
+        const bool has_next = row < bs_next;  // rows still alive at step t+1 carry recurrent gradient
+        const int par = s & 1;
+        const int* pf = p.pflag + ((int64_t)m_blk[r] * p.T + t) * PB_FLAGS_PER_STEP;
+        float* my_part = p.part + ((int64_t)m_blk[r] * (NS * NS) + rank) * 2 * PB_PART_FLOATS;
+        if (s > 0) {
+          // ---- phase 1: this K-split's partial tile, chunk c (32 units of the 128-unit tile) -> scratch ----
+          mbar_wait(&tfull[r * 2 + par], (uint32_t)(((s >> 1) & 1) ^ (par ^ 1)));
+          if (stamp && r == 0) DBG_STAMP(s, 4);
+          tcgen05_fence_after();
+          uint32_t rr[32];
+          tmem_ld32(tmem_base + (uint32_t)(r * 256 + par * 128 + c * 32) + ((uint32_t)(q * 32) << 16), rr);
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          {
+            const int x0 = 32 * c;  // tile column -> (finalizer slice, 8-unit group inside the slice)
+            float* base = my_part + (int64_t)par * PB_PART_FLOATS +
+                          (((int64_t)(x0 / WS) * KP + (x0 % WS) / 8) * 128 + row_l1) * 8;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              float4* dst = reinterpret_cast<float4*>(base + (int64_t)kk * 128 * 8);
+              __stcg(dst, make_float4(__uint_as_float(rr[8 * kk]), __uint_as_float(rr[8 * kk + 1]),
+                                      __uint_as_float(rr[8 * kk + 2]), __uint_as_float(rr[8 * kk + 3])));
+              __stcg(dst + 1, make_float4(__uint_as_float(rr[8 * kk + 4]), __uint_as_float(rr[8 * kk + 5]),
+                                          __uint_as_float(rr[8 * kk + 6]), __uint_as_float(rr[8 * kk + 7])));
+            }
+          }
+          if (stamp && r == 0) DBG_STAMP(s, 5);
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
+          if (threadIdx.x == 128) atomicAdd(const_cast<int*>(pf) + rank, 1);
+          if (stamp && r == 0) DBG_STAMP(s, 6);
+          // ---- wait for the NS partials of this N tile (CTAs nq*NS .. nq*NS+NS-1) ----
+          if (warp == 4) {
+            const long long t0 = clock64();
+            for (;;) {
+              const int v = lane < NS ? ld_acquire_gpu(pf + nq * NS + lane) : 1;
+              if (__all_sync(0xffffffffu, v >= 1)) break;
+              if (clock64() - t0 > SNT_MBAR_TIMEOUT_CYCLES) {
+                if (lane == 0) printf("snt: lstm bwd partial timeout block %d step %d\n", (int)blockIdx.x, t);
+                __trap();
+              }
+            }
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
+          if (stamp && r == 0) DBG_STAMP(s, 7);
+        }
+        // ---- phase 2: final dL/dh for this CTA's units, cell backward, publish dG'_t ----
+#pragma unroll
+        for (int g = 0; g < UG; ++g) {
+          if (g > 0) load_inputs(t, m_blk[r], g);
+          if (ok) {
+            float2 rec[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) rec[kk] = make_float2(0.f, 0.f);
+            if (s > 0 && has_next) {
+              float2 x[NS][4];
+#pragma unroll
+              for (int k = 0; k < NS; ++k) {
+                const float* src = p.part + (((int64_t)m_blk[r] * (NS * NS) + nq * NS + k) * 2 + par) * PB_PART_FLOATS +
+                                   (((int64_t)ks * KP + 4 * g) * 128 + row_l) * 8 + 2 * j;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) x[k][kk] = __ldcg(reinterpret_cast<const float2*>(src + (int64_t)kk * 128 * 8));
+              }
+#pragma unroll
+              for (int k = 0; k < NS; ++k)  // fixed order: deterministic
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) { rec[kk].x += x[k][kk].x; rec[kk].y += x[k][kk].y; }
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t a[4] = {a4[kk].x, a4[kk].y, a4[kk].z, a4[kk].w};
+              const float dhv[2] = {dh2[kk].x + rec[kk].x, dh2[kk].y + rec[kk].y};
+              const float cv[2] = {c2[kk].x, c2[kk].y}, pv[2] = {p2[kk].x, p2[kk].y};
+              uint32_t go[4];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float2 if_ = unpack_bf2(a[2 * e]), go_ = unpack_bf2(a[2 * e + 1]);
+                const float i_ = if_.x, f_ = if_.y, g_ = go_.x, o_ = go_.y;
+                const float tc_ = tanh_(cv[e]);
+                const float dh = dhv[e];
+                const float dc = dcreg[r][g][2 * kk + e] + dh * o_ * (1.f - tc_ * tc_);
+                go[2 * e] = pack_bf2(dc * g_ * i_ * (1.f - i_), dc * pv[e] * f_ * (1.f - f_));
+                go[2 * e + 1] = pack_bf2(dc * i_ * (1.f - g_ * g_), dh * tc_ * o_ * (1.f - o_));
+                dcreg[r][g][2 * kk + e] = dc * f_;
+              }
+              const int u = u0 + 8 * (4 * g + kk) + 2 * j;
+              *reinterpret_cast<uint4*>(p.dg + ((int64_t)pk.off[t] + row) * H4 + 4 * u) = make_uint4(go[0], go[1], go[2], go[3]);
+            }
+          }
+        }
+        if (stamp && r == 0) DBG_STAMP(s, 8);
+        if (t > 0) {
+          publish_fence();
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
+          if (threadIdx.x == 128)
+            atomicAdd(p.dgflag + ((int64_t)m_blk[r] * p.T + t) * PB_FLAGS_PER_STEP + rank, 1);
+          if (stamp && r == 0) DBG_STAMP(s, 9);
+        }
+        // inputs of the next item in the walk: the next alive row block of this step, else row block 0 of step t - 1
         {
-          const int x0 = 32 * c;  // tile column -> (finalizer slice, 8-unit group inside the slice)
-          float* base = my_part + (int64_t)par * PB_PART_FLOATS +
-                        (((int64_t)(x0 / WS) * KP + (x0 % WS) / 8) * 128 + row_l1) * 8;
+          bool found = false;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            float4* dst = reinterpret_cast<float4*>(base + (int64_t)kk * 128 * 8);
-            __stcg(dst, make_float4(__uint_as_float(r[8 * kk]), __uint_as_float(r[8 * kk + 1]),
-                                    __uint_as_float(r[8 * kk + 2]), __uint_as_float(r[8 * kk + 3])));
-            __stcg(dst + 1, make_float4(__uint_as_float(r[8 * kk + 4]), __uint_as_float(r[8 * kk + 5]),
-                                        __uint_as_float(r[8 * kk + 6]), __uint_as_float(r[8 * kk + 7])));
-          }
+          for (int r2 = r + 1; r2 < RB; ++r2)
+            if (!found && t < t_end[r2]) { load_inputs(t, m_blk[r2], 0); found = true; }
+          if (!found && t > 0) load_inputs(t - 1, m_blk[0], 0);
         }
-        if (stamp) DBG_STAMP(s, 5);
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
-        if (threadIdx.x == 128) atomicAdd(const_cast<int*>(pf) + rank, 1);
-        if (stamp) DBG_STAMP(s, 6);
-        // ---- wait for the NS partials of this N tile (CTAs nq*NS .. nq*NS+NS-1) ----
-        if (warp == 4) {
-          const long long t0 = clock64();
-          for (;;) {
-            const int v = lane < NS ? ld_acquire_gpu(pf + nq * NS + lane) : 1;
-            if (__all_sync(0xffffffffu, v >= 1)) break;
-            if (clock64() - t0 > SNT_MBAR_TIMEOUT_CYCLES) {
-              if (lane == 0) printf("snt: lstm bwd partial timeout block %d step %d\n", (int)blockIdx.x, t);
-              __trap();
-            }
-          }
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
-        if (stamp) DBG_STAMP(s, 7);
-      }
-      // ---- phase 2: final dL/dh for this CTA's units, cell backward, publish dG'_t ----
-#pragma unroll
-      for (int g = 0; g < UG; ++g) {
-        if (g > 0) load_inputs(t, g);
-        if (ok) {
-          float2 rec[4];
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) rec[kk] = make_float2(0.f, 0.f);
-          if (s > 0 && has_next) {
-            float2 x[NS][4];
-#pragma unroll
-            for (int k = 0; k < NS; ++k) {
-              const float* src = p.part + (((int64_t)m_blk * (NS * NS) + nq * NS + k) * 2 + par) * PB_PART_FLOATS +
-                                 (((int64_t)ks * KP + 4 * g) * 128 + row_l) * 8 + 2 * j;
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) x[k][kk] = __ldcg(reinterpret_cast<const float2*>(src + (int64_t)kk * 128 * 8));
-            }
-#pragma unroll
-            for (int k = 0; k < NS; ++k)  // fixed order: deterministic
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) { rec[kk].x += x[k][kk].x; rec[kk].y += x[k][kk].y; }
-          }
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint32_t a[4] = {a4[kk].x, a4[kk].y, a4[kk].z, a4[kk].w};
-            const float dhv[2] = {dh2[kk].x + rec[kk].x, dh2[kk].y + rec[kk].y};
-            const float cv[2] = {c2[kk].x, c2[kk].y}, pv[2] = {p2[kk].x, p2[kk].y};
-            uint32_t go[4];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float2 if_ = unpack_bf2(a[2 * e]), go_ = unpack_bf2(a[2 * e + 1]);
-              const float i_ = if_.x, f_ = if_.y, g_ = go_.x, o_ = go_.y;
-              const float tc_ = tanh_(cv[e]);
-              const float dh = dhv[e];
-              const float dc = dcreg[g][2 * kk + e] + dh * o_ * (1.f - tc_ * tc_);
-              go[2 * e] = pack_bf2(dc * g_ * i_ * (1.f - i_), dc * pv[e] * f_ * (1.f - f_));
-              go[2 * e + 1] = pack_bf2(dc * i_ * (1.f - g_ * g_), dh * tc_ * o_ * (1.f - o_));
-              dcreg[g][2 * kk + e] = dc * f_;
-            }
-            const int u = u0 + 8 * (4 * g + kk) + 2 * j;
-            *reinterpret_cast<uint4*>(p.dg + ((int64_t)pk.off[t] + row) * H4 + 4 * u) = make_uint4(go[0], go[1], go[2], go[3]);
-          }
-        }
-      }
-      if (stamp) DBG_STAMP(s, 8);
-      if (s + 1 < t_end) {
-        publish_fence();
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * PF_EPI_WARPS) : "memory");
-        if (threadIdx.x == 128)
-          atomicAdd(p.dgflag + ((int64_t)m_blk * p.T + t) * PB_FLAGS_PER_STEP + rank, 1);
-        if (stamp) DBG_STAMP(s, 9);
-        load_inputs(t - 1, 0);
       }
     }
   }
@@ -707,7 +746,328 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 256 * RB);
+  }
+}
+
+// PHASE-SPLIT variant (the default for RB = 2).  In the kernel above one group of 16 epilogue warps walks phase 1 and phase 2
+// of every item in turn, and with two row blocks per CTA those ~10k busy cycles per item - mostly fences and L2 round
+// trips - add up to more than the step's dependency chain (measured: BPTT 188 -> 300 us).  Here the two phases belong to
+// two warp groups that meet only through the global partial counters the finalisers poll anyway: P1 (4 warps, one per TMEM
+// lane quadrant) drains accumulators to the scratch and publishes "partial written"; P2 (16 warps, the coalesced row
+// mapping) sums the partials, runs the cell backward and publishes dG'.  P1 of the next item overlaps P2 of this one.
+// XRB = row blocks per CTA.  A step of this recurrence is a chain of L2 round trips (two counter exchanges, two fenced
+// publications) during which the CTA's tensor core, TMA ring and epilogue warps mostly wait.  With RB = 2 a CTA owns the
+// same weight slice for TWO consecutive 128-row blocks and every role walks the items (t, row block 0), (t, row block 1),
+// (t-1, row block 0), ... in that one order: while row block 0's step is on the wire, row block 1's is computed.  The
+// recurrence then needs half the CTAs (64 instead of 128 at B = 1024) for about the same wall time, and the step executor
+// runs the dW_out contraction on the SMs that are left (csrc/step.cu).  Item i depends only on items < i of the CTAs of
+// the same group, and every role of every CTA walks the items in the same order: no circular wait.
+template <int NS, int RB>
+__global__ void __launch_bounds__(PS_THREADS, 1)
+lstm_bwd_persistent_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ PackInfo pk, const PersistBwdParams p) {
+  using namespace tc;
+  constexpr int KB = 8;             // 512 gate columns per K-split
+  constexpr int WS = 128 / NS;      // units this CTA finalises
+  constexpr int UG = WS / 32;       // groups of 8 units per epilogue thread
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;                                 // KB x 16 KB, resident
+  uint8_t* sA = smem + KB * 16384;                    // PB_STAGES x 16 KB ring
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + PB_STAGES * 16384);
+  uint64_t* empty = full + PB_STAGES;
+  uint64_t* wbar = empty + PB_STAGES;
+  uint64_t* tfull = wbar + 1;                         // [RB][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2 * RB);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int rank = blockIdx.x % (NS * NS);
+  const int nq = rank / NS, ks = rank % NS;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < PB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(wbar, 1);
+    for (int i = 0; i < 2 * RB; ++i) mbar_init(&tfull[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256 * RB);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Row block r of this CTA is alive for steps [0, t_end[r]); going backward it starts at t_end[r] - 1.  Its step index
+  // s = t_end[r] - 1 - t counts from there; s = 0 has no recurrent term (no row of the block is alive at t + 1).
+  // batch_sizes is non-increasing, so t_end[0] >= t_end[1]; a row block past the end of the batch has t_end = 0.
+  int m_blk[RB], t_end[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    m_blk[r] = p.m_base + (int)(blockIdx.x / (NS * NS)) * RB + r;
+    int te = 0;
+    while (te < p.T && m_blk[r] * BM < pk.off[te + 1] - pk.off[te]) ++te;
+    t_end[r] = te;
+  }
+
+  if (warp == 0) {
+    // ============ TMA producer (lane 0 issues; lanes 0..NS-1 poll the CTAs that publish this K range) ============
+    int stage = 0;
+    uint32_t phase = 0;
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, (uint32_t)(KB * 16384));
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * 16384, &tmB, wbar, 512 * ks + kb * BK, 128 * nq);
+    }
+    for (int t = t_end[0] - 2; t >= 0; --t) {
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        if (t + 1 >= t_end[r]) continue;  // s = 0 (or row block not alive): nothing to contract
+        const int s = t_end[r] - 1 - t;
+        // gate columns 512ks + 64kb.. are units 128ks + 16kb..: finalised by CTA (nq' = ks, ks' = kb * NS / 8)
+        const int* f = p.dgflag + ((int64_t)m_blk[r] * p.T + (t + 1)) * PB_FLAGS_PER_STEP + ks * NS;
+        int kb = 0;
+        const long long t0 = clock64();
+        while (kb < KB) {
+          const int v = lane < NS ? ld_acquire_gpu(f + lane) : 0;
+          const unsigned waiting = __ballot_sync(0xffffffffu, lane < NS && v < 1);
+          const int ready = waiting ? (KB / NS) * (__ffs((int)waiting) - 1) : KB;
+          if (ready <= kb) {
+            if (clock64() - t0 > SNT_MBAR_TIMEOUT_CYCLES) {
+              if (lane == 0) printf("snt: lstm bwd persistent flag timeout block %d step %d\n", (int)blockIdx.x, t);
+              __trap();
+            }
+            continue;
+          }
+          if (lane == 0) {
+            if (kb == 0 && r == 0) DBG_STAMP(s, 0);
+            for (int k = kb; k < ready; ++k) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full[stage], 16384);
+              tma_load_2d(sA + stage * 16384, &tmA, &full[stage], 512 * ks + k * BK, pk.off[t + 1] + m_blk[r] * BM);
+              if (++stage == PB_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (ready == KB && r == 0) DBG_STAMP(s, 1);
+          }
+          kb = ready;
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ================= MMA issuer =================
+      constexpr uint32_t idesc = make_idesc_bf16(BM, 128, false, false);
+      mbar_wait(wbar, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t_end[0] - 2; t >= 0; --t) {
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          if (t + 1 >= t_end[r]) continue;
+          const int s = t_end[r] - 1 - t;
+          // accumulator (r, s & 1) is free: its previous reader (step s-2's phase 1) finished before dG'_{t+1} could exist
+          const uint32_t tmem_d = tmem_base + (uint32_t)(r * 256 + (s & 1) * 128);
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&full[stage], phase);
+            if (kb == 0 && r == 0) DBG_STAMP(s, 2);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(sA + stage * 16384);
+            const uint32_t b_addr = smem_u32(sW + kb * 16384);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_d, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
+                        idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty[stage]);
+            if (++stage == PB_STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (r == 0) DBG_STAMP(s, 3);
+          umma_commit(&tfull[r * 2 + (s & 1)]);
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ================= P1: TMEM -> scratch, one warp per lane quadrant, thread = one row of the tile =================
+    const int q = warp & 3;
+    const int row_l1 = q * 32 + lane;
+    constexpr int KP = WS / 8;          // 8-unit groups in a finaliser's slice
+    const bool stamp = threadIdx.x == 128;
+    for (int t = t_end[0] - 2; t >= 0; --t) {
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        if (t + 1 >= t_end[r]) continue;
+        const int s = t_end[r] - 1 - t;
+        const int par = s & 1;
+        int* pf = p.pflag + ((int64_t)m_blk[r] * p.T + t) * PB_FLAGS_PER_STEP;
+        float* my_part = p.part + ((int64_t)m_blk[r] * (NS * NS) + rank) * 2 * PB_PART_FLOATS;
+        mbar_wait(&tfull[r * 2 + par], (uint32_t)(((s >> 1) & 1) ^ (par ^ 1)));
+        if (stamp && r == 0) DBG_STAMP(s, 4);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {  // 32-column chunks of the 128-unit tile
+          uint32_t rr[32];
+          tmem_ld32(tmem_base + (uint32_t)(r * 256 + par * 128 + c * 32) + ((uint32_t)(q * 32) << 16), rr);
+          tmem_ld_wait();
+          const int x0 = 32 * c;  // tile column -> (finalizer slice, 8-unit group inside the slice)
+          float* base = my_part + (int64_t)par * PB_PART_FLOATS +
+                        (((int64_t)(x0 / WS) * KP + (x0 % WS) / 8) * 128 + row_l1) * 8;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            float4* dst = reinterpret_cast<float4*>(base + (int64_t)kk * 128 * 8);
+            __stcg(dst, make_float4(__uint_as_float(rr[8 * kk]), __uint_as_float(rr[8 * kk + 1]),
+                                    __uint_as_float(rr[8 * kk + 2]), __uint_as_float(rr[8 * kk + 3])));
+            __stcg(dst + 1, make_float4(__uint_as_float(rr[8 * kk + 4]), __uint_as_float(rr[8 * kk + 5]),
+                                        __uint_as_float(rr[8 * kk + 6]), __uint_as_float(rr[8 * kk + 7])));
+          }
+        }
+        tcgen05_fence_before();
+        if (stamp && r == 0) DBG_STAMP(s, 5);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) atomicAdd(pf + rank, 1);
+        if (stamp && r == 0) DBG_STAMP(s, 6);
+      }
+    }
+  } else if (warp >= 8) {
+    // ================= P2: cell backward.  Threads are mapped so that global accesses coalesce: warp wi owns rows
+    // 8wi..8wi+7, the 4 lanes of a row own interleaved unit pairs {8k + 2j, 8k + 2j + 1}, so one store instruction writes
+    // 64 contiguous bytes of dG' per row (and one scratch load reads 256 contiguous bytes). =================
+    const int wi = warp - 8, j = lane & 3;
+    const int row_l = wi * 8 + (lane >> 2);
+    const int H = p.H, H4 = 4 * p.H;
+    const int u0 = 128 * nq + WS * ks;  // first unit this CTA finalises
+    constexpr int KP = WS / 8;          // 8-unit groups in this CTA's slice
+    const bool stamp = threadIdx.x == 256;
+    float dcreg[RB][UG][8];
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+      for (int g = 0; g < UG; ++g)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dcreg[r][g][u] = 0.f;
+    // inputs of one item (step t of row block mb) for this thread's row and the 4 unit pairs k = 4g..4g+3
+    float2 dh2[4], c2[4], p2[4];
+    uint4 a4[4];
+    auto load_inputs = [&](int t, int mb, int g) {
+      const int bs = pk.off[t + 1] - pk.off[t];
+      const int row = mb * BM + row_l;
+      if (row < bs) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int u = u0 + 8 * (4 * g + kk) + 2 * j;
+          const int64_t o1 = ((int64_t)pk.off[t] + row) * H + u;
+          dh2[kk] = *reinterpret_cast<const float2*>(p.d_hs + o1);
+          c2[kk] = *reinterpret_cast<const float2*>(p.cs + o1);
+          p2[kk] = t > 0 ? *reinterpret_cast<const float2*>(p.cs + ((int64_t)pk.off[t - 1] + row) * H + u)
+                         : make_float2(0.f, 0.f);
+          a4[kk] = *reinterpret_cast<const uint4*>(p.act + ((int64_t)pk.off[t] + row) * H4 + 4 * u);
+        }
+      }
+    };
+    if (t_end[0] > 0) load_inputs(t_end[0] - 1, m_blk[0], 0);
+    for (int t = t_end[0] - 1; t >= 0; --t) {
+      const int bs = pk.off[t + 1] - pk.off[t];
+      const int bs_next = t + 1 < p.T ? pk.off[t + 2] - pk.off[t + 1] : 0;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        if (t >= t_end[r]) continue;
+        const int s = t_end[r] - 1 - t;
+        const int row = m_blk[r] * BM + row_l;
+        const bool ok = row < bs;
+        const bool has_next = row < bs_next;  // rows still alive at step t+1 carry recurrent gradient
+        const int par = s & 1;
+        const int* pf = p.pflag + ((int64_t)m_blk[r] * p.T + t) * PB_FLAGS_PER_STEP;
+        if (s > 0) {
+          // ---- wait for the NS partials of this N tile (P1 of CTAs nq*NS .. nq*NS+NS-1, this CTA's among them) ----
+          if (warp == 8) {
+            const long long t0 = clock64();
+            for (;;) {
+              const int v = lane < NS ? ld_acquire_gpu(pf + nq * NS + lane) : 1;
+              if (__all_sync(0xffffffffu, v >= 1)) break;
+              if (clock64() - t0 > SNT_MBAR_TIMEOUT_CYCLES) {
+                if (lane == 0) printf("snt: lstm bwd partial timeout block %d step %d\n", (int)blockIdx.x, t);
+                __trap();
+              }
+            }
+          }
+          asm volatile("bar.sync 2, 512;" ::: "memory");
+          if (stamp && r == 0) DBG_STAMP(s, 7);
+        }
+        // ---- final dL/dh for this CTA's units, cell backward, publish dG'_t ----
+#pragma unroll
+        for (int g = 0; g < UG; ++g) {
+          if (g > 0) load_inputs(t, m_blk[r], g);
+          if (ok) {
+            float2 rec[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) rec[kk] = make_float2(0.f, 0.f);
+            if (s > 0 && has_next) {
+              float2 x[NS][4];
+#pragma unroll
+              for (int k = 0; k < NS; ++k) {
+                const float* src = p.part + (((int64_t)m_blk[r] * (NS * NS) + nq * NS + k) * 2 + par) * PB_PART_FLOATS +
+                                   (((int64_t)ks * KP + 4 * g) * 128 + row_l) * 8 + 2 * j;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) x[k][kk] = __ldcg(reinterpret_cast<const float2*>(src + (int64_t)kk * 128 * 8));
+              }
+#pragma unroll
+              for (int k = 0; k < NS; ++k)  // fixed order: deterministic
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) { rec[kk].x += x[k][kk].x; rec[kk].y += x[k][kk].y; }
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t a[4] = {a4[kk].x, a4[kk].y, a4[kk].z, a4[kk].w};
+              const float dhv[2] = {dh2[kk].x + rec[kk].x, dh2[kk].y + rec[kk].y};
+              const float cv[2] = {c2[kk].x, c2[kk].y}, pv[2] = {p2[kk].x, p2[kk].y};
+              uint32_t go[4];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float2 if_ = unpack_bf2(a[2 * e]), go_ = unpack_bf2(a[2 * e + 1]);
+                const float i_ = if_.x, f_ = if_.y, g_ = go_.x, o_ = go_.y;
+                const float tc_ = tanh_(cv[e]);
+                const float dh = dhv[e];
+                const float dc = dcreg[r][g][2 * kk + e] + dh * o_ * (1.f - tc_ * tc_);
+                go[2 * e] = pack_bf2(dc * g_ * i_ * (1.f - i_), dc * pv[e] * f_ * (1.f - f_));
+                go[2 * e + 1] = pack_bf2(dc * i_ * (1.f - g_ * g_), dh * tc_ * o_ * (1.f - o_));
+                dcreg[r][g][2 * kk + e] = dc * f_;
+              }
+              const int u = u0 + 8 * (4 * g + kk) + 2 * j;
+              *reinterpret_cast<uint4*>(p.dg + ((int64_t)pk.off[t] + row) * H4 + 4 * u) = make_uint4(go[0], go[1], go[2], go[3]);
+            }
+          }
+        }
+        if (stamp && r == 0) DBG_STAMP(s, 8);
+        if (t > 0) {
+          publish_fence();
+          asm volatile("bar.sync 3, 512;" ::: "memory");
+          if (threadIdx.x == 256)
+            atomicAdd(p.dgflag + ((int64_t)m_blk[r] * p.T + t) * PB_FLAGS_PER_STEP + rank, 1);
+          if (stamp && r == 0) DBG_STAMP(s, 9);
+        }
+        // inputs of the next item in the walk: the next alive row block of this step, else row block 0 of step t - 1
+        {
+          bool found = false;
+#pragma unroll
+          for (int r2 = r + 1; r2 < RB; ++r2)
+            if (!found && t < t_end[r2]) { load_inputs(t, m_blk[r2], 0); found = true; }
+          if (!found && t > 0) load_inputs(t - 1, m_blk[0], 0);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 256 * RB);
   }
 }
 
@@ -821,7 +1181,7 @@ template <class Params>
 static int launch_persistent(void (*k1)(CUtensorMap, CUtensorMap, PackInfo, Params),
                              void (*k4)(CUtensorMap, CUtensorMap, PackInfo, Params), int ctas, int num_n, size_t smem,
                              const CUtensorMap& ta, const CUtensorMap& tb, const PackInfo& pk, const Params& pp,
-                             cudaStream_t st) {
+                             cudaStream_t st, int threads = PF_THREADS) {
   static int mode = -1;  // per instantiation: 4 = clusters of 4 fit, 1 = no clusters
   // Measured on B200 (profiles/r01_lstm_persistent_timeline.txt): clusters of 4 with multicast loads do not shorten the
   // per-step exchange (L2 already serves the 4 unicast requests of a line from one fill), and cooperative + cluster
@@ -835,7 +1195,7 @@ static int launch_persistent(void (*k1)(CUtensorMap, CUtensorMap, PackInfo, Para
     SNT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)ctas);
-    cfg.blockDim = dim3(PF_THREADS);
+    cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -1069,6 +1429,30 @@ int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const flo
 static thread_local cudaEvent_t g_bptt_gate = nullptr;
 void lstm_bwd_gate_event(cudaEvent_t e) { g_bptt_gate = e; }
 bool lstm_bwd_is_persistent(int64_t H) { return (H == 256 || H == 512) && !getenv("SNT_NO_PERSISTENT"); }
+// Row blocks per CTA of the persistent BPTT kernel.  Measured at B = 1024 / H = 512 (profiles/r02_bptt_row_blocks.txt):
+// one row block per CTA on 128 SMs 188 us; two per CTA on 64 SMs 302 us in order, 277 us phase-split, 317 us with every
+// role serving whichever chain is ready first.  A step moves ~290 KB per row block through the SM's L2 port (128 KB of
+// dG', 64 KB of partials out and in, the cell inputs), which is already half of the 9.4 us chain, so two chains on one SM
+// cannot hide in each other's latency.  Two row blocks per CTA therefore only where the batch would otherwise need
+// several launches (more row blocks than fit side by side): one 277 us launch instead of two 188 us ones.
+// SNT_PERSIST_RB=1|2 forces either.
+static int bptt_row_blocks_per_cta(int num_m0, int group) {
+  const char* e = getenv("SNT_PERSIST_RB");
+  if (e && atoi(e) == 1) return 1;
+  if (e && atoi(e) == 2) return num_m0 >= 2 ? 2 : 1;
+  return num_m0 > group ? 2 : 1;
+}
+// CTAs (= SMs: one CTA per SM) the widest launch of the persistent BPTT recurrence occupies for a batch of B sequences;
+// 0 when the recurrence of this hidden size runs as per-step launches.
+int lstm_bwd_persistent_ctas(int64_t B, int64_t H) {
+  if (!lstm_bwd_is_persistent(H)) return 0;
+  const int ns = (int)(H / 128), num_m0 = (int)((B + tc::BM - 1) / tc::BM);
+  const int group = tc::sm_count() / (ns * ns);
+  if (group < 1) return 0;
+  const int rb = bptt_row_blocks_per_cta(num_m0, group);
+  const int groups = (num_m0 + rb - 1) / rb;
+  return (groups < group ? groups : group) * ns * ns;
+}
 
 int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* cs, const void* hprev,
              const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh, float* d_w_ih,
@@ -1113,15 +1497,24 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
       cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * SNT_MAX_T * 12, st);
       pp.dbg = dbg_dev;
 #endif
-      for (int m0 = 0; m0 < num_m0; m0 += group) {
+      // rb row blocks per CTA (see the kernel): a launch covers up to group * rb row blocks
+      const int rb = bptt_row_blocks_per_cta(num_m0, group);
+      for (int m0 = 0; m0 < num_m0; m0 += group * rb) {
         pp.m_base = m0;
-        const int nb = num_m0 - m0 < group ? num_m0 - m0 : group;
+        const int nb = num_m0 - m0 < group * rb ? num_m0 - m0 : group * rb;
+        const int ctas = ((nb + rb - 1) / rb) * ns * ns;
+        // two row blocks per CTA: the phase-split kernel (SNT_BPTT_MODE=seq: one epilogue group walks both phases)
+        const char* me = getenv("SNT_BPTT_MODE");
+        const bool ps = rb == 2 && !(me && !strcmp(me, "seq"));
+        void (*kern)(CUtensorMap, CUtensorMap, PackInfo, PersistBwdParams);
         if (ns == 4)
-          SNT_CHECK(launch_persistent<PersistBwdParams>(lstm_bwd_persistent_kernel<4>, nullptr, nb * ns * ns, 1, smem,
-                                                        ta, tb, pk, pp, st));
+          kern = rb == 1 ? lstm_bwd_persistent_kernel<4, 1>
+                         : ps ? lstm_bwd_persistent_ps_kernel<4, 2> : lstm_bwd_persistent_kernel<4, 2>;
         else
-          SNT_CHECK(launch_persistent<PersistBwdParams>(lstm_bwd_persistent_kernel<2>, nullptr, nb * ns * ns, 1, smem,
-                                                        ta, tb, pk, pp, st));
+          kern = rb == 1 ? lstm_bwd_persistent_kernel<2, 1>
+                         : ps ? lstm_bwd_persistent_ps_kernel<2, 2> : lstm_bwd_persistent_kernel<2, 2>;
+        SNT_CHECK(launch_persistent<PersistBwdParams>(kern, nullptr, ctas, 1, smem, ta, tb, pk, pp, st,
+                                                      ps ? PS_THREADS : PF_THREADS));
       }
 #ifdef SNT_LSTM_DBG
       {

@@ -38,14 +38,6 @@ __global__ void scale_scalar_kernel(float* x, float s) { x[0] *= s; }
 
 inline int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
 
-// SMs left over next to the persistent recurrence kernels (8 row blocks x 16 CTAs = 128 at H = 512), minus the SMs
-// reserved for collectives in flight (snt_set_sm_reserve): the width of the narrow column-sum grid that runs beside the
-// BPTT.  At least 8, so that the pass still ends within the recurrence.
-int free_sms_beside_recurrence() {
-  const int f = tc::grid_sms() - 128;
-  return f < 8 ? 8 : f;
-}
-
 // Optional per-stage timing (snt_step_profile): one CUDA-event pair per stage slot, recorded on the stream the stage is
 // enqueued on.  Off by default (no events, no overhead).
 enum { ST_HEAD_F = 0, ST_EMBED_F = 1, ST_LSTM_F = 2, ST_CE_F = 10, ST_CE_B = 11, ST_LSTM_B = 12, ST_EMBED_B = 20,
@@ -71,6 +63,15 @@ struct StageTimer {
   }
 };
 
+// dW_out beside the BPTT recurrence (see snt_step_run): bf16 mode, the recurrence runs as the persistent kernel and leaves
+// at least a third of the SMs free, and the two side streams exist.
+bool dw_out_beside_bptt(int prec, int64_t B, int64_t H) {
+  if (prec != SNT_PREC_BF16 || getenv("SNT_NO_BIAS_DEFER") || getenv("SNT_NO_DW_DEFER")) return false;
+  if (!side_stream(1) || !side_stream(2)) return false;
+  const int ctas = bf16::lstm_bwd_persistent_ctas(B, H);
+  return ctas > 0 && tc::grid_sms() - ctas >= tc::grid_sms() / 3;
+}
+
 struct Layer { float* gates; float* cs; void* hs; void* hprev; };
 struct StepBufs {
   float *feats, *yhat, *rstd;
@@ -80,6 +81,8 @@ struct StepBufs {
   float *lse, *inv_s, *d_hs, *dx[2];
   void *u, *hs_scaled, *w_bf16;
   float *bias_part, *bias_db;  // scratch of the deferred d_b_out column sums (bf16 mode)
+  float* dw_sws;               // split-K scratch of the deferred dW_out contraction (bf16 mode, persistent BPTT)
+  int64_t dw_sws_elems;
   void *scratch, *head_ws, *emb_ws;
   int64_t scratch_bytes, head_bytes, emb_bytes;
   bool ok;
@@ -134,6 +137,8 @@ StepBufs carve(int prec, int L, int64_t B, int64_t N, int64_t E, int64_t H, int6
   b.head_ws = K > 0 ? w.take<char>(b.head_bytes) : nullptr;
   b.emb_bytes = snt_embed_bwd_workspace_bytes(N, V);
   b.emb_ws = w.take<char>(b.emb_bytes);
+  b.dw_sws_elems = (prec == SNT_PREC_BF16 && bf16::lstm_bwd_is_persistent(H)) ? bf16::vocab_ce_train_sws_elems(N, H, V) : 0;
+  b.dw_sws = b.dw_sws_elems > 0 ? w.take<float>(b.dw_sws_elems) : nullptr;
   b.ok = w.ok();
   return b;
 }
@@ -164,8 +169,11 @@ extern "C" int64_t snt_step_workspace_bytes(int prec, int L, int64_t B, int64_t 
   add(stage_scratch_bytes(prec, L, B, N, E, H, V, K));
   if (K > 0) add(snt_head_workspace_bytes(prec, B, K, E));
   add(snt_embed_bwd_workspace_bytes(N, V));
+  if (prec == SNT_PREC_BF16 && bf16::lstm_bwd_is_persistent(H)) add(bf16::vocab_ce_train_sws_elems(N, H, V) * 4);
   return t;
 }
+
+extern "C" int snt_step_overlaps_dw_out(int prec, int64_t B, int64_t H) { return dw_out_beside_bptt(prec, B, H) ? 1 : 0; }
 
 extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
   SNT_REQUIRE(d != nullptr && d->struct_bytes == (int32_t)sizeof(snt_step),
@@ -207,6 +215,17 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
   const bool background = side != nullptr && cudaStreamGetPriority((cudaStream_t)stream, &st_prio) == cudaSuccess &&
                           st_prio < 0 && !getenv("SNT_NO_BACKGROUND");
   const bool defer_bias = bf && side != nullptr && bf16::lstm_bwd_is_persistent(H) && !getenv("SNT_NO_BIAS_DEFER");
+  // dW_out beside the BPTT too: the recurrence needs dHs only, and with two row blocks per CTA (csrc/lstm_tc.cu) it
+  // occupies 64 of the 148 SMs at batch 1024.  The contraction runs on its own side stream from a grid capped at the SMs
+  // the recurrence leaves free, released by the same gate event as the column sums.  Only when this call covers both
+  // phases (d_w_out is final when BWD_LSTM ends: a caller that exchanges linear.weight between the two phases runs them
+  // separately and keeps the contraction in BWD_CE), and only when enough SMs are left for it to end within the
+  // recurrence.
+  SideStream* side_dw = side_stream(2);
+  const int bptt_ctas = bf ? bf16::lstm_bwd_persistent_ctas(B, H) : 0;
+  const int free_sms = tc::grid_sms() - bptt_ctas;
+  const bool defer_dw = defer_bias && side_dw != nullptr && (phases & SNT_STEP_BWD_CE) && (phases & SNT_STEP_BWD_LSTM) &&
+                        b.dw_sws != nullptr && dw_out_beside_bptt(prec, B, H);
 
   if (phases & SNT_STEP_FWD) {
     if (side) {  // token-dependent half of the embedding gradient: needs the captions only
@@ -261,7 +280,7 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
     StageTimer tm(ST_CE_B, st);
     if (bf)  // with a side stream, d_b_out is deferred to the BPTT phase (below)
       SNT_CHECK(bf16::vocab_ce_train_bwd(b.u, b.inv_s, b.hs_scaled, b.w_bf16, nullptr, d->grad_scale, N, H, V, b.d_hs,
-                                         d->d_w_out, d->d_b_out, b.scratch, b.scratch_bytes, st, defer_bias));
+                                         d->d_w_out, d->d_b_out, b.scratch, b.scratch_bytes, st, defer_bias, defer_dw));
     else
       SNT_CHECK(snt_vocab_ce_bwd(prec, hs_last, d->w_out, d->b_out, targets, b.lse, nullptr, d->grad_scale, N, H, V,
                                  b.d_hs, d->d_w_out, d->d_b_out, b.scratch, b.scratch_bytes, st));
@@ -287,8 +306,9 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
         SNT_CUDA(cudaEventRecord(side->fork, st));
       }
       bias_pending = true;
-      bias_blocks = background ? 0 : free_sms_beside_recurrence();
+      bias_blocks = background ? 0 : (defer_dw ? 8 : (free_sms < 8 ? 8 : free_sms));
     }
+    const int dw_ctas = background ? free_sms : free_sms - 8;
     const float* d_out = b.d_hs;
     for (int k = L - 1; k >= 0; --k) {
       SNT_REQUIRE(d->d_w_ih[k] && d->d_w_hh[k] && d->d_b_ih[k] && d->d_b_hh[k],
@@ -308,10 +328,17 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
         SNT_CHECK(bf16::vocab_ce_train_bias(b.u, b.inv_s, nullptr, d->grad_scale, N, V, d->d_b_out, b.bias_part,
                                             b.bias_db, side->s, bias_blocks));
         SNT_CUDA(cudaEventRecord(side->aux, side->s));
+        if (defer_dw) {
+          SNT_CUDA(cudaStreamWaitEvent(side_dw->s, side->fork, 0));
+          SNT_CHECK(bf16::vocab_ce_train_dw(b.u, b.hs_scaled, nullptr, d->grad_scale, N, H, V, d->d_w_out, b.dw_sws,
+                                            b.dw_sws_elems, side_dw->s, dw_ctas));
+          SNT_CUDA(cudaEventRecord(side_dw->join, side_dw->s));
+        }
       }
       d_out = dx;
     }
     if (defer_bias) SNT_CUDA(cudaStreamWaitEvent(st, side->aux, 0));  // d_b_out is final when this phase ends
+    if (defer_dw) SNT_CUDA(cudaStreamWaitEvent(st, side_dw->join, 0));  // and so is d_w_out
   }
 
   if (phases & SNT_STEP_BWD_TAIL) {

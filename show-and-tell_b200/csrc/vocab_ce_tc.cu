@@ -900,9 +900,25 @@ int vocab_ce_train_bias(const void* u, const float* inv_s, const float* dloss, f
   return SNT_OK;
 }
 
+// The dW_out half of vocab_ce_train_bwd(defer_dw = true) on any stream, from a grid of at most `max_ctas` CTAs (0: all
+// SMs), with caller-owned split-K scratch of vocab_ce_train_sws_elems(N, H, V) floats: the call may overlap later stages
+// that reuse the stage workspace.
+int64_t vocab_ce_train_sws_elems(int64_t N, int64_t H, int64_t V) { return train_sws_elems(N, H, V); }
+int vocab_ce_train_dw(const void* u, const void* hs_scaled, const float* dloss, float grad_scale, int64_t N, int64_t H,
+                      int64_t V, float* d_w_out, float* sws, int64_t sws_elems, cudaStream_t st, int max_ctas) {
+  SNT_REQUIRE(u && hs_scaled && d_w_out, "vocab_ce_train_dw: NULL argument");
+  const int bn = H >= 256 ? 256 : 128;
+  const int old_cap = tc::set_grid_cap(max_ctas);
+  const int rc = tc::gemm_tc_balanced(true, true, V, H, N, grad_scale / (float)N, (const bf*)u, pad8(V),
+                                      (const bf*)hs_scaled, H, d_w_out, H, sws, sws_elems, st, dloss, bn);
+  tc::set_grid_cap(old_cap);
+  return rc;
+}
+
 int vocab_ce_train_bwd(const void* u, const float* inv_s, const void* hs_scaled, const void* w_bf16,
                        const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
-                       float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st, bool defer_bias) {
+                       float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st, bool defer_bias,
+                       bool defer_dw) {
   if (H % 8 != 0) { set_error("bf16 mode: H=%lld must be a multiple of 8", (long long)H); return SNT_EUNSUPPORTED; }
   CeTrainWs w = carve_train(ws, ws_bytes, N, H, V);
   if (!w.ok) { set_error("bf16 vocab_ce_train_bwd: workspace too small"); return SNT_EWORKSPACE; }
@@ -927,8 +943,10 @@ int vocab_ce_train_bwd(const void* u, const float* inv_s, const void* hs_scaled,
   SNT_CHECK(tc::gemm_tc_balanced(false, true, N, H, V, scale, ub, w.Vp, wb, H, d_hs, H, w.sws, sws_elems, st, dloss, bn,
                                  inv_s));
   // dW_out[V,H] = scale * U'^T[V,N] . (r * Hs)[N,H]          (both operands MN-major)
-  SNT_CHECK(tc::gemm_tc_balanced(true, true, V, H, N, scale, ub, w.Vp, (const bf*)hs_scaled, H, d_w_out, H, w.sws,
-                                 sws_elems, st, dloss, bn));
+  // (defer_dw: the caller runs vocab_ce_train_dw beside the persistent BPTT recurrence, which needs dHs only)
+  if (!defer_dw)
+    SNT_CHECK(tc::gemm_tc_balanced(true, true, V, H, N, scale, ub, w.Vp, (const bf*)hs_scaled, H, d_w_out, H, w.sws,
+                                   sws_elems, st, dloss, bn));
   if (side) {
     SNT_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   } else if (!defer_bias) {

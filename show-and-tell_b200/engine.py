@@ -243,6 +243,11 @@ class StepEngine:
     def run(self, phases=PH_ALL):
         _lib.call("snt_step_run", C.c_void_p(C.addressof(self.d)), int(phases), _lib.stream_ptr())
 
+    def overlaps_dw_out(self):
+        """True when run(PH_BWD_CE | PH_BWD_LSTM [| ...]) of the prepared batch computes d_w_out beside the BPTT recurrence:
+        linear.weight's gradient is then final after BWD_LSTM only (include/snt_b200.h: snt_step_overlaps_dw_out)."""
+        return bool(self.lib.snt_step_overlaps_dw_out(int(self.d.prec), int(self.d.B), int(self.d.H)))
+
     def profile(self, enable=True):
         _lib.check(self.lib.snt_step_profile(1 if enable else 0), "snt_step_profile")
 

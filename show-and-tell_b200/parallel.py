@@ -183,12 +183,14 @@ class DataParallelStep:
         # (priority between the step's stream and the executor's side streams: when thread slots free up on an SM the
         # exchange blocks are placed before more column-sum blocks, but never before the step's own kernels)
         self._xstream = torch.cuda.Stream(device=flat.p.device, priority=-1)
+        self._xstream2 = torch.cuda.Stream(device=flat.p.device, priority=-1)   # last bucket, when the first two are late
+        self._defer_dw = os.environ.get("SNT_DP_DEFER_DW", "1") != "0"
         sms = torch.cuda.get_device_properties(flat.p.device).multi_processor_count
         self._narrow = 8 * max(8, sms - 128)  # blocks of a bucket exchanged beside the cooperative recurrence kernel
         self._pipelined = os.environ.get("SNT_DP_PIPELINE", "1") != "0"
         self._dbg = [] if os.environ.get("SNT_DP_DEBUG") else None     # (bucket, _, events) per exchange: exchange_report()
 
-    def _exchange_bucket(self, bucket, channel, narrow):
+    def _exchange_bucket(self, bucket, channel, narrow, xstream=None):
         """Exchange + update of one readiness bucket on the exchange stream, ordered after everything enqueued so far on
         the step's stream: barrier (this bucket's gradients are final on every rank) -> snt_dp_adam_shard."""
         hg, hp = self._symm
@@ -197,8 +199,9 @@ class DataParallelStep:
         ev.record(cur)
         lo, hi = self._bucket_shard[bucket]
         dbg = self._dbg
-        with torch.cuda.stream(self._xstream):
-            self._xstream.wait_event(ev)
+        xstream = xstream or self._xstream
+        with torch.cuda.stream(xstream):
+            xstream.wait_event(ev)
             if dbg is not None:
                 e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
                 e[0].record()
@@ -343,12 +346,23 @@ class DataParallelStep:
             # broadcast while the BPTT runs (on the SMs the recurrence leaves free), the LSTM weights during the tail of
             # backward; only embed.weight + head remain for the end of the step
             self.t += 1
-            eng.run(PH_FWD | PH_BWD_CE)
-            self._exchange_bucket("early", 0, narrow=True)
-            eng.run(PH_BWD_LSTM)
-            self._exchange_bucket("mid", 1, narrow=True)
-            eng.run(PH_BWD_TAIL)
-            self._exchange_bucket("late", 2, narrow=False)
+            if self._defer_dw and eng.overlaps_dw_out():
+                # the executor runs the d_w_out contraction BESIDE the BPTT recurrence (csrc/step.cu): linear.weight is
+                # final after BWD_LSTM, so its exchange moves next to the tail of backward and the last bucket goes on a
+                # second exchange stream (its own barrier channel), so that it does not queue behind the first two
+                eng.run(PH_FWD | PH_BWD_CE | PH_BWD_LSTM)
+                self._exchange_bucket("early", 0, narrow=True)
+                self._exchange_bucket("mid", 1, narrow=True)
+                eng.run(PH_BWD_TAIL)
+                self._exchange_bucket("late", 2, narrow=False, xstream=self._xstream2)
+                self._xstream.wait_stream(self._xstream2)
+            else:
+                eng.run(PH_FWD | PH_BWD_CE)
+                self._exchange_bucket("early", 0, narrow=True)
+                eng.run(PH_BWD_LSTM)
+                self._exchange_bucket("mid", 1, narrow=True)
+                eng.run(PH_BWD_TAIL)
+                self._exchange_bucket("late", 2, narrow=False)
             with torch.cuda.stream(self._xstream):
                 self._symm[1].barrier(3)                      # every rank's parameters have arrived
             torch.cuda.current_stream(flat.p.device).wait_stream(self._xstream)

@@ -63,7 +63,12 @@ def test_native_step_equals_autograd_path(prec, B, E, H, V, L, head):
         loss_n = float(st.step(inp, caps, b["lengths"], targets))
         assert loss_n == loss_a
         for k, v in g_a.items():
-            assert torch.equal(st.flat.grad(_native_names(k)), v), k
+            g = st.flat.grad(_native_names(k))
+            if k == "linear.weight" and st.engine.overlaps_dw_out():
+                # the executor runs this contraction beside the BPTT from a narrower grid: another K split, same products
+                assert rel_err(g.cpu().numpy(), v.cpu().numpy()) < 1e-4, k
+            else:
+                assert torch.equal(g, v), k
         if enc2 is not None:
             assert torch.equal(enc2.bn.running_mean, stats_a[0]) and torch.equal(enc2.bn.running_var, stats_a[1])
     assert dec2.linear.weight.grad is st.flat.grad("linear.weight")      # param.grad is the flat buffer's slice

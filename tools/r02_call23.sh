@@ -1,0 +1,18 @@
+# RB=2 BPTT kernel + dW_out beside the recurrence: correctness first, then A/B timings
+set -u
+O=gpurun_out/r02b; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_step.py tests/test_gpu_fullsize.py -x -q > $O/t1.log 2>&1; echo "pytest step+fullsize rc=$?"; tail -4 $O/t1.log
+B="python bench.py --gpus 1 --steps 30 --warmup 5 --no-cpu-baseline --no-greedy --no-extras --no-gpu-reference --stages"
+for v in default nodefer rb1; do
+  case $v in default) E="";; nodefer) E="SNT_NO_DW_DEFER=1";; rb1) E="SNT_PERSIST_RB=1 SNT_NO_DW_DEFER=1";; esac
+  env $E timeout 300 $B > $O/bench_$v.json 2> $O/bench_$v.err; echo "bench $v rc=$?"
+  python - <<PY
+import json
+try:
+    d=json.loads([l for l in open('$O/bench_$v.json') if l.startswith('{')][-1])
+    print('$v', 'value',round(d['value']),'ms',round(d['ms_per_step'],4),'e2e',round(d['e2e']['value']), 'loss', d.get('loss'))
+    print('  ', [(s['stage'],round(s['us_per_step'],1)) for s in d['stages']])
+except Exception as e:
+    print('$v failed', e); print(open('$O/bench_$v.err').read()[-1500:])
+PY
+done
