@@ -14,7 +14,7 @@ value   : train captions/s with the inputs resident in HBM, CUDA events, max ove
           NB = 8 DISTINCT ragged batches (different lengths, tokens and features each), so nothing depends on one
           replayed batch signature; `fixed_batch` repeats batch 0 for comparison.
 e2e     : the same loop with HOST (pinned) inputs: every step pays the H2D copies of its own pooled features and
-          captions (double-buffered on a side stream) and a D2H read of its loss inside the timed region.
+          captions (three slots, on a side stream) and a D2H read of its loss inside the timed region.
 roofline: the stage with the largest share of the step, timed by CUDA events inside snt_step_run (snt_step_profile);
           `traffic` is read from the ncu capture committed under profiles/ (profiles/r02_traffic.json), never a literal.
 greedy  : the second half of BASELINE's metric - greedy sample() of 4096 image features per GPU x 20 tokens
@@ -440,7 +440,7 @@ class Workload:
 
 
 class E2E:
-    """Host-input loop: step i's H2D copies are issued on a side stream while step i-1 computes (double buffered), and
+    """Host-input loop: step i's H2D copies are issued on a side stream while step i-1 computes (three slots), and
     the loss of step i-1 is read back (pinned D2H + event) while step i runs; every step still pays its own copies and
     its own loss read inside the timed region."""
 
@@ -451,23 +451,26 @@ class E2E:
         tc = max(b["hc"].shape[1] for b in wl.batches)
         self.bufs = [dict(p=torch.empty_like(wl.batches[0]["dp"]),
                           c=torch.empty(wl.b_local, tc, dtype=torch.int64, device=dev),
-                          ev=torch.cuda.Event(), done=torch.cuda.Event()) for _ in range(2)]
+                          ev=torch.cuda.Event(), done=torch.cuda.Event()) for _ in range(3)]
         self.loss_host = torch.zeros(1).pin_memory()
         self.loss_ev = torch.cuda.Event()
         self.i, self.pending, self.last = 0, False, float("nan")
         self.h2d = int(np.mean([b["hp"].numel() * 4 + b["hc"].numel() * 8 for b in wl.batches]))
 
     def _issue(self, k):
-        b, src = self.bufs[k & 1], self.wl.batches[k % len(self.wl.batches)]
+        b, src = self.bufs[k % 3], self.wl.batches[k % len(self.wl.batches)]
         with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(b["done"])          # the step that last used this slot has finished
+            # Three slots: the slot's last user is step k - 3, finished long ago, so the copy never waits and is not tied to a
+            # step boundary.  With two slots it could only start when step k - 2 ended, i.e. it ran beside the head of the
+            # next step, and that loop measured 40-90 us per step slower (profiles/r02_e2e_copy_window.txt).
+            self.copy_stream.wait_event(b["done"])
             b["p"].copy_(src["hp"], non_blocking=True)
             b["c"][:, :src["hc"].shape[1]].copy_(src["hc"], non_blocking=True)
             b["ev"].record(self.copy_stream)
 
     def step(self):
         wl, i = self.wl, self.i
-        b, src = self.bufs[i & 1], wl.batches[i % len(wl.batches)]
+        b, src = self.bufs[i % 3], wl.batches[i % len(wl.batches)]
         if i == 0:
             self._issue(0)
         self._issue(i + 1)                                  # prefetch the next step's inputs

@@ -15,12 +15,30 @@ int wgrad_tn(const float* dy, const float* a, int64_t M, int64_t N, int64_t K, f
              int64_t ws_bytes, cudaStream_t st);
 
 int64_t lstm_ws_bytes(int64_t N, int64_t B, int64_t In, int64_t H);
+// What lstm_fwd / lstm_bwd derive from the fp32 weights before their first contraction (gate-interleaved bf16 copies, the
+// summed bias, the transposed W_hh' of the persistent BPTT kernel) and the regions they clear (h_{-1}, arrival
+// counters).  A caller that runs whole steps (csrc/step.cu) prepares all of it in caller-owned memory with
+// lstm_prepare() on a side stream, beside the encoder head, and hands it to both calls: they then launch no preparation
+// kernel of their own.
+struct LstmPrepared {
+  __nv_bfloat16* w_ih;    // [4H, In]
+  __nv_bfloat16* w_hh;    // [4H, H]
+  __nv_bfloat16* w_hh_t;  // [H, 4H]
+  float* bsum;            // [4H]
+  int* flags_fwd;         // lstm_prepared_flag_ints(B) each, cleared by lstm_prepare
+  int* flags_bwd;
+};
+int64_t lstm_prepared_flag_ints(int64_t B);
+// also clears the first B*H elements of `hprev` (h_{-1} = 0)
+int lstm_prepare(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int64_t In, int64_t H,
+                 int64_t B, const LstmPrepared& out, void* hprev, cudaStream_t st);
 int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh,
              const float* b_ih, const float* b_hh, float* gates, float* cs, void* hs, void* hprev, void* ws,
-             int64_t ws_bytes, cudaStream_t st);
+             int64_t ws_bytes, cudaStream_t st, const LstmPrepared* prep = nullptr);
 int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* cs, const void* hprev,
              const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh, float* d_w_ih,
-             float* d_w_hh, float* d_bias, float* dx, void* ws, int64_t ws_bytes, cudaStream_t st);
+             float* d_w_hh, float* d_bias, float* dx, void* ws, int64_t ws_bytes, cudaStream_t st,
+             const LstmPrepared* prep = nullptr);
 
 // step executor hooks (lstm_tc.cu): event recorded right before the next lstm_bwd() launches its recurrence; whether the
 // recurrence of this hidden size runs as the persistent cooperative kernel (128 of 148 SMs, latency-bound)
@@ -47,7 +65,8 @@ int vocab_ce_bwd(const void* hs, const float* w_out, const float* b_out, const i
 int64_t vocab_ce_train_ws_bytes(int64_t N, int64_t H, int64_t V);
 int vocab_ce_train_fwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, int64_t N,
                        int64_t H, int64_t V, float* lse, float* loss, void* u, float* inv_s, void* hs_scaled,
-                       void* w_bf16, void* ws, int64_t ws_bytes, cudaStream_t st, float loss_scale = 1.f);
+                       void* w_bf16, void* ws, int64_t ws_bytes, cudaStream_t st, float loss_scale = 1.f,
+                       bool w_prepared = false);  // w_prepared: w_bf16 already holds bf16(w_out)
 int vocab_ce_train_bwd(const void* u, const float* inv_s, const void* hs_scaled, const void* w_bf16,
                        const float* dloss, float grad_scale, int64_t N, int64_t H, int64_t V, float* d_hs,
                        float* d_w_out, float* d_b_out, void* ws, int64_t ws_bytes, cudaStream_t st,

@@ -1,4 +1,5 @@
 // Error plumbing, packed-sequence geometry and the small utility exports of the C ABI.
+#include <stdlib.h>
 #include "kernels.cuh"
 
 #include <atomic>

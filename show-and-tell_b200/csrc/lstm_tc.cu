@@ -1326,9 +1326,20 @@ static int prep_launch(const float* w_ih, const float* w_hh, const float* b_ih, 
 
 // `gates` (caller-owned, N*4H*4 bytes) holds, in bf16 mode: [0, N*4H) bf16 saved activations (interleaved columns),
 // [N*4H, 2*N*4H) bf16 pre-activation gradients written by lstm_bwd.
+int64_t lstm_prepared_flag_ints(int64_t B) { return ((B + 127) / 128) * SNT_MAX_T * PB_FLAGS_PER_STEP * 2; }
+int lstm_prepare(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int64_t In, int64_t H,
+                 int64_t B, const LstmPrepared& o, void* hprev, cudaStream_t st) {
+  SNT_REQ8(In, "In");
+  SNT_REQ8(H, "H");
+  SNT_REQUIRE(o.w_ih && o.w_hh && o.w_hh_t && o.bsum && o.flags_fwd && o.flags_bwd && hprev, "lstm_prepare: NULL buffer");
+  SNT_REQUIRE(o.flags_bwd == o.flags_fwd + lstm_prepared_flag_ints(B), "lstm_prepare: counter regions must be adjacent");
+  return prep_launch(w_ih, w_hh, b_ih, b_hh, In, H, o.w_ih, o.w_hh, o.bsum, o.w_hh_t, hprev, (int64_t)sizeof(bf) * B * H,
+                     o.flags_fwd, (int64_t)sizeof(int) * 2 * lstm_prepared_flag_ints(B), st);
+}
+
 int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh,
              const float* b_ih, const float* b_hh, float* gates, float* cs, void* hs, void* hprev, void* ws,
-             int64_t ws_bytes, cudaStream_t st) {
+             int64_t ws_bytes, cudaStream_t st, const LstmPrepared* prep) {
   SNT_REQ8(In, "In");
   SNT_REQ8(H, "H");
   const int T = pk.T;
@@ -1338,10 +1349,14 @@ int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const flo
   bf* hs_b = (bf*)hs;
   bf* hp_b = (bf*)hprev;
   bf* act = (bf*)gates;
-  // one launch: interleaved bf16 weights + bias, h_{-1} = 0 (first B rows of hprev), cleared arrival counters
-  SNT_CHECK(prep_launch(w_ih, w_hh, b_ih, b_hh, In, H, w.w_ih, w.w_hh, w.bsum, nullptr, hp_b,
-                        (int64_t)sizeof(bf) * B * H, w.flags,
-                        w.flags ? (int64_t)sizeof(int) * ((B + tc::BM - 1) / tc::BM) * T * PF_FLAGS_PER_STEP : 0, st));
+  if (prep) {  // prepared by the caller (lstm_prepare): weights, bias, h_{-1} = 0, cleared counters
+    w.w_ih = prep->w_ih; w.w_hh = prep->w_hh; w.bsum = prep->bsum; w.flags = prep->flags_fwd;
+  } else {
+    // one launch: interleaved bf16 weights + bias, h_{-1} = 0 (first B rows of hprev), cleared arrival counters
+    SNT_CHECK(prep_launch(w_ih, w_hh, b_ih, b_hh, In, H, w.w_ih, w.w_hh, w.bsum, nullptr, hp_b,
+                          (int64_t)sizeof(bf) * B * H, w.flags,
+                          w.flags ? (int64_t)sizeof(int) * ((B + tc::BM - 1) / tc::BM) * T * PF_FLAGS_PER_STEP : 0, st));
+  }
   // the input projection of every timestep as ONE tensor-core contraction: Gx' = x . W_ih'^T + (b_ih + b_hh)'
   SNT_CHECK(tc::gemm_tc(false, false, N, 4 * H, In, 1.f, (const bf*)x, In, w.w_ih, In, 0.f, nullptr, w.gx, 4 * H,
                         w.bsum, 1, nullptr, st));
@@ -1456,13 +1471,15 @@ int lstm_bwd_persistent_ctas(int64_t B, int64_t H) {
 
 int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* cs, const void* hprev,
              const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh, float* d_w_ih,
-             float* d_w_hh, float* d_bias, float* dx, void* ws, int64_t ws_bytes, cudaStream_t st) {
+             float* d_w_hh, float* d_bias, float* dx, void* ws, int64_t ws_bytes, cudaStream_t st,
+             const LstmPrepared* prep) {
   SNT_REQ8(In, "In");
   SNT_REQ8(H, "H");
   const int T = pk.T;
   const int64_t N = pk.off[T], B = pk.off[1];
   LstmWs w = carve(ws, ws_bytes, N, B, In, H);
   if (!w.ok) { set_error("bf16 lstm_bwd: workspace too small"); return SNT_EWORKSPACE; }
+  if (prep) { w.w_ih = prep->w_ih; w.w_hh = prep->w_hh; w.w_hh_t = prep->w_hh_t; w.flags = prep->flags_bwd; }
   const bf* act = (const bf*)gates;
   bf* dg = (bf*)gates + N * 4 * H;
   bool persistent = false;
@@ -1477,9 +1494,10 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
     const bool can_persist = coop == 1 && !getenv("SNT_NO_PERSISTENT") && (H == 256 || H == 512) && group >= 1 &&
                              smem <= (size_t)max_smem && w.flags && w.w_hh_t && w.part;
     // one launch: W_ih' (for dX), and either W_hh'^T + cleared counters (persistent) or W_hh' (per-step path)
-    SNT_CHECK(prep_launch(w_ih, w_hh, nullptr, nullptr, In, H, w.w_ih, can_persist ? nullptr : w.w_hh, nullptr,
-                          can_persist ? w.w_hh_t : nullptr, can_persist ? w.flags : nullptr,
-                          (int64_t)sizeof(int) * 2 * nflags, nullptr, 0, st));
+    if (!prep)
+      SNT_CHECK(prep_launch(w_ih, w_hh, nullptr, nullptr, In, H, w.w_ih, can_persist ? nullptr : w.w_hh, nullptr,
+                            can_persist ? w.w_hh_t : nullptr, can_persist ? w.flags : nullptr,
+                            (int64_t)sizeof(int) * 2 * nflags, nullptr, 0, st));
     if (g_bptt_gate) {  // see lstm_bwd_gate_event(): released at the moment the recurrence kernel becomes eligible
       SNT_CUDA(cudaEventRecord(g_bptt_gate, st));
       g_bptt_gate = nullptr;

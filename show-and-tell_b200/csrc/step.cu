@@ -83,6 +83,8 @@ struct StepBufs {
   float *bias_part, *bias_db;  // scratch of the deferred d_b_out column sums (bf16 mode)
   float* dw_sws;               // split-K scratch of the deferred dW_out contraction (bf16 mode, persistent BPTT)
   int64_t dw_sws_elems;
+  bf16::LstmPrepared prep[SNT_MAX_LAYERS];  // bf16 mode: what the recurrence calls derive from the fp32 weights
+  bool has_prep;
   void *scratch, *head_ws, *emb_ws;
   int64_t scratch_bytes, head_bytes, emb_bytes;
   bool ok;
@@ -139,6 +141,16 @@ StepBufs carve(int prec, int L, int64_t B, int64_t N, int64_t E, int64_t H, int6
   b.emb_ws = w.take<char>(b.emb_bytes);
   b.dw_sws_elems = (prec == SNT_PREC_BF16 && bf16::lstm_bwd_is_persistent(H)) ? bf16::vocab_ce_train_sws_elems(N, H, V) : 0;
   b.dw_sws = b.dw_sws_elems > 0 ? w.take<float>(b.dw_sws_elems) : nullptr;
+  b.has_prep = prec == SNT_PREC_BF16;
+  for (int k = 0; k < L && b.has_prep; ++k) {
+    const int64_t In = k == 0 ? E : H, fl = bf16::lstm_prepared_flag_ints(B);
+    b.prep[k].w_ih = w.take<__nv_bfloat16>(4 * H * In);
+    b.prep[k].w_hh = w.take<__nv_bfloat16>(4 * H * H);
+    b.prep[k].w_hh_t = w.take<__nv_bfloat16>(4 * H * H);
+    b.prep[k].bsum = w.take<float>(4 * H);
+    b.prep[k].flags_fwd = w.take<int>(2 * fl);  // forward counters, then the BPTT's
+    b.prep[k].flags_bwd = b.prep[k].flags_fwd ? b.prep[k].flags_fwd + fl : nullptr;
+  }
   b.ok = w.ok();
   return b;
 }
@@ -170,6 +182,11 @@ extern "C" int64_t snt_step_workspace_bytes(int prec, int L, int64_t B, int64_t 
   if (K > 0) add(snt_head_workspace_bytes(prec, B, K, E));
   add(snt_embed_bwd_workspace_bytes(N, V));
   if (prec == SNT_PREC_BF16 && bf16::lstm_bwd_is_persistent(H)) add(bf16::vocab_ce_train_sws_elems(N, H, V) * 4);
+  for (int k = 0; k < L && prec == SNT_PREC_BF16; ++k) {
+    const int64_t In = k == 0 ? E : H;
+    add(4 * H * In * 2); add(4 * H * H * 2); add(4 * H * H * 2); add(4 * H * 4);
+    add(2 * bf16::lstm_prepared_flag_ints(B) * 4);
+  }
   return t;
 }
 
@@ -227,14 +244,20 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
   const bool defer_dw = defer_bias && side_dw != nullptr && (phases & SNT_STEP_BWD_CE) && (phases & SNT_STEP_BWD_LSTM) &&
                         b.dw_sws != nullptr && dw_out_beside_bptt(prec, B, H);
 
+  // Weight preparation off the critical path: the bf16 gate-interleaved LSTM weights (both directions' layouts), the
+  // summed bias, the cleared recurrence counters and bf16(W_out) depend on the parameters only, so they are produced on a
+  // side stream while the main stream runs the encoder head and the gather; lstm_fwd / lstm_bwd / the vocabulary stage
+  // then start with their first contraction.  (Per step: two preparation launches per layer and the 20 MB cast used to
+  // sit in front of the recurrences and the vocabulary pass, ~30 us.)  SNT_NO_EARLY_PREP=1: each stage prepares for itself.
+  const bool early_prep = bf && b.has_prep && side_dw != nullptr && (phases & SNT_STEP_FWD) && !getenv("SNT_NO_EARLY_PREP");
+  // later phases of a step whose forward phase prepared early find the prepared buffers in the workspace
+  const bool use_prep = bf && b.has_prep && side_dw != nullptr && !getenv("SNT_NO_EARLY_PREP");
   if (phases & SNT_STEP_FWD) {
-    if (side) {  // token-dependent half of the embedding gradient: needs the captions only
-      SNT_CUDA(cudaEventRecord(side->fork, st));
-      SNT_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
-      SNT_CHECK(embed_pack_bwd(pk, nullptr, d->captions, d->cap_stride, B, 0, V, nullptr, nullptr, b.emb_ws, b.emb_bytes,
-                               side->s, 1));
-      SNT_CUDA(cudaEventRecord(side->join, side->s));
-    }
+    // the side streams' work is ENQUEUED after the main stream's first kernels (a caller that reads the loss back every
+    // step has an idle GPU at this point: whatever is enqueued first starts first), but ordered behind the fork events
+    // recorded here, i.e. it runs beside the head
+    if (early_prep) SNT_CUDA(cudaEventRecord(side_dw->fork, st));
+    if (side) SNT_CUDA(cudaEventRecord(side->fork, st));
     if (K > 0) {
       StageTimer tm(ST_HEAD_F, st);
       SNT_CHECK(snt_head_fwd(prec, d->input, d->w_fc, d->b_fc, d->bn_w, d->bn_b, d->bn_rm, d->bn_rv, d->training,
@@ -250,20 +273,44 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
     SNT_CHECK(embed_pack_fwd(pk, feats, d->w_emb, d->captions, d->cap_stride, E, V, bf ? nullptr : (float*)b.x,
                              bf ? (__nv_bfloat16*)b.x : nullptr, st));
     }
+    if (early_prep) {
+      cudaStream_t ps = side_dw->s;
+      SNT_CUDA(cudaStreamWaitEvent(ps, side_dw->fork, 0));
+      for (int k = 0; k < L; ++k)
+        SNT_CHECK(bf16::lstm_prepare(d->w_ih[k], d->w_hh[k], d->b_ih[k], d->b_hh[k], k == 0 ? E : H, H, B, b.prep[k],
+                                     b.layer[k].hprev, ps));
+      SNT_CUDA(cudaEventRecord(side_dw->aux, ps));    // the recurrence's inputs are ready
+      SNT_CHECK(cast_bf16(d->w_out, (__nv_bfloat16*)b.w_bf16, V * H, ps));
+      SNT_CUDA(cudaEventRecord(side_dw->join, ps));   // and bf16(W_out)
+    }
+    if (side) {  // token-dependent half of the embedding gradient: needs the captions only
+      SNT_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+      SNT_CHECK(embed_pack_bwd(pk, nullptr, d->captions, d->cap_stride, B, 0, V, nullptr, nullptr, b.emb_ws, b.emb_bytes,
+                               side->s, 1));
+      SNT_CUDA(cudaEventRecord(side->join, side->s));
+    }
     const void* inp = b.x;
     int64_t in_dim = E;
+    if (early_prep) SNT_CUDA(cudaStreamWaitEvent(st, side_dw->aux, 0));
     for (int k = 0; k < L; ++k) {
       StageTimer tm(ST_LSTM_F + k, st);
-      SNT_CHECK(snt_lstm_fwd(prec, inp, in_dim, H, d->w_ih[k], d->w_hh[k], d->b_ih[k], d->b_hh[k], d->batch_sizes, T,
-                             b.layer[k].gates, b.layer[k].cs, b.layer[k].hs, b.layer[k].hprev, b.scratch,
-                             b.scratch_bytes, st));
+      if (early_prep)
+        SNT_CHECK(bf16::lstm_fwd(pk, inp, in_dim, H, d->w_ih[k], d->w_hh[k], d->b_ih[k], d->b_hh[k], b.layer[k].gates,
+                                 b.layer[k].cs, b.layer[k].hs, b.layer[k].hprev, b.scratch, b.scratch_bytes, st,
+                                 &b.prep[k]));
+      else
+        SNT_CHECK(snt_lstm_fwd(prec, inp, in_dim, H, d->w_ih[k], d->w_hh[k], d->b_ih[k], d->b_hh[k], d->batch_sizes, T,
+                               b.layer[k].gates, b.layer[k].cs, b.layer[k].hs, b.layer[k].hprev, b.scratch,
+                               b.scratch_bytes, st));
       inp = b.layer[k].hs;
       in_dim = H;
     }
+    if (early_prep) SNT_CUDA(cudaStreamWaitEvent(st, side_dw->join, 0));
     StageTimer tm_c(ST_CE_F, st);
     if (bf) {
       SNT_CHECK(bf16::vocab_ce_train_fwd(inp, d->w_out, d->b_out, targets, N, H, V, b.lse, d->loss, b.u, b.inv_s,
-                                         b.hs_scaled, b.w_bf16, b.scratch, b.scratch_bytes, st, d->grad_scale));
+                                         b.hs_scaled, b.w_bf16, b.scratch, b.scratch_bytes, st, d->grad_scale,
+                                         early_prep));
     } else {
       SNT_CHECK(snt_vocab_ce_fwd(prec, inp, d->w_out, d->b_out, targets, N, H, V, b.lse, d->loss, b.scratch,
                                  b.scratch_bytes, st));
@@ -317,9 +364,14 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
       const int64_t in_dim = k == 0 ? E : H;
       float* dx = b.dx[k & 1];
       StageTimer tm(ST_LSTM_B + k, st);
-      SNT_CHECK(snt_lstm_bwd(prec, d_out, b.layer[k].gates, b.layer[k].cs, b.layer[k].hprev, inp, in_dim, H, d->w_ih[k],
-                             d->w_hh[k], d->batch_sizes, T, d->d_w_ih[k], d->d_w_hh[k], d->d_b_ih[k], dx, b.scratch,
-                             b.scratch_bytes, st));
+      if (use_prep)
+        SNT_CHECK(bf16::lstm_bwd(pk, d_out, b.layer[k].gates, b.layer[k].cs, b.layer[k].hprev, inp, in_dim, H, d->w_ih[k],
+                                 d->w_hh[k], d->d_w_ih[k], d->d_w_hh[k], d->d_b_ih[k], dx, b.scratch, b.scratch_bytes, st,
+                                 &b.prep[k]));
+      else
+        SNT_CHECK(snt_lstm_bwd(prec, d_out, b.layer[k].gates, b.layer[k].cs, b.layer[k].hprev, inp, in_dim, H, d->w_ih[k],
+                               d->w_hh[k], d->batch_sizes, T, d->d_w_ih[k], d->d_w_hh[k], d->d_b_ih[k], dx, b.scratch,
+                               b.scratch_bytes, st));
       // b_ih and b_hh enter the gates as a sum: they receive the same gradient
       SNT_CUDA(cudaMemcpyAsync(d->d_b_hh[k], d->d_b_ih[k], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
       if (bias_pending) {  // enqueued after the top layer's launches: its gate event has been recorded by now

@@ -854,14 +854,14 @@ int64_t vocab_ce_train_ws_bytes(int64_t N, int64_t H, int64_t V) {
 
 int vocab_ce_train_fwd(const void* hs, const float* w_out, const float* b_out, const int64_t* targets, int64_t N,
                        int64_t H, int64_t V, float* lse, float* loss, void* u, float* inv_s, void* hs_scaled,
-                       void* w_bf16, void* ws, int64_t ws_bytes, cudaStream_t st, float loss_scale) {
+                       void* w_bf16, void* ws, int64_t ws_bytes, cudaStream_t st, float loss_scale, bool w_prepared) {
   if (H % 8 != 0) { set_error("bf16 mode: H=%lld must be a multiple of 8", (long long)H); return SNT_EUNSUPPORTED; }
   SNT_REQUIRE(V < (1LL << 31) && N < (1LL << 31), "vocab_ce_train_fwd: extent too large");
   CeTrainWs w = carve_train(ws, ws_bytes, N, H, V);
   if (!w.ok) { set_error("bf16 vocab_ce_train_fwd: workspace too small"); return SNT_EWORKSPACE; }
   const bf* hs_b = (const bf*)hs;
   bf* wb = (bf*)w_bf16;
-  SNT_CHECK(cast_bf16(w_out, wb, V * H, st));
+  if (!w_prepared) SNT_CHECK(cast_bf16(w_out, wb, V * H, st));
   CUtensorMap ta, tb;
   SNT_CHECK(tc::make_operand_tmap(&ta, hs_b, false, N, H, H, tc::BM));
   SNT_CHECK(tc::make_operand_tmap(&tb, wb, false, V, H, H, CE_BN));
