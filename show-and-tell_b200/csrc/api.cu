@@ -52,6 +52,13 @@ extern "C" int snt_head_fwd(int prec, const float* pooled, const float* w_fc, co
                             const float* gamma, const float* beta, float* running_mean, float* running_var,
                             int training, float momentum, float eps, int64_t B, int64_t K, int64_t E,
                             float* features, float* yhat, float* rstd, void* ws, int64_t ws_bytes, void* stream) {
+  return snt::head_fwd(prec, pooled, w_fc, b_fc, gamma, beta, running_mean, running_var, training, momentum, eps, B, K, E,
+                       features, yhat, rstd, ws, ws_bytes, (cudaStream_t)stream, nullptr);
+}
+int snt::head_fwd(int prec, const float* pooled, const float* w_fc, const float* b_fc, const float* gamma,
+                  const float* beta, float* running_mean, float* running_var, int training, float momentum, float eps,
+                  int64_t B, int64_t K, int64_t E, float* features, float* yhat, float* rstd, void* ws, int64_t ws_bytes,
+                  cudaStream_t stream, __nv_bfloat16* features_bf16) {
   SNT_REQUIRE(valid_prec(prec), "snt_head_fwd: bad prec %d", prec);
   SNT_REQUIRE(B >= 1 && K >= 1 && E >= 1, "snt_head_fwd: bad sizes");
   SNT_REQUIRE(pooled && w_fc && b_fc && gamma && beta && running_mean && running_var && features && yhat && rstd,
@@ -67,7 +74,8 @@ extern "C" int snt_head_fwd(int prec, const float* pooled, const float* w_fc, co
   } else {
     SNT_CHECK(gemm_f32(0, 1, B, E, K, 1.f, pooled, K, w_fc, K, 0.f, y, E, b_fc, st));
   }
-  return bn_fwd(y, gamma, beta, running_mean, running_var, training, momentum, eps, B, E, features, yhat, rstd, st);
+  return bn_fwd(y, gamma, beta, running_mean, running_var, training, momentum, eps, B, E, features, yhat, rstd, st,
+                features_bf16);
 }
 
 extern "C" int snt_head_bwd(int prec, const float* dfeatures, const float* pooled, const float* yhat,

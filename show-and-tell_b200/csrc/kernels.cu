@@ -22,11 +22,10 @@ __global__ void __launch_bounds__(256)
 embed_pack_fwd_kernel(const __grid_constant__ PackInfo pk, const float* __restrict__ features,
                       const float* __restrict__ w_emb, const int64_t* __restrict__ captions,
                       int64_t cap_stride, int E, int64_t V, float* __restrict__ x_f32,
-                      __nv_bfloat16* __restrict__ x_bf16, int* flags) {
+                      __nv_bfloat16* __restrict__ x_bf16, int* flags, int row0, int row1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  const int N = pk.off[pk.T];
-  if (row >= N) return;
+  const int row = row0 + blockIdx.x * 8 + warp;
+  if (row >= row1) return;
   const int t = find_step(pk, row);
   const int b = row - pk.off[t];
   const float* src;
@@ -65,10 +64,12 @@ embed_pack_fwd_kernel(const __grid_constant__ PackInfo pk, const float* __restri
 
 int embed_pack_fwd(const PackInfo& pk, const float* features, const float* w_emb, const int64_t* captions,
                    int64_t cap_stride, int64_t E, int64_t V, float* x_f32, __nv_bfloat16* x_bf16,
-                   cudaStream_t st) {
+                   cudaStream_t st, int64_t row0, int64_t row1) {
   const int N = pk.off[pk.T];
-  embed_pack_fwd_kernel<<<nblocks(N, 8), 256, 0, st>>>(pk, features, w_emb, captions, cap_stride, (int)E, V,
-                                                      x_f32, x_bf16, device_flags());
+  if (row1 < 0 || row1 > N) row1 = N;
+  if (row0 >= row1) return SNT_OK;
+  embed_pack_fwd_kernel<<<nblocks(row1 - row0, 8), 256, 0, st>>>(pk, features, w_emb, captions, cap_stride, (int)E, V,
+                                                                x_f32, x_bf16, device_flags(), (int)row0, (int)row1);
   SNT_LAUNCH_CHECK("embed_pack_fwd_kernel");
   return SNT_OK;
 }
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(BN_FEATS * BN_LANES)
 bn_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
               float* __restrict__ running_mean, float* __restrict__ running_var, int training, float momentum,
               float eps, int B, int E, float* __restrict__ out, float* __restrict__ yhat,
-              float* __restrict__ rstd_out) {
+              float* __restrict__ rstd_out, __nv_bfloat16* __restrict__ out_bf16) {
   __shared__ float red[BN_LANES / 4][BN_FEATS];
   const int tx = threadIdx.x & (BN_FEATS - 1), ty = threadIdx.x / BN_FEATS;
   const int e = blockIdx.x * BN_FEATS + tx;
@@ -437,21 +438,25 @@ bn_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, cons
     if (r < B) {
       const float yh = (v[k] - mu) * rs;
       yhat[(int64_t)r * E + e] = yh;
-      out[(int64_t)r * E + e] = yh * ga + be;
+      const float o = yh * ga + be;
+      out[(int64_t)r * E + e] = o;
+      if (out_bf16) out_bf16[(int64_t)r * E + e] = __float2bfloat16_rn(o);
     }
   }
   for (int r = ty + BN_LANES * BN_CACHE; r < B; r += BN_LANES) {
     const float yh = (y[(int64_t)r * E + e] - mu) * rs;
     yhat[(int64_t)r * E + e] = yh;
-    out[(int64_t)r * E + e] = yh * ga + be;
+    const float o = yh * ga + be;
+    out[(int64_t)r * E + e] = o;
+    if (out_bf16) out_bf16[(int64_t)r * E + e] = __float2bfloat16_rn(o);
   }
 }
 int bn_fwd(const float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
            int training, float momentum, float eps, int64_t B, int64_t E, float* out, float* yhat,
-           float* rstd, cudaStream_t st) {
+           float* rstd, cudaStream_t st, __nv_bfloat16* out_bf16) {
   bn_fwd_kernel<<<nblocks(E, BN_FEATS), BN_FEATS * BN_LANES, 0, st>>>(y, gamma, beta, running_mean, running_var,
                                                                      training, momentum, eps, (int)B, (int)E, out,
-                                                                     yhat, rstd);
+                                                                     yhat, rstd, out_bf16);
   SNT_LAUNCH_CHECK("bn_fwd_kernel");
   return SNT_OK;
 }

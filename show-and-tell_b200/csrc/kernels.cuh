@@ -6,7 +6,7 @@ namespace snt {
 
 int embed_pack_fwd(const PackInfo& pk, const float* features, const float* w_emb, const int64_t* captions,
                    int64_t cap_stride, int64_t E, int64_t V, float* x_f32, __nv_bfloat16* x_bf16,
-                   cudaStream_t st);
+                   cudaStream_t st, int64_t row0 = 0, int64_t row1 = -1);  // packed rows [row0, row1) only (-1: all)
 
 // out[c] = beta*out[c] + sum_r in[r*ld + c], deterministic two-pass; partial needs colsum_partial_count(R,C) floats
 int64_t colsum_partial_count(int64_t R, int64_t C);
@@ -39,7 +39,12 @@ int argmax_gather(const float* logits, int64_t B, int64_t V, int64_t ld, const f
 
 int bn_fwd(const float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
            int training, float momentum, float eps, int64_t B, int64_t E, float* out, float* yhat,
-           float* rstd, cudaStream_t st);
+           float* rstd, cudaStream_t st, __nv_bfloat16* out_bf16 = nullptr);  // out_bf16: `out` again, rounded to bf16
+// snt_head_fwd with the features also written as bf16 rows (the t = 0 rows of the packed LSTM input), api.cu
+int head_fwd(int prec, const float* pooled, const float* w_fc, const float* b_fc, const float* gamma, const float* beta,
+             float* running_mean, float* running_var, int training, float momentum, float eps, int64_t B, int64_t K,
+             int64_t E, float* features, float* yhat, float* rstd, void* ws, int64_t ws_bytes, cudaStream_t st,
+             __nv_bfloat16* features_bf16);
 int bn_bwd(const float* dout, const float* yhat, const float* rstd, const float* gamma, int training,
            int64_t B, int64_t E, float* dy, float* dgamma, float* dbeta, cudaStream_t st);
 

@@ -15,7 +15,7 @@
 #include "kernels.cuh"
 #include "bf16.cuh"
 
-namespace snt { namespace tc { int grid_sms(); } }
+namespace snt { namespace tc { int grid_sms(); int set_grid_cap(int n); } }
 using namespace snt;
 
 namespace {
@@ -253,25 +253,34 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
   // later phases of a step whose forward phase prepared early find the prepared buffers in the workspace
   const bool use_prep = bf && b.has_prep && side_dw != nullptr && !getenv("SNT_NO_EARLY_PREP");
   if (phases & SNT_STEP_FWD) {
-    // the side streams' work is ENQUEUED after the main stream's first kernels (a caller that reads the loss back every
+    // The side streams' work is ENQUEUED after the main stream's first kernels (a caller that reads the loss back every
     // step has an idle GPU at this point: whatever is enqueued first starts first), but ordered behind the fork events
-    // recorded here, i.e. it runs beside the head
+    // recorded here, i.e. it runs beside the head.
     if (early_prep) SNT_CUDA(cudaEventRecord(side_dw->fork, st));
     if (side) SNT_CUDA(cudaEventRecord(side->fork, st));
+    // The packed rows of t >= 1 (rows [B, N)) are embeddings of caption tokens: they do not depend on the head, so with
+    // early preparation they are gathered on the side stream beside the head, and the B rows of t = 0 are written as bf16
+    // by the head's BatchNorm kernel itself: no gather launch is left between the head and the recurrence.  The front of
+    // a step is a chain of small dependent launches at 5-12 us each (profiles/r02_step_front.txt); what counts is how
+    // many of them the recurrence has to wait for.
+    const bool gather_aside = early_prep && N > B && !getenv("SNT_NO_GATHER_ASIDE");
+    const bool targets_aside = side != nullptr && !d->targets;  // pack(captions, lengths): needed by the vocabulary stage only
+    const bool x0_by_head = gather_aside && K > 0;
     if (K > 0) {
       StageTimer tm(ST_HEAD_F, st);
-      SNT_CHECK(snt_head_fwd(prec, d->input, d->w_fc, d->b_fc, d->bn_w, d->bn_b, d->bn_rm, d->bn_rv, d->training,
-                             d->bn_momentum, d->bn_eps, B, K, E, b.feats, b.yhat, b.rstd, b.scratch, b.scratch_bytes,
-                             st));
+      SNT_CHECK(head_fwd(prec, d->input, d->w_fc, d->b_fc, d->bn_w, d->bn_b, d->bn_rm, d->bn_rv, d->training,
+                         d->bn_momentum, d->bn_eps, B, K, E, b.feats, b.yhat, b.rstd, b.scratch, b.scratch_bytes, st,
+                         x0_by_head ? (__nv_bfloat16*)b.x : nullptr));
     }
     {
     StageTimer tm(ST_EMBED_F, st);
-    if (!d->targets) {
+    if (!d->targets && !targets_aside) {
       pack_targets_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pk, d->captions, d->cap_stride, b.targets);
       SNT_LAUNCH_CHECK("pack_targets_kernel");
     }
-    SNT_CHECK(embed_pack_fwd(pk, feats, d->w_emb, d->captions, d->cap_stride, E, V, bf ? nullptr : (float*)b.x,
-                             bf ? (__nv_bfloat16*)b.x : nullptr, st));
+    if (!x0_by_head)
+      SNT_CHECK(embed_pack_fwd(pk, feats, d->w_emb, d->captions, d->cap_stride, E, V, bf ? nullptr : (float*)b.x,
+                               bf ? (__nv_bfloat16*)b.x : nullptr, st, 0, gather_aside ? B : -1));
     }
     if (early_prep) {
       cudaStream_t ps = side_dw->s;
@@ -279,12 +288,21 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
       for (int k = 0; k < L; ++k)
         SNT_CHECK(bf16::lstm_prepare(d->w_ih[k], d->w_hh[k], d->b_ih[k], d->b_hh[k], k == 0 ? E : H, H, B, b.prep[k],
                                      b.layer[k].hprev, ps));
+      if (gather_aside)
+        SNT_CHECK(embed_pack_fwd(pk, feats, d->w_emb, d->captions, d->cap_stride, E, V, nullptr, (__nv_bfloat16*)b.x, ps,
+                                 B, N));
       SNT_CUDA(cudaEventRecord(side_dw->aux, ps));    // the recurrence's inputs are ready
       SNT_CHECK(cast_bf16(d->w_out, (__nv_bfloat16*)b.w_bf16, V * H, ps));
       SNT_CUDA(cudaEventRecord(side_dw->join, ps));   // and bf16(W_out)
     }
-    if (side) {  // token-dependent half of the embedding gradient: needs the captions only
+    if (side) {
       SNT_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+      if (targets_aside) {
+        pack_targets_kernel<<<(unsigned)((N + 255) / 256), 256, 0, side->s>>>(pk, d->captions, d->cap_stride, b.targets);
+        SNT_LAUNCH_CHECK("pack_targets_kernel");
+        SNT_CUDA(cudaEventRecord(side->aux, side->s));
+      }
+      // token-dependent half of the embedding gradient: needs the captions only
       SNT_CHECK(embed_pack_bwd(pk, nullptr, d->captions, d->cap_stride, B, 0, V, nullptr, nullptr, b.emb_ws, b.emb_bytes,
                                side->s, 1));
       SNT_CUDA(cudaEventRecord(side->join, side->s));
@@ -306,6 +324,7 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
       in_dim = H;
     }
     if (early_prep) SNT_CUDA(cudaStreamWaitEvent(st, side_dw->join, 0));
+    if (targets_aside) SNT_CUDA(cudaStreamWaitEvent(st, side->aux, 0));
     StageTimer tm_c(ST_CE_F, st);
     if (bf) {
       SNT_CHECK(bf16::vocab_ce_train_fwd(inp, d->w_out, d->b_out, targets, N, H, V, b.lse, d->loss, b.u, b.inv_s,

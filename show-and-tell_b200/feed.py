@@ -206,7 +206,9 @@ class PrefetchLoader:
         if self.trunk is not None and self.store is None:
             ticket = self.trunk.submit(self._pin(images))
             images = None
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        # No wait for the consumer's stream: the destination tensors are fresh allocations of the copy stream (the caching
+        # allocator orders their reuse through record_stream in _finish), so the copy may start at once instead of at the
+        # end of the step being computed - i.e. beside the head of the next step (profiles/r02_e2e_copy_window.txt).
         with torch.cuda.stream(self.stream):
             if images is not None:
                 images = self._pin(images).to(self.device, non_blocking=True)
