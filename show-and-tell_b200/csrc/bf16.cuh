@@ -38,7 +38,11 @@ int lstm_fwd(const PackInfo& pk, const void* x, int64_t In, int64_t H, const flo
 int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* cs, const void* hprev,
              const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh, float* d_w_ih,
              float* d_w_hh, float* d_bias, float* dx, void* ws, int64_t ws_bytes, cudaStream_t st,
-             const LstmPrepared* prep = nullptr);
+             const LstmPrepared* prep = nullptr, bool* wgrad_pending = nullptr);
+// wgrad_pending != NULL allows lstm_bwd to return with dX complete in stream order but the weight and bias gradients
+// still in flight on side streams (*wgrad_pending = true); the caller orders `st` after them with lstm_bwd_join(st)
+// before anything reads d_w_ih / d_w_hh / d_bias or reuses the stage workspace.
+int lstm_bwd_join(cudaStream_t st);
 
 // step executor hooks (lstm_tc.cu): event recorded right before the next lstm_bwd() launches its recurrence; whether the
 // recurrence of this hidden size runs as the persistent cooperative kernel (128 of 148 SMs, latency-bound)

@@ -27,7 +27,7 @@ int* device_flags();  // sticky device-side flag word
 // record `fork` on the main stream, make `s` wait for it, launch, record `join` on `s`, make the main stream wait.
 struct SideStream {
   cudaStream_t s = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr, aux = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, aux = nullptr, aux2 = nullptr;
 };
 // which = 0: the stream the stage functions use for their column sums; which = 1: the step executor's stream for whole
 // stages that run next to the main stream (head backward, embedding-gradient plan); which = 2: the executor's stream for

@@ -68,6 +68,7 @@ SideStream* side_stream(int which) {
     cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&x.aux, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&x.aux2, cudaEventDisableTiming);
   }
   return &x;
 }

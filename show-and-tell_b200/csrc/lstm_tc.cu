@@ -1472,7 +1472,8 @@ int lstm_bwd_persistent_ctas(int64_t B, int64_t H) {
 int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* cs, const void* hprev,
              const void* x, int64_t In, int64_t H, const float* w_ih, const float* w_hh, float* d_w_ih,
              float* d_w_hh, float* d_bias, float* dx, void* ws, int64_t ws_bytes, cudaStream_t st,
-             const LstmPrepared* prep) {
+             const LstmPrepared* prep, bool* wgrad_pending) {
+  if (wgrad_pending) *wgrad_pending = false;
   SNT_REQ8(In, "In");
   SNT_REQ8(H, "H");
   const int T = pk.T;
@@ -1606,6 +1607,28 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
     SNT_CUDA(cudaEventRecord(side->fork, st));
     SNT_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
   }
+  // Deferred mode (the step executor, last layer of the backward pass): only dX is on the caller's critical path - the
+  // embedding gradient and the head backward wait for it, nothing waits for the weight gradients before the optimizer.
+  // dX goes first on the caller's stream; both weight-gradient contractions and the bias column sums run on side streams
+  // beside whatever the caller enqueues next (a dozen small launch-bound kernels), and the caller joins them later.
+  SideStream* side2 = wgrad_pending ? side_stream(2) : nullptr;
+  if (wgrad_pending && side && side2 && c1 > 0 && dx && !getenv("SNT_NO_WGRAD_DEFER")) {
+    SNT_CHECK(tc::gemm_tc(false, true, N, In, 4 * H, 1.f, dg, 4 * H, w.w_ih, In, 0.f, dx, nullptr, In, nullptr, 1,
+                          nullptr, st));
+    SNT_CUDA(cudaStreamWaitEvent(side2->s, side->fork, 0));
+    float* sws2 = w.sws + align_up((int64_t)c1 * 4 * H * In, 64);
+    SNT_CHECK(tc::gemm_tc(true, true, 4 * H, In, N, 1.f, dg, 4 * H, (const bf*)x, In, 0.f, d_w_ih, nullptr, In,
+                          nullptr, c1, w.sws, side->s, (int)H, nullptr, false, nullptr, 256));
+    SNT_CHECK(tc::gemm_tc(true, true, 4 * H, H, N, 1.f, dg, 4 * H, (const bf*)hprev, H, 0.f, d_w_hh, nullptr, H,
+                          nullptr, c2, sws2, side2->s, (int)H, nullptr, false, nullptr, 256));
+    SNT_CHECK(colsum_bf16(dg, N, 4 * H, 4 * H, 0.f, w.tmp, w.cpart, side->s));
+    unperm_vec_kernel<<<(unsigned)((4 * H + 255) / 256), 256, 0, side->s>>>(w.tmp, (int)H, d_bias);
+    SNT_LAUNCH_CHECK("unperm_vec_kernel");
+    SNT_CUDA(cudaEventRecord(side->aux2, side->s));
+    SNT_CUDA(cudaEventRecord(side2->aux2, side2->s));
+    *wgrad_pending = true;
+    return SNT_OK;
+  }
   if (c1 > 0) {
     float* sws2 = w.sws + align_up((int64_t)c1 * 4 * H * In, 64);
     SNT_CHECK(tc::gemm_tc(true, true, 4 * H, In, N, 1.f, dg, 4 * H, (const bf*)x, In, 0.f, d_w_ih, nullptr, In,
@@ -1633,6 +1656,15 @@ int lstm_bwd(const PackInfo& pk, const float* d_hs, float* gates, const float* c
     SNT_CHECK(tc::gemm_tc(false, true, N, In, 4 * H, 1.f, dg, 4 * H, w.w_ih, In, 0.f, dx, nullptr, In, nullptr, 1,
                           nullptr, st));
   if (side) SNT_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+  return SNT_OK;
+}
+
+int lstm_bwd_join(cudaStream_t st) {
+  SideStream* side = side_stream();
+  SideStream* side2 = side_stream(2);
+  SNT_REQUIRE(side && side2, "lstm_bwd_join: no side streams");
+  SNT_CUDA(cudaStreamWaitEvent(st, side->aux2, 0));
+  SNT_CUDA(cudaStreamWaitEvent(st, side2->aux2, 0));
   return SNT_OK;
 }
 

@@ -72,6 +72,12 @@ bool dw_out_beside_bptt(int prec, int64_t B, int64_t H) {
   return ctas > 0 && tc::grid_sms() - ctas >= tc::grid_sms() / 3;
 }
 
+// moves the end of a stage's span to "now" on `st` (a stage whose last kernels were left in flight on side streams and
+// joined later: its span then ends at the join, i.e. it is reported conservatively, including what ran beside it)
+void stage_extend(int slot, cudaStream_t st) {
+  if (g_prof.on && g_prof.used[slot] && g_prof.ev[slot][1]) cudaEventRecord(g_prof.ev[slot][1], st);
+}
+
 struct Layer { float* gates; float* cs; void* hs; void* hprev; };
 struct StepBufs {
   float *feats, *yhat, *rstd;
@@ -352,6 +358,12 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
                                  b.d_hs, d->d_w_out, d->d_b_out, b.scratch, b.scratch_bytes, st));
   }
 
+  // The first layer's weight and bias gradients may stay in flight on side streams beyond BWD_LSTM when the tail of
+  // backward follows in the same call (bf16::lstm_bwd, deferred mode): nothing before the optimizer reads them, and the
+  // tail's small kernels run beside the two contractions instead of behind them.  A caller that exchanges the LSTM
+  // gradients between the two phases issues them in separate calls and finds them final when BWD_LSTM returns.
+  const bool tail_follows = (phases & SNT_STEP_BWD_LSTM) && (phases & SNT_STEP_BWD_TAIL);
+  bool wgrad_pending = false;
   // gradient w.r.t. the input of layer k lands in dx[k & 1]; layer 0's is dx[0]
   if (phases & SNT_STEP_BWD_LSTM) {
     SNT_REQUIRE(d->d_b_out, "snt_step_run: NULL output-layer gradient");
@@ -386,13 +398,14 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
       if (use_prep)
         SNT_CHECK(bf16::lstm_bwd(pk, d_out, b.layer[k].gates, b.layer[k].cs, b.layer[k].hprev, inp, in_dim, H, d->w_ih[k],
                                  d->w_hh[k], d->d_w_ih[k], d->d_w_hh[k], d->d_b_ih[k], dx, b.scratch, b.scratch_bytes, st,
-                                 &b.prep[k]));
+                                 &b.prep[k], (k == 0 && tail_follows) ? &wgrad_pending : nullptr));
       else
         SNT_CHECK(snt_lstm_bwd(prec, d_out, b.layer[k].gates, b.layer[k].cs, b.layer[k].hprev, inp, in_dim, H, d->w_ih[k],
                                d->w_hh[k], d->batch_sizes, T, d->d_w_ih[k], d->d_w_hh[k], d->d_b_ih[k], dx, b.scratch,
                                b.scratch_bytes, st));
       // b_ih and b_hh enter the gates as a sum: they receive the same gradient
-      SNT_CUDA(cudaMemcpyAsync(d->d_b_hh[k], d->d_b_ih[k], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
+      if (!(k == 0 && wgrad_pending))
+        SNT_CUDA(cudaMemcpyAsync(d->d_b_hh[k], d->d_b_ih[k], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
       if (bias_pending) {  // enqueued after the top layer's launches: its gate event has been recorded by now
         bias_pending = false;
         SNT_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
@@ -438,6 +451,11 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
       SNT_CHECK(embed_pack_bwd(pk, dx0, d->captions, d->cap_stride, B, E, V, K == 0 ? d->d_features : nullptr,
                                d->d_w_emb, b.emb_ws, b.emb_bytes, st, 0));
     }
+    }
+    if (wgrad_pending) {
+      SNT_CHECK(bf16::lstm_bwd_join(st));
+      stage_extend(ST_LSTM_B, st);  // layer 0's stage ends where its weight gradients are final
+      SNT_CUDA(cudaMemcpyAsync(d->d_b_hh[0], d->d_b_ih[0], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
     }
     if (fork_head) {
       SNT_CUDA(cudaStreamWaitEvent(st, side->join, 0));
