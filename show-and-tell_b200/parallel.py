@@ -115,6 +115,11 @@ class DataParallelStep:
         self._stream = None
         if self.flat.p.is_cuda and os.environ.get("SNT_STEP_PRIORITY", "1") != "0":
             self._stream = torch.cuda.Stream(device=self.flat.p.device, priority=-2)
+        # one GPU: background stream (default = lowest priority) for the early share of the optimizer, see _step
+        self._bgstream = None
+        if self._stream is not None and self.world == 1 and os.environ.get("SNT_EARLY_ADAM", "1") != "0":
+            self._bgstream = torch.cuda.Stream(device=self.flat.p.device)
+            self._bg_ev, self._bg_done = torch.cuda.Event(), torch.cuda.Event()
         if self.world > 1:
             self.sync_from_rank0()
 
@@ -367,6 +372,27 @@ class DataParallelStep:
                 self._symm[1].barrier(3)                      # every rank's parameters have arrived
             torch.cuda.current_stream(flat.p.device).wait_stream(self._xstream)
             flat.attach_grads()
+            return self._finish_step(cuda)
+        if (self.world == 1 and self.optimizer and self._bgstream is not None and not eng.overlaps_dw_out()
+                and flat.bucket_range["early"][1] > flat.bucket_range["early"][0]):
+            # One GPU: linear.weight - more than half of all parameters - is final after the vocab-CE backward and nothing
+            # reads the fp32 master copy again in this step (the backward contraction uses the bf16 copy made in forward),
+            # so its share of clip + Adam (HBM-bound, ~30 us) runs as background work beside the BPTT recurrence (HBM idle)
+            # instead of after the step, like the fused exchange of several GPUs does.  (Not when the executor runs
+            # d_w_out itself beside the BPTT: small batches, engine.overlaps_dw_out.)
+            self.t += 1
+            eng.run(PH_FWD | PH_BWD_CE)
+            cur = torch.cuda.current_stream(flat.p.device)
+            self._bg_ev.record(cur)
+            with torch.cuda.stream(self._bgstream):
+                self._bgstream.wait_event(self._bg_ev)
+                eng.adam(*flat.bucket_range["early"], self.t, self.lr, self.betas, self.eps, self.grad_clip)
+                self._bg_done.record(self._bgstream)
+            eng.run(PH_BWD_LSTM | PH_BWD_TAIL)
+            flat.attach_grads()
+            cur.wait_event(self._bg_done)
+            eng.adam(flat.bucket_range["mid"][0], flat.bucket_range["late"][1], self.t, self.lr, self.betas, self.eps,
+                     self.grad_clip)
             return self._finish_step(cuda)
         if self.world == 1 or self._symm is not None:
             eng.run(PH_ALL)      # (fused exchange in one piece: update())
