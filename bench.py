@@ -22,8 +22,9 @@ greedy  : the second half of BASELINE's metric - greedy sample() of 4096 image f
           the torch/cuDNN arm on the same GPU.
 configs3: the scaled decoder (E512/H1024/L2/V32000, batch 2048) timed the same way (N=1), also as `--config scaled`.
 strong_8192 (N>1): BASELINE configs[4] as written - global batch 8192 sharded over the N ranks.
-cpu_baseline / --impl reference: the reference's CPU composition (oracle/torch_port.py, pinned to the reference's
-          golden vectors) timed on this box's host cores.
+cpu_baseline / --impl reference: the reference's own models.py (oracle/_ref, placed there unmodified by build(); kind
+          "reference") - or, when that is absent, its pinned restatement oracle/torch_port.py (kind "port") - timed on
+          this box's host cores.
 gpu_torch_reference: the same torch.nn composition on THIS GPU (cuDNN LSTM, cuBLAS; fp32, TF32, bf16 autocast), timed
           in a child process after the timed regions - the bar to beat.
 """
@@ -198,23 +199,35 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # reference arms
 # ---------------------------------------------------------------------------------------------------------------------
+def cpu_arm():
+    """(module, kind, description) of the CPU arm: the reference's own models.py when build() placed it under
+    oracle/_ref (it travels to the GPU box with the snapshot), else the pinned restatement oracle/torch_port.py."""
+    from oracle import ref_arm as RA     # test / bench infrastructure, never shipped
+    if RA.available():
+        return RA, "reference", RA.what()
+    from oracle import torch_port as TP
+    return TP, "port", (f"torch {torch.__version__} CPU, oracle/torch_port.py pinned to the reference's goldens "
+                        "(oracle/_ref absent)")
+
+
 def cpu_train_baseline(c, steps, warmup, threads):
-    """oracle/torch_port.py (head + decoder fwd, CE, bwd, clip, Adam) on the host cores: (captions/s, s/step, loss)."""
+    """The reference's CPU step (head + decoder fwd, CE, bwd, clip, Adam) on the host cores:
+    (captions/s, s/step, loss, tokens, kind, description)."""
     import show_and_tell_b200 as snt
-    from oracle import torch_port as TP   # the checker timed as the CPU baseline, never shipped
+    arm, kind, what = cpu_arm()
     b = snt.synthetic.make_batch(c["B"], c["V"], embed=c["E"], seed=1, pooled_dim=c["POOLED"])
     b["targets"] = snt.synthetic.pack_host(b["captions"], b["lengths"])
-    cps, dt, loss = TP.time_full_train(c["B"], c["E"], c["H"], c["V"], c["L"], b, steps=steps, warmup=warmup,
-                                       threads=threads)
-    return cps, dt, loss, int(sum(b["lengths"]))
+    cps, dt, loss = arm.time_full_train(c["B"], c["E"], c["H"], c["V"], c["L"], b, steps=steps, warmup=warmup,
+                                        threads=threads)
+    return cps, dt, loss, int(sum(b["lengths"])), kind, what
 
 
 def cpu_greedy_baseline(c, batch, threads):
-    """oracle/torch_port.py greedy loop on a bounded sample of the decode batch: (tokens/s, s per sample)."""
-    from oracle import torch_port as TP
+    """The reference's greedy loop on a bounded sample of the decode batch: (tokens/s, s per sample, kind, description)."""
+    arm, kind, what = cpu_arm()
     feats = np.random.default_rng(1).standard_normal((batch, c["E"])).astype(np.float32)
-    tps, dt = TP.time_greedy(batch, c["E"], c["H"], c["V"], c["L"], feats, steps=2, warmup=1, threads=threads)
-    return tps, dt
+    tps, dt = arm.time_greedy(batch, c["E"], c["H"], c["V"], c["L"], feats, steps=2, warmup=1, threads=threads)
+    return tps, dt, kind, what
 
 
 def run_reference(args, rank):
@@ -225,15 +238,13 @@ def run_reference(args, rank):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     steps, warm = max(1, args.steps), max(1, args.warmup)
-    cps, dt, loss, n_tok = cpu_train_baseline(c, steps, warm, threads)
-    g_tps, g_dt = cpu_greedy_baseline(c, 512, threads)
-    what = (f"torch {torch.__version__} CPU, oracle/torch_port.py pinned to the reference's goldens "
-            f"(/root/reference is absent on the GPU box)")
+    cps, dt, loss, n_tok, kind, what = cpu_train_baseline(c, steps, warm, threads)
+    g_tps, g_dt, _, _ = cpu_greedy_baseline(c, 512, threads)
     line = {"impl": "reference", "metric": "train_captions_per_s", "value": cps, "unit": "captions/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(c, c["B"], 1, "fp32", n_tok, 20, device="cpu", threads=threads),
-            "cpu_baseline": {"value": cps, "unit": "captions/s", "cores": threads, "kind": "port",
+            "cpu_baseline": {"value": cps, "unit": "captions/s", "cores": threads, "kind": kind,
                              "sample": f"{steps} full steps of B={c['B']} (N={n_tok} tokens), {what}"},
             "e2e": {"value": cps, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "greedy": {"metric": "greedy_decode_tokens_per_s", "value": g_tps, "unit": "tokens/s",
@@ -556,10 +567,10 @@ def measure_greedy(snt, dec, c, dev, world, timed, peaks, rank, with_cpu):
     dec.train()
     if with_cpu and rank == 0:
         threads = os.cpu_count() or 1
-        tps, dt = cpu_greedy_baseline(c, 512, threads)
-        out["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
+        tps, dt, kind, what = cpu_greedy_baseline(c, 512, threads)
+        out["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": kind,
                                "sample": f"2 x sample() of 512 image features x 20 tokens ({dt:.2f} s each) after 1 warm-up, "
-                                         f"torch {torch.__version__} CPU (oracle/torch_port.py)"}
+                                         f"{what}"}
     return out
 
 
@@ -872,11 +883,10 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            cps, dt, _, ntk = cpu_train_baseline(c, 3, 1, threads)
-            cpu = {"value": cps, "unit": "captions/s", "cores": threads, "kind": "port",
+            cps, dt, _, ntk, kind, what = cpu_train_baseline(c, 3, 1, threads)
+            cpu = {"value": cps, "unit": "captions/s", "cores": threads, "kind": kind,
                    "sample": f"3 full train steps (head+decoder fwd, CE, bwd, clip, Adam) of B={c['B']} ({dt:.2f} s/step) "
-                             f"after 1 warm-up, torch {torch.__version__} CPU (oracle/torch_port.py, pinned to the "
-                             "reference's goldens)"}
+                             f"after 1 warm-up, {what}"}
         gpu_ref = None
         if world == 1 and not args.no_gpu_reference and args.config == "default":
             gpu_ref = gpu_torch_reference(local)

@@ -125,3 +125,37 @@ def test_trim_captions_follows_eval_loop():
     for b in range(len(ids)):
         assert " ".join(idx2word[int(w)] for w in out[b, :lengths[b]]) == sentences[b]
         assert (out[b, lengths[b]:] == 0).all()
+
+
+@pytest.mark.parametrize("name", DEC_CASES)
+def test_reference_arm_reproduces_goldens(name):
+    """bench.py's `kind: "reference"` arm (oracle/ref_arm.py over the unmodified models.py under oracle/_ref) gives the
+    vectors the reference gave when the goldens were made, and the restated port agrees with it."""
+    import torch
+    from oracle import ref_arm as RA
+    if not RA.available() and RA.build_ref() is None:
+        pytest.skip("oracle/_ref is only populated where /root/reference exists (build container)")
+    ref = RA.load()
+    g = load_golden(name)
+    dec = ref.DecoderRNN(int(g["E"]), int(g["H"]), int(g["V"]), int(g["L"]))
+    dec.load_state_dict({k: torch.from_numpy(v) for k, v in golden_params(g).items()})
+    f, c, t = torch.from_numpy(g["features"]), torch.from_numpy(g["captions"]), torch.from_numpy(g["targets"])
+    dec.zero_grad()
+    loss = torch.nn.CrossEntropyLoss()(dec(f, c, g["lengths"].tolist()), t)
+    loss.backward()
+    assert abs(float(loss) - g["f32.loss"]) / g["f32.loss"] < 1e-6
+    for k, p in dec.named_parameters():
+        assert rel(p.grad.numpy(), g[f"f32.grad.{k}"]) < 1e-5, k
+    np.testing.assert_array_equal(RA.sample_keepdim(dec.eval(), f).numpy(), g["f32.greedy_ids"])
+
+
+def test_reference_arm_file_is_unmodified():
+    import hashlib
+    import os
+    from oracle import ref_arm as RA
+    if not RA.available() and RA.build_ref() is None:
+        pytest.skip("oracle/_ref absent")
+    want = open(RA.REF_SHA).read().split()[0]
+    assert hashlib.sha256(open(RA.REF_FILE, "rb").read()).hexdigest() == want
+    if os.path.isfile(RA.REF_SRC):
+        assert open(RA.REF_SRC, "rb").read() == open(RA.REF_FILE, "rb").read()
