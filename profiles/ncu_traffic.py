@@ -7,7 +7,7 @@ cudaProfilerStart/Stop; `ncu -i step_full.ncu-rep --page raw --csv > step_full_r
 
     python profiles/ncu_traffic.py gpurun_out/r02/step_full_raw.csv profiles/r02_traffic.json > profiles/r02_ncu_step_full.txt
 
-Launches are mapped to the stages of snt_step_run (csrc/step.cu) by their order and kernel names."""
+Launches are mapped to the stages of snt_step_run (csrc/step.cu) by kernel name and grid size."""
 import csv
 import json
 import re
@@ -24,33 +24,59 @@ def col(hdr, key):
     return None
 
 
-def stage_of(names):
-    """Stage of every launch of one step, in launch order (see csrc/step.cu for the sequence)."""
-    out, phase = [], "head_fwd"
-    seen_lstm_prep = 0
-    for n in names:
+def stage_of(names, grids):
+    """Stage of every launch of one step.  By kernel name and grid, not by position: the executor (csrc/step.cu) runs
+    weight preparation, gathers, the token plan, column sums and part of the optimizer on side streams, so the launch
+    order interleaves the stages.  d_b_out's column sums (a pass over the stored numerators that runs beside the BPTT
+    kernel) are booked under vocab_ce_bwd, whose gradient they are."""
+    out, seen_bptt, seen_bn_bwd, last_gemm, last_colsum = [], False, False, "head_fwd", "lstm_bwd"
+    for n, g in zip(names, grids):
+        g0 = int(re.sub(r"[^0-9,]", "", g).split(",")[0] or 0)
         if n.startswith("void at::") or n.startswith("at::"):
-            out.append("host_glue(torch)")
-            continue
-        if re.search(r"emb_(tok|scan|place|small|sort|chunk|final)_kernel", n):
-            out.append("embed_pack_bwd")
-            continue
-        if "pack_targets_kernel" in n or "embed_pack_fwd_kernel" in n:
-            phase = "embed_pack_fwd"
-        elif "lstm_prep_kernel" in n:
-            seen_lstm_prep += 1
-            phase = "lstm_fwd" if phase in ("head_fwd", "embed_pack_fwd", "lstm_fwd") else "lstm_bwd"
-        elif phase == "lstm_fwd" and ("cast_bf16_kernel" in n or "RowMaxEpi" in n or "CeStoreEpi" in n or "CeFwdEpi" in n):
-            phase = "vocab_ce_fwd"
-        elif phase == "vocab_ce_fwd" and "ce_finish" in n:
-            out.append("vocab_ce_fwd")
-            phase = "vocab_ce_bwd"
-            continue
+            st = "host_glue(torch)"
+        elif re.search(r"emb_(tok|scan|place|small|sort|chunk|final)_kernel", n):
+            st = "embed_pack_bwd"
+        elif "pack_targets_kernel" in n or "embed_pack_fwd_kernel" in n:
+            st = "embed_pack_fwd"
+        elif "bn_fwd_kernel" in n:
+            st = "head_fwd"
         elif "bn_bwd_kernel" in n:
-            phase = "head_bwd"
-        elif "clamp_adam" in n:
-            phase = "clamp_adam"
-        out.append(phase)
+            st, seen_bn_bwd = "head_bwd", True
+        elif "snt::colsum_partial_kernel" in n or "snt::colsum_final_kernel" in n or "cast2d_kernel" in n:
+            st = "head_bwd"
+        elif "lstm_prep" in n:
+            st = "lstm_bwd" if seen_bptt else "lstm_fwd"
+        elif "lstm_fwd_persistent" in n or "LstmFwdEpi" in n or "PlainEpi<256, 1>" in n:
+            st = "lstm_fwd"
+        elif "RowMaxEpi" in n or "CeStoreEpi" in n or "CeFwdEpi" in n or "ce_finish" in n:
+            st = "vocab_ce_fwd"
+        elif "lstm_bwd_persistent" in n or "lstm_bwd_point" in n:
+            st, seen_bptt = "lstm_bwd", True
+        elif "gemm_tc_kernel<256, 0, 1" in n:
+            st = last_gemm = "vocab_ce_bwd"                       # dHs = U' . W_out
+        elif "gemm_tc_kernel<256, 1, 1" in n:
+            st = last_gemm = "lstm_bwd" if (seen_bptt or g0 < 100) else "vocab_ce_bwd"   # dW_ih / dW_hh (48 / 96 CTAs) or dW_out
+        elif "gemm_tc_kernel<128, 0, 1" in n:
+            st = last_gemm = "lstm_bwd"                           # dX
+        elif "gemm_tc_kernel<128, 0, 0" in n:
+            st = last_gemm = "head_fwd"
+        elif "gemm_tc_kernel<128, 1, 1" in n:
+            st = last_gemm = "head_bwd"
+        elif "splitk_reduce" in n:
+            st = last_gemm
+        elif "colsum_bf16_partial_kernel" in n:
+            st = last_colsum = "vocab_ce_bwd" if g0 >= 1000 else "lstm_bwd"   # d_b_out (N x V pass) or the LSTM bias
+        elif "colsum_bf16_final_kernel" in n or "scale_vec_kernel" in n:
+            st = last_colsum
+        elif "unperm_vec_kernel" in n:
+            st = "lstm_bwd"
+        elif "cast_bf16_kernel" in n:
+            st = "vocab_ce_fwd" if g0 >= 4000 else ("head_bwd" if seen_bn_bwd else "head_fwd")
+        elif "clamp_adam" in n or "dp_adam" in n:
+            st = "clamp_adam"
+        else:
+            st = "other"
+        out.append(st)
     return out
 
 
@@ -72,7 +98,7 @@ def main():
         return float(r[i].replace(",", "")) * UNIT.get(units[i], 1.0)
 
     names = [r[kn] for r in data]
-    stages = stage_of(names)
+    stages = stage_of(names, [r[gi] for r in data])
     per = {}
     print(f"# {sys.argv[1]}: {len(data)} launches of one training step (configs[1]: B=1024, E256/H512/V10000), ncu --set full,")
     print("# --clock-control none; durations are cold-cache and serialised (compare shares); DRAM bytes are per launch.")

@@ -57,8 +57,8 @@ int linear_nt(const float* a, const float* w, const float* bias, int64_t M, int6
   if (!wk.ok()) { set_error("bf16 linear: workspace too small"); return SNT_EWORKSPACE; }
   wk.take<bf>(M * pad8(N));
   float* sws = wk.take<float>(MAX_SPLITS * N * K);  // shared with wgrad_tn's split-K scratch
-  SNT_CHECK(cast_bf16(a, ab, M * K, st));
-  SNT_CHECK(cast_bf16(w, wb, N * K, st));
+  SNT_CHECK(cast_bf16(a, ab, M * K, st, /*chain=*/true));   // casts -> contraction -> reduction -> BatchNorm: one chain
+  SNT_CHECK(cast_bf16(w, wb, N * K, st, /*chain=*/true));
   // few output tiles (8 x 2 at B=1024, E=256) but a long contraction: split K over the idle SMs
   int splits = sws ? tc::choose_splits(M, N, K, 0) : 1;
   while (splits > 1 && (int64_t)splits * M > (int64_t)MAX_SPLITS * K) --splits;

@@ -89,6 +89,30 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---- chained launches (programmatic dependent launch) ------------------------------------------------------------------
+// A kernel launched with launch_chained() may become resident while its predecessor in the stream is still running (as
+// soon as every block of the predecessor has executed pdl_launch_dependents() or exited), so that its launch latency and
+// prologue overlap the predecessor's tail.  The rule every such kernel follows: NO global-memory access before
+// pdl_wait(), which returns when the preceding grid has completed and its writes are visible.  In a kernel launched the
+// ordinary way both instructions are no-ops.  SNT_NO_PDL=1 launches everything in plain stream order.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_all();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_all() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- internal launchers shared across translation units -------------------------------------------------
 int gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
              int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc,

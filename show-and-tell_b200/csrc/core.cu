@@ -73,6 +73,11 @@ SideStream* side_stream(int which) {
   return &x;
 }
 
+bool pdl_all() {
+  static const bool on = [] { const char* e = getenv("SNT_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
+
 }  // namespace snt
 
 using namespace snt;

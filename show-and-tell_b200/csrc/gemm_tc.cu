@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t M, int64_t N, int64_t ldc,
                      int64_t split_stride, float beta, const float* __restrict__ bias, float* __restrict__ C,
                      __nv_bfloat16* __restrict__ Cb) {
+  pdl_launch_dependents();
+  pdl_wait();  // the partial slices come from the preceding contraction
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= M * N) return;
   const int64_t m = i / N, n = i % N;
@@ -105,6 +107,8 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t M, int64_
 __global__ void __launch_bounds__(256)
 splitk_reduce4_kernel(const float* __restrict__ ws, int splits, int64_t M, int64_t N4, int64_t ldc,
                       int64_t split_stride, float beta, const float* __restrict__ bias, float* __restrict__ C) {
+  pdl_launch_dependents();
+  pdl_wait();  // the partial slices come from the preceding contraction
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= M * N4) return;
   const int64_t m = i / N4, n = (i - m * N4) * 4;
@@ -220,12 +224,12 @@ int gemm_tc(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K, float alpha, 
                      ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(split_ws) |
                        reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
     if (vec) {
-      splitk_reduce4_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>(split_ws, splits, M, N / 4, ldc,
-                                                                                 split_stride, beta, bias, C);
+      SNT_CUDA(launch_chained(splitk_reduce4_kernel, dim3((unsigned)((total / 4 + 255) / 256)), dim3(256), 0, st,
+                              (const float*)split_ws, splits, M, N / 4, ldc, split_stride, beta, bias, C));
       SNT_LAUNCH_CHECK("splitk_reduce4_kernel");
     } else {
-      splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(split_ws, splits, M, N, ldc, split_stride,
-                                                                             beta, bias, C, Cb);
+      SNT_CUDA(launch_chained(splitk_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st,
+                              (const float*)split_ws, splits, M, N, ldc, split_stride, beta, bias, C, Cb));
       SNT_LAUNCH_CHECK("splitk_reduce_kernel");
     }
   }

@@ -65,8 +65,10 @@ __device__ __forceinline__ uint32_t stage_addr(uint32_t base, int row, int piece
   return base + (uint32_t)(row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
 }
 
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+using ::snt::pdl_wait;
+using ::snt::pdl_launch_dependents;
+using ::snt::pdl_all;
+using ::snt::launch_chained;
 
 // Epi must provide:
 //   static constexpr int kWarps            (4, 8 or 16 epilogue warps)
@@ -273,7 +275,7 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TileSch
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = (pdl || pdl_all()) ? 1 : 0;
   count_launch();
   SNT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, ts, epi));
   return SNT_OK;

@@ -133,7 +133,13 @@ int add_vec(const float* a, const float* b, float* out, int64_t n, cudaStream_t 
   return SNT_OK;
 }
 
+// CHAIN: the cast is a link of a chain of launches (common.cuh) - the encoder head's operands in front of its contraction
+template <bool CHAIN>
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  if (CHAIN) {
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n && ((reinterpret_cast<uintptr_t>(src + i) & 15) == 0) &&
       ((reinterpret_cast<uintptr_t>(dst + i) & 7) == 0)) {
@@ -147,9 +153,12 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
     for (int k = 0; k < 4 && i + k < n; ++k) dst[i + k] = __float2bfloat16_rn(src[i + k]);
   }
 }
-int cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t st) {
+int cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t st, bool chain) {
   if (n <= 0) return SNT_OK;
-  cast_bf16_kernel<<<nblocks((n + 3) / 4, 256), 256, 0, st>>>(src, dst, n);
+  if (chain)
+    SNT_CUDA(launch_chained(cast_bf16_kernel<true>, dim3(nblocks((n + 3) / 4, 256)), dim3(256), 0, st, src, dst, n));
+  else
+    cast_bf16_kernel<false><<<nblocks((n + 3) / 4, 256), 256, 0, st>>>(src, dst, n);
   SNT_LAUNCH_CHECK("cast_bf16_kernel");
   return SNT_OK;
 }
@@ -393,6 +402,8 @@ bn_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, cons
               float* __restrict__ running_mean, float* __restrict__ running_var, int training, float momentum,
               float eps, int B, int E, float* __restrict__ out, float* __restrict__ yhat,
               float* __restrict__ rstd_out, __nv_bfloat16* __restrict__ out_bf16) {
+  pdl_launch_dependents();
+  pdl_wait();  // launched chained (common.cuh): nothing global before this point
   __shared__ float red[BN_LANES / 4][BN_FEATS];
   const int tx = threadIdx.x & (BN_FEATS - 1), ty = threadIdx.x / BN_FEATS;
   const int e = blockIdx.x * BN_FEATS + tx;
@@ -454,9 +465,8 @@ bn_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, cons
 int bn_fwd(const float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
            int training, float momentum, float eps, int64_t B, int64_t E, float* out, float* yhat,
            float* rstd, cudaStream_t st, __nv_bfloat16* out_bf16) {
-  bn_fwd_kernel<<<nblocks(E, BN_FEATS), BN_FEATS * BN_LANES, 0, st>>>(y, gamma, beta, running_mean, running_var,
-                                                                     training, momentum, eps, (int)B, (int)E, out,
-                                                                     yhat, rstd, out_bf16);
+  SNT_CUDA(launch_chained(bn_fwd_kernel, dim3(nblocks(E, BN_FEATS)), dim3(BN_FEATS * BN_LANES), 0, st, y, gamma, beta,
+                          running_mean, running_var, training, momentum, eps, (int)B, (int)E, out, yhat, rstd, out_bf16));
   SNT_LAUNCH_CHECK("bn_fwd_kernel");
   return SNT_OK;
 }
@@ -868,8 +878,9 @@ int64_t embed_bwd_ws_bytes(int64_t N, int64_t V) {
          ws_bytes_for(emb_chunk_slots(N) * 1024, 4) + ws_bytes_for(4, 4);
 }
 // phase 0: everything.  phase 1: only the token-dependent half (histogram + scan: needs captions, not dx) - it may run
-// early, on another stream.  phase 2: the rest, for a workspace that already went through phase 1 with the same
-// captions / geometry.  Phase 0 issues exactly the launches of phase 1 + phase 2 in the original order.
+// early, on another stream; given d_w_emb (and E) it also zeroes the gradient buffer and the chunk counter there.
+// phase 2: the rest, for a workspace that already went through phase 1 with the same captions / geometry.  phase 3:
+// as 2, after a phase 1 that did the zeroing.  Phase 0 issues exactly the launches of phase 1 + phase 2.
 int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions, int64_t cap_stride,
                    int64_t B, int64_t E, int64_t V, float* dfeatures, float* d_w_emb, void* ws,
                    int64_t ws_bytes, cudaStream_t st, int phase) {
@@ -896,13 +907,14 @@ int embed_pack_bwd(const PackInfo& pk, const float* dx, const int64_t* captions,
   float* partial = w.take<float>(emb_chunk_slots(N) * 1024);
   cl.counter = w.take<int>(4);
   if (!w.ok()) { set_error("embed_pack_bwd: workspace too small"); return SNT_EWORKSPACE; }
-  SNT_REQUIRE(phase == 1 || (E % 4 == 0 && E <= 1024), "embed_pack_bwd: E must be a multiple of 4 and <= 1024");
+  SNT_REQUIRE((phase == 1 && !d_w_emb) || (E % 4 == 0 && E <= 1024), "embed_pack_bwd: E must be a multiple of 4 and <= 1024");
   SNT_REQUIRE(V < (1LL << 31), "embed_pack_bwd: V too large");
-  if (phase != 1) SNT_CUDA(cudaMemsetAsync(d_w_emb, 0, sizeof(float) * (size_t)V * E, st));
+  const bool zero_here = phase == 0 || phase == 2 || (phase == 1 && d_w_emb != nullptr);
+  if (zero_here) SNT_CUDA(cudaMemsetAsync(d_w_emb, 0, sizeof(float) * (size_t)V * E, st));
   if (n1 <= 0) return SNT_OK;
-  if (phase != 2) SNT_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(V + 1), st));
-  if (phase != 1) SNT_CUDA(cudaMemsetAsync(cl.counter, 0, sizeof(int) * 4, st));
-  if (phase != 2) {
+  if (phase < 2) SNT_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(V + 1), st));
+  if (zero_here) SNT_CUDA(cudaMemsetAsync(cl.counter, 0, sizeof(int) * 4, st));
+  if (phase < 2) {
     emb_tok_kernel<<<nblocks(n1, 256), 256, 0, st>>>(pk, captions, cap_stride, V, tok, count, device_flags());
     SNT_LAUNCH_CHECK("emb_tok_kernel");
     emb_scan_kernel<<<1, 1024, 0, st>>>(count, (int)V, start, cursor, multi, small, device_flags());

@@ -14,7 +14,7 @@ int colsum(const float* in, int64_t R, int64_t C, int64_t ld, float beta, float*
            cudaStream_t st);
 
 int add_vec(const float* a, const float* b, float* out, int64_t n, cudaStream_t st);
-int cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t st);
+int cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t st, bool chain = false);
 int cast_f32(const __nv_bfloat16* src, float* dst, int64_t n, cudaStream_t st);
 
 // one LSTM timestep, pointwise part.  gates_t: [bs,4H] pre-activations in, activations out.

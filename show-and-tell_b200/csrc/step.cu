@@ -256,6 +256,18 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
   // then start with their first contraction.  (Per step: two preparation launches per layer and the 20 MB cast used to
   // sit in front of the recurrences and the vocabulary pass, ~30 us.)  SNT_NO_EARLY_PREP=1: each stage prepares for itself.
   const bool early_prep = bf && b.has_prep && side_dw != nullptr && (phases & SNT_STEP_FWD) && !getenv("SNT_NO_EARLY_PREP");
+  // The embedding-gradient buffer (V x E floats, 10 MB at configs[1]) is zeroed beside the forward pass, on the stream
+  // that builds the token plan, when this call starts a training step (forward and the first backward phase together:
+  // the tail of backward follows by contract).  The tail - in this call or a later one on the same workspace - then
+  // finds the marker and skips the two memsets in front of its first kernel.  SNT_NO_EMB_ZERO_EARLY=1: zero in the tail.
+  static const void* emb_zeroed_ws = nullptr;   // workspace whose embedding gradient the last forward phase zeroed
+  static const float* emb_zeroed_dw = nullptr;
+  const bool emb_zero_early = side != nullptr && (phases & SNT_STEP_FWD) && (phases & SNT_STEP_BWD_CE) &&
+                              d->d_w_emb != nullptr && E % 4 == 0 && E <= 1024 && !getenv("SNT_NO_EMB_ZERO_EARLY");
+  if (phases & SNT_STEP_FWD) {
+    emb_zeroed_ws = emb_zero_early ? d->ws : nullptr;
+    emb_zeroed_dw = emb_zero_early ? d->d_w_emb : nullptr;
+  }
   // later phases of a step whose forward phase prepared early find the prepared buffers in the workspace
   const bool use_prep = bf && b.has_prep && side_dw != nullptr && !getenv("SNT_NO_EARLY_PREP");
   if (phases & SNT_STEP_FWD) {
@@ -309,8 +321,9 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
         SNT_CUDA(cudaEventRecord(side->aux, side->s));
       }
       // token-dependent half of the embedding gradient: needs the captions only
-      SNT_CHECK(embed_pack_bwd(pk, nullptr, d->captions, d->cap_stride, B, 0, V, nullptr, nullptr, b.emb_ws, b.emb_bytes,
-                               side->s, 1));
+      // (the whole step in one call: the gradient buffer is zeroed here too, off the critical path of the tail)
+      SNT_CHECK(embed_pack_bwd(pk, nullptr, d->captions, d->cap_stride, B, emb_zero_early ? E : 0, V, nullptr,
+                               emb_zero_early ? d->d_w_emb : nullptr, b.emb_ws, b.emb_bytes, side->s, 1));
       SNT_CUDA(cudaEventRecord(side->join, side->s));
     }
     const void* inp = b.x;
@@ -430,6 +443,9 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
     SNT_REQUIRE(K == 0 || (d->d_w_fc && d->d_b_fc && d->d_bn_w && d->d_bn_b), "snt_step_run: NULL head gradient");
     const float* dx0 = b.dx[0];
     const bool fork_head = K > 0 && side != nullptr;
+    const bool emb_zeroed = side != nullptr && emb_zeroed_ws == d->ws && emb_zeroed_dw == d->d_w_emb;
+    emb_zeroed_ws = nullptr;
+    emb_zeroed_dw = nullptr;
     if (side) SNT_CUDA(cudaStreamWaitEvent(st, side->join, 0));  // the embedding plan of the forward phase
     if (fork_head) {
       // dfeatures = dx0[:B] (the t = 0 rows); the head backward does not depend on the embedding-gradient kernels
@@ -446,7 +462,7 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
     StageTimer tm(ST_EMBED_B, st);
     if (side) {
       SNT_CHECK(embed_pack_bwd(pk, dx0, d->captions, d->cap_stride, B, E, V, K == 0 ? d->d_features : nullptr,
-                               d->d_w_emb, b.emb_ws, b.emb_bytes, st, 2));
+                               d->d_w_emb, b.emb_ws, b.emb_bytes, st, emb_zeroed ? 3 : 2));
     } else {
       SNT_CHECK(embed_pack_bwd(pk, dx0, d->captions, d->cap_stride, B, E, V, K == 0 ? d->d_features : nullptr,
                                d->d_w_emb, b.emb_ws, b.emb_bytes, st, 0));

@@ -738,6 +738,8 @@ ce_finish_u_kernel(const float* __restrict__ part, int slabs, int64_t N, const f
                    int64_t ldu, const bf* __restrict__ hs, int H, float* __restrict__ lse, float* __restrict__ inv_s,
                    bf* __restrict__ hs_scaled, float* __restrict__ block_sum, int* __restrict__ ticket, float inv_n,
                    float* __restrict__ loss, int* flags) {
+  tc::pdl_launch_dependents();
+  tc::pdl_wait();  // partial sums, target logits and the stored numerators come from the preceding contraction
   __shared__ float red[8][64];
   __shared__ float s_inv[64];
   __shared__ float wred[16];
@@ -880,9 +882,9 @@ int vocab_ce_train_fwd(const void* hs, const float* w_out, const float* b_out, c
   SNT_CHECK((tc::launch_gemm_tc<CE_BN, false, false, CeStoreEpi>(ta, tb, ts, e, st)));
   int* ticket = ce_ticket();
   if (!ticket) { set_error("vocab_ce_train_fwd: could not allocate the reduction ticket"); return SNT_EINVAL; }
-  ce_finish_u_kernel<<<(unsigned)((N + 63) / 64), 512, 0, st>>>(w.part, w.slabs, N, w.pm, w.tl, targets, V, (bf*)u, w.Vp,
-                                                               hs_b, (int)H, lse, inv_s, (bf*)hs_scaled, w.bsum, ticket,
-                                                               loss_scale / (float)N, loss, device_flags());
+  SNT_CUDA(tc::launch_chained(ce_finish_u_kernel, dim3((unsigned)((N + 63) / 64)), dim3(512), 0, st, (const float*)w.part,
+                              w.slabs, N, (const float*)w.pm, (const float*)w.tl, targets, V, (bf*)u, w.Vp, hs_b, (int)H,
+                              lse, inv_s, (bf*)hs_scaled, w.bsum, ticket, loss_scale / (float)N, loss, device_flags()));
   SNT_LAUNCH_CHECK("ce_finish_u_kernel");
   return SNT_OK;
 }
