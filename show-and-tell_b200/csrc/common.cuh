@@ -98,6 +98,18 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_all();
+// Plain stream order for the launches of this thread while the object lives: for a chain of full-GPU contractions that
+// has bandwidth-bound work running BESIDE it on another stream - chained contractions take over every SM the moment
+// their predecessor leaves it, and the blocks of the side work only get in when the whole chain has drained (measured
+// at configs[3]: the output-bias column sums beside the vocabulary contractions, +2.5 % step time).
+struct PdlSuppress {
+  explicit PdlSuppress(bool active);
+  ~PdlSuppress();
+  PdlSuppress(const PdlSuppress&) = delete;
+  PdlSuppress& operator=(const PdlSuppress&) = delete;
+ private:
+  bool active_;
+};
 template <class... KArgs, class... Args>
 inline cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};

@@ -73,10 +73,13 @@ SideStream* side_stream(int which) {
   return &x;
 }
 
+static thread_local int g_pdl_suppress = 0;
 bool pdl_all() {
   static const bool on = [] { const char* e = getenv("SNT_NO_PDL"); return !(e && e[0] == '1'); }();
-  return on;
+  return on && g_pdl_suppress == 0;
 }
+PdlSuppress::PdlSuppress(bool active) : active_(active) { if (active_) ++g_pdl_suppress; }
+PdlSuppress::~PdlSuppress() { if (active_) --g_pdl_suppress; }
 
 }  // namespace snt
 

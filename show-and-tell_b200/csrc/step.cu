@@ -237,6 +237,11 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
   int st_prio = 0;
   const bool background = side != nullptr && cudaStreamGetPriority((cudaStream_t)stream, &st_prio) == cudaSuccess &&
                           st_prio < 0 && !getenv("SNT_NO_BACKGROUND");
+  // Chained launches (common.cuh) pay where the step is a sequence of short dependent launches around the two persistent
+  // recurrence kernels (configs[1]: -9 us per step).  Where the recurrence is a train of per-step launches (H > 512) the
+  // step measured the same or slower with them (configs[3], profiles/r02_chained_launches.txt): plain stream order there;
+  // the per-step forward chain keeps the explicit chaining it always had.
+  PdlSuppress plain_order(!(bf && bf16::lstm_bwd_is_persistent(H)));
   const bool defer_bias = bf && side != nullptr && bf16::lstm_bwd_is_persistent(H) && !getenv("SNT_NO_BIAS_DEFER");
   // dW_out beside the BPTT too: the recurrence needs dHs only, and with two row blocks per CTA (csrc/lstm_tc.cu) it
   // occupies 64 of the 148 SMs at batch 1024.  The contraction runs on its own side stream from a grid capped at the SMs

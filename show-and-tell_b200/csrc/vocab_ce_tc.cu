@@ -940,6 +940,7 @@ int vocab_ce_train_bwd(const void* u, const float* inv_s, const void* hs_scaled,
   }
   const int bn = H >= 256 ? 256 : 128;
   const int64_t sws_elems = train_sws_elems(N, H, V);
+  PdlSuppress plain_order(side != nullptr);  // the column sums above run beside the two contractions: leave them gaps
   // dHs[N,H] = diag(scale * r) . U'[N,V] . W_out[V,H]      (B operand MN-major); the column tiles of one 128-row panel
   // run next to each other so that the panel of U is fetched from HBM once
   SNT_CHECK(tc::gemm_tc_balanced(false, true, N, H, V, scale, ub, w.Vp, wb, H, d_hs, H, w.sws, sws_elems, st, dloss, bn,
