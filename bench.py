@@ -20,6 +20,8 @@ roofline: the stage with the largest share of the step, timed by CUDA events ins
 greedy  : the second half of BASELINE's metric - greedy sample() of 4096 image features per GPU x 20 tokens
           (configs[2]) - as an object with its own roofline, cpu_baseline, e2e (features from the host, ids back) and
           the torch/cuDNN arm on the same GPU.
+configs0: BASELINE configs[0] - the reference's own CPU case, its whole model with the ResNet-152 trunk, batch 128: timed on
+          the host cores by `--impl reference` (`configs0`) and on the GPU as `f_rows.configs0` (trunk on cuDNN + native step).
 configs3: the scaled decoder (E512/H1024/L2/V32000, batch 2048) timed the same way (N=1), also as `--config scaled`.
 strong_8192 (N>1): BASELINE configs[4] as written - global batch 8192 sharded over the N ranks.
 cpu_baseline / --impl reference: the reference's own models.py (oracle/_ref, placed there unmodified by build(); kind
@@ -50,6 +52,10 @@ CONFIGS = {
     "scaled": dict(B=2048, E=512, H=1024, V=32000, L=2, POOLED=2048, name="BASELINE configs[3]"),
 }
 CFG = CONFIGS["default"]
+CONFIGS0 = dict(B=128, E=512, H=1024, V=10000, L=1, POOLED=2048, name="BASELINE configs[0]")   # config.py:17,27-29
+CONFIGS0_WHAT = ("BASELINE configs[0]: frozen ResNet-152 trunk -> Linear+BN head -> 1-layer LSTM decoder at config.py's sizes "
+                 "(embed 512 / hidden 1024, 10k vocabulary), teacher-forced train step, batch 128 synthetic 224x224 images, "
+                 "captions <= 20 tokens")
 GREEDY_B = 4096                                                       # BASELINE.json configs[2]
 STRONG_GLOBAL_B = 8192                                                # BASELINE.json configs[4]
 NB = 8                                                                # distinct ragged batches in the timed region
@@ -240,6 +246,17 @@ def run_reference(args, rank):
     steps, warm = max(1, args.steps), max(1, args.warmup)
     cps, dt, loss, n_tok, kind, what = cpu_train_baseline(c, steps, warm, threads)
     g_tps, g_dt, _, _ = cpu_greedy_baseline(c, 512, threads)
+    configs0 = None
+    if kind == "reference" and not args.no_extras and args.config == "default":
+        # BASELINE configs[0], the reference's own CPU-runnable case: its whole model (ResNet-152 trunk included) on the
+        # host cores; the GPU counterpart is f_rows.configs0 of the native line
+        try:
+            arm, _, _ = cpu_arm()
+            ips, dt0, loss0 = arm.time_configs0(threads=threads, steps=1, warmup=0)
+            configs0 = {"metric": "train_images_per_s", "value": ips, "unit": "images/s", "s_per_step": dt0, "loss": loss0,
+                        "config": CONFIGS0_WHAT, "sample": "ONE step of batch 128 (no warm-up step: a step takes ~10-20 s)"}
+        except Exception as e:   # noqa: BLE001
+            configs0 = {"error": repr(e)[:300]}
     line = {"impl": "reference", "metric": "train_captions_per_s", "value": cps, "unit": "captions/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -249,7 +266,7 @@ def run_reference(args, rank):
             "e2e": {"value": cps, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "greedy": {"metric": "greedy_decode_tokens_per_s", "value": g_tps, "unit": "tokens/s",
                        "sample": f"2 x sample() of 512 image features x 20 tokens ({g_dt:.2f} s each), {what}"},
-            "loss": loss}
+            "configs0": configs0, "loss": loss}
     print(json.dumps(line), flush=True)
 
 
@@ -650,7 +667,32 @@ def measure_f_rows(snt, dev, c, peaks):
         out["trunk_feed"] = measure_trunk_feed(snt, dev, c)
     except Exception as e:   # noqa: BLE001
         out["trunk_feed"] = {"error": repr(e)[:300]}
+    # BASELINE configs[0] (the reference's CPU case) on the GPU: the same whole-model step, trunk on cuDNN, head and decoder
+    # through the native step; `serial_images_per_s` is the number that compares with the reference arm's `configs0`.
+    # In a child process: a size no other leg of this line runs must not be able to cost the line.
+    out["configs0"] = configs0_gpu(dev.index or 0)
     return out
+
+
+def configs0_gpu_child(device_index):
+    import show_and_tell_b200 as snt
+    dev = torch.device("cuda", device_index)
+    torch.cuda.set_device(dev)
+    r = measure_trunk_feed(snt, dev, CONFIGS0)
+    r["config"] = CONFIGS0_WHAT
+    print(json.dumps(r), flush=True)
+
+
+def configs0_gpu(device_index, timeout_s=240):
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "configs0-gpu", "--gpus", "1",
+                            "--device-index", str(device_index)], capture_output=True, text=True, timeout=timeout_s)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": f"child exited {r.returncode}: {r.stderr.strip()[-300:]}"}
+        return json.loads(lines[-1])
+    except Exception as e:   # noqa: BLE001
+        return {"error": repr(e)[:300]}
 
 
 def measure_trunk_feed(snt, dev, c, batch=128, iters=6):
@@ -700,7 +742,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="native", choices=["native", "reference", "torch-gpu"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "torch-gpu", "configs0-gpu"])
     ap.add_argument("--config", default="default", choices=sorted(CONFIGS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="strong: BASELINE configs[4] as written, global batch 8192 sharded over the ranks")
@@ -720,6 +762,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.impl == "configs0-gpu":     # internal: the child of configs0_gpu()
+        configs0_gpu_child(args.device_index)
         return
     if args.impl == "torch-gpu":        # internal: the child of gpu_torch_reference()
         gpu_torch_reference_child(args.device_index)

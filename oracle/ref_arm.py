@@ -140,6 +140,48 @@ def time_full_train(B, E, H, V, L, batch, steps=3, warmup=1, threads=None):
     return B / dt, dt, float(loss.detach())
 
 
+def time_configs0(E=512, H=1024, V=10000, L=1, B=128, steps=1, warmup=1, threads=None, seed=0):
+    """BASELINE configs[0]: the reference's whole model on the CPU - frozen ResNet-152 trunk -> Linear + BN head ->
+    1-layer LSTM decoder at config.py's sizes (config.py:17,27-29), batch 128 synthetic 224x224 images, captions <= 20
+    tokens - one teacher-forced train step as train.py:134-146 runs it (EncoderCNN.forward, models.py:25-29, unmodified).
+    -> (images/s, seconds per step, loss)."""
+    if threads:
+        torch.set_num_threads(threads)
+    enc, dec = make_models(E, H, V, L, seed=seed)
+    enc.train()
+    dec.train()
+    rng = np.random.default_rng(seed + 1)
+    images = torch.from_numpy(rng.standard_normal((B, 3, 224, 224)).astype(np.float32))
+    lengths = np.sort(rng.integers(6, 21, size=B))[::-1].copy()
+    lengths[0] = 20
+    width = int(lengths[0]) - 1                                  # captions[:, :-1] of train.py:139
+    captions = torch.from_numpy(rng.integers(0, V, size=(B, width)).astype(np.int64))
+    lengths = [int(x) for x in lengths]
+    from torch.nn.utils.rnn import pack_padded_sequence
+    tgt_src = torch.from_numpy(rng.integers(0, V, size=(B, width + 1)).astype(np.int64))
+    targets = pack_padded_sequence(tgt_src, lengths, batch_first=True)[0]       # train.py:135
+    params = [p for p in list(enc.parameters()) + list(dec.parameters()) if p.requires_grad]   # train.py:55-56
+    opt = torch.optim.Adam(params, lr=1e-3)
+    criterion = nn.CrossEntropyLoss()
+    ts, loss = [], None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        enc.zero_grad()
+        dec.zero_grad()
+        outputs = dec(enc(images), captions, lengths)            # train.py:139 through models.py:25-29 and :47-54
+        loss = criterion(outputs, targets)
+        loss.backward()
+        for group in opt.param_groups:
+            for p in group["params"]:
+                if p.grad is not None:
+                    p.grad.data.clamp_(-0.1, 0.1)
+        opt.step()
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    dt = float(np.mean(ts))
+    return B / dt, dt, float(loss.detach())
+
+
 @torch.no_grad()
 def sample_keepdim(dec, features, states=None, steps=20):
     """models.py:56-67 on the reference's layers, `max(1, keepdim=True)` restoring the 2017 shape of `predicted`."""
