@@ -265,8 +265,8 @@ extern "C" int snt_step_run(const snt_step* d, int phases, void* stream) {
   // that builds the token plan, when this call starts a training step (forward and the first backward phase together:
   // the tail of backward follows by contract).  The tail - in this call or a later one on the same workspace - then
   // finds the marker and skips the two memsets in front of its first kernel.  SNT_NO_EMB_ZERO_EARLY=1: zero in the tail.
-  static const void* emb_zeroed_ws = nullptr;   // workspace whose embedding gradient the last forward phase zeroed
-  static const float* emb_zeroed_dw = nullptr;
+  static thread_local const void* emb_zeroed_ws = nullptr;   // workspace whose embedding gradient this thread's last forward phase zeroed
+  static thread_local const float* emb_zeroed_dw = nullptr;
   const bool emb_zero_early = side != nullptr && (phases & SNT_STEP_FWD) && (phases & SNT_STEP_BWD_CE) &&
                               d->d_w_emb != nullptr && E % 4 == 0 && E <= 1024 && !getenv("SNT_NO_EMB_ZERO_EARLY");
   if (phases & SNT_STEP_FWD) {
